@@ -1,0 +1,445 @@
+#!/usr/bin/env python
+"""bench.py — the reference's headline metric on B200: fp64 SpMV GFLOP/s (+ effective HBM GB/s vs the
+roofline) on BASELINE.json's configs[1], the synthetic 2D 5-point Poisson 4096 x 4096 grid
+(16.7M rows, 83.9M nnz per GPU), plus CG iterations/s on the 3D 27-point 256^3 system.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A step is one pass of the hot path, y = A x, over the whole (per-rank) matrix.
+  value   device-resident: matrix, x and y live in HBM; K steps timed with CUDA events on the launch
+          stream between barriers; max over ranks.
+  e2e     the same metric through the host-buffer C ABI call cask_b200_spmv (what the reference's
+          Spmv::spmv(const Vector&) maps to): pinned host x -> H2D, kernel, D2H of y, every step.
+  roofline  algorithmic bytes 12 nnz + 8 (rows + cols) per launch / mean kernel time, against the
+          measured HBM copy peak in MEASURED_PEAKS.json.
+  cpu_baseline  the OpenMP CSR port of the reference's CPU product (oracle/), all host cores,
+          the same matrix; `--impl reference` times the compiled reference itself
+          (oracle/_ref: CsrMatrix::dot) on a bounded sample.
+N > 1 (torchrun, one rank per GPU): every rank owns one 4096 x 4096 block of rows of a (4096 N) x 4096
+grid (weak scaling); the x halo (one grid line per neighbour) travels over NCCL and overlaps the
+interior slices.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GRID = 4096  # BASELINE.json configs[1]
+CG_GRID = 256  # BASELINE.json configs[3]
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--grid", type=int, default=GRID)
+    ap.add_argument("--no-cg", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cache", type=int, default=8192)
+    return ap.parse_args()
+
+
+def algorithmic_bytes(nnz, rows, cols):
+    return 12 * nnz + 8 * (rows + cols)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the SpMV kernel, from the committed
+    ncu --set full capture (profiles/roofline_traffic.json); None until one exists."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get("spmv_ell_staged_kernel_bytes_per_launch")
+    return None
+
+
+def cpu_port_baseline(grid):
+    """OpenMP CSR row loop (what Eigen's row-major product / mkl_dcsrgemv compute; MKL and Eigen are
+    not available, restated in oracle/cask_oracle.c) on the SAME matrix, all host cores."""
+    import numpy as np
+    from oracle import oraclebind as O
+    n, rp, ci, va = O.gen_poisson2d(grid)
+    x = (np.arange(n) % 1024) * 0.25
+    y = np.zeros(n)
+    O.csr_spmv_omp(n, rp, ci, va, x, y)  # warm-up
+    best, reps, t_all = 1e30, 0, time.perf_counter()
+    while reps < 10 or (time.perf_counter() - t_all < 5.0 and reps < 50):
+        t0 = time.perf_counter()
+        _, threads = O.csr_spmv_omp(n, rp, ci, va, x, y)
+        best = min(best, time.perf_counter() - t0)
+        reps += 1
+    nnz = len(va)
+    return {"value": 2.0 * nnz / best / 1e9, "unit": "GFLOP/s", "cores": int(threads), "kind": "port",
+            "gbs": algorithmic_bytes(nnz, n, n) / best / 1e9,
+            "sample": "full workload: 2D 5-pt Poisson %dx%d, best of %d OpenMP CSR SpMV (restated; MKL/Eigen unavailable)"
+                      % (grid, grid, reps)}
+
+
+def reference_arm(args):
+    """The reference's own CPU y = A x — cask::CsrMatrix::dot (src/runtime/SparseMatrix.hpp:422-424),
+    compiled in place from /root/reference into oracle/_ref — on a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle import oraclebind as O
+    from oracle import refbind as R
+    sample_grid = 512  # 262 144 rows, 1.3M nnz: same operator, bounded so K steps end within minutes
+    n, rp, ci, va = O.gen_poisson2d(sample_grid)
+    nnz = len(va)
+    x = (np.arange(n) % 1024) * 0.25
+    line = {"impl": "reference", "metric": "fp64 SpMV GFLOP/s", "unit": "GFLOP/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C2 2D 5-pt Poisson %dx%d grid per GPU" % (args.grid, args.grid),
+                       "sample": "same operator on a %dx%d grid" % (sample_grid, sample_grid)}}
+    steps = max(1, min(args.steps, 20))
+    warm = max(1, min(args.warmup, 2))
+    if R.available():
+        m = R.RefMatrix.from_csr(n, n, rp, ci, va)
+        for _ in range(warm):
+            m.dot(x)
+        t = 0.0
+        for _ in range(steps):
+            y, s = m.dot(x, return_seconds=True)
+            t += s
+        assert np.array_equal(y, O.csr_dot(n, rp, ci, va, x))
+        kind, cores = "reference", 1
+        sample = ("cask::CsrMatrix::dot (reference code, single-threaded by construction) on 2D 5-pt Poisson "
+                  "%dx%d, %d timed calls" % (sample_grid, sample_grid, steps))
+    else:
+        y = np.zeros(n)
+        for _ in range(warm):
+            O.csr_spmv_omp(n, rp, ci, va, x, y)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            _, cores = O.csr_spmv_omp(n, rp, ci, va, x, y)
+        t = time.perf_counter() - t0
+        kind = "port"
+        sample = "oracle port (OpenMP CSR loop) on 2D 5-pt Poisson %dx%d, %d timed calls" % (sample_grid, sample_grid, steps)
+    v = 2.0 * nnz * steps / t / 1e9
+    line.update({"value": v, "ms_per_step": 1e3 * t / steps, "steps": steps, "warmup": warm,
+                 "cpu_baseline": {"value": v, "unit": "GFLOP/s", "cores": cores, "kind": kind, "sample": sample},
+                 "e2e": {"value": v, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    if not args.no_cpu:
+        try:
+            line["port_all_cores"] = cpu_port_baseline(min(args.grid, 2048))
+        except Exception as e:  # informational only
+            line["port_all_cores"] = {"error": str(e)}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import cask_b200 as cb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: cask_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ctx = cb.Context(local)
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx.set_stream(stream)
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(cb.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        ctx.dist_init(rank, world, bytes(idt.cpu().numpy().tobytes()))
+
+    # ---- workload: rank r owns grid rows [r*G, (r+1)*G) of a (G*world) x G five-point grid ----------
+    G = args.grid
+    kind = cb.SYNTH_POISSON2D
+
+    # the generator is square-grid; weak scaling stacks `world` square grids along i: emulate with the
+    # row-stripe generator of a (G*world)-long strip by generating rows of an N = G grid per rank and
+    # shifting? No: rows of different ranks must couple through the i+-1 neighbours.  Use the 3-D
+    # generator's cousin: a 2-D grid of G*world x G is NOT square, so build it from the 7-pt-free path:
+    n_local = G * G
+    n_global = n_local * world
+    rows_i = torch.arange(n_local, device=dev, dtype=torch.int64) + rank * n_local
+    gi, gj = rows_i // G, rows_i % G
+    has = torch.stack([gi > 0, gj > 0, torch.ones_like(gi, dtype=torch.bool), gj < G - 1, gi < G * world - 1], 1)
+    offs = torch.tensor([-G, -1, 0, 1, G], device=dev, dtype=torch.int64)
+    vals5 = torch.tensor([-1.0, -1.0, 4.0, -1.0, -1.0], device=dev, dtype=torch.float64)
+    cols = (rows_i[:, None] + offs[None, :])[has].to(torch.int32).contiguous()
+    vals = vals5[None, :].expand(n_local, 5)[has].contiguous()
+    rp = torch.zeros(n_local + 1, dtype=torch.int32, device=dev)
+    rp[1:] = torch.cumsum(has.sum(1), 0).to(torch.int32)
+    nnz_local = int(rp[-1].item())
+    del rows_i, gi, gj, has
+    if world == 1:
+        # cross-check the torch-built stripe against the library's own device generator
+        nnz_chk = cb.synth_nnz(kind, G, 0, n_local)
+        assert nnz_chk == nnz_local
+    dsg = cb.design(num_pipes=1, cache_size=args.cache, input_width=16)
+    t0 = time.perf_counter()
+    if world > 1:
+        ctx.preprocess_shard_device(dsg, n_global, n_global, rank * n_local, n_local, nnz_local,
+                                    rp.data_ptr(), cols.data_ptr(), vals.data_ptr())
+    else:
+        ctx.preprocess_device(dsg, n_local, n_local, nnz_local, rp.data_ptr(), cols.data_ptr(), vals.data_ptr())
+    ctx.synchronize()
+    preprocess_s = time.perf_counter() - t0
+    stats = ctx.plan_stats()
+
+    x_full = ((torch.arange(n_global, device=dev) % 1024).double() * 0.25).contiguous()
+    y = torch.empty(n_local, dtype=torch.float64, device=dev)
+
+    # ---- device-resident timing ----------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        ctx.spmv_device(x_full.data_ptr(), y.data_ptr())
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        ctx.spmv_device(x_full.data_ptr(), y.data_ptr())
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    # correctness of the timed result: interior rows vanish for this x, boundary rows are known
+    xg = x_full.view(G * world, G)
+    lo, hi = rank * G, (rank + 1) * G
+    ref = 4 * xg[lo:hi].clone()
+    ref[:, 1:] -= xg[lo:hi, :-1]
+    ref[:, :-1] -= xg[lo:hi, 1:]
+    if lo > 0:
+        ref -= xg[lo - 1:hi - 1]
+    else:
+        ref[1:] -= xg[lo:hi - 1]
+    if hi < G * world:
+        ref -= xg[lo + 1:hi + 1]
+    else:
+        ref[:-1] -= xg[lo + 1:hi]
+    if not torch.equal(y.view(G, G), ref):
+        raise SystemExit("bench: SpMV result differs from the closed-form stencil result")
+    del ref, xg
+
+    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item())
+    nnz_total = nnz_local * world  # boundary ranks have 4096 entries fewer; weak-scaling approximation
+    if world > 1:
+        z = torch.tensor([nnz_local], dtype=torch.float64, device=dev)
+        dist.all_reduce(z)
+        nnz_total = int(z.item())
+    flops = 2.0 * nnz_total
+    value = flops * args.steps / (ms * 1e-3) / 1e9
+    bytes_per_launch = algorithmic_bytes(nnz_local, n_local, n_local)
+    kernel_ms = ms / args.steps
+    achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
+    peak, peak_src = measured_peak()
+
+    # ---- end to end: host buffers through the C ABI ---------------------------------------------
+    e2e_steps = max(3, min(args.steps, 20))
+    if world == 1:
+        hx = torch.empty(n_local, dtype=torch.float64).pin_memory()
+        hy = torch.empty(n_local, dtype=torch.float64).pin_memory()
+        hx.copy_(x_full.cpu())
+        for _ in range(3):
+            ctx.spmv_into(hx.numpy(), hy.numpy())
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            ctx.spmv_into(hx.numpy(), hy.numpy())
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        assert torch.equal(hy, y.cpu())
+    else:
+        hx = torch.empty(n_local, dtype=torch.float64).pin_memory()
+        hy = torch.empty(n_local, dtype=torch.float64).pin_memory()
+        hx.copy_(x_full[rank * n_local:(rank + 1) * n_local].cpu())
+        xs = x_full[rank * n_local:(rank + 1) * n_local]
+
+        def step():
+            xs.copy_(hx, non_blocking=True)
+            ctx.spmv_device(x_full.data_ptr(), y.data_ptr())
+            hy.copy_(y, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        for _ in range(3):
+            step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    e2e = {"value": flops / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": 8 * n_local * world,
+           "d2h_bytes_per_step": 8 * n_local * world, "ms_per_step": 1e3 * e2e_s, "steps": e2e_steps,
+           "api": "cask_b200_spmv(ctx, x_host, y_host)" if world == 1 else "H2D + cask_b200_spmv_device + D2H per rank"}
+
+    # ---- CG iterations / s on the 3D 27-point system (strong scaling: fixed 256^3 grid) -----------
+    cg = None
+    if not args.no_cg:
+        del x_full, y, cols, vals, rp
+        torch.cuda.empty_cache()
+        cg = bench_cg(ctx, cb, torch, dist, dev, rank, world, barrier)
+
+    if rank == 0:
+        line = {
+            "metric": "fp64 SpMV GFLOP/s", "value": value, "unit": "GFLOP/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": kernel_ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "C2: 2D 5-pt Poisson %dx%d grid per GPU (%d rows, %d nnz per GPU), y = A x"
+                                   % (G, G, n_local, nnz_local),
+                       "global_rows": n_global, "sharding": "row stripes over ranks (Spmv.cpp:334-364), NCCL x halo",
+                       "l2": "inputs (%.2f GB per launch) larger than L2 (126 MB); no flush needed" % (bytes_per_launch / 1e9),
+                       "design": {"num_pipes": 1, "cache_size": args.cache, "input_width": 16},
+                       "preprocess_s": preprocess_s, "plan": stats},
+            "hbm_gbs": achieved, "frac_of_nominal_8tbs": achieved / 8000.0,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "spmv_ell_staged_kernel",
+                         "algorithmic_bytes_per_launch": bytes_per_launch},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if cg:
+            line["cg"] = cg
+        if world == 1 and not args.no_cpu:
+            try:
+                line["cpu_baseline"] = cpu_port_baseline(G)
+            except Exception as e:
+                line["cpu_baseline"] = {"value": None, "unit": "GFLOP/s", "cores": 0, "kind": "port", "sample": "failed: %s" % e}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_cg(ctx, cb, torch, dist, dev, rank, world, barrier):
+    """BASELINE configs[3]: CG (the reference's pcg loop, identity preconditioner) on the 3D 27-point
+    256^3 Poisson system, row-sharded over the ranks; b = A x_true, x_true[k] = 1 + 0.25 (k mod 4)."""
+    N = CG_GRID
+    kind = cb.SYNTH_POISSON3D27
+    n = cb.synth_rows(kind, N)
+    r0, nr = cb.shard_rows(n, world, rank)
+    nnz = cb.synth_nnz(kind, N, r0, nr)
+    rp = torch.empty(nr + 1, dtype=torch.int32, device=dev)
+    ci = torch.empty(nnz, dtype=torch.int32, device=dev)
+    va = torch.empty(nnz, dtype=torch.float64, device=dev)
+    cb.synth_device(kind, N, r0, nr, rp.data_ptr(), ci.data_ptr(), va.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    dsg = cb.design(num_pipes=1, cache_size=8192, input_width=16)
+    if world > 1:
+        ctx.preprocess_shard_device(dsg, n, n, r0, nr, nnz, rp.data_ptr(), ci.data_ptr(), va.data_ptr())
+    else:
+        ctx.preprocess_device(dsg, n, n, nnz, rp.data_ptr(), ci.data_ptr(), va.data_ptr())
+    xt = (1.0 + 0.25 * (torch.arange(n, device=dev) % 4).double()).contiguous()
+    b = torch.empty(nr, dtype=torch.float64, device=dev)
+    ctx.spmv_device(xt.data_ptr(), b.data_ptr())
+    ctx.synchronize()
+    x = torch.zeros(nr, dtype=torch.float64, device=dev)
+    ctx.cg_device(b.data_ptr(), x.data_ptr(), maxiters=20)  # warm-up
+    x.zero_()
+    barrier()
+    l0 = ctx.launch_count()
+    t0 = time.perf_counter()
+    conv, iters, rs, trips = ctx.cg_device(b.data_ptr(), x.data_ptr(), maxiters=2000, tol=1e-5)
+    barrier()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt.item())
+    err = float((x - xt[r0:r0 + nr]).abs().max().item())
+    et = torch.tensor([err], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(et, op=dist.ReduceOp.MAX)
+    nnz_total = cb.synth_nnz(kind, N, 0, n)
+    return {"workload": "C4: CG on 3D 27-pt Poisson %d^3 (%d rows, %d nnz), row-sharded over %d GPU(s)" % (N, n, nnz_total, world),
+            "scaling": "strong", "iters_per_s": trips / dt, "loop_trips": trips, "iterations_reported": iters,
+            "converged": conv, "rs_final": rs, "seconds": dt, "max_abs_err_vs_x_true": float(et.item()),
+            "gpu_launches": int(ctx.launch_count() - l0),
+            "traffic_bound_iters_per_s_1gpu": 1.0 / ((algorithmic_bytes(nnz_total, n, n) + 72 * n) / (measured_peak()[0] * 1e9))}
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,283 @@
+"""cask_b200 — B200-native SpMV / CG hot path of CASK behind a C ABI.
+
+The product is `libcask_b200.so` (hand-written CUDA for sm_100a, `cask_b200/csrc/`) and the C++ host
+mirror of the reference interface (`cask_b200/host/`).  This Python module is only the thinnest
+ctypes view of that C ABI (`include/cask_b200.h`) for tests and bench.py: it holds no arithmetic and
+no fallback — if the library is missing or no GPU is usable, calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcask_b200.so")
+
+OK, ERR_INVALID_ARGUMENT, ERR_RUNTIME, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED, ERR_NCCL = range(7)
+ARCH_SIMPLE, ARCH_SKIPEMPTY = 0, 1
+SYNTH_POISSON2D, SYNTH_POISSON3D27, SYNTH_CONVDIFF3D7 = 0, 1, 2
+
+PAIR_DTYPE = np.dtype([("value", "<f8"), ("indptr", "<i4")], align=False)  # indptr_value, Spmv.hpp:13-20
+
+EXPORTED_SYMBOLS = (
+    "cask_b200_device_count", "cask_b200_create", "cask_b200_destroy", "cask_b200_last_error",
+    "cask_b200_set_stream", "cask_b200_use_own_stream", "cask_b200_synchronize", "cask_b200_set_option", "cask_b200_preprocess",
+    "cask_b200_preprocess_device", "cask_b200_plan_get_stats", "cask_b200_partition_get_info",
+    "cask_b200_partition_export", "cask_b200_spmv", "cask_b200_spmv_device", "cask_b200_spmv_refformat",
+    "cask_b200_cg", "cask_b200_cg_device", "cask_b200_bicgstab", "cask_b200_bicgstab_device",
+    "cask_b200_nccl_unique_id", "cask_b200_dist_init", "cask_b200_shard_rows",
+    "cask_b200_preprocess_shard_device", "cask_b200_dist_halo_counts", "cask_b200_synth_rows",
+    "cask_b200_synth_nnz", "cask_b200_synth_device", "cask_b200_launch_count",
+)
+
+
+class Design(C.Structure):
+    """cask_b200_design == the parameters of GeneratedSpmvImplementation (GeneratedImplSupport.hpp:58)."""
+    _fields_ = [(k, C.c_int32) for k in ("num_pipes", "cache_size", "input_width", "max_rows",
+                                         "num_controllers", "dram_reduction_enabled", "arch")]
+
+
+class PartitionInfo(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("nBlocks", "n", "paddingCycles", "totalCycles", "vector_load_cycles",
+                                         "outSize", "reductionCycles", "emptyCycles", "m_colptr_unpaddedLength",
+                                         "m_indptr_values_unpaddedLength")] + [("len_colptr", C.c_int64),
+                                                                               ("len_pairs", C.c_int64)]
+
+
+class PlanStats(C.Structure):
+    _fields_ = [("n", C.c_int64), ("m", C.c_int64), ("nnz", C.c_int64), ("slice_rows", C.c_int32),
+                ("num_slices", C.c_int32), ("slices_staged_ell", C.c_int32), ("slices_gather_csr", C.c_int32),
+                ("csr_lanes_per_row", C.c_int32), ("max_row_length", C.c_int32),
+                ("ell_padded_entries", C.c_int64), ("ell_nnz", C.c_int64), ("xcache_doubles_total", C.c_int64),
+                ("device_bytes", C.c_int64), ("row_length_histogram", C.c_int64 * 8)]
+
+    def as_dict(self):
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "row_length_histogram"}
+        d["row_length_histogram"] = list(self.row_length_histogram)
+        return d
+
+
+class CaskError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("cask_b200 error %d: %s" % (code, msg))
+        self.code = code
+        self.message = msg
+
+
+_lib = None
+
+
+def lib():
+    """Loads libcask_b200.so; raises if it has not been built (no fallback of any kind)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("libcask_b200.so is not built: run `python -m cask_b200.build` "
+                              "(or __graft_entry__.build()); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        L.cask_b200_last_error.restype = C.c_char_p
+        vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+        L.cask_b200_create.argtypes = [C.POINTER(vp), C.c_int]
+        L.cask_b200_destroy.argtypes = [vp]
+        L.cask_b200_set_stream.argtypes = [vp, vp]
+        L.cask_b200_synchronize.argtypes = [vp]
+        L.cask_b200_use_own_stream.argtypes = [vp]
+        L.cask_b200_set_option.argtypes = [vp, C.c_char_p, dbl]
+        L.cask_b200_preprocess.argtypes = [vp, C.POINTER(Design), i64, i64, i64, vp, vp, vp]
+        L.cask_b200_preprocess_device.argtypes = [vp, C.POINTER(Design), i64, i64, i64, vp, vp, vp]
+        L.cask_b200_preprocess_shard_device.argtypes = [vp, C.POINTER(Design), i64, i64, i64, i64, i64, vp, vp, vp]
+        L.cask_b200_plan_get_stats.argtypes = [vp, C.POINTER(PlanStats)]
+        L.cask_b200_partition_get_info.argtypes = [vp, i32, C.POINTER(PartitionInfo)]
+        L.cask_b200_partition_export.argtypes = [vp, i32, vp, vp]
+        L.cask_b200_spmv.argtypes = [vp, vp, vp]
+        L.cask_b200_spmv_device.argtypes = [vp, vp, vp]
+        L.cask_b200_spmv_refformat.argtypes = [vp, vp, vp]
+        L.cask_b200_cg.argtypes = [vp, vp, vp, i32, dbl, vp, vp, vp]
+        L.cask_b200_cg_device.argtypes = [vp, vp, vp, i32, dbl, vp, vp, vp, vp]
+        L.cask_b200_bicgstab.argtypes = [vp, vp, vp, vp, vp]
+        L.cask_b200_bicgstab_device.argtypes = [vp, vp, vp, vp, vp]
+        L.cask_b200_nccl_unique_id.argtypes = [vp]
+        L.cask_b200_dist_init.argtypes = [vp, i32, i32, vp]
+        L.cask_b200_shard_rows.argtypes = [i64, i32, i32, vp, vp]
+        L.cask_b200_dist_halo_counts.argtypes = [vp, vp]
+        L.cask_b200_synth_rows.argtypes = [i32, i32, vp]
+        L.cask_b200_synth_nnz.argtypes = [i32, i32, i64, i64, vp]
+        L.cask_b200_synth_device.argtypes = [i32, i32, i64, i64, vp, vp, vp, vp]
+        L.cask_b200_launch_count.argtypes = [vp, vp]
+        L.cask_b200_device_count.argtypes = [vp]
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != OK:
+        raise CaskError(rc, lib().cask_b200_last_error().decode())
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(int(a))  # raw device pointer
+
+
+def design(num_pipes=1, cache_size=8192, input_width=16, max_rows=0, num_controllers=1,
+           dram_reduction_enabled=0, arch=ARCH_SIMPLE):
+    return Design(num_pipes, cache_size, input_width, max_rows, num_controllers, dram_reduction_enabled, arch)
+
+
+def shard_rows(n, world, rank):
+    r0, nr = C.c_int64(), C.c_int64()
+    check(lib().cask_b200_shard_rows(n, world, rank, C.byref(r0), C.byref(nr)))
+    return r0.value, nr.value
+
+
+def synth_rows(kind, N):
+    n = C.c_int64()
+    check(lib().cask_b200_synth_rows(kind, N, C.byref(n)))
+    return n.value
+
+
+def synth_nnz(kind, N, row0, nrows):
+    z = C.c_int64()
+    check(lib().cask_b200_synth_nnz(kind, N, row0, nrows, C.byref(z)))
+    return z.value
+
+
+class Context:
+    """One cask_b200_ctx: one GPU, one stream."""
+
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        check(lib().cask_b200_create(C.byref(self.h), device))
+        self.n = self.m = 0
+
+    def close(self):
+        if self.h:
+            lib().cask_b200_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, stream_ptr):
+        """Share a caller's cudaStream_t (0 = CUDA's default stream), e.g. torch.cuda.current_stream().cuda_stream."""
+        check(lib().cask_b200_set_stream(self.h, C.c_void_p(stream_ptr)))
+
+    def use_own_stream(self):
+        check(lib().cask_b200_use_own_stream(self.h))
+
+    def synchronize(self):
+        check(lib().cask_b200_synchronize(self.h))
+
+    def set_option(self, name, value):
+        check(lib().cask_b200_set_option(self.h, name.encode(), float(value)))
+
+    def preprocess(self, dsg, n, m, row_ptr, col_ind, values):
+        rp = np.ascontiguousarray(row_ptr, np.int32)
+        ci = np.ascontiguousarray(col_ind, np.int32)
+        va = np.ascontiguousarray(values, np.float64)
+        check(lib().cask_b200_preprocess(self.h, C.byref(dsg), n, m, len(va), _p(rp), _p(ci), _p(va)))
+        self.n, self.m = n, m
+
+    def preprocess_device(self, dsg, n, m, nnz, d_row_ptr, d_col_ind, d_values):
+        check(lib().cask_b200_preprocess_device(self.h, C.byref(dsg), n, m, nnz, _p(d_row_ptr), _p(d_col_ind),
+                                                _p(d_values)))
+        self.n, self.m = n, m
+
+    def preprocess_shard_device(self, dsg, n_global, m, row0, nrows, nnz, d_row_ptr, d_col_ind, d_values):
+        check(lib().cask_b200_preprocess_shard_device(self.h, C.byref(dsg), n_global, m, row0, nrows, nnz,
+                                                      _p(d_row_ptr), _p(d_col_ind), _p(d_values)))
+        self.n, self.m = nrows, m
+
+    def plan_stats(self):
+        st = PlanStats()
+        check(lib().cask_b200_plan_get_stats(self.h, C.byref(st)))
+        return st.as_dict()
+
+    def partition(self, pipe, arrays=True):
+        """(info dict, colptr, pairs) of reference partition `pipe`, produced by the GPU partitioner."""
+        info = PartitionInfo()
+        check(lib().cask_b200_partition_get_info(self.h, pipe, C.byref(info)))
+        d = {k: int(getattr(info, k)) for k, _ in PartitionInfo._fields_}
+        if not arrays:
+            return d, None, None
+        colptr = np.empty(info.len_colptr, np.int32)
+        pairs = np.empty(info.len_pairs, PAIR_DTYPE)
+        check(lib().cask_b200_partition_export(self.h, pipe, _p(colptr), _p(pairs)))
+        return d, colptr, pairs
+
+    def spmv(self, x):
+        x = np.ascontiguousarray(x, np.float64)
+        if self.m and len(x) != self.m:
+            raise ValueError('x has %d entries, matrix has %d columns' % (len(x), self.m))
+        y = np.empty(self.n, np.float64)
+        check(lib().cask_b200_spmv(self.h, _p(x), _p(y)))
+        return y
+
+    def spmv_into(self, x, y):
+        check(lib().cask_b200_spmv(self.h, _p(x), _p(y)))
+
+    def spmv_refformat(self, x):
+        x = np.ascontiguousarray(x, np.float64)
+        y = np.empty(self.n, np.float64)
+        check(lib().cask_b200_spmv_refformat(self.h, _p(x), _p(y)))
+        return y
+
+    def spmv_device(self, d_x, d_y):
+        check(lib().cask_b200_spmv_device(self.h, _p(d_x), _p(d_y)))
+
+    def cg(self, rhs, x0=None, maxiters=2000, tol=1e-5, iterations=0):
+        """Returns (converged, iterations, x, rs_final) — iterations with the reference's convention."""
+        rhs = np.ascontiguousarray(rhs, np.float64)
+        x = np.zeros(self.n, np.float64) if x0 is None else np.array(x0, np.float64)
+        it, conv, rs = C.c_int32(iterations), C.c_int32(0), C.c_double(0)
+        check(lib().cask_b200_cg(self.h, _p(rhs), _p(x), maxiters, tol, C.byref(it), C.byref(conv), C.byref(rs)))
+        return bool(conv.value), it.value, x, rs.value
+
+    def cg_device(self, d_rhs, d_x, maxiters=2000, tol=1e-5, iterations=0):
+        it, conv, rs, trips = C.c_int32(iterations), C.c_int32(0), C.c_double(0), C.c_int32(0)
+        check(lib().cask_b200_cg_device(self.h, _p(d_rhs), _p(d_x), maxiters, tol, C.byref(it), C.byref(conv),
+                                        C.byref(rs), C.byref(trips)))
+        return bool(conv.value), it.value, rs.value, trips.value
+
+    def bicgstab(self, b, tol=0.0, maxit=0):
+        b = np.ascontiguousarray(b, np.float64)
+        x = np.zeros(self.n, np.float64)
+        it, te = C.c_int32(maxit), C.c_double(tol)
+        check(lib().cask_b200_bicgstab(self.h, _p(b), _p(x), C.byref(it), C.byref(te)))
+        return x, it.value, te.value
+
+    def bicgstab_device(self, d_b, d_x, tol=0.0, maxit=0):
+        it, te = C.c_int32(maxit), C.c_double(tol)
+        check(lib().cask_b200_bicgstab_device(self.h, _p(d_b), _p(d_x), C.byref(it), C.byref(te)))
+        return it.value, te.value
+
+    def dist_init(self, rank, world, unique_id_bytes):
+        buf = (C.c_char * 128).from_buffer_copy(unique_id_bytes) if unique_id_bytes else None
+        check(lib().cask_b200_dist_init(self.h, rank, world, buf))
+
+    def halo_counts(self, world):
+        out = np.zeros(world, np.int64)
+        check(lib().cask_b200_dist_halo_counts(self.h, _p(out)))
+        return out
+
+    def launch_count(self):
+        c = C.c_int64()
+        check(lib().cask_b200_launch_count(self.h, C.byref(c)))
+        return c.value
+
+
+def nccl_unique_id():
+    buf = (C.c_char * 128)()
+    check(lib().cask_b200_nccl_unique_id(buf))
+    return bytes(buf)
+
+
+def synth_device(kind, N, row0, nrows, d_row_ptr, d_col_ind, d_values, stream_ptr=0):
+    check(lib().cask_b200_synth_device(kind, N, row0, nrows, _p(d_row_ptr), _p(d_col_ind), _p(d_values),
+                                       C.c_void_p(stream_ptr)))

@@ -1,0 +1,339 @@
+// extern "C" entry points of libcask_b200.so (contract: include/cask_b200.h).
+#include <algorithm>
+#include <cstring>
+
+#include "ctx.cuh"
+
+namespace caskb200 {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+int ensure_device(cask_b200_ctx* ctx) {
+  cudaError_t e = cudaSetDevice(ctx->device);
+  if (e != cudaSuccess) return fail(CASK_B200_ERR_NO_DEVICE, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+  return CASK_B200_OK;
+}
+
+namespace {
+
+int check_design(const cask_b200_design* d) {
+  if (!d) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "design is null");
+  if (d->num_pipes <= 0 || d->cache_size <= 0 || d->input_width <= 0)
+    return fail(CASK_B200_ERR_INVALID_ARGUMENT, "num_pipes, cache_size and input_width must be positive");
+  if (d->arch != CASK_B200_ARCH_SIMPLE && d->arch != CASK_B200_ARCH_SKIPEMPTY)
+    return fail(CASK_B200_ERR_INVALID_ARGUMENT, "unknown arch");
+  return CASK_B200_OK;
+}
+
+void reset_matrix(cask_b200_ctx* ctx) {
+  free_ref_partitions(ctx);
+  free_plan(ctx);
+  ctx->have_design = false;
+}
+
+int finish_preprocess(cask_b200_ctx* ctx) {
+  CB_TRY(build_plan(ctx));
+  ctx->have_design = true;
+  if (dist_active(ctx)) CB_TRY(dist_plan_halo(ctx));
+  return CASK_B200_OK;
+}
+
+int grow(double** buf, int64_t* len, int64_t need) {
+  if (*len >= need) return CASK_B200_OK;
+  cudaFree(*buf);
+  *buf = nullptr;
+  *len = 0;
+  CB_CUDA(cudaMalloc(buf, sizeof(double) * std::max<int64_t>(need, 2)));
+  *len = need;
+  return CASK_B200_OK;
+}
+
+}  // namespace
+}  // namespace caskb200
+
+using namespace caskb200;
+
+extern "C" {
+
+const char* cask_b200_last_error(void) { return g_last_error.c_str(); }
+
+int cask_b200_device_count(int* count) {
+  if (!count) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "device_count: null");
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess) { *count = 0; return fail(CASK_B200_ERR_NO_DEVICE, cudaGetErrorString(e)); }
+  *count = c;
+  return CASK_B200_OK;
+}
+
+int cask_b200_create(cask_b200_ctx** out, int device) {
+  if (!out) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "create: null output");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(CASK_B200_ERR_NO_DEVICE, std::string("no CUDA device: cask_b200 has no CPU fallback (") +
+                                             (e != cudaSuccess ? cudaGetErrorString(e) : "0 devices") + ")");
+  if (device < 0 || device >= count) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "create: device index out of range");
+  cask_b200_ctx* ctx = new cask_b200_ctx();
+  ctx->device = device;
+  if (ensure_device(ctx) != CASK_B200_OK) { delete ctx; return CASK_B200_ERR_NO_DEVICE; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming) != cudaSuccess) {
+    delete ctx;
+    return fail(CASK_B200_ERR_CUDA, "create: stream/event creation failed");
+  }
+  ctx->stream = ctx->own_stream;
+  *out = ctx;
+  return CASK_B200_OK;
+}
+
+int cask_b200_destroy(cask_b200_ctx* ctx) {
+  if (!ctx) return CASK_B200_OK;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  dist_free(ctx);
+  free_solver_work(ctx);
+  reset_matrix(ctx);
+  cudaFree(ctx->d_x);
+  cudaFree(ctx->d_y);
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
+  if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+  delete ctx;
+  return CASK_B200_OK;
+}
+
+int cask_b200_set_stream(cask_b200_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "set_stream: null context");
+  ctx->stream = (cudaStream_t)cuda_stream;  // NULL is CUDA's legacy default stream, a valid choice
+  return CASK_B200_OK;
+}
+
+int cask_b200_use_own_stream(cask_b200_ctx* ctx) {
+  if (!ctx) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "use_own_stream: null context");
+  ctx->stream = ctx->own_stream;
+  return CASK_B200_OK;
+}
+
+int cask_b200_synchronize(cask_b200_ctx* ctx) {
+  if (!ctx) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "synchronize: null context");
+  CB_TRY(ensure_device(ctx));
+  CB_CUDA(cudaStreamSynchronize(ctx->stream));
+  CB_CUDA(cudaStreamSynchronize(ctx->comm_stream));
+  return CASK_B200_OK;
+}
+
+int cask_b200_set_option(cask_b200_ctx* ctx, const char* name, double value) {
+  if (!ctx || !name) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "set_option: null");
+  const std::string k(name);
+  if (k == "ell_min_fill") ctx->ell_min_fill = value;
+  else if (k == "force_kind") ctx->force_kind = (int32_t)value;
+  else if (k == "force_csr_vec") ctx->force_csr_vec = (int32_t)value;
+  else return fail(CASK_B200_ERR_INVALID_ARGUMENT, "set_option: unknown option " + k);
+  return CASK_B200_OK;
+}
+
+int cask_b200_launch_count(cask_b200_ctx* ctx, int64_t* count) {
+  if (!ctx || !count) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "launch_count: null");
+  *count = ctx->launches;
+  return CASK_B200_OK;
+}
+
+// ---- preprocess -------------------------------------------------------------------------------
+int cask_b200_preprocess_shard_device(cask_b200_ctx* ctx, const cask_b200_design* design, int64_t n_global,
+                                      int64_t m, int64_t row0, int64_t nrows, int64_t nnz_local,
+                                      const int32_t* d_row_ptr, const int32_t* d_col_ind, const double* d_values) {
+  if (!ctx) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "preprocess: null context");
+  CB_TRY(check_design(design));
+  CB_TRY(ensure_device(ctx));
+  if (n_global < 0 || m < 0 || nrows < 0 || row0 < 0 || row0 + nrows > n_global || nnz_local < 0)
+    return fail(CASK_B200_ERR_INVALID_ARGUMENT, "preprocess: bad dimensions");
+  if (nrows > INT32_MAX - 2 * kSliceRows || m > INT32_MAX - 64 || nnz_local > INT32_MAX)
+    return fail(CASK_B200_ERR_UNSUPPORTED, "preprocess: a stripe is limited to 2^31 rows / columns / nonzeros");
+  if (nrows && (!d_row_ptr || (nnz_local && (!d_col_ind || !d_values))))
+    return fail(CASK_B200_ERR_INVALID_ARGUMENT, "preprocess: null CSR arrays");
+  reset_matrix(ctx);
+  ctx->design = *design;
+  Plan& p = ctx->plan;
+  p.n = nrows; p.m = m; p.nnz = nnz_local; p.n_global = n_global; p.row0_global = row0;
+  p.d_row_ptr = d_row_ptr; p.d_col = d_col_ind; p.d_val = d_values; p.owns_csr = false;
+  if (dist_active(ctx)) {
+    // one stripe per rank: the rank IS the pipe
+    ctx->design.num_pipes = 1;
+  }
+  return finish_preprocess(ctx);
+}
+
+int cask_b200_preprocess_device(cask_b200_ctx* ctx, const cask_b200_design* design, int64_t n, int64_t m, int64_t nnz,
+                                const int32_t* d_row_ptr, const int32_t* d_col_ind, const double* d_values) {
+  return cask_b200_preprocess_shard_device(ctx, design, n, m, 0, n, nnz, d_row_ptr, d_col_ind, d_values);
+}
+
+int cask_b200_preprocess(cask_b200_ctx* ctx, const cask_b200_design* design, int64_t n, int64_t m, int64_t nnz,
+                         const int32_t* row_ptr, const int32_t* col_ind, const double* values) {
+  if (!ctx) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "preprocess: null context");
+  CB_TRY(check_design(design));
+  CB_TRY(ensure_device(ctx));
+  if (n < 0 || m < 0 || nnz < 0 || n > INT32_MAX - 2 * kSliceRows || nnz > INT32_MAX)
+    return fail(CASK_B200_ERR_INVALID_ARGUMENT, "preprocess: bad dimensions");
+  if (!row_ptr || (nnz && (!col_ind || !values))) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "preprocess: null CSR arrays");
+  if (row_ptr[n] != nnz) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "preprocess: row_ptr[n] != nnz");
+  reset_matrix(ctx);
+  int32_t *d_rp = nullptr, *d_ci = nullptr;
+  double* d_va = nullptr;
+  CB_CUDA(cudaMalloc(&d_rp, sizeof(int32_t) * (n + 1)));
+  CB_CUDA(cudaMalloc(&d_ci, sizeof(int32_t) * std::max<int64_t>(nnz, 1)));
+  CB_CUDA(cudaMalloc(&d_va, sizeof(double) * std::max<int64_t>(nnz, 1)));
+  CB_CUDA(cudaMemcpyAsync(d_rp, row_ptr, sizeof(int32_t) * (n + 1), cudaMemcpyHostToDevice, ctx->stream));
+  if (nnz) {
+    CB_CUDA(cudaMemcpyAsync(d_ci, col_ind, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, ctx->stream));
+    CB_CUDA(cudaMemcpyAsync(d_va, values, sizeof(double) * nnz, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CB_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->design = *design;
+  Plan& p = ctx->plan;
+  p.n = n; p.m = m; p.nnz = nnz; p.n_global = n; p.row0_global = 0;
+  p.d_row_ptr = d_rp; p.d_col = d_ci; p.d_val = d_va; p.owns_csr = true;
+  return finish_preprocess(ctx);
+}
+
+int cask_b200_plan_get_stats(cask_b200_ctx* ctx, cask_b200_plan_stats* out) {
+  if (!ctx || !out || !ctx->have_design) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "plan_get_stats: preprocess first");
+  *out = ctx->plan.stats;
+  return CASK_B200_OK;
+}
+
+// ---- parity hook --------------------------------------------------------------------------------
+int cask_b200_partition_get_info(cask_b200_ctx* ctx, int32_t pipe, cask_b200_partition_info* out) {
+  if (!ctx || !out || !ctx->have_design) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "partition_get_info: preprocess first");
+  CB_TRY(ensure_device(ctx));
+  CB_TRY(build_ref_partitions(ctx));
+  if (pipe < 0 || pipe >= (int32_t)ctx->ref_parts.size()) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "partition index out of range");
+  *out = ctx->ref_parts[pipe].info;
+  return CASK_B200_OK;
+}
+
+int cask_b200_partition_export(cask_b200_ctx* ctx, int32_t pipe, int32_t* colptr, void* pairs) {
+  if (!ctx || !ctx->have_design) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "partition_export: preprocess first");
+  CB_TRY(ensure_device(ctx));
+  CB_TRY(build_ref_partitions(ctx));
+  if (pipe < 0 || pipe >= (int32_t)ctx->ref_parts.size()) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "partition index out of range");
+  const RefPartition& q = ctx->ref_parts[pipe];
+  if (colptr && q.info.len_colptr)
+    CB_CUDA(cudaMemcpyAsync(colptr, q.d_colptr, sizeof(int32_t) * q.info.len_colptr, cudaMemcpyDeviceToHost, ctx->stream));
+  if (pairs && q.info.len_pairs)
+    CB_CUDA(cudaMemcpyAsync(pairs, q.d_pairs, 12 * q.info.len_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+  CB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CASK_B200_OK;
+}
+
+// ---- SpMV ---------------------------------------------------------------------------------------
+static int check_spmv(cask_b200_ctx* ctx) {
+  if (!ctx || !ctx->have_design) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "spmv: preprocess a matrix first");
+  const cask_b200_design& d = ctx->design;
+  // argument checks of Spmv::spmv, src/runtime/Spmv.cpp:189-232, same wording
+  if (d.dram_reduction_enabled) {
+    if (ctx->plan.n_global < 35000)
+      return fail(CASK_B200_ERR_INVALID_ARGUMENT, "Matrix is too small! Minimum supported rows with DRAM reduction: 35000 actual rows: " +
+                                                      std::to_string(ctx->plan.n_global));
+  } else if (d.max_rows > 0 && d.max_rows < ctx->plan.n_global) {
+    return fail(CASK_B200_ERR_INVALID_ARGUMENT, "Matrix is too large! Maximum supported rows: " + std::to_string(d.max_rows) +
+                                                    " actual rows: " + std::to_string(ctx->plan.n_global));
+  }
+  if (d.num_controllers > 0) {
+    if (d.num_pipes % d.num_controllers != 0) return fail(CASK_B200_ERR_RUNTIME, "numPipes should be a multiple of numControllers");
+    if (d.num_controllers > d.num_pipes) return fail(CASK_B200_ERR_RUNTIME, "numPipes should be larger than numControllers");
+  }
+  return ensure_device(ctx);
+}
+
+int cask_b200_spmv_device(cask_b200_ctx* ctx, const double* d_x, double* d_y) {
+  CB_TRY(check_spmv(ctx));
+  if (!d_x || (!d_y && ctx->plan.n)) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "spmv: null vector");
+  if (dist_active(ctx)) {
+    // d_x is the full-layout vector (global length); halo entries are refreshed in place
+    CB_TRY(dist_exchange_begin(ctx, const_cast<double*>(d_x), ctx->stream));
+    CB_TRY(launch_spmv(ctx, d_x, d_y, 1, ctx->stream, nullptr));
+    CB_TRY(dist_exchange_wait(ctx, ctx->stream));
+    return launch_spmv(ctx, d_x, d_y, 2, ctx->stream, nullptr);
+  }
+  return launch_spmv(ctx, d_x, d_y, 0, ctx->stream, nullptr);
+}
+
+static int stage_in(cask_b200_ctx* ctx, const double* x, int64_t m, int64_t n) {
+  CB_TRY(grow(&ctx->d_x, &ctx->d_x_len, m));
+  CB_TRY(grow(&ctx->d_y, &ctx->d_y_len, n));
+  if (m) CB_CUDA(cudaMemcpyAsync(ctx->d_x, x, sizeof(double) * m, cudaMemcpyHostToDevice, ctx->stream));
+  return CASK_B200_OK;
+}
+
+int cask_b200_spmv(cask_b200_ctx* ctx, const double* x, double* y) {
+  CB_TRY(check_spmv(ctx));
+  if (dist_active(ctx)) return fail(CASK_B200_ERR_UNSUPPORTED, "spmv (host buffers) is single-rank; use spmv_device when sharded");
+  const Plan& p = ctx->plan;
+  if ((!x && p.m) || (!y && p.n)) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "spmv: null vector");
+  CB_TRY(stage_in(ctx, x, p.m, p.n));
+  CB_TRY(launch_spmv(ctx, ctx->d_x, ctx->d_y, 0, ctx->stream, nullptr));
+  if (p.n) CB_CUDA(cudaMemcpyAsync(y, ctx->d_y, sizeof(double) * p.n, cudaMemcpyDeviceToHost, ctx->stream));
+  CB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CASK_B200_OK;
+}
+
+int cask_b200_spmv_refformat(cask_b200_ctx* ctx, const double* x, double* y) {
+  CB_TRY(check_spmv(ctx));
+  const Plan& p = ctx->plan;
+  if ((!x && p.m) || (!y && p.n)) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "spmv: null vector");
+  CB_TRY(stage_in(ctx, x, p.m, p.n));
+  CB_TRY(spmv_refformat_device(ctx, ctx->d_x, ctx->d_y));
+  if (p.n) CB_CUDA(cudaMemcpyAsync(y, ctx->d_y, sizeof(double) * p.n, cudaMemcpyDeviceToHost, ctx->stream));
+  CB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CASK_B200_OK;
+}
+
+// ---- solvers with host buffers -------------------------------------------------------------------
+int cask_b200_cg(cask_b200_ctx* ctx, const double* rhs, double* x, int32_t maxiters, double tol, int32_t* iterations,
+                 int32_t* converged, double* rs_final) {
+  if (!ctx || !ctx->have_design) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "cg: preprocess a matrix first");
+  if (dist_active(ctx)) return fail(CASK_B200_ERR_UNSUPPORTED, "cg (host buffers) is single-rank; use cg_device when sharded");
+  CB_TRY(ensure_device(ctx));
+  const int64_t n = ctx->plan.n;
+  if (!rhs || !x) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "cg: null vector");
+  CB_TRY(grow(&ctx->d_x, &ctx->d_x_len, n));
+  CB_TRY(grow(&ctx->d_y, &ctx->d_y_len, n));
+  CB_CUDA(cudaMemcpyAsync(ctx->d_x, x, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+  CB_CUDA(cudaMemcpyAsync(ctx->d_y, rhs, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+  CB_TRY(cask_b200_cg_device(ctx, ctx->d_y, ctx->d_x, maxiters, tol, iterations, converged, rs_final, nullptr));
+  CB_CUDA(cudaMemcpyAsync(x, ctx->d_x, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CASK_B200_OK;
+}
+
+int cask_b200_bicgstab(cask_b200_ctx* ctx, const double* b, double* x, int32_t* iters, double* tol_error) {
+  if (!ctx || !ctx->have_design) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "bicgstab: preprocess a matrix first");
+  if (dist_active(ctx)) return fail(CASK_B200_ERR_UNSUPPORTED, "bicgstab (host buffers) is single-rank; use bicgstab_device");
+  CB_TRY(ensure_device(ctx));
+  const int64_t n = ctx->plan.n;
+  if (!b || !x) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "bicgstab: null vector");
+  CB_TRY(grow(&ctx->d_x, &ctx->d_x_len, n));
+  CB_TRY(grow(&ctx->d_y, &ctx->d_y_len, n));
+  CB_CUDA(cudaMemcpyAsync(ctx->d_y, b, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+  CB_TRY(cask_b200_bicgstab_device(ctx, ctx->d_y, ctx->d_x, iters, tol_error));
+  CB_CUDA(cudaMemcpyAsync(x, ctx->d_x, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CASK_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,176 @@
+// Internal declarations shared by the translation units of libcask_b200.so.
+// Nothing here is part of the ABI; the ABI is include/cask_b200.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/cask_b200.h"
+
+namespace caskb200 {
+
+// ---- error plumbing ------------------------------------------------------------------------
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+
+#define CB_CUDA(expr)                                                                         \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess)                                                                    \
+      return ::caskb200::fail(CASK_B200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+#define CB_TRY(expr)                 \
+  do {                               \
+    int _rc = (expr);                \
+    if (_rc != CASK_B200_OK) return _rc; \
+  } while (0)
+
+// ---- compute format ---------------------------------------------------
+constexpr int kGranuleShift = 4;               // x is staged in granules of 16 doubles (128 B)
+constexpr int kGranule = 1 << kGranuleShift;
+constexpr int kZeroSlots = 2;                  // xs[0..1] = 0.0: target of padding entries, keeps runs 16-B aligned
+constexpr int kEllThreads = 256;               // threads per CTA of the staged kernel
+constexpr int kEllRowsPerThread = 4;           // rows per thread -> 128-bit value loads
+constexpr int kSliceRows = kEllThreads * kEllRowsPerThread;  // 1024 rows per slice
+constexpr int kBitmapWords = 8192;             // granule bitmap of a slice: 8192*32 granules = 4M columns of span
+constexpr int kMaxRuns = 1024;                 // contiguous x runs staged per slice
+constexpr int kMaxCacheDoubles = 24576;        // 192 KB of shared memory for the x cache at most
+
+enum SliceKind : int32_t { kSliceStagedEll = 0, kSliceGatherCsr = 1 };
+
+struct SliceDesc {     // one row slice (<= kSliceRows consecutive rows of one stripe)
+  int32_t row0;        // first row, local to this rank's stripe
+  int32_t nrows;       // valid rows
+  int32_t width;       // ELL width (max row length in the slice)
+  int32_t kind;        // SliceKind
+  int64_t val_off;     // entry offset into ell_vals / ell_idx
+  int32_t run_off;     // offset into runs[]
+  int32_t nruns;
+  int32_t xcache_len;  // doubles staged in shared memory, including the zero slots
+  int32_t nnz;
+  int32_t remote;      // 1 if some staged column lies outside this rank's own x slice (dist only)
+  int32_t pad_;
+};
+
+struct Run {           // one contiguous window of x staged by a single bulk copy
+  int32_t col0;        // first column (multiple of kGranule)
+  int32_t len;         // doubles (clipped at m)
+  int32_t local_base;  // position in the slice's shared-memory x cache
+  int32_t pad_;
+};
+
+struct RefPartition {  // reference-format partition resident on the device
+  cask_b200_partition_info info{};
+  int32_t* d_colptr = nullptr;
+  uint8_t* d_pairs = nullptr;  // packed 12-byte records
+  int64_t row0 = 0;
+  bool values_zeroed = false;
+};
+
+struct Plan {
+  int64_t n = 0, m = 0, nnz = 0;       // local rows, global columns, local nnz
+  int64_t n_global = 0, row0_global = 0;
+  const int32_t* d_row_ptr = nullptr;  // CSR (owned or borrowed)
+  const int32_t* d_col = nullptr;
+  const double* d_val = nullptr;
+  bool owns_csr = false;
+
+  int32_t slice_rows = kSliceRows;
+  int32_t nslices = 0;
+  SliceDesc* d_slices = nullptr;
+  Run* d_runs = nullptr;
+  double* d_ell_vals = nullptr;
+  uint16_t* d_ell_idx = nullptr;
+  int32_t* d_list_ell = nullptr;      // slice ids, staged ELL, interior first then halo-dependent
+  int32_t* d_list_csr = nullptr;
+  int32_t n_ell = 0, n_ell_interior = 0;
+  int32_t n_csr = 0, n_csr_interior = 0;
+  int32_t csr_vec = 4;
+  int32_t max_xcache = 0;
+  cask_b200_plan_stats stats{};
+  std::vector<SliceDesc> h_slices;
+};
+
+struct DistState;  // dist.cu
+
+struct SolverWork {  // device scratch of the CG / BiCGStab loops
+  double* d_vec[8] = {nullptr};
+  int64_t vec_len = 0;
+  double* d_scalars = nullptr;   // see solvers.cu
+  double* d_partials = nullptr;
+  unsigned int* d_counters = nullptr;
+  int32_t* h_flags = nullptr;    // pinned
+  double* h_scalars = nullptr;   // pinned
+};
+
+}  // namespace caskb200
+
+struct cask_b200_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  int sm_count = 148;
+  int64_t launches = 0;
+
+  cask_b200_design design{};
+  bool have_design = false;
+  caskb200::Plan plan;
+  std::vector<caskb200::RefPartition> ref_parts;
+  bool ref_built = false;
+
+  // tuning knobs (cask_b200_set_option)
+  double ell_min_fill = 0.75;
+  int32_t force_kind = -1;   // -1 auto, 0 staged ELL wherever possible, 1 gather CSR everywhere
+  int32_t force_csr_vec = 0;
+
+  // host-call staging buffers
+  double* d_x = nullptr; int64_t d_x_len = 0;
+  double* d_y = nullptr; int64_t d_y_len = 0;
+  double* h_pinned = nullptr; int64_t h_pinned_len = 0;
+
+  caskb200::SolverWork work;
+  caskb200::DistState* dist = nullptr;
+};
+
+namespace caskb200 {
+
+// refformat.cu
+int build_ref_partitions(cask_b200_ctx* ctx);
+void free_ref_partitions(cask_b200_ctx* ctx);
+int spmv_refformat_device(cask_b200_ctx* ctx, const double* d_x, double* d_y);
+
+// plan.cu
+int build_plan(cask_b200_ctx* ctx);
+void free_plan(cask_b200_ctx* ctx);
+
+// spmv.cu
+struct SpmvFusion {           // optional fused epilogue: partial dot products per CTA
+  const double* d_dot_with = nullptr;  // if set: partial sum of y[r] * dot_with[r] (local rows)
+  double* d_partials = nullptr;        // one partial per CTA of the launch (+offset)
+  int fuse_self_dot = 0;               // also accumulate y[r]*y[r]
+};
+int launch_spmv(cask_b200_ctx* ctx, const double* d_x_full, double* d_y, int part /*0 all,1 interior,2 boundary*/,
+                cudaStream_t stream, const SpmvFusion* fusion);
+int spmv_num_ctas(cask_b200_ctx* ctx, int part);
+
+// dist.cu
+int dist_exchange_begin(cask_b200_ctx* ctx, double* d_x_full, cudaStream_t after);
+int dist_exchange_wait(cask_b200_ctx* ctx, cudaStream_t consumer);
+int dist_allreduce_sum(cask_b200_ctx* ctx, double* d_vals, int count, cudaStream_t stream);
+void dist_free(cask_b200_ctx* ctx);
+bool dist_active(const cask_b200_ctx* ctx);
+int dist_plan_halo(cask_b200_ctx* ctx);
+
+// solvers.cu
+void free_solver_work(cask_b200_ctx* ctx);
+
+// helpers
+int ensure_device(cask_b200_ctx* ctx);
+
+}  // namespace caskb200

@@ -1,0 +1,393 @@
+// GPU-side partitioner for the THROUGHPUT format.
+//
+// Same partitioning decisions as the reference — row stripes of Spmv::preprocess
+// (src/runtime/Spmv.cpp:334-364) and an on-chip x cache of `cache_size` doubles per unit of work
+// (the column blocks of CsrMatrix::sliceColumns, src/runtime/SparseMatrix.hpp:459-482) — but stored
+// for a B200 instead of a dataflow pipe:
+//
+//   * every stripe is cut into slices of kSliceRows rows;
+//   * for each slice the set of 128-byte x granules its rows touch is found with a shared-memory
+//     bitmap; consecutive granules merge into "runs", each staged by ONE TMA bulk copy; if the
+//     staged doubles fit the cache budget the slice becomes a STAGED-ELL slice: values stored
+//     column-major (thread-per-row, 128-bit coalesced loads) and column indices rewritten to 16-bit
+//     positions inside the slice's shared-memory x cache;
+//   * slices whose rows are too irregular (ELL fill below ell_min_fill) or whose columns are too
+//     scattered for the cache keep plain CSR and are executed vector-per-row with x gathered
+//     through L2; the lanes-per-row width is chosen from the row-length histogram.
+#include <algorithm>
+#include <cstring>
+
+#include "ctx.cuh"
+
+namespace caskb200 {
+
+namespace {
+
+struct SliceCount {     // output of the analysis pass, one per slice
+  int32_t width;        // max row length
+  int32_t nnz;
+  int32_t nruns;        // -1: span too wide for the bitmap
+  int32_t xlen;         // staged doubles incl. zero slots (valid when nruns >= 0)
+};
+
+__device__ __forceinline__ int32_t warp_max(int32_t v) {
+#pragma unroll
+  for (int d = 16; d; d >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, d));
+  return v;
+}
+__device__ __forceinline__ int32_t warp_min(int32_t v) {
+#pragma unroll
+  for (int d = 16; d; d >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, d));
+  return v;
+}
+__device__ __forceinline__ int32_t warp_sum(int32_t v) {
+#pragma unroll
+  for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+
+// Shared state of one slice while its x-cache layout is derived.
+struct SliceSmem {
+  uint32_t bitmap[kBitmapWords];   // bit g set: granule gmin+g is referenced
+  uint16_t prefix[kBitmapWords];   // number of set bits in words before this one (<= 1536 granules)
+  int32_t red[3][8];
+  int32_t gmin, gmax, width, nruns, ngran, ok;
+};
+
+// Finds gmin/gmax/width, fills bitmap + prefix.  Returns false (for the whole CTA) if the granule
+// span does not fit the bitmap or more granules are referenced than max_gran.
+__device__ bool analyse_slice(SliceSmem& sm, const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
+                              int32_t row0, int32_t nrows, int32_t max_gran) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int32_t k0 = row_ptr[row0], k1 = row_ptr[row0 + nrows];
+  int32_t lmax = 0, cmin = INT32_MAX, cmax = -1;
+  for (int32_t r = tid; r < nrows; r += blockDim.x)
+    lmax = max(lmax, row_ptr[row0 + r + 1] - row_ptr[row0 + r]);
+  for (int32_t k = k0 + tid; k < k1; k += blockDim.x) {
+    const int32_t c = col[k];
+    cmin = min(cmin, c);
+    cmax = max(cmax, c);
+  }
+  lmax = warp_max(lmax); cmin = warp_min(cmin); cmax = warp_max(cmax);
+  if (lane == 0) { sm.red[0][warp] = lmax; sm.red[1][warp] = cmin; sm.red[2][warp] = cmax; }
+  __syncthreads();
+  if (tid == 0) {
+    int32_t a = 0, b = INT32_MAX, c = -1;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) { a = max(a, sm.red[0][w]); b = min(b, sm.red[1][w]); c = max(c, sm.red[2][w]); }
+    sm.width = a;
+    sm.gmin = b == INT32_MAX ? 0 : (b >> kGranuleShift);
+    sm.gmax = c < 0 ? -1 : (c >> kGranuleShift);
+    sm.ok = (sm.gmax - sm.gmin + 1) <= kBitmapWords * 32;
+  }
+  __syncthreads();
+  if (!sm.ok) return false;
+  const int32_t gmin = sm.gmin;
+  const int32_t words = sm.gmax < gmin ? 0 : ((sm.gmax - gmin) >> 5) + 1;
+  for (int32_t w = tid; w < words; w += blockDim.x) sm.bitmap[w] = 0;
+  __syncthreads();
+  for (int32_t k = k0 + tid; k < k1; k += blockDim.x) {
+    const int32_t g = (col[k] >> kGranuleShift) - gmin;
+    atomicOr(&sm.bitmap[g >> 5], 1u << (g & 31));
+  }
+  __syncthreads();
+  // prefix popcounts + run count; words <= 8192, done by warp 0 in chunks of 32 words
+  if (warp == 0) {
+    int32_t carry = 0, runs = 0;
+    uint32_t prev_msb = 0;
+    for (int32_t base = 0; base < words; base += 32) {
+      const int32_t w = base + lane;
+      const uint32_t bits = w < words ? sm.bitmap[w] : 0u;
+      int32_t pc = __popc(bits), incl = pc;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        int32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+      }
+      uint32_t below = __shfl_up_sync(0xffffffffu, bits, 1);
+      const uint32_t carry_in = lane ? (below >> 31) : prev_msb;
+      runs += __popc(bits & ~((bits << 1) | carry_in));  // bits that start a run
+      const int32_t excl = carry + incl - pc;
+      if (w < words) sm.prefix[w] = (uint16_t)min(excl, 65535);
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+      prev_msb = __shfl_sync(0xffffffffu, bits, 31) >> 31;
+    }
+    runs = warp_sum(runs);
+    if (lane == 0) { sm.ngran = carry; sm.nruns = runs; sm.ok = carry <= max_gran && runs <= kMaxRuns; }
+  }
+  __syncthreads();
+  return sm.ok;
+}
+
+__global__ void __launch_bounds__(256)
+plan_count_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col, const int32_t* __restrict__ slice_row0,
+                  const int32_t* __restrict__ slice_nrows, int32_t max_gran, SliceCount* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  SliceSmem& sm = *reinterpret_cast<SliceSmem*>(raw);
+  const int32_t s = blockIdx.x;
+  const int32_t row0 = slice_row0[s], nrows = slice_nrows[s];
+  const bool ok = analyse_slice(sm, row_ptr, col, row0, nrows, max_gran);
+  if (threadIdx.x == 0) {
+    SliceCount c;
+    c.width = sm.width;
+    c.nnz = row_ptr[row0 + nrows] - row_ptr[row0];
+    c.nruns = ok ? sm.nruns : -1;
+    c.xlen = ok ? kZeroSlots + sm.ngran * kGranule : 0;
+    out[s] = c;
+  }
+}
+
+// Second pass for staged-ELL slices: rebuild the bitmap, write the runs, rewrite the slice into the
+// ELL arrays.  Layout inside a slice (T = kEllThreads, RPT = kEllRowsPerThread):
+//   entry (k, row) with row = j*T + t  lives at  val_off + (k*T + t)*RPT + j
+// so thread t reads RPT consecutive values with 128-bit loads and, for a fixed j, the lanes of a
+// warp own consecutive rows (coalesced y, conflict-free shared-memory x reads on banded matrices).
+__global__ void __launch_bounds__(256)
+plan_fill_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col, const double* __restrict__ val,
+                 const SliceDesc* __restrict__ slices, const int32_t* __restrict__ list, int32_t max_gran, int32_t m,
+                 Run* __restrict__ runs, double* __restrict__ ell_vals, uint16_t* __restrict__ ell_idx) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  SliceSmem& sm = *reinterpret_cast<SliceSmem*>(raw);
+  const SliceDesc sd = slices[list[blockIdx.x]];
+  analyse_slice(sm, row_ptr, col, sd.row0, sd.nrows, max_gran);
+  const int tid = threadIdx.x;
+  const int32_t gmin = sm.gmin;
+  const int32_t words = sm.gmax < gmin ? 0 : ((sm.gmax - gmin) >> 5) + 1;
+  // runs: a bit starts a run if the bit below is clear; its rank among run starts = popcount of
+  // earlier starts (small: recount serially per word owner), its length = distance to the next clear bit.
+  __shared__ int32_t run_cursor;
+  if (tid == 0) run_cursor = 0;
+  __syncthreads();
+  // Deterministic order: thread 0 of warp 0 walks the words (<= 8192) — cheap next to the nnz pass.
+  if (tid == 0) {
+    int32_t r = 0;
+    int32_t open_start = -1;
+    for (int32_t w = 0; w < words; w++) {
+      uint32_t bits = sm.bitmap[w];
+      if (bits == 0u) {
+        if (open_start >= 0) {
+          Run q; q.col0 = (gmin + open_start) << kGranuleShift; q.len = ((w << 5) - open_start) << kGranuleShift;
+          q.local_base = 0; q.pad_ = 0; runs[sd.run_off + r++] = q; open_start = -1;
+        }
+        continue;
+      }
+      if (bits == 0xffffffffu) { if (open_start < 0) open_start = w << 5; continue; }
+      for (int b = 0; b < 32; b++) {
+        const bool set = (bits >> b) & 1u;
+        if (set && open_start < 0) open_start = (w << 5) + b;
+        if (!set && open_start >= 0) {
+          Run q; q.col0 = (gmin + open_start) << kGranuleShift; q.len = (((w << 5) + b) - open_start) << kGranuleShift;
+          q.local_base = 0; q.pad_ = 0; runs[sd.run_off + r++] = q; open_start = -1;
+        }
+      }
+    }
+    if (open_start >= 0) {
+      Run q; q.col0 = (gmin + open_start) << kGranuleShift; q.len = ((words << 5) - open_start) << kGranuleShift;
+      q.local_base = 0; q.pad_ = 0; runs[sd.run_off + r++] = q;
+    }
+    // local bases and clipping at m
+    int32_t base = kZeroSlots;
+    for (int32_t i = 0; i < r; i++) {
+      Run q = runs[sd.run_off + i];
+      q.local_base = base;
+      base += q.len;
+      if (q.col0 + q.len > m) q.len = m - q.col0;
+      runs[sd.run_off + i] = q;
+    }
+  }
+  // ELL fill: one thread per row walks its entries; padding entries point at the zero slot.
+  const int32_t T = kEllThreads, RPT = kEllRowsPerThread;
+  for (int32_t row = tid; row < T * RPT; row += blockDim.x) {
+    const int32_t t = row % T, j = row / T;
+    int32_t k = 0, kb = 0, ke = 0;
+    if (row < sd.nrows) { kb = row_ptr[sd.row0 + row]; ke = row_ptr[sd.row0 + row + 1]; }
+    for (; k < sd.width; k++) {
+      const int64_t pos = sd.val_off + ((int64_t)k * T + t) * RPT + j;
+      if (kb + k < ke) {
+        const int32_t c = col[kb + k];
+        const int32_t g = (c >> kGranuleShift) - gmin;
+        const int32_t rank = sm.prefix[g >> 5] + __popc(sm.bitmap[g >> 5] & ((1u << (g & 31)) - 1u));
+        ell_vals[pos] = val[kb + k];
+        ell_idx[pos] = (uint16_t)(kZeroSlots + rank * kGranule + (c & (kGranule - 1)));
+      } else {
+        ell_vals[pos] = 0.0;
+        ell_idx[pos] = 0;
+      }
+    }
+  }
+}
+
+__global__ void row_length_histogram_kernel(const int32_t* __restrict__ row_ptr, int64_t n,
+                                            unsigned long long* __restrict__ hist, int32_t* __restrict__ maxlen) {
+  __shared__ unsigned int sh[8];
+  if (threadIdx.x < 8) sh[threadIdx.x] = 0;
+  __syncthreads();
+  int32_t lm = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t len = row_ptr[i + 1] - row_ptr[i];
+    lm = max(lm, len);
+    int b = len == 0 ? 0 : len <= 2 ? 1 : len <= 4 ? 2 : len <= 8 ? 3 : len <= 16 ? 4 : len <= 32 ? 5 : len <= 64 ? 6 : 7;
+    atomicAdd(&sh[b], 1u);
+  }
+  lm = warp_max(lm);
+  if ((threadIdx.x & 31) == 0) atomicMax(maxlen, lm);
+  __syncthreads();
+  if (threadIdx.x < 8) atomicAdd(&hist[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+}
+
+}  // namespace
+
+void free_plan(cask_b200_ctx* ctx) {
+  Plan& p = ctx->plan;
+  if (p.owns_csr) {
+    cudaFree((void*)p.d_row_ptr);
+    cudaFree((void*)p.d_col);
+    cudaFree((void*)p.d_val);
+  }
+  cudaFree(p.d_slices); cudaFree(p.d_runs); cudaFree(p.d_ell_vals); cudaFree(p.d_ell_idx);
+  cudaFree(p.d_list_ell); cudaFree(p.d_list_csr);
+  p = Plan();
+}
+
+int build_plan(cask_b200_ctx* ctx) {
+  Plan& p = ctx->plan;
+  const cask_b200_design& d = ctx->design;
+  cudaStream_t s = ctx->stream;
+  const int64_t n = p.n;
+  p.slice_rows = kSliceRows;
+
+  // ---- slices: stripes of Spmv::preprocess, cut every slice_rows rows -------------------------
+  // (sharded runs: the stripe IS the rank's row range, Spmv.cpp:334-364 applied over ranks)
+  std::vector<int32_t> row0s, nrows;
+  {
+    const int64_t P = d.num_pipes > 0 ? d.num_pipes : 1;
+    const int64_t rpp = n / P;
+    int64_t start = 0;
+    for (int64_t q = 0; q < P; q++) {
+      int64_t rows = rpp == 0 ? (q == 0 ? n : 0) : (q == P - 1 ? n - start : rpp);
+      for (int64_t r = 0; r < rows; r += p.slice_rows) {
+        row0s.push_back((int32_t)(start + r));
+        nrows.push_back((int32_t)std::min<int64_t>(p.slice_rows, rows - r));
+      }
+      start += rows;
+    }
+  }
+  p.nslices = (int32_t)row0s.size();
+  p.stats = cask_b200_plan_stats{};
+  p.stats.n = n; p.stats.m = p.m; p.stats.nnz = p.nnz;
+  p.stats.slice_rows = p.slice_rows;
+  p.stats.num_slices = p.nslices;
+  if (p.nslices == 0) return CASK_B200_OK;
+
+  int32_t cache = d.cache_size;
+  if (cache > kMaxCacheDoubles) cache = kMaxCacheDoubles;
+  const int32_t max_gran = std::max(0, (cache - kZeroSlots) / kGranule);
+
+  int32_t *d_row0 = nullptr, *d_nrows = nullptr;
+  SliceCount* d_counts = nullptr;
+  CB_CUDA(cudaMalloc(&d_row0, sizeof(int32_t) * p.nslices));
+  CB_CUDA(cudaMalloc(&d_nrows, sizeof(int32_t) * p.nslices));
+  CB_CUDA(cudaMalloc(&d_counts, sizeof(SliceCount) * p.nslices));
+  CB_CUDA(cudaMemcpyAsync(d_row0, row0s.data(), sizeof(int32_t) * p.nslices, cudaMemcpyHostToDevice, s));
+  CB_CUDA(cudaMemcpyAsync(d_nrows, nrows.data(), sizeof(int32_t) * p.nslices, cudaMemcpyHostToDevice, s));
+  CB_CUDA(cudaFuncSetAttribute(plan_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SliceSmem)));
+  CB_CUDA(cudaFuncSetAttribute(plan_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SliceSmem)));
+  plan_count_kernel<<<p.nslices, 256, sizeof(SliceSmem), s>>>(p.d_row_ptr, p.d_col, d_row0, d_nrows, max_gran, d_counts);
+  ctx->launches++;
+
+  unsigned long long* d_hist = nullptr;
+  int32_t* d_maxlen = nullptr;
+  CB_CUDA(cudaMalloc(&d_hist, sizeof(unsigned long long) * 8));
+  CB_CUDA(cudaMalloc(&d_maxlen, sizeof(int32_t)));
+  CB_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * 8, s));
+  CB_CUDA(cudaMemsetAsync(d_maxlen, 0, sizeof(int32_t), s));
+  row_length_histogram_kernel<<<std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, s>>>(p.d_row_ptr, n, d_hist, d_maxlen);
+  ctx->launches++;
+
+  std::vector<SliceCount> counts(p.nslices);
+  unsigned long long hist[8];
+  int32_t maxlen = 0;
+  CB_CUDA(cudaMemcpyAsync(counts.data(), d_counts, sizeof(SliceCount) * p.nslices, cudaMemcpyDeviceToHost, s));
+  CB_CUDA(cudaMemcpyAsync(hist, d_hist, sizeof(hist), cudaMemcpyDeviceToHost, s));
+  CB_CUDA(cudaMemcpyAsync(&maxlen, d_maxlen, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  CB_CUDA(cudaStreamSynchronize(s));
+  CB_CUDA(cudaGetLastError());
+
+  // ---- kernel selection from the histogram and the band profile --------------------------------
+  p.h_slices.assign(p.nslices, SliceDesc{});
+  std::vector<int32_t> list_ell, list_csr;
+  int64_t val_off = 0;
+  int32_t run_off = 0;
+  int64_t csr_rows = 0, csr_nnz = 0;
+  p.max_xcache = 0;
+  const int64_t stripe_lo = p.row0_global, stripe_hi = p.row0_global + p.n;
+  (void)stripe_lo; (void)stripe_hi;
+  for (int32_t i = 0; i < p.nslices; i++) {
+    SliceDesc& sd = p.h_slices[i];
+    const SliceCount& c = counts[i];
+    sd.row0 = row0s[i]; sd.nrows = nrows[i]; sd.width = c.width; sd.nnz = c.nnz;
+    const double fill = c.width > 0 ? (double)c.nnz / ((double)c.width * nrows[i]) : 1.0;
+    bool staged = c.nruns >= 0 && c.xlen <= cache && fill >= ctx->ell_min_fill && c.width <= 4096;
+    if (ctx->force_kind == 1) staged = false;
+    if (ctx->force_kind == 0) staged = c.nruns >= 0 && c.xlen <= cache;
+    if (staged) {
+      sd.kind = kSliceStagedEll;
+      sd.val_off = val_off;
+      sd.run_off = run_off;
+      sd.nruns = c.nruns;
+      sd.xcache_len = c.xlen;
+      val_off += (int64_t)c.width * p.slice_rows;
+      run_off += c.nruns;
+      p.max_xcache = std::max(p.max_xcache, c.xlen);
+      list_ell.push_back(i);
+      p.stats.ell_padded_entries += (int64_t)c.width * p.slice_rows;
+      p.stats.ell_nnz += c.nnz;
+      p.stats.xcache_doubles_total += c.xlen;
+    } else {
+      sd.kind = kSliceGatherCsr;
+      list_csr.push_back(i);
+      csr_rows += nrows[i];
+      csr_nnz += c.nnz;
+    }
+  }
+  // lanes per row for the CSR slices: smallest power of two >= mean row length / 2, in [2, 32]
+  int32_t vec = 2;
+  if (csr_rows > 0) {
+    const double mean = (double)csr_nnz / (double)csr_rows;
+    while (vec < 32 && vec * 2 <= mean) vec <<= 1;
+  }
+  if (ctx->force_csr_vec) vec = ctx->force_csr_vec;
+  p.csr_vec = vec;
+  p.n_ell = (int32_t)list_ell.size();
+  p.n_ell_interior = p.n_ell;
+  p.n_csr = (int32_t)list_csr.size();
+  p.n_csr_interior = p.n_csr;
+
+  CB_CUDA(cudaMalloc(&p.d_slices, sizeof(SliceDesc) * p.nslices));
+  CB_CUDA(cudaMemcpyAsync(p.d_slices, p.h_slices.data(), sizeof(SliceDesc) * p.nslices, cudaMemcpyHostToDevice, s));
+  CB_CUDA(cudaMalloc(&p.d_list_ell, sizeof(int32_t) * std::max(p.n_ell, 1)));
+  CB_CUDA(cudaMalloc(&p.d_list_csr, sizeof(int32_t) * std::max(p.n_csr, 1)));
+  if (p.n_ell) CB_CUDA(cudaMemcpyAsync(p.d_list_ell, list_ell.data(), sizeof(int32_t) * p.n_ell, cudaMemcpyHostToDevice, s));
+  if (p.n_csr) CB_CUDA(cudaMemcpyAsync(p.d_list_csr, list_csr.data(), sizeof(int32_t) * p.n_csr, cudaMemcpyHostToDevice, s));
+  CB_CUDA(cudaMalloc(&p.d_runs, sizeof(Run) * std::max(run_off, 1)));
+  CB_CUDA(cudaMalloc(&p.d_ell_vals, sizeof(double) * std::max<int64_t>(val_off, 1)));
+  CB_CUDA(cudaMalloc(&p.d_ell_idx, sizeof(uint16_t) * std::max<int64_t>(val_off, 8)));
+  if (p.n_ell) {
+    plan_fill_kernel<<<p.n_ell, 256, sizeof(SliceSmem), s>>>(p.d_row_ptr, p.d_col, p.d_val, p.d_slices, p.d_list_ell,
+                                                             max_gran, (int32_t)p.m, p.d_runs, p.d_ell_vals, p.d_ell_idx);
+    ctx->launches++;
+  }
+  CB_CUDA(cudaStreamSynchronize(s));
+  CB_CUDA(cudaGetLastError());
+  cudaFree(d_row0); cudaFree(d_nrows); cudaFree(d_counts); cudaFree(d_hist); cudaFree(d_maxlen);
+
+  p.stats.slices_staged_ell = p.n_ell;
+  p.stats.slices_gather_csr = p.n_csr;
+  p.stats.csr_lanes_per_row = vec;
+  p.stats.max_row_length = maxlen;
+  for (int i = 0; i < 8; i++) p.stats.row_length_histogram[i] = (int64_t)hist[i];
+  p.stats.device_bytes = val_off * 10 + (int64_t)run_off * sizeof(Run) + (int64_t)p.nslices * sizeof(SliceDesc) +
+                         (p.n_csr ? (csr_nnz * 12 + csr_rows * 4) : 0);
+  return CASK_B200_OK;
+}
+
+}  // namespace caskb200

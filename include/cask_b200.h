@@ -1,0 +1,180 @@
+/* cask_b200 — C ABI of the B200-native CASK SpMV / CG hot path.
+ *
+ * This header is the drop-in boundary: plain C, plain pointers and sizes, no C++ or torch types.
+ * Every entry point names the reference interface (caskorg/cask @ 9e561d7, paths relative to the
+ * reference root) that it stands in for.  All functions return CASK_B200_OK (0) or an error code;
+ * the message is available from cask_b200_last_error() (thread-local).  No exception crosses this
+ * boundary; the C++ mirror in cask_b200/host/ rethrows the reference's exception types.
+ *
+ * Ownership: host and device pointers passed in are borrowed for the duration of the call, except
+ * the CSR arrays given to cask_b200_preprocess_device(), which must stay valid until the next
+ * preprocess or cask_b200_destroy().  One context = one device + one stream; a context is not
+ * thread-safe (the reference's GeneratedSpmvImplementation is not either,
+ * src/runtime/GeneratedImplSupport.hpp:51-95).
+ *
+ * There is NO CPU fallback: every compute entry point fails with CASK_B200_ERR_NO_DEVICE when no
+ * CUDA device is usable.
+ */
+#ifndef CASK_B200_H
+#define CASK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CASK_B200_OK 0
+#define CASK_B200_ERR_INVALID_ARGUMENT 1 /* std::invalid_argument in the reference (Spmv.cpp:195-206) */
+#define CASK_B200_ERR_RUNTIME 2          /* std::runtime_error in the reference (Spmv.cpp:222-232)    */
+#define CASK_B200_ERR_CUDA 3
+#define CASK_B200_ERR_NO_DEVICE 4
+#define CASK_B200_ERR_UNSUPPORTED 5
+#define CASK_B200_ERR_NCCL 6
+
+#define CASK_B200_ARCH_SIMPLE 0    /* cask::spmv::Spmv,              src/runtime/Spmv.hpp:49-202  */
+#define CASK_B200_ARCH_SKIPEMPTY 1 /* cask::spmv::SkipEmptyRowsSpmv, src/runtime/Spmv.hpp:211-259 */
+
+typedef struct cask_b200_ctx cask_b200_ctx;
+
+/* The architecture parameters of GeneratedSpmvImplementation (GeneratedImplSupport.hpp:58).
+ * Meaning on B200:
+ *   num_pipes       row stripes, split exactly as Spmv::preprocess does (Spmv.cpp:334-364)
+ *   cache_size      capacity, in doubles, of the on-chip x cache: column-block width of the exported
+ *                   reference format AND the shared-memory x-cache budget of a row slice
+ *   input_width     pair-stream padding of the exported reference format (Spmv.cpp:81-82)
+ *   max_rows        capacity check of Spmv::spmv (Spmv.cpp:201-207); <= 0 disables it
+ *   num_controllers must divide num_pipes (Spmv.cpp:226-232)
+ */
+typedef struct {
+  int32_t num_pipes;
+  int32_t cache_size;
+  int32_t input_width;
+  int32_t max_rows;
+  int32_t num_controllers;
+  int32_t dram_reduction_enabled;
+  int32_t arch; /* CASK_B200_ARCH_* */
+} cask_b200_design;
+
+/* struct Partition scalars (src/runtime/Spmv.hpp:25-29) + the two array lengths. */
+typedef struct {
+  int32_t nBlocks, n, paddingCycles, totalCycles, vector_load_cycles, outSize;
+  int32_t reductionCycles, emptyCycles;
+  int32_t m_colptr_unpaddedLength, m_indptr_values_unpaddedLength;
+  int64_t len_colptr, len_pairs;
+} cask_b200_partition_info;
+
+/* What the row-length histogram / band profile selected (the B200 analogue of the DSE record,
+ * src/runtime/Dse.cpp:32-74). */
+typedef struct {
+  int64_t n, m, nnz;
+  int32_t slice_rows;           /* rows per slice */
+  int32_t num_slices;
+  int32_t slices_staged_ell;    /* x window staged in shared memory by TMA bulk copy, thread-per-row */
+  int32_t slices_gather_csr;    /* x gathered through L2, vector-per-row */
+  int32_t csr_lanes_per_row;    /* sub-warp width chosen from the row-length histogram */
+  int32_t max_row_length;
+  int64_t ell_padded_entries;   /* stored entries incl. padding in staged slices */
+  int64_t ell_nnz;              /* true nonzeros in staged slices */
+  int64_t xcache_doubles_total; /* sum over staged slices of staged x doubles */
+  int64_t device_bytes;         /* bytes of the compute format resident in HBM */
+  int64_t row_length_histogram[8]; /* rows with length 0, 1-2, 3-4, 5-8, 9-16, 17-32, 33-64, >64 */
+} cask_b200_plan_stats;
+
+/* ---- context ---------------------------------------------------------------------------- */
+int cask_b200_device_count(int* count);
+int cask_b200_create(cask_b200_ctx** out, int device);
+int cask_b200_destroy(cask_b200_ctx* ctx);
+const char* cask_b200_last_error(void);
+/* Run on a caller-owned cudaStream_t (e.g. torch's current stream; NULL = CUDA's legacy default
+ * stream) instead of the context's own non-blocking stream; use_own_stream switches back.  A context
+ * on its own stream is NOT ordered with work the caller queued on other streams: device-pointer
+ * callers either share a stream this way or synchronize before and after. */
+int cask_b200_set_stream(cask_b200_ctx* ctx, void* cuda_stream);
+int cask_b200_use_own_stream(cask_b200_ctx* ctx);
+int cask_b200_synchronize(cask_b200_ctx* ctx);
+/* Tuning knobs of the kernel selector (tests and sweeps): "ell_min_fill" (default 0.75),
+ * "force_kind" (-1 auto, 0 staged ELL wherever the x windows fit, 1 gather CSR everywhere),
+ * "force_csr_vec" (0 auto, else 2/4/8/16/32 lanes per row).  Takes effect at the next preprocess. */
+int cask_b200_set_option(cask_b200_ctx* ctx, const char* name, double value);
+
+/* ---- preprocess: replaces Spmv::preprocess(const CsrMatrix&), src/runtime/Spmv.cpp:329-365 ---- */
+/* Host CSR (0-based, row_ptr has n+1 entries: cask::CsrMatrix, SparseMatrix.hpp:272-319). */
+int cask_b200_preprocess(cask_b200_ctx* ctx, const cask_b200_design* design, int64_t n, int64_t m,
+                         int64_t nnz, const int32_t* row_ptr, const int32_t* col_ind,
+                         const double* values);
+/* Same with CSR arrays already resident in device memory (borrowed until the next preprocess). */
+int cask_b200_preprocess_device(cask_b200_ctx* ctx, const cask_b200_design* design, int64_t n,
+                                int64_t m, int64_t nnz, const int32_t* d_row_ptr,
+                                const int32_t* d_col_ind, const double* d_values);
+int cask_b200_plan_get_stats(cask_b200_ctx* ctx, cask_b200_plan_stats* out);
+
+/* ---- parity hook: the reference's partition arrays, produced on the GPU --------------------- */
+/* Partition p of Spmv::partitions (Spmv.hpp:51) as do_blocking builds it (Spmv.cpp:42-107).
+ * colptr receives info.len_colptr int32, pairs receives info.len_pairs packed 12-byte
+ * indptr_value records (Spmv.hpp:13-20).  Either pointer may be NULL. */
+int cask_b200_partition_get_info(cask_b200_ctx* ctx, int32_t pipe, cask_b200_partition_info* out);
+int cask_b200_partition_export(cask_b200_ctx* ctx, int32_t pipe, int32_t* colptr, void* pairs);
+
+/* ---- y = A x: replaces cask::Vector Spmv::spmv(const cask::Vector&), Spmv.cpp:185-328 --------- */
+/* Host buffers: x has m doubles, y has n doubles; includes H2D of x and D2H of y. */
+int cask_b200_spmv(cask_b200_ctx* ctx, const double* x, double* y);
+/* Device buffers (x 16-byte aligned); asynchronous on the context's stream. */
+int cask_b200_spmv_device(cask_b200_ctx* ctx, const double* d_x, double* d_y);
+/* y computed from the exported reference-format arrays exactly as the dataflow engine consumes
+ * them: proves the emitted format is a complete description of A. Host buffers. */
+int cask_b200_spmv_refformat(cask_b200_ctx* ctx, const double* x, double* y);
+
+/* ---- solvers ------------------------------------------------------------------------------ */
+/* pcg<double, IdentityPreconditioner>, src/runtime/SparseLinearSolvers.hpp:162-239, on the matrix
+ * given to preprocess (full symmetric CSR).  x: initial guess in, solution out.  *iterations follows
+ * the reference's convention (index of the last non-converged iteration; untouched if the loop
+ * converges in its first two iterations), so pass the caller's initial value in.  tol is the
+ * reference's 1e-5 (test: r.r <= tol*tol, absolute); maxiters its 2000. */
+int cask_b200_cg(cask_b200_ctx* ctx, const double* rhs, double* x, int32_t maxiters, double tol,
+                 int32_t* iterations, int32_t* converged, double* rs_final);
+int cask_b200_cg_device(cask_b200_ctx* ctx, const double* d_rhs, double* d_x, int32_t maxiters,
+                        double tol, int32_t* iterations, int32_t* converged, double* rs_final,
+                        int32_t* loop_trips);
+/* Eigen::BiCGSTAB<SparseMatrix<double>> with its default Jacobi preconditioner, as called by
+ * solveBICG / EigenSolver::solve, src/runtime/SparseLinearSolvers.cpp:18-26,62-67.
+ * In: *iters = max iterations (<=0: 2*n), *tol_error = tolerance (<=0: DBL_EPSILON).
+ * Out: iterations performed and ||r||/||b||.  x is overwritten (initial guess 0, as Eigen's solve()). */
+int cask_b200_bicgstab(cask_b200_ctx* ctx, const double* b, double* x, int32_t* iters,
+                       double* tol_error);
+int cask_b200_bicgstab_device(cask_b200_ctx* ctx, const double* d_b, double* d_x, int32_t* iters,
+                              double* tol_error);
+
+/* ---- one process per GPU: row-sharded execution over NCCL ----------------------------------- */
+/* Row stripes follow Spmv::preprocess (rows_per = n / world, remainder to the last rank). */
+int cask_b200_nccl_unique_id(void* out_128_bytes);
+int cask_b200_dist_init(cask_b200_ctx* ctx, int32_t rank, int32_t world, const void* unique_id_128_bytes);
+/* Host-side shard arithmetic (no GPU needed): rows [row0, row0+nrows) owned by `rank`. */
+int cask_b200_shard_rows(int64_t n, int32_t world, int32_t rank, int64_t* row0, int64_t* nrows);
+/* Local stripe of the global n x m matrix: d_row_ptr has nrows+1 entries rebased to 0 (exactly
+ * CsrMatrix::sliceRows, SparseMatrix.hpp:426-443), column indices stay global. */
+int cask_b200_preprocess_shard_device(cask_b200_ctx* ctx, const cask_b200_design* design,
+                                      int64_t n_global, int64_t m, int64_t row0, int64_t nrows,
+                                      int64_t nnz_local, const int32_t* d_row_ptr,
+                                      const int32_t* d_col_ind, const double* d_values);
+/* Host-side halo plan of the last preprocess_shard: for each peer, the number of x doubles this
+ * rank receives from it per SpMV. counts has `world` entries. */
+int cask_b200_dist_halo_counts(cask_b200_ctx* ctx, int64_t* recv_counts);
+
+/* ---- synthetic matrices of BASELINE.json, generated on the device ----------------------------- */
+#define CASK_B200_SYNTH_POISSON2D 0   /* 5-point, N x N grid  */
+#define CASK_B200_SYNTH_POISSON3D27 1 /* 27-point, N^3 grid   */
+#define CASK_B200_SYNTH_CONVDIFF3D7 2 /* 7-point upwind convection-diffusion, N^3 grid */
+int cask_b200_synth_rows(int32_t kind, int32_t N, int64_t* n);
+int cask_b200_synth_nnz(int32_t kind, int32_t N, int64_t row0, int64_t nrows, int64_t* nnz);
+int cask_b200_synth_device(int32_t kind, int32_t N, int64_t row0, int64_t nrows, int32_t* d_row_ptr,
+                           int32_t* d_col_ind, double* d_values, void* cuda_stream);
+
+/* ---- instrumentation ---------------------------------------------------------------------- */
+/* Kernels launched by this context since creation (for bench.py's gpu_launches). */
+int cask_b200_launch_count(cask_b200_ctx* ctx, int64_t* count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CASK_B200_H */
