@@ -27,7 +27,8 @@ EXPORTED_SYMBOLS = (
     "cask_b200_cg", "cask_b200_cg_device", "cask_b200_bicgstab", "cask_b200_bicgstab_device",
     "cask_b200_nccl_unique_id", "cask_b200_dist_init", "cask_b200_shard_rows",
     "cask_b200_preprocess_shard_device", "cask_b200_dist_halo_counts", "cask_b200_synth_rows",
-    "cask_b200_synth_nnz", "cask_b200_synth_device", "cask_b200_launch_count",
+    "cask_b200_synth_nnz", "cask_b200_synth_device", "cask_b200_launch_count", "cask_b200_legacy_write",
+    "cask_b200_legacy_read", "cask_b200_legacy_run", "cask_b200_legacy_reset", "cask_b200_legacy_launch_count",
 )
 
 

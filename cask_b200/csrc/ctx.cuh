@@ -144,6 +144,8 @@ namespace caskb200 {
 int build_ref_partitions(cask_b200_ctx* ctx);
 void free_ref_partitions(cask_b200_ctx* ctx);
 int spmv_refformat_device(cask_b200_ctx* ctx, const double* d_x, double* d_y);
+int refformat_stripe(cudaStream_t s, int64_t* launches, const int32_t* d_colptr, int64_t len, const uint8_t* d_pairs,
+                     int32_t ns, int32_t nb, int32_t cache, int32_t w, int64_t m, const double* d_x, double* d_y);
 
 // plan.cu
 int build_plan(cask_b200_ctx* ctx);

@@ -363,6 +363,32 @@ __global__ void refformat_rows_kernel(const int32_t* __restrict__ colptr, const 
 
 }  // namespace
 
+// One stripe: y[0..ns) += A_stripe x, from raw device arrays in the reference layout.  `m` bounds the
+// readable part of x (columns beyond it read as the zero padding of Spmv.cpp:211-213).
+int refformat_stripe(cudaStream_t s, int64_t* launches, const int32_t* d_colptr, int64_t len, const uint8_t* d_pairs,
+                     int32_t ns, int32_t nb, int32_t cache, int32_t w, int64_t m, const double* d_x, double* d_y) {
+  if (len == 0 || ns == 0) return CASK_B200_OK;
+  int64_t *rows = nullptr, *keys = nullptr, *bp = nullptr;
+  CB_CUDA(cudaMalloc(&rows, sizeof(int64_t) * len));
+  CB_CUDA(cudaMalloc(&keys, sizeof(int64_t) * len));
+  CB_CUDA(cudaMalloc(&bp, sizeof(int64_t) * std::max(nb, 1)));
+  const unsigned grid = (unsigned)((len + 255) / 256);
+  entry_rows_kernel<<<grid, 256, 0, s>>>(d_colptr, len, rows);
+  CB_CUDA((device_inclusive_scan<int64_t, OpAddI64>(rows, rows, len, OpAddI64(), 0, s, launches)));
+  entry_keys_kernel<<<grid, 256, 0, s>>>(d_colptr, rows, len, ns, keys);
+  CB_CUDA((device_inclusive_scan<int64_t, OpMaxI64>(keys, keys, len, OpMaxI64(), (int64_t)-1, s, launches)));
+  CB_CUDA(cudaMemsetAsync(bp, 0, sizeof(int64_t) * std::max(nb, 1), s));
+  block_nnz_kernel<<<grid, 256, 0, s>>>(rows, keys, len, ns, w, bp);
+  CB_CUDA((device_inclusive_scan<int64_t, OpAddI64>(bp, bp, nb, OpAddI64(), 0, s, launches)));
+  refformat_rows_kernel<<<grid, 256, 0, s>>>(d_colptr, rows, keys, bp, (const uint32_t*)d_pairs, len, ns, cache,
+                                             (int32_t)m, d_x, d_y);
+  if (launches) *launches += 4;
+  CB_CUDA(cudaStreamSynchronize(s));
+  CB_CUDA(cudaGetLastError());
+  cudaFree(rows); cudaFree(keys); cudaFree(bp);
+  return CASK_B200_OK;
+}
+
 int spmv_refformat_device(cask_b200_ctx* ctx, const double* d_x, double* d_y) {
   CB_TRY(build_ref_partitions(ctx));
   const Plan& pl = ctx->plan;
@@ -375,27 +401,8 @@ int spmv_refformat_device(cask_b200_ctx* ctx, const double* d_x, double* d_y) {
   const int32_t live = (n / d.num_pipes == 0) ? 1 : d.num_pipes;
   for (int32_t p = 0; p < live; p++) {
     const RefPartition& q = ctx->ref_parts[p];
-    const int64_t len = q.info.len_colptr;
-    const int32_t ns = q.info.n, nb = q.info.nBlocks;
-    if (len == 0 || ns == 0) continue;
-    int64_t *rows = nullptr, *keys = nullptr, *bp = nullptr;
-    CB_CUDA(cudaMalloc(&rows, sizeof(int64_t) * len));
-    CB_CUDA(cudaMalloc(&keys, sizeof(int64_t) * len));
-    CB_CUDA(cudaMalloc(&bp, sizeof(int64_t) * nb));
-    const unsigned grid = (unsigned)((len + 255) / 256);
-    entry_rows_kernel<<<grid, 256, 0, s>>>(q.d_colptr, len, rows);
-    CB_CUDA((device_inclusive_scan<int64_t, OpAddI64>(rows, rows, len, OpAddI64(), 0, s, &ctx->launches)));
-    entry_keys_kernel<<<grid, 256, 0, s>>>(q.d_colptr, rows, len, ns, keys);
-    CB_CUDA((device_inclusive_scan<int64_t, OpMaxI64>(keys, keys, len, OpMaxI64(), (int64_t)-1, s, &ctx->launches)));
-    CB_CUDA(cudaMemsetAsync(bp, 0, sizeof(int64_t) * nb, s));
-    block_nnz_kernel<<<grid, 256, 0, s>>>(rows, keys, len, ns, d.input_width, bp);
-    CB_CUDA((device_inclusive_scan<int64_t, OpAddI64>(bp, bp, nb, OpAddI64(), 0, s, &ctx->launches)));
-    refformat_rows_kernel<<<grid, 256, 0, s>>>(q.d_colptr, rows, keys, bp, (const uint32_t*)q.d_pairs, len, ns,
-                                               d.cache_size, (int32_t)pl.m, d_x, d_y + q.row0);
-    ctx->launches += 4;
-    CB_CUDA(cudaStreamSynchronize(s));
-    CB_CUDA(cudaGetLastError());
-    cudaFree(rows); cudaFree(keys); cudaFree(bp);
+    CB_TRY(refformat_stripe(s, &ctx->launches, q.d_colptr, q.info.len_colptr, q.d_pairs, q.info.n, q.info.nBlocks,
+                            d.cache_size, d.input_width, pl.m, d_x, d_y + q.row0));
   }
   return CASK_B200_OK;
 }

@@ -170,6 +170,26 @@ int cask_b200_synth_nnz(int32_t kind, int32_t N, int64_t row0, int64_t nrows, in
 int cask_b200_synth_device(int32_t kind, int32_t N, int64_t row0, int64_t nrows, int32_t* d_row_ptr,
                            int32_t* d_col_ind, double* d_values, void* cuda_stream);
 
+/* ---- the reference's own device boundary, for the UNMODIFIED reference Spmv::spmv ------------- */
+/* Flat byte-addressed memory per controller + a blocking run, exactly what SLiC generates for a design
+ * (src/spmv/src/SpmvDeviceInterface.h:21-73; mock versions src/runtime/GeneratedImplSupport.hpp:31-49).
+ * The plugin cask_b200/host/libSpmv_b200.so wraps these three into the `void` callbacks that
+ * GeneratedSpmvImplementation stores (GeneratedImplSupport.hpp:59-61); num_pipes, num_controllers and
+ * input_width are the design's build parameters, which a SLiC design has baked in.  Arrays of
+ * legacy_run have num_pipes entries, those of write/read num_controllers entries with exactly one
+ * non-zero size (msinglearray, Spmv.cpp:109-114). */
+int cask_b200_legacy_write(int32_t num_controllers, int64_t size_bytes_cpu, const int64_t* size_bytes_memory_ctl,
+                           const int64_t* start_bytes_memory_ctl, const uint8_t* instream_fromcpu);
+int cask_b200_legacy_read(int32_t num_controllers, int64_t size_bytes_cpu, const int64_t* size_bytes_memory_ctl,
+                          const int64_t* start_bytes_memory_ctl, uint8_t* outstream_tocpu);
+int cask_b200_legacy_run(int32_t num_pipes, int32_t num_controllers, int32_t input_width, int64_t nIterations,
+                         int64_t nPartitions, int64_t vectorLoadCycles, const int64_t* colPtrStartAddresses,
+                         const int32_t* colptrSizes, const int64_t* indptrValuesAddresses,
+                         const int32_t* indptrValuesSizes, const int32_t* nrows, const int64_t* outStartAddresses,
+                         const int32_t* reductionCycles, const int32_t* totalCycles, const int64_t* vStartAddresses);
+int cask_b200_legacy_reset(void);
+int cask_b200_legacy_launch_count(int64_t* count);
+
 /* ---- instrumentation ---------------------------------------------------------------------- */
 /* Kernels launched by this context since creation (for bench.py's gpu_launches). */
 int cask_b200_launch_count(cask_b200_ctx* ctx, int64_t* count);
