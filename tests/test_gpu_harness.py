@@ -64,11 +64,11 @@ def test_host_mirror_solver_and_client_suites(tmp_path, golden):
         rp, ci, va = np.array(s["row_ptr"]), np.array(s["col_ind"]), np.array(s["values"])
         rows = np.repeat(np.arange(n), np.diff(rp))
         with open(tmp_path / (name + ".mtx"), "w") as f:
-            f.write("%%MatrixMarket matrix coordinate real symmetric\n%\n%d %d %d\n" % (n, n, len(va)))
+            f.write("%%%%MatrixMarket matrix coordinate real symmetric\n%%\n%d %d %d\n" % (n, n, len(va)))
             f.write("".join("%d %d %s\n" % (r + 1, c + 1, repr(float(v))) for r, c, v in zip(rows, ci, va)))
         for suffix, vec in (("_b", s["rhs"]), ("_sol", s["sol_file"])):
             with open(tmp_path / (name + suffix + ".mtx"), "w") as f:
-                f.write("%%MatrixMarket matrix array real general\n%\n%d 1\n" % n)
+                f.write("%%%%MatrixMarket matrix array real general\n%%\n%d 1\n" % n)
                 f.write("".join("%s\n" % repr(float(v)) for v in vec))
     rc, out = _run([exe, str(tmp_path)])
     assert rc == 0 and "PASSED (0 failures)" in out, out[-4000:]
