@@ -1,5 +1,6 @@
 // extern "C" entry points of libcask_b200.so (contract: include/cask_b200.h).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "ctx.cuh"
@@ -94,6 +95,9 @@ int cask_b200_create(cask_b200_ctx** out, int device) {
     return fail(CASK_B200_ERR_CUDA, "create: stream/event creation failed");
   }
   ctx->stream = ctx->own_stream;
+  // A/B switches for profiling sessions (same meaning as cask_b200_set_option)
+  if (const char* e = getenv("CASK_B200_ELL_KERNEL")) ctx->ell_kernel = atoi(e);
+  if (const char* e = getenv("CASK_B200_PERSIST_KU")) ctx->persist_ku = atoi(e);
   *out = ctx;
   return CASK_B200_OK;
 }
@@ -142,6 +146,8 @@ int cask_b200_set_option(cask_b200_ctx* ctx, const char* name, double value) {
   if (k == "ell_min_fill") ctx->ell_min_fill = value;
   else if (k == "force_kind") ctx->force_kind = (int32_t)value;
   else if (k == "force_csr_vec") ctx->force_csr_vec = (int32_t)value;
+  else if (k == "ell_kernel") ctx->ell_kernel = (int32_t)value;
+  else if (k == "persist_ku") ctx->persist_ku = (int32_t)value;
   else return fail(CASK_B200_ERR_INVALID_ARGUMENT, "set_option: unknown option " + k);
   return CASK_B200_OK;
 }

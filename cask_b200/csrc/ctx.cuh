@@ -42,6 +42,15 @@ constexpr int kMaxCacheDoubles = 24576;        // 192 KB of shared memory for th
 
 enum SliceKind : int32_t { kSliceStagedEll = 0, kSliceGatherCsr = 1 };
 
+struct Run {           // one contiguous window of x staged by a single bulk copy
+  int32_t col0;        // first column (multiple of kGranule)
+  int32_t len;         // doubles (clipped at m)
+  int32_t local_base;  // position in the slice's shared-memory x cache
+  int32_t pad_;
+};
+
+constexpr int kInlineRuns = 6;  // runs carried inside the descriptor: one load gives a producer everything
+
 struct SliceDesc {     // one row slice (<= kSliceRows consecutive rows of one stripe)
   int32_t row0;        // first row, local to this rank's stripe
   int32_t nrows;       // valid rows
@@ -54,13 +63,7 @@ struct SliceDesc {     // one row slice (<= kSliceRows consecutive rows of one s
   int32_t nnz;
   int32_t remote;      // 1 if some staged column lies outside this rank's own x slice (dist only)
   int32_t pad_;
-};
-
-struct Run {           // one contiguous window of x staged by a single bulk copy
-  int32_t col0;        // first column (multiple of kGranule)
-  int32_t len;         // doubles (clipped at m)
-  int32_t local_base;  // position in the slice's shared-memory x cache
-  int32_t pad_;
+  Run inl[kInlineRuns]; // copy of runs[run_off ..] when nruns <= kInlineRuns (written by plan_fill_kernel)
 };
 
 struct RefPartition {  // reference-format partition resident on the device
@@ -91,6 +94,12 @@ struct Plan {
   int32_t n_csr = 0, n_csr_interior = 0;
   int32_t csr_vec = 4;
   int32_t max_xcache = 0;
+  // persistent staged-ELL kernel configuration (spmv.cu: configure_persistent)
+  int32_t persist_ku = 0;       // ELL columns per ring stage (0: persistent kernel not usable)
+  int32_t persist_stages = 0;
+  int32_t persist_ctas_per_sm = 0;
+  int32_t persist_xbuf = 0;     // doubles per x buffer
+  size_t persist_smem = 0;
   cask_b200_plan_stats stats{};
   std::vector<SliceDesc> h_slices;
 };
@@ -128,6 +137,8 @@ struct cask_b200_ctx {
   double ell_min_fill = 0.75;
   int32_t force_kind = -1;   // -1 auto, 0 staged ELL wherever possible, 1 gather CSR everywhere
   int32_t force_csr_vec = 0;
+  int32_t ell_kernel = 1;    // 1 persistent warp-specialised kernel, 0 one CTA per slice
+  int32_t persist_ku = 0;    // 0 auto, else 2 or 4
 
   // host-call staging buffers
   double* d_x = nullptr; int64_t d_x_len = 0;
@@ -160,6 +171,7 @@ struct SpmvFusion {           // optional fused epilogue: partial dot products p
 int launch_spmv(cask_b200_ctx* ctx, const double* d_x_full, double* d_y, int part /*0 all,1 interior,2 boundary*/,
                 cudaStream_t stream, const SpmvFusion* fusion);
 int spmv_num_ctas(cask_b200_ctx* ctx, int part);
+int configure_persistent(cask_b200_ctx* ctx);
 
 // dist.cu
 int dist_exchange_begin(cask_b200_ctx* ctx, double* d_x_full, cudaStream_t after);

@@ -143,7 +143,7 @@ plan_count_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict
 // warp own consecutive rows (coalesced y, conflict-free shared-memory x reads on banded matrices).
 __global__ void __launch_bounds__(256)
 plan_fill_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col, const double* __restrict__ val,
-                 const SliceDesc* __restrict__ slices, const int32_t* __restrict__ list, int32_t max_gran, int32_t m,
+                 SliceDesc* __restrict__ slices, const int32_t* __restrict__ list, int32_t max_gran, int32_t m,
                  Run* __restrict__ runs, double* __restrict__ ell_vals, uint16_t* __restrict__ ell_idx) {
   extern __shared__ __align__(16) unsigned char raw[];
   SliceSmem& sm = *reinterpret_cast<SliceSmem*>(raw);
@@ -154,9 +154,6 @@ plan_fill_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict_
   const int32_t words = sm.gmax < gmin ? 0 : ((sm.gmax - gmin) >> 5) + 1;
   // runs: a bit starts a run if the bit below is clear; its rank among run starts = popcount of
   // earlier starts (small: recount serially per word owner), its length = distance to the next clear bit.
-  __shared__ int32_t run_cursor;
-  if (tid == 0) run_cursor = 0;
-  __syncthreads();
   // Deterministic order: thread 0 of warp 0 walks the words (<= 8192) — cheap next to the nnz pass.
   if (tid == 0) {
     int32_t r = 0;
@@ -192,6 +189,7 @@ plan_fill_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict_
       base += q.len;
       if (q.col0 + q.len > m) q.len = m - q.col0;
       runs[sd.run_off + i] = q;
+      if (r <= kInlineRuns) slices[list[blockIdx.x]].inl[i] = q;
     }
   }
   // ELL fill: one thread per row walks its entries; padding entries point at the zero slot.
@@ -380,6 +378,7 @@ int build_plan(cask_b200_ctx* ctx) {
   CB_CUDA(cudaGetLastError());
   cudaFree(d_row0); cudaFree(d_nrows); cudaFree(d_counts); cudaFree(d_hist); cudaFree(d_maxlen);
 
+  CB_TRY(configure_persistent(ctx));
   p.stats.slices_staged_ell = p.n_ell;
   p.stats.slices_gather_csr = p.n_csr;
   p.stats.csr_lanes_per_row = vec;

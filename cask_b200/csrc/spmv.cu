@@ -13,6 +13,8 @@
 //                          histogram), x gathered through the read-only path, warp-shuffle reduction.
 //
 // Both can fuse the per-CTA partial of dot(y, w) (CG's p.Ap) into their epilogue.
+#include <algorithm>
+
 #include "ctx.cuh"
 
 namespace caskb200 {
@@ -27,6 +29,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
@@ -173,6 +178,151 @@ spmv_ell_staged_kernel(const SliceDesc* __restrict__ slices, const int32_t* __re
   }
 }
 
+
+// ---- persistent, warp-specialised staged-ELL kernel ------------------------------------------------
+// One producer warp moves EVERYTHING with TMA bulk copies: the x windows of slice i+1 into the second x
+// buffer and the ELL column chunks (KU columns = KU*1024 values + KU*1024 16-bit indices) into a ring of
+// `stages` shared-memory buffers.  Eight consumer warps touch shared memory only.  Every buffer has a
+// full/empty mbarrier pair, so global loads stay in flight across chunk AND slice boundaries and the
+// per-slice chain (descriptor -> runs -> x -> compute) of the one-CTA-per-slice kernel disappears.
+constexpr int kConsumerThreads = kEllThreads;           // 256: thread t owns rows t, t+256, t+512, t+768
+constexpr int kPersistThreads = kConsumerThreads + 32;  // + the producer warp
+constexpr int kMaxStages = 8;
+constexpr int kPersistHeaderBytes = 256;
+
+struct PersistHeader {
+  uint64_t full_x[2], empty_x[2];
+  uint64_t full_c[kMaxStages], empty_c[kMaxStages];
+  int32_t meta[2][4];  // per x buffer: row0, nrows, width
+};
+static_assert(sizeof(PersistHeader) <= kPersistHeaderBytes, "header must fit its reservation");
+
+template <int KU, bool kDot>
+__global__ void __launch_bounds__(kPersistThreads, 1)
+spmv_ell_persistent_kernel(const SliceDesc* __restrict__ slices, const int32_t* __restrict__ list, int count,
+                           const Run* __restrict__ runs, const double* __restrict__ ell_vals,
+                           const uint16_t* __restrict__ ell_idx, const double* __restrict__ x, double* __restrict__ y,
+                           const double* __restrict__ dot_with, double* __restrict__ partials, int xbuf_doubles,
+                           int stages) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  PersistHeader* hdr = reinterpret_cast<PersistHeader*>(smem_raw);
+  double* xbuf = reinterpret_cast<double*>(smem_raw + kPersistHeaderBytes);
+  double* cvals = xbuf + 2 * (size_t)xbuf_doubles;
+  uint16_t* cidx = reinterpret_cast<uint16_t*>(cvals + (size_t)stages * KU * kSliceRows);
+  __shared__ double red[kPersistThreads / 32];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    for (int b = 0; b < 2; b++) {
+      mbar_init(smem_u32(&hdr->full_x[b]), 1);
+      mbar_init(smem_u32(&hdr->empty_x[b]), kConsumerThreads / 32);
+      xbuf[(size_t)b * xbuf_doubles] = 0.0;      // zero slots: target of every padding entry,
+      xbuf[(size_t)b * xbuf_doubles + 1] = 0.0;  // never overwritten (runs start at local index 2)
+    }
+    for (int s = 0; s < stages; s++) {
+      mbar_init(smem_u32(&hdr->full_c[s]), 1);
+      mbar_init(smem_u32(&hdr->empty_c[s]), kConsumerThreads / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  double dot = 0.0;
+  if (warp == kConsumerThreads / 32) {
+    // ===== producer warp =====
+    int chunk_no = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < count; item += gridDim.x, it++) {
+      const SliceDesc* sdp = slices + list[item];
+      const int L = sdp->width, nruns = sdp->nruns;
+      const int64_t val_off = sdp->val_off;
+      const int xb = it & 1;
+      mbar_wait(smem_u32(&hdr->empty_x[xb]), ((it >> 1) & 1) ^ 1);
+      double* xs = xbuf + (size_t)xb * xbuf_doubles;
+      const uint32_t fx = smem_u32(&hdr->full_x[xb]);
+      const Run* rr = nruns <= kInlineRuns ? sdp->inl : runs + sdp->run_off;
+      uint32_t bytes = 0;
+      for (int i = lane; i < nruns; i += 32) {
+        const Run r = rr[i];
+        const uint32_t b = (uint32_t)(r.len & ~1) * 8u;
+        bytes += b;
+        if (b) bulk_g2s(smem_u32(xs + r.local_base), x + r.col0, b, fx);
+        if (r.len & 1) xs[r.local_base + r.len - 1] = x[r.col0 + r.len - 1];  // odd tail at column m-1
+      }
+#pragma unroll
+      for (int d = 16; d; d >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, d);
+      if (lane == 0) {
+        hdr->meta[xb][0] = sdp->row0;
+        hdr->meta[xb][1] = sdp->nrows;
+        hdr->meta[xb][2] = L;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_expect_tx(fx, bytes);  // arrive (release): meta and odd tails become visible with it
+      const int nchunks = (L + KU - 1) / KU;
+      for (int c = 0; c < nchunks; c++, chunk_no++) {
+        const int s = chunk_no % stages;
+        mbar_wait(smem_u32(&hdr->empty_c[s]), ((chunk_no / stages) & 1) ^ 1);
+        if (lane == 0) {
+          const int cols = min(KU, L - c * KU);
+          const uint32_t fc = smem_u32(&hdr->full_c[s]);
+          mbar_expect_tx(fc, (uint32_t)cols * kSliceRows * 10u);
+          const size_t src = (size_t)val_off + (size_t)c * KU * kSliceRows;
+          bulk_g2s(smem_u32(cvals + (size_t)s * KU * kSliceRows), ell_vals + src, (uint32_t)cols * kSliceRows * 8u, fc);
+          bulk_g2s(smem_u32(cidx + (size_t)s * KU * kSliceRows), ell_idx + src, (uint32_t)cols * kSliceRows * 2u, fc);
+        }
+      }
+    }
+  } else {
+    // ===== consumer warps =====
+    int chunk_no = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < count; item += gridDim.x, it++) {
+      const int xb = it & 1;
+      mbar_wait(smem_u32(&hdr->full_x[xb]), (it >> 1) & 1);
+      const int row0 = hdr->meta[xb][0], nrows = hdr->meta[xb][1], L = hdr->meta[xb][2];
+      const double* xs = xbuf + (size_t)xb * xbuf_doubles;
+      double acc[RPT] = {0.0, 0.0, 0.0, 0.0};
+      const int nchunks = (L + KU - 1) / KU;
+      for (int c = 0; c < nchunks; c++, chunk_no++) {
+        const int s = chunk_no % stages;
+        mbar_wait(smem_u32(&hdr->full_c[s]), (chunk_no / stages) & 1);
+        const int cols = min(KU, L - c * KU);
+        const double* vb = cvals + (size_t)s * KU * kSliceRows + (size_t)tid * RPT;
+        const uint16_t* ib = cidx + (size_t)s * KU * kSliceRows + (size_t)tid * RPT;
+#pragma unroll
+        for (int u = 0; u < KU; u++) {
+          if (u < cols) {
+            const double2 v0 = *reinterpret_cast<const double2*>(vb + (size_t)u * kSliceRows);
+            const double2 v1 = *reinterpret_cast<const double2*>(vb + (size_t)u * kSliceRows + 2);
+            const uint2 ix = *reinterpret_cast<const uint2*>(ib + (size_t)u * kSliceRows);
+            // ascending column order, separate multiply and add (DokMatrix::dot, SparseMatrix.hpp:255-264)
+            acc[0] = __dadd_rn(acc[0], __dmul_rn(v0.x, xs[ix.x & 0xffffu]));
+            acc[1] = __dadd_rn(acc[1], __dmul_rn(v0.y, xs[ix.x >> 16]));
+            acc[2] = __dadd_rn(acc[2], __dmul_rn(v1.x, xs[ix.y & 0xffffu]));
+            acc[3] = __dadd_rn(acc[3], __dmul_rn(v1.y, xs[ix.y >> 16]));
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&hdr->empty_c[s]));
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&hdr->empty_x[xb]));
+#pragma unroll
+      for (int j = 0; j < RPT; j++) {
+        const int row = j * kConsumerThreads + tid;
+        if (row < nrows) {
+          y[row0 + row] = acc[j];
+          if (kDot) dot += acc[j] * dot_with[row0 + row];
+        }
+      }
+    }
+  }
+  if (kDot) {
+    const double t = cta_sum_d(dot, red);  // deterministic: fixed slice->CTA map, fixed order inside the CTA
+    if (tid == 0) partials[blockIdx.x] = t;
+  }
+}
+
 template <int VEC, bool kDot>
 __global__ void __launch_bounds__(256)
 spmv_csr_vec_kernel(const SliceDesc* __restrict__ slices, const int32_t* __restrict__ list,
@@ -221,11 +371,50 @@ void launch_csr(int vec, int grid, cudaStream_t s, const SliceDesc* sl, const in
 
 }  // namespace
 
+static int ell_grid(const cask_b200_ctx* ctx, int n_slices) {
+  const Plan& p = ctx->plan;
+  if (ctx->ell_kernel == 1 && p.persist_ku) return std::min(n_slices, ctx->sm_count * p.persist_ctas_per_sm);
+  return n_slices;
+}
+
+// number of per-CTA partial dots a fused launch over `part` writes
 int spmv_num_ctas(cask_b200_ctx* ctx, int part) {
   const Plan& p = ctx->plan;
-  if (part == 1) return p.n_ell_interior + p.n_csr_interior;
-  if (part == 2) return (p.n_ell - p.n_ell_interior) + (p.n_csr - p.n_csr_interior);
-  return p.n_ell + p.n_csr;
+  if (part == 1) return ell_grid(ctx, p.n_ell_interior) + p.n_csr_interior;
+  if (part == 2) return ell_grid(ctx, p.n_ell - p.n_ell_interior) + (p.n_csr - p.n_csr_interior);
+  return ell_grid(ctx, p.n_ell) + p.n_csr;
+}
+
+// Picks KU (ELL columns per ring stage), the ring depth and the CTAs per SM of the persistent kernel from
+// the shared memory the plan's largest x cache leaves: two CTAs per SM with >= 3 stages of 2 columns if
+// that fits, else one CTA per SM with up to 4 stages of 4 columns.
+int configure_persistent(cask_b200_ctx* ctx) {
+  Plan& p = ctx->plan;
+  p.persist_ku = 0;
+  if (p.n_ell == 0) return CASK_B200_OK;
+  int dev_smem = 0;
+  CB_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+  const size_t xbuf = ((size_t)p.max_xcache + 15) & ~(size_t)15;  // doubles, keeps every buffer 128-B aligned
+  const size_t fixed = kPersistHeaderBytes + 2 * xbuf * sizeof(double);
+  const size_t per_sm = 228 * 1024, reserve = 1024 + 64;  // 1 KB per CTA is the driver's + static reduction scratch
+  auto stage_bytes = [](int ku) { return (size_t)ku * kSliceRows * 10; };
+  int ku = 0, stages = 0, ctas = 0;
+  auto fits = [&](int k, int st, int c) { return c * (fixed + st * stage_bytes(k) + reserve) <= per_sm &&
+                                                  fixed + st * stage_bytes(k) <= (size_t)dev_smem; };
+  if ((ctx->persist_ku == 0 || ctx->persist_ku == 2) && fits(2, 3, 2)) { ku = 2; stages = 3; ctas = 2; while (stages < 4 && fits(2, stages + 1, 2)) stages++; }
+  if (!ku || ctx->persist_ku == 4) {
+    ku = 0;
+    for (int st = 4; st >= 2 && !ku; st--)
+      if (fits(4, st, 1)) { ku = 4; stages = st; ctas = 1; }
+  }
+  if (!ku && fits(2, 2, 1)) { ku = 2; stages = 2; ctas = 1; while (stages < kMaxStages && fits(2, stages + 1, 1)) stages++; }
+  if (!ku) return CASK_B200_OK;  // x cache too large for the ring: the one-CTA-per-slice kernel is used
+  p.persist_ku = ku;
+  p.persist_stages = stages;
+  p.persist_ctas_per_sm = ctas;
+  p.persist_xbuf = (int32_t)xbuf;
+  p.persist_smem = fixed + stages * stage_bytes(ku);
+  return CASK_B200_OK;
 }
 
 // part: 0 = every slice, 1 = slices that read only this rank's own x (interior), 2 = the rest.
@@ -241,7 +430,22 @@ int launch_spmv(cask_b200_ctx* ctx, const double* d_x, double* d_y, int part, cu
   const bool dot = fusion && fusion->d_dot_with;
   double* partials = dot ? fusion->d_partials : nullptr;
   const double* w = dot ? fusion->d_dot_with : nullptr;
-  if (ell_hi > ell_lo) {
+  if (ell_hi > ell_lo && ctx->ell_kernel == 1 && p.persist_ku) {
+    const int grid = ell_grid(ctx, ell_hi - ell_lo);
+#define CB_PERSIST(KU, DOT)                                                                                          \
+  do {                                                                                                               \
+    CB_CUDA(cudaFuncSetAttribute(spmv_ell_persistent_kernel<KU, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                 (int)p.persist_smem));                                                              \
+    spmv_ell_persistent_kernel<KU, DOT><<<grid, kPersistThreads, p.persist_smem, s>>>(                               \
+        p.d_slices, p.d_list_ell + ell_lo, ell_hi - ell_lo, p.d_runs, p.d_ell_vals, p.d_ell_idx, d_x, d_y, w,        \
+        partials, p.persist_xbuf, p.persist_stages);                                                                 \
+  } while (0)
+    if (p.persist_ku == 2) { if (dot) CB_PERSIST(2, true); else CB_PERSIST(2, false); }
+    else { if (dot) CB_PERSIST(4, true); else CB_PERSIST(4, false); }
+#undef CB_PERSIST
+    ctx->launches++;
+    if (partials) partials += grid;
+  } else if (ell_hi > ell_lo) {
     const size_t smem = 16 + sizeof(double) * (size_t)p.max_xcache;
     static thread_local int attr_smem[2] = {0, 0};
     if ((int)smem > attr_smem[dot ? 1 : 0]) {
@@ -256,9 +460,10 @@ int launch_spmv(cask_b200_ctx* ctx, const double* d_x, double* d_y, int part, cu
       spmv_ell_staged_kernel<false><<<ell_hi - ell_lo, kEllThreads, smem, s>>>(
           p.d_slices, p.d_list_ell + ell_lo, p.d_runs, p.d_ell_vals, p.d_ell_idx, d_x, d_y, nullptr, nullptr);
     ctx->launches++;
+    if (partials) partials += ell_hi - ell_lo;
   }
   if (csr_hi > csr_lo) {
-    double* pp = partials ? partials + (ell_hi - ell_lo) : nullptr;
+    double* pp = partials;
     if (dot) launch_csr<true>(p.csr_vec, csr_hi - csr_lo, s, p.d_slices, p.d_list_csr + csr_lo, p, d_x, d_y, w, pp);
     else launch_csr<false>(p.csr_vec, csr_hi - csr_lo, s, p.d_slices, p.d_list_csr + csr_lo, p, d_x, d_y, nullptr, nullptr);
     ctx->launches++;
