@@ -98,6 +98,7 @@ int cask_b200_create(cask_b200_ctx** out, int device) {
   // A/B switches for profiling sessions (same meaning as cask_b200_set_option)
   if (const char* e = getenv("CASK_B200_ELL_KERNEL")) ctx->ell_kernel = atoi(e);
   if (const char* e = getenv("CASK_B200_PERSIST_KU")) ctx->persist_ku = atoi(e);
+  if (const char* e = getenv("CASK_B200_HOST_CHUNKS")) ctx->host_pipeline_chunks = atoi(e);
   *out = ctx;
   return CASK_B200_OK;
 }
@@ -114,6 +115,9 @@ int cask_b200_destroy(cask_b200_ctx* ctx) {
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+  for (auto e : ctx->pipe_events) cudaEventDestroy(e);
+  if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+  if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
   delete ctx;
@@ -147,6 +151,7 @@ int cask_b200_set_option(cask_b200_ctx* ctx, const char* name, double value) {
   else if (k == "force_kind") ctx->force_kind = (int32_t)value;
   else if (k == "force_csr_vec") ctx->force_csr_vec = (int32_t)value;
   else if (k == "ell_kernel") ctx->ell_kernel = (int32_t)value;
+  else if (k == "host_pipeline_chunks") ctx->host_pipeline_chunks = (int32_t)value;
   else if (k == "persist_ku") ctx->persist_ku = (int32_t)value;
   else return fail(CASK_B200_ERR_INVALID_ARGUMENT, "set_option: unknown option " + k);
   return CASK_B200_OK;
@@ -286,11 +291,63 @@ static int stage_in(cask_b200_ctx* ctx, const double* x, int64_t m, int64_t n) {
   return CASK_B200_OK;
 }
 
+// Host-buffer SpMV as a three-stage pipeline over chunks of consecutive slices: the x columns a chunk needs
+// are uploaded on one stream, its kernels run on the context's stream, its y rows are downloaded on a
+// third — PCIe is full duplex, so for banded matrices the call costs about max(H2D, D2H) instead of their
+// sum.  A chunk waits only for the upload that covers its largest referenced column (SliceDesc::col_hi);
+// matrices whose slices reference far columns degrade gracefully to upload-all-then-overlap-download.
+static int spmv_host_pipelined(cask_b200_ctx* ctx, const double* x, double* y) {
+  const Plan& p = ctx->plan;
+  const int K = std::max(1, std::min<int>(ctx->host_pipeline_chunks, p.nslices / 64));
+  CB_TRY(grow(&ctx->d_x, &ctx->d_x_len, p.m));
+  CB_TRY(grow(&ctx->d_y, &ctx->d_y_len, p.n));
+  if (!ctx->h2d_stream) CB_CUDA(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+  if (!ctx->d2h_stream) CB_CUDA(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+  while ((int)ctx->pipe_events.size() < 2 * K + 1) {
+    cudaEvent_t e;
+    CB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->pipe_events.push_back(e);
+  }
+  cudaStream_t cs = ctx->stream;
+  // uploads must not start before earlier work queued on the compute stream (e.g. a previous async call) is done
+  CB_CUDA(cudaEventRecord(ctx->pipe_events[2 * K], cs));
+  CB_CUDA(cudaStreamWaitEvent(ctx->h2d_stream, ctx->pipe_events[2 * K], 0));
+  int64_t uploaded = 0;
+  size_t ie = 0, ic = 0;  // cursors into the (ascending) slice lists
+  for (int c = 0; c < K; c++) {
+    const int s_lo = (int)((int64_t)p.nslices * c / K), s_hi = (int)((int64_t)p.nslices * (c + 1) / K);
+    if (s_hi == s_lo) continue;
+    int64_t need = 0;
+    for (int s = s_lo; s < s_hi; s++) need = std::max<int64_t>(need, p.h_slices[s].col_hi);
+    need = std::min<int64_t>(std::max<int64_t>(need, 0), p.m);
+    if (c == K - 1) need = std::max(need, uploaded);  // nothing beyond `need` is ever read
+    if (need > uploaded) {
+      CB_CUDA(cudaMemcpyAsync(ctx->d_x + uploaded, x + uploaded, sizeof(double) * (need - uploaded), cudaMemcpyHostToDevice,
+                              ctx->h2d_stream));
+      uploaded = need;
+    }
+    CB_CUDA(cudaEventRecord(ctx->pipe_events[2 * c], ctx->h2d_stream));
+    CB_CUDA(cudaStreamWaitEvent(cs, ctx->pipe_events[2 * c], 0));
+    const size_t e_lo = ie, c_lo = ic;
+    while (ie < p.h_list_ell.size() && p.h_list_ell[ie] < s_hi) ie++;
+    while (ic < p.h_list_csr.size() && p.h_list_csr[ic] < s_hi) ic++;
+    CB_TRY(launch_spmv_range(ctx, ctx->d_x, ctx->d_y, (int)e_lo, (int)ie, (int)c_lo, (int)ic, cs, nullptr));
+    CB_CUDA(cudaEventRecord(ctx->pipe_events[2 * c + 1], cs));
+    CB_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, ctx->pipe_events[2 * c + 1], 0));
+    const int64_t r_lo = p.h_slices[s_lo].row0, r_hi = (int64_t)p.h_slices[s_hi - 1].row0 + p.h_slices[s_hi - 1].nrows;
+    CB_CUDA(cudaMemcpyAsync(y + r_lo, ctx->d_y + r_lo, sizeof(double) * (r_hi - r_lo), cudaMemcpyDeviceToHost, ctx->d2h_stream));
+  }
+  CB_CUDA(cudaStreamSynchronize(ctx->d2h_stream));
+  CB_CUDA(cudaStreamSynchronize(cs));
+  return CASK_B200_OK;
+}
+
 int cask_b200_spmv(cask_b200_ctx* ctx, const double* x, double* y) {
   CB_TRY(check_spmv(ctx));
   if (dist_active(ctx)) return fail(CASK_B200_ERR_UNSUPPORTED, "spmv (host buffers) is single-rank; use spmv_device when sharded");
   const Plan& p = ctx->plan;
   if ((!x && p.m) || (!y && p.n)) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "spmv: null vector");
+  if (ctx->host_pipeline_chunks > 1 && p.nslices >= 128) return spmv_host_pipelined(ctx, x, y);
   CB_TRY(stage_in(ctx, x, p.m, p.n));
   CB_TRY(launch_spmv(ctx, ctx->d_x, ctx->d_y, 0, ctx->stream, nullptr));
   if (p.n) CB_CUDA(cudaMemcpyAsync(y, ctx->d_y, sizeof(double) * p.n, cudaMemcpyDeviceToHost, ctx->stream));

@@ -62,7 +62,7 @@ struct SliceDesc {     // one row slice (<= kSliceRows consecutive rows of one s
   int32_t xcache_len;  // doubles staged in shared memory, including the zero slots
   int32_t nnz;
   int32_t remote;      // 1 if some staged column lies outside this rank's own x slice (dist only)
-  int32_t pad_;
+  int32_t col_hi;      // one past the largest column the slice references (host-side pipelining of x uploads)
   Run inl[kInlineRuns]; // copy of runs[run_off ..] when nruns <= kInlineRuns (written by plan_fill_kernel)
 };
 
@@ -102,6 +102,7 @@ struct Plan {
   size_t persist_smem = 0;
   cask_b200_plan_stats stats{};
   std::vector<SliceDesc> h_slices;
+  std::vector<int32_t> h_list_ell, h_list_csr;  // host copies of the slice lists (ascending slice id unless sharded)
 };
 
 struct DistState;  // dist.cu
@@ -144,6 +145,10 @@ struct cask_b200_ctx {
   double* d_x = nullptr; int64_t d_x_len = 0;
   double* d_y = nullptr; int64_t d_y_len = 0;
   double* h_pinned = nullptr; int64_t h_pinned_len = 0;
+  // host-buffer SpMV pipeline: x upload, kernels and y download overlap chunk by chunk
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  std::vector<cudaEvent_t> pipe_events;
+  int32_t host_pipeline_chunks = 16;
 
   caskb200::SolverWork work;
   caskb200::DistState* dist = nullptr;
@@ -170,13 +175,15 @@ struct SpmvFusion {           // optional fused epilogue: partial dot products p
 };
 int launch_spmv(cask_b200_ctx* ctx, const double* d_x_full, double* d_y, int part /*0 all,1 interior,2 boundary*/,
                 cudaStream_t stream, const SpmvFusion* fusion);
+int launch_spmv_range(cask_b200_ctx* ctx, const double* d_x, double* d_y, int ell_lo, int ell_hi, int csr_lo, int csr_hi,
+                      cudaStream_t stream, const SpmvFusion* fusion);
 int spmv_num_ctas(cask_b200_ctx* ctx, int part);
 int configure_persistent(cask_b200_ctx* ctx);
 
 // dist.cu
 int dist_exchange_begin(cask_b200_ctx* ctx, double* d_x_full, cudaStream_t after);
 int dist_exchange_wait(cask_b200_ctx* ctx, cudaStream_t consumer);
-int dist_allreduce_sum(cask_b200_ctx* ctx, double* d_vals, int count, cudaStream_t stream);
+int dist_allreduce_sum(cask_b200_ctx* ctx, const double* d_local, double* d_global, int count, cudaStream_t stream);
 void dist_free(cask_b200_ctx* ctx);
 bool dist_active(const cask_b200_ctx* ctx);
 int dist_plan_halo(cask_b200_ctx* ctx);

@@ -261,8 +261,8 @@ int dist_exchange_wait(cask_b200_ctx* ctx, cudaStream_t consumer) {
   return CASK_B200_OK;
 }
 
-int dist_allreduce_sum(cask_b200_ctx* ctx, double* d_vals, int count, cudaStream_t stream) {
-  CB_NCCL(g_nccl.AllReduce(d_vals, d_vals, (size_t)count, kNcclFloat64, kNcclSum, ctx->dist->comm_red, stream));
+int dist_allreduce_sum(cask_b200_ctx* ctx, const double* d_local, double* d_global, int count, cudaStream_t stream) {
+  CB_NCCL(g_nccl.AllReduce(d_local, d_global, (size_t)count, kNcclFloat64, kNcclSum, ctx->dist->comm_red, stream));
   ctx->launches++;
   return CASK_B200_OK;
 }

@@ -28,6 +28,8 @@ struct SliceCount {     // output of the analysis pass, one per slice
   int32_t nnz;
   int32_t nruns;        // -1: span too wide for the bitmap
   int32_t xlen;         // staged doubles incl. zero slots (valid when nruns >= 0)
+  int32_t col_hi;       // one past the largest referenced column, rounded up to a granule
+  int32_t pad_[3];
 };
 
 __device__ __forceinline__ int32_t warp_max(int32_t v) {
@@ -132,6 +134,8 @@ plan_count_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict
     c.nnz = row_ptr[row0 + nrows] - row_ptr[row0];
     c.nruns = ok ? sm.nruns : -1;
     c.xlen = ok ? kZeroSlots + sm.ngran * kGranule : 0;
+    c.col_hi = (sm.gmax + 1) << kGranuleShift;
+    c.pad_[0] = c.pad_[1] = c.pad_[2] = 0;
     out[s] = c;
   }
 }
@@ -323,6 +327,7 @@ int build_plan(cask_b200_ctx* ctx) {
     SliceDesc& sd = p.h_slices[i];
     const SliceCount& c = counts[i];
     sd.row0 = row0s[i]; sd.nrows = nrows[i]; sd.width = c.width; sd.nnz = c.nnz;
+    sd.col_hi = (int32_t)std::min<int64_t>(c.col_hi, p.m);
     const double fill = c.width > 0 ? (double)c.nnz / ((double)c.width * nrows[i]) : 1.0;
     bool staged = c.nruns >= 0 && c.xlen <= cache && fill >= ctx->ell_min_fill && c.width <= 4096;
     if (ctx->force_kind == 1) staged = false;
@@ -355,6 +360,8 @@ int build_plan(cask_b200_ctx* ctx) {
   }
   if (ctx->force_csr_vec) vec = ctx->force_csr_vec;
   p.csr_vec = vec;
+  p.h_list_ell = list_ell;
+  p.h_list_csr = list_csr;
   p.n_ell = (int32_t)list_ell.size();
   p.n_ell_interior = p.n_ell;
   p.n_csr = (int32_t)list_csr.size();

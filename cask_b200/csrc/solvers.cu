@@ -23,9 +23,11 @@ enum {
   S_RS0 = 0, S_RS1 = 1,  // r.r ping-pong: iteration i reads slot i&1, writes (i+1)&1
   S_PAP = 2, S_TOL2 = 3, S_RS_FINAL = 4,
   // BiCGStab
-  B_RHO = 5, B_RHO_OLD = 6, B_ALPHA = 7, B_W = 8, B_R0V = 9, B_TS = 10, B_TT = 11, B_RR = 12,
-  B_R0SQ = 13, B_RHSSQ = 14, B_TOL2 = 15, B_R0R = 16, B_TMP = 17,
-  S_COUNT = 24
+  B_RHO = 5, B_RHO_OLD = 6, B_ALPHA = 7, B_W = 8, B_R0V = 9, B_TS = 10, B_TT = 11, B_RR = 12, B_R0R = 13,
+  B_R0SQ = 14, B_RHSSQ = 15, B_TOL2 = 16, B_TMP = 17,
+  S_COUNT = 24  // when row-sharded, slots [S_COUNT, 2*S_COUNT) stage each rank's LOCAL sums: the all-reduce reads
+                // them and writes the global value to the slot proper, so repeating it is harmless (iterations
+                // enqueued past convergence still run their collectives)
 };
 // device flag slots (int32)
 enum { F_DONE = 0, F_CONVERGED = 1, F_ITERATIONS = 2, F_TRIPS = 3, F_RESTART = 4, F_RESTARTS = 5, F_I = 6, F_MAXIT = 7, F_COUNT = 8 };
@@ -285,6 +287,11 @@ __global__ void bicg_tail_kernel(double* scal, int32_t* flags) {
   flags[F_TRIPS] += 1;
 }
 
+// partial dots written by one fused SpMV: interior and halo-dependent launches are sized separately when sharded
+int spmv_partials(cask_b200_ctx* ctx) {
+  return dist_active(ctx) ? spmv_num_ctas(ctx, 1) + spmv_num_ctas(ctx, 2) : spmv_num_ctas(ctx, 0);
+}
+
 int vec_grid(int64_t n) { return (int)((n + (int64_t)kVecThreads * kVecItems - 1) / ((int64_t)kVecThreads * kVecItems)); }
 
 int ensure_work(cask_b200_ctx* ctx, int nvec, int64_t len_full) {
@@ -299,11 +306,11 @@ int ensure_work(cask_b200_ctx* ctx, int nvec, int64_t len_full) {
       CB_CUDA(cudaMemsetAsync(w.d_vec[i], 0, sizeof(double) * std::max<int64_t>(len_full, 2), ctx->stream));
     }
   w.vec_len = std::max(w.vec_len, len_full);
-  if (!w.d_scalars) CB_CUDA(cudaMalloc(&w.d_scalars, sizeof(double) * S_COUNT));
+  if (!w.d_scalars) CB_CUDA(cudaMalloc(&w.d_scalars, sizeof(double) * 2 * S_COUNT));
   if (!w.d_counters) CB_CUDA(cudaMalloc(&w.d_counters, sizeof(int32_t) * (F_COUNT + 1)));
   if (!w.h_flags) CB_CUDA(cudaMallocHost(&w.h_flags, sizeof(int32_t) * (F_COUNT + 1) * 4));
   if (!w.h_scalars) CB_CUDA(cudaMallocHost(&w.h_scalars, sizeof(double) * S_COUNT));
-  const int64_t np = 2 * (int64_t)std::max(std::max(spmv_num_ctas(ctx, 0), vec_grid(ctx->plan.n)), 1);
+  const int64_t np = 2 * (int64_t)std::max(std::max(spmv_partials(ctx), vec_grid(ctx->plan.n)), 1);
   static_assert(sizeof(int64_t) == 8, "");
   cudaFree(w.d_partials);
   w.d_partials = nullptr;
@@ -323,6 +330,19 @@ int spmv_full(cask_b200_ctx* ctx, double* d_full, double* d_y, const SpmvFusion*
   CB_TRY(launch_spmv(ctx, d_full, d_y, 1, s, f ? &fi : nullptr));   // interior rows: no remote x
   CB_TRY(dist_exchange_wait(ctx, s));
   CB_TRY(launch_spmv(ctx, d_full, d_y, 2, s, f ? &fb : nullptr));   // rows that read the halo
+  return CASK_B200_OK;
+}
+
+// sums `count` per-CTA partials (nq = 1 or 2 quantities, `stride` apart) into scal[slot0], scal[slot0 + 1];
+// across ranks too when sharded
+int reduce_dots(cask_b200_ctx* ctx, int count, int stride, int nq, int slot0, const int32_t* flags) {
+  SolverWork& w = ctx->work;
+  cudaStream_t s = ctx->stream;
+  const bool dist = dist_active(ctx);
+  double* dst = w.d_scalars + (dist ? S_COUNT : 0);
+  reduce_partials_kernel<<<1, 1024, 0, s>>>(w.d_partials, count, stride, nq, dst, slot0, slot0 + 1, flags);
+  ctx->launches++;
+  if (dist) CB_TRY(dist_allreduce_sum(ctx, w.d_scalars + S_COUNT + slot0, w.d_scalars + slot0, nq, s));
   return CASK_B200_OK;
 }
 
@@ -372,9 +392,8 @@ extern "C" int cask_b200_cg_device(cask_b200_ctx* ctx, const double* d_rhs, doub
   CB_CUDA(cudaMemcpyAsync(p, d_x, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
   CB_TRY(spmv_full(ctx, p_full, r, nullptr));
   cg_init_kernel<<<vg, kVecThreads, 0, s>>>(n, d_rhs, r, p, w.d_partials);
-  reduce_partials_kernel<<<1, 1024, 0, s>>>(w.d_partials, vg, 0, 1, scal, S_RS0, S_RS0, nullptr);
-  ctx->launches += 2;
-  if (dist) CB_TRY(dist_allreduce_sum(ctx, scal + S_RS0, 1, s));
+  ctx->launches++;
+  CB_TRY(reduce_dots(ctx, vg, 0, 1, S_RS0, nullptr));
 
   // Enqueue batches of iterations; poll the device's done flag one batch behind so the host never
   // stalls the stream.  Kernels of iterations enqueued past convergence see F_DONE and do nothing.
@@ -389,13 +408,11 @@ extern "C" int cask_b200_cg_device(cask_b200_ctx* ctx, const double* d_rhs, doub
       f.d_dot_with = p;
       f.d_partials = w.d_partials;
       CB_TRY(spmv_full(ctx, p_full, Ap, &f));                                        // :206
-      reduce_partials_kernel<<<1, 1024, 0, s>>>(w.d_partials, spmv_num_ctas(ctx, 0), 0, 1, scal, S_PAP, S_PAP, flags);
-      if (dist) CB_TRY(dist_allreduce_sum(ctx, scal + S_PAP, 1, s));
+      CB_TRY(reduce_dots(ctx, spmv_partials(ctx), 0, 1, S_PAP, flags));
       cg_update_xr_kernel<<<vg, kVecThreads, 0, s>>>(n, it, scal, flags, p, Ap, d_x, r, w.d_partials);   // :208-218
-      reduce_partials_kernel<<<1, 1024, 0, s>>>(w.d_partials, vg, 0, 1, scal, S_RS0 + ((it + 1) & 1), 0, flags);
-      if (dist) CB_TRY(dist_allreduce_sum(ctx, scal + S_RS0 + ((it + 1) & 1), 1, s));
+      CB_TRY(reduce_dots(ctx, vg, 0, 1, S_RS0 + ((it + 1) & 1), flags));
       cg_update_p_kernel<<<vg, kVecThreads, 0, s>>>(n, it, scal, flags, r, p);         // :220-231
-      ctx->launches += 4;
+      ctx->launches += 2;
     }
     enq = hi;
     CB_CUDA(cudaMemcpyAsync(hf + (batch & 1) * (F_COUNT + 1), flags, sizeof(int32_t) * (F_COUNT + 1),
@@ -438,7 +455,7 @@ extern "C" int cask_b200_bicgstab_device(cask_b200_ctx* ctx, const double* d_b, 
   double* scal = w.d_scalars;
   int32_t* flags = reinterpret_cast<int32_t*>(w.d_counters);
   const int vg = vec_grid(n);
-  const int stride = std::max(std::max(spmv_num_ctas(ctx, 0), vg), 1);
+  const int stride = std::max(std::max(spmv_partials(ctx), vg), 1);
   const bool dist = dist_active(ctx);
   const double tol = *tol_error > 0 ? *tol_error : DBL_EPSILON;
   const int64_t maxit64 = *iters > 0 ? *iters : 2 * pl.n_global;
@@ -459,11 +476,10 @@ extern "C" int cask_b200_bicgstab_device(cask_b200_ctx* ctx, const double* d_b, 
   // r = b - A x ; r0 = r ; r0_sq = r.r ; rhs_sq = b.b
   CB_TRY(spmv_full(ctx, y_full, t, nullptr));
   bicg_residual_kernel<<<vg, kVecThreads, 0, st>>>(n, flags, 0, d_b, r, r0, t, w.d_partials);
-  reduce_partials_kernel<<<1, 1024, 0, st>>>(w.d_partials, vg, 0, 1, scal, B_R0SQ, 0, nullptr);
+  CB_TRY(reduce_dots(ctx, vg, 0, 1, B_R0SQ, nullptr));
   dot2_kernel<<<vg, kVecThreads, 0, st>>>(n, nullptr, d_b, d_b, nullptr, nullptr, w.d_partials, stride);
-  reduce_partials_kernel<<<1, 1024, 0, st>>>(w.d_partials, vg, 0, 1, scal, B_RHSSQ, 0, nullptr);
-  ctx->launches += 5;
-  if (dist) { CB_TRY(dist_allreduce_sum(ctx, scal + B_R0SQ, 2, st)); }
+  CB_TRY(reduce_dots(ctx, vg, 0, 1, B_RHSSQ, nullptr));
+  ctx->launches += 3;
   CB_CUDA(cudaMemcpyAsync(w.h_scalars, scal, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, st));
   CB_CUDA(cudaStreamSynchronize(st));
   const double rhs_sq = w.h_scalars[B_RHSSQ];
@@ -484,19 +500,16 @@ extern "C" int cask_b200_bicgstab_device(cask_b200_ctx* ctx, const double* d_b, 
     bicg_p_kernel<<<vg, kVecThreads, 0, st>>>(n, scal, flags, r, v, invd, p, y);
     SpmvFusion f1; f1.d_dot_with = r0; f1.d_partials = w.d_partials;
     CB_TRY(spmv_full(ctx, y_full, v, &f1));                                  // v = A y, partials of r0.v
-    reduce_partials_kernel<<<1, 1024, 0, st>>>(w.d_partials, spmv_num_ctas(ctx, 0), 0, 1, scal, B_R0V, 0, flags);
-    if (dist) CB_TRY(dist_allreduce_sum(ctx, scal + B_R0V, 1, st));
+    CB_TRY(reduce_dots(ctx, spmv_partials(ctx), 0, 1, B_R0V, flags));
     bicg_alpha_kernel<<<1, 1, 0, st>>>(scal, flags);
     bicg_s_kernel<<<vg, kVecThreads, 0, st>>>(n, scal, flags, r, v, invd, s, z);
     CB_TRY(spmv_full(ctx, z_full, t, nullptr));                               // t = A z
     dot2_kernel<<<vg, kVecThreads, 0, st>>>(n, flags, t, s, t, t, w.d_partials, stride);
-    reduce_partials_kernel<<<1, 1024, 0, st>>>(w.d_partials, vg, stride, 2, scal, B_TS, B_TT, flags);
-    if (dist) CB_TRY(dist_allreduce_sum(ctx, scal + B_TS, 2, st));
+    CB_TRY(reduce_dots(ctx, vg, stride, 2, B_TS, flags));
     bicg_xr_kernel<<<vg, kVecThreads, 0, st>>>(n, scal, flags, y, z, s, t, r0, d_x, r, w.d_partials, stride);
-    reduce_partials_kernel<<<1, 1024, 0, st>>>(w.d_partials, vg, stride, 2, scal, B_RR, B_R0R, flags);
-    if (dist) { CB_TRY(dist_allreduce_sum(ctx, scal + B_RR, 1, st)); CB_TRY(dist_allreduce_sum(ctx, scal + B_R0R, 1, st)); }
+    CB_TRY(reduce_dots(ctx, vg, stride, 2, B_RR, flags));
     bicg_tail_kernel<<<1, 1, 0, st>>>(scal, flags);
-    ctx->launches += 9;
+    ctx->launches += 6;
     return CASK_B200_OK;
   };
   const int kBatch = 4;
@@ -524,10 +537,9 @@ extern "C" int cask_b200_bicgstab_device(cask_b200_ctx* ctx, const double* d_b, 
         CB_CUDA(cudaMemcpyAsync(z, d_x, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
         CB_TRY(spmv_full(ctx, z_full, t, nullptr));
         bicg_residual_kernel<<<vg, kVecThreads, 0, st>>>(n, flags, 1, d_b, r, r0, t, w.d_partials);
-        reduce_partials_kernel<<<1, 1024, 0, st>>>(w.d_partials, vg, 0, 1, scal, B_TMP, 0, nullptr);
-        if (dist) CB_TRY(dist_allreduce_sum(ctx, scal + B_TMP, 1, st));
+        CB_TRY(reduce_dots(ctx, vg, 0, 1, B_TMP, nullptr));
         bicg_restart_scalars_kernel<<<1, 1, 0, st>>>(scal, flags);
-        ctx->launches += 3;
+        ctx->launches += 2;
         CB_TRY(enqueue_body());
         CB_CUDA(cudaStreamSynchronize(st));
         skip_check = true;   // the flag copy already in flight predates the restart

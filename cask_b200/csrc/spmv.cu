@@ -422,11 +422,18 @@ int configure_persistent(cask_b200_ctx* ctx) {
 int launch_spmv(cask_b200_ctx* ctx, const double* d_x, double* d_y, int part, cudaStream_t s,
                 const SpmvFusion* fusion) {
   const Plan& p = ctx->plan;
-  if ((reinterpret_cast<uintptr_t>(d_x) & 15u) != 0)
-    return fail(CASK_B200_ERR_INVALID_ARGUMENT, "x must be 16-byte aligned (TMA bulk copies)");
   int ell_lo = 0, ell_hi = p.n_ell, csr_lo = 0, csr_hi = p.n_csr;
   if (part == 1) { ell_hi = p.n_ell_interior; csr_hi = p.n_csr_interior; }
   if (part == 2) { ell_lo = p.n_ell_interior; csr_lo = p.n_csr_interior; }
+  return launch_spmv_range(ctx, d_x, d_y, ell_lo, ell_hi, csr_lo, csr_hi, s, fusion);
+}
+
+// entries [ell_lo, ell_hi) of the staged-ELL list and [csr_lo, csr_hi) of the gather-CSR list
+int launch_spmv_range(cask_b200_ctx* ctx, const double* d_x, double* d_y, int ell_lo, int ell_hi, int csr_lo, int csr_hi,
+                      cudaStream_t s, const SpmvFusion* fusion) {
+  const Plan& p = ctx->plan;
+  if ((reinterpret_cast<uintptr_t>(d_x) & 15u) != 0)
+    return fail(CASK_B200_ERR_INVALID_ARGUMENT, "x must be 16-byte aligned (TMA bulk copies)");
   const bool dot = fusion && fusion->d_dot_with;
   double* partials = dot ? fusion->d_partials : nullptr;
   const double* w = dot ? fusion->d_dot_with : nullptr;

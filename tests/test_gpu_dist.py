@@ -1,0 +1,102 @@
+"""Row-sharded execution over NCCL, one process per GPU (needs >= 2 GPUs: `gpurun --gpus 2`)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+WORKER = r'''
+import os, sys, json
+sys.path.insert(0, %r)
+import numpy as np, torch, torch.distributed as dist
+import cask_b200 as cb
+from oracle import oraclebind as O
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dev = torch.device("cuda", rank)
+dist.init_process_group("nccl", device_id=dev)
+ctx = cb.Context(rank)
+ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+if rank == 0:
+    idt.copy_(torch.frombuffer(bytearray(cb.nccl_unique_id()), dtype=torch.uint8))
+dist.broadcast(idt, 0)
+ctx.dist_init(rank, world, idt.cpu().numpy().tobytes())
+out = {}
+for name, gen, N in (("poisson2d", O.gen_poisson2d, 96), ("poisson3d27", O.gen_poisson3d27, 24), ("rmat", lambda s: O.gen_rmat(s, 8, 3), 12)):
+    n, rp, ci, va = gen(N)
+    r0, nr = cb.shard_rows(n, world, rank)
+    lrp = torch.tensor(rp[r0:r0 + nr + 1] - rp[r0], dtype=torch.int32, device=dev)
+    lci = torch.tensor(ci[rp[r0]:rp[r0 + nr]], dtype=torch.int32, device=dev)
+    lva = torch.tensor(va[rp[r0]:rp[r0 + nr]], dtype=torch.float64, device=dev)
+    ctx.preprocess_shard_device(cb.design(1, 8192, 16), n, n, r0, nr, len(lva), lrp.data_ptr(), lci.data_ptr(), lva.data_ptr())
+    halo = ctx.halo_counts(world).tolist()
+    x = np.random.default_rng(5).random(n)
+    xf = torch.zeros(n, dtype=torch.float64, device=dev)
+    xf[r0:r0 + nr] = torch.tensor(x[r0:r0 + nr], device=dev)          # only the own slice is valid on entry
+    y = torch.empty(nr, dtype=torch.float64, device=dev)
+    ctx.spmv_device(xf.data_ptr(), y.data_ptr()); ctx.synchronize()
+    exp = O.csr_dot(n, rp, ci, va, x)[r0:r0 + nr]
+    got = y.cpu().numpy()
+    scale = np.maximum(np.abs(exp), 1e-300)
+    out[name] = {"spmv_max_rel": float((np.abs(got - exp) / np.maximum(scale, 1.0)).max()), "bitexact": bool(np.array_equal(got, exp)), "halo": halo}
+    if name != "rmat":
+        xt = 1.0 + 0.25 * (np.arange(n) %% 4)
+        b = O.csr_dot(n, rp, ci, va, xt)
+        oc, oi, ox, ors = O.pcg(n, rp, ci, va, b, lower=False)
+        db = torch.tensor(b[r0:r0 + nr], device=dev)
+        dx = torch.zeros(nr, dtype=torch.float64, device=dev)
+        conv, it, rs, trips = ctx.cg_device(db.data_ptr(), dx.data_ptr())
+        out[name].update({"cg_conv": conv, "cg_it": it, "oracle_it": oi, "cg_err": float(np.abs(dx.cpu().numpy() - ox[r0:r0 + nr]).max())})
+        if name == "poisson2d":
+            n2, rp2, ci2, va2 = O.gen_convdiff3d7(16)
+n, rp, ci, va = O.gen_convdiff3d7(16)
+r0, nr = cb.shard_rows(n, world, rank)
+lrp = torch.tensor(rp[r0:r0 + nr + 1] - rp[r0], dtype=torch.int32, device=dev)
+lci = torch.tensor(ci[rp[r0]:rp[r0 + nr]], dtype=torch.int32, device=dev)
+lva = torch.tensor(va[rp[r0]:rp[r0 + nr]], dtype=torch.float64, device=dev)
+ctx.preprocess_shard_device(cb.design(1, 8192, 16), n, n, r0, nr, len(lva), lrp.data_ptr(), lci.data_ptr(), lva.data_ptr())
+b = O.csr_dot(n, rp, ci, va, np.ones(n))
+ox, oit, oerr = O.bicgstab(n, rp, ci, va, b, tol=1e-10)
+db = torch.tensor(b[r0:r0 + nr], device=dev)
+dx = torch.zeros(nr, dtype=torch.float64, device=dev)
+it, err = ctx.bicgstab_device(db.data_ptr(), dx.data_ptr(), tol=1e-10)
+out["bicgstab"] = {"it": it, "oracle_it": oit, "err": err, "sol_err": float(np.abs(dx.cpu().numpy() - 1.0).max())}
+if rank == 0:
+    print("RESULT " + json.dumps(out))
+ctx.close()
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_spmv_and_solvers(world, tmp_path):
+    if _ngpus() < world:
+        pytest.skip("needs %d GPUs" % world)
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % ROOT)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(29500 + world), str(script)]
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-6000:]
+    line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")][-1]
+    res = json.loads(line[7:])
+    for name in ("poisson2d", "poisson3d27"):
+        r = res[name]
+        assert r["bitexact"], r                      # stencils: staged-ELL rows, reference summation order
+        assert sum(r["halo"]) > 0 and r["halo"][0] == 0   # rank 0 receives only from its neighbour(s)
+        assert r["cg_conv"] and abs(r["cg_it"] - r["oracle_it"]) <= 1 and r["cg_err"] < 1e-6, r
+    assert res["rmat"]["spmv_max_rel"] < 1e-12, res["rmat"]
+    bi = res["bicgstab"]
+    assert bi["err"] <= 1e-10 and bi["sol_err"] < 1e-7 and abs(bi["it"] - bi["oracle_it"]) <= max(2, bi["oracle_it"] // 10), bi
