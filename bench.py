@@ -38,11 +38,12 @@ CG_GRID = 256  # BASELINE.json configs[3]
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--grid", type=int, default=GRID)
     ap.add_argument("--no-cg", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C3 (R-MAT SpMV) and C5 (BiCGStab) side measurements")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cache", type=int, default=8192)
     return ap.parse_args()
@@ -64,7 +65,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -265,12 +266,12 @@ def main():
     y = torch.empty(n_local, dtype=torch.float64, device=dev)
 
     # ---- device-resident timing ----------------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        ctx.spmv_device(x_full.data_ptr(), y.data_ptr())
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        ctx.spmv_device(x_full.data_ptr(), y.data_ptr())
+    barrier()
     l0 = ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -358,11 +359,17 @@ def main():
            "api": "cask_b200_spmv(ctx, x_host, y_host)" if world == 1 else "H2D + cask_b200_spmv_device + D2H per rank"}
 
     # ---- CG iterations / s on the 3D 27-point system (strong scaling: fixed 256^3 grid) -----------
-    cg = None
+    cg = bicg = rmat = None
+    del x_full, y, cols, vals, rp
+    torch.cuda.empty_cache()
     if not args.no_cg:
-        del x_full, y, cols, vals, rp
-        torch.cuda.empty_cache()
         cg = bench_cg(ctx, cb, torch, dist, dev, rank, world, barrier)
+        torch.cuda.empty_cache()
+    if not args.no_extra:
+        bicg = bench_bicgstab(ctx, cb, torch, dist, dev, rank, world, barrier)
+        torch.cuda.empty_cache()
+        rmat = bench_rmat(ctx, cb, torch, dist, dev, rank, world, barrier)
+        torch.cuda.empty_cache()
 
     if rank == 0:
         line = {
@@ -384,6 +391,10 @@ def main():
         }
         if cg:
             line["cg"] = cg
+        if bicg:
+            line["bicgstab"] = bicg
+        if rmat:
+            line["rmat_spmv"] = rmat
         if world == 1 and not args.no_cpu:
             try:
                 line["cpu_baseline"] = cpu_port_baseline(G)
@@ -439,6 +450,130 @@ def bench_cg(ctx, cb, torch, dist, dev, rank, world, barrier):
             "converged": conv, "rs_final": rs, "seconds": dt, "max_abs_err_vs_x_true": float(et.item()),
             "gpu_launches": int(ctx.launch_count() - l0),
             "traffic_bound_iters_per_s_1gpu": 1.0 / ((algorithmic_bytes(nnz_total, n, n) + 72 * n) / (measured_peak()[0] * 1e9))}
+
+
+def bench_bicgstab(ctx, cb, torch, dist, dev, rank, world, barrier):
+    """BASELINE configs[4]: BiCGStab (Eigen's loop, Jacobi preconditioner) on the nonsymmetric 3D 7-point
+    convection-diffusion system, 512^3 grid (134M rows, 0.94B nnz), row-sharded; b = A 1; 40 iterations timed."""
+    N = 512
+    kind = cb.SYNTH_CONVDIFF3D7
+    n = cb.synth_rows(kind, N)
+    r0, nr = cb.shard_rows(n, world, rank)
+    nnz = cb.synth_nnz(kind, N, r0, nr)
+    rp = torch.empty(nr + 1, dtype=torch.int32, device=dev)
+    ci = torch.empty(nnz, dtype=torch.int32, device=dev)
+    va = torch.empty(nnz, dtype=torch.float64, device=dev)
+    cb.synth_device(kind, N, r0, nr, rp.data_ptr(), ci.data_ptr(), va.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    dsg = cb.design(num_pipes=1, cache_size=8192, input_width=16)
+    if world > 1:
+        ctx.preprocess_shard_device(dsg, n, n, r0, nr, nnz, rp.data_ptr(), ci.data_ptr(), va.data_ptr())
+    else:
+        ctx.preprocess_device(dsg, n, n, nnz, rp.data_ptr(), ci.data_ptr(), va.data_ptr())
+    ones = torch.ones(n, dtype=torch.float64, device=dev)
+    b = torch.empty(nr, dtype=torch.float64, device=dev)
+    ctx.spmv_device(ones.data_ptr(), b.data_ptr())
+    ctx.synchronize()
+    del ones
+    x = torch.zeros(nr, dtype=torch.float64, device=dev)
+    ctx.bicgstab_device(b.data_ptr(), x.data_ptr(), tol=1e-10, maxit=3)  # warm-up
+    barrier()
+    l0 = ctx.launch_count()
+    t0 = time.perf_counter()
+    its, err = ctx.bicgstab_device(b.data_ptr(), x.data_ptr(), tol=1e-10, maxit=40)
+    barrier()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt.item())
+    e = torch.tensor([float((x - 1.0).abs().max().item())], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e, op=dist.ReduceOp.MAX)
+    nnz_total = cb.synth_nnz(kind, N, 0, n)
+    return {"workload": "C5: BiCGStab on 3D 7-pt convection-diffusion %d^3 (%d rows, %d nnz), row-sharded over %d GPU(s)"
+                        % (N, n, nnz_total, world),
+            "scaling": "strong", "iters_per_s": its / dt, "iterations": its, "rel_residual": err, "seconds": dt,
+            "max_abs_err_vs_ones": float(e.item()), "spmv_per_iteration": 2,
+            "gpu_launches": int(ctx.launch_count() - l0)}
+
+
+def bench_rmat(ctx, cb, torch, dist, dev, rank, world, barrier, scale=25, edge_factor=15):
+    """BASELINE configs[2]: R-MAT power-law matrix, 2^25 rows, ~5e8 nnz, (a,b,c,d) = (0.57,0.19,0.19,0.05),
+    duplicates merged, rows sorted by column; generated on the device with torch (bench-side synthetic data),
+    row-sharded; y = A x with x gathered through L2 (irregular rows -> vector-per-row kernels)."""
+    n = 1 << scale
+    r0, nr = cb.shard_rows(n, world, rank)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1)
+    E = edge_factor << scale
+    keys = []
+    chunk = 1 << 26
+    for e0 in range(0, E, chunk):
+        m = min(chunk, E - e0)
+        row = torch.zeros(m, dtype=torch.int64, device=dev)
+        col = torch.zeros(m, dtype=torch.int64, device=dev)
+        for _ in range(scale):
+            u = torch.rand(m, device=dev, generator=g)
+            rb = (u >= 0.76).to(torch.int64)                       # quadrants c, d
+            cbit = (((u >= 0.57) & (u < 0.76)) | (u >= 0.95)).to(torch.int64)  # quadrants b, d
+            row = row * 2 + rb
+            col = col * 2 + cbit
+        keep = (row >= r0) & (row < r0 + nr)
+        keys.append(((row[keep] - r0) << scale) | col[keep])
+        del row, col, u, rb, cbit, keep
+    key = torch.cat(keys)
+    del keys
+    key = torch.unique(key, sorted=True)
+    nnz = int(key.numel())
+    rows_l = (key >> scale)
+    ci = (key & (n - 1)).to(torch.int32).contiguous()
+    del key
+    counts = torch.bincount(rows_l, minlength=nr)
+    del rows_l
+    rp = torch.zeros(nr + 1, dtype=torch.int32, device=dev)
+    rp[1:] = torch.cumsum(counts, 0).to(torch.int32)
+    del counts
+    va = (torch.rand(nnz, device=dev, dtype=torch.float64, generator=g) * 2.0 - 1.0).contiguous()
+    dsg = cb.design(num_pipes=1, cache_size=8192, input_width=16)
+    t0 = time.perf_counter()
+    if world > 1:
+        ctx.preprocess_shard_device(dsg, n, n, r0, nr, nnz, rp.data_ptr(), ci.data_ptr(), va.data_ptr())
+    else:
+        ctx.preprocess_device(dsg, n, n, nnz, rp.data_ptr(), ci.data_ptr(), va.data_ptr())
+    ctx.synchronize()
+    prep = time.perf_counter() - t0
+    stats = ctx.plan_stats()
+    x = torch.rand(n, device=dev, dtype=torch.float64, generator=g).contiguous()
+    y = torch.empty(nr, dtype=torch.float64, device=dev)
+    for _ in range(3):
+        ctx.spmv_device(x.data_ptr(), y.data_ptr())
+    barrier()
+    steps = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        ctx.spmv_device(x.data_ptr(), y.data_ptr())
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    z = torch.tensor([float(nnz)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(z)
+    ms, nnz_total = float(ms.item()), int(z.item())
+    # spot check against torch's own CSR product on a sample of rows
+    sample = torch.randint(0, nr, (4096,), device=dev, generator=g)
+    lo, hi = rp[sample].long(), rp[sample + 1].long()
+    ref = torch.stack([(va[a:b] * x[ci[a:b].long()]).sum() for a, b in zip(lo.tolist()[:256], hi.tolist()[:256])])
+    got = y[sample[:256]]
+    rel = float(((got - ref).abs() / (ref.abs() + 1e-30)).max().item())
+    return {"workload": "C3: R-MAT scale %d, %d rows, %d nnz (after merging duplicates), y = A x, row-sharded over %d GPU(s)"
+                        % (scale, n, nnz_total, world),
+            "scaling": "strong", "ms_per_spmv": ms, "gflops": 2.0 * nnz_total / (ms * 1e-3) / 1e9,
+            "algorithmic_gbs": algorithmic_bytes(nnz_total, n, n) / (ms * 1e-3) / 1e9, "preprocess_s": prep,
+            "max_rel_diff_256_sampled_rows": rel,
+            "plan": {k: stats[k] for k in ("slices_staged_ell", "slices_gather_csr", "csr_lanes_per_row", "max_row_length",
+                                           "row_length_histogram")}}
 
 
 if __name__ == "__main__":

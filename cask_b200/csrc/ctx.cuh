@@ -66,6 +66,20 @@ struct SliceDesc {     // one row slice (<= kSliceRows consecutive rows of one s
   Run inl[kInlineRuns]; // copy of runs[run_off ..] when nruns <= kInlineRuns (written by plan_fill_kernel)
 };
 
+// Unit of work of the gather-CSR path: a run of consecutive rows holding ~8K nonzeros, or one segment of a
+// single long row (R-MAT hubs) so that no CTA ever owns more than kCsrSegment nonzeros.
+struct CsrItem {
+  int32_t row0, nrows;  // local rows
+  int32_t k_lo, k_hi;   // nonzero range (used by single-row items)
+  int32_t scratch;      // >= 0: partial sum of a split row goes to scratch[scratch]; -1: write y directly
+  int32_t vec;          // lanes per row (2..32) for multi-row items; 0: the whole CTA works on one row
+  int32_t pad_[2];
+};
+struct SplitRow { int32_t row, first, nseg, pad_; };
+constexpr int kCsrItemNnz = 8192;    // target nonzeros per multi-row item
+constexpr int kCsrLongRow = 2048;    // rows at least this long get a CTA (or several) of their own
+constexpr int kCsrSegment = 16384;   // nonzeros per segment of a split row
+
 struct RefPartition {  // reference-format partition resident on the device
   cask_b200_partition_info info{};
   int32_t* d_colptr = nullptr;
@@ -93,6 +107,10 @@ struct Plan {
   int32_t n_ell = 0, n_ell_interior = 0;
   int32_t n_csr = 0, n_csr_interior = 0;
   int32_t csr_vec = 4;
+  CsrItem* d_csr_items = nullptr;
+  SplitRow* d_split_rows = nullptr;
+  double* d_csr_scratch = nullptr;
+  std::vector<int32_t> h_item_begin, h_split_begin;  // per position of the CSR slice list (+1 sentinel)
   int32_t max_xcache = 0;
   // persistent staged-ELL kernel configuration (spmv.cu: configure_persistent)
   int32_t persist_ku = 0;       // ELL columns per ring stage (0: persistent kernel not usable)
@@ -165,6 +183,7 @@ int refformat_stripe(cudaStream_t s, int64_t* launches, const int32_t* d_colptr,
 
 // plan.cu
 int build_plan(cask_b200_ctx* ctx);
+int build_csr_items(cask_b200_ctx* ctx);
 void free_plan(cask_b200_ctx* ctx);
 
 // spmv.cu

@@ -220,6 +220,9 @@ int dist_plan_halo(cask_b200_ctx* ctx) {
   if (!ell.empty()) CB_CUDA(cudaMemcpyAsync(p.d_list_ell, ell.data(), sizeof(int32_t) * ell.size(), cudaMemcpyHostToDevice, s));
   if (!csr.empty()) CB_CUDA(cudaMemcpyAsync(p.d_list_csr, csr.data(), sizeof(int32_t) * csr.size(), cudaMemcpyHostToDevice, s));
   CB_CUDA(cudaStreamSynchronize(s));
+  p.h_list_ell = ell;
+  p.h_list_csr = csr;
+  CB_TRY(build_csr_items(ctx));  // items follow the (re-ordered) slice list
   return CASK_B200_OK;
 }
 

@@ -247,7 +247,74 @@ void free_plan(cask_b200_ctx* ctx) {
   }
   cudaFree(p.d_slices); cudaFree(p.d_runs); cudaFree(p.d_ell_vals); cudaFree(p.d_ell_idx);
   cudaFree(p.d_list_ell); cudaFree(p.d_list_csr);
+  cudaFree(p.d_csr_items); cudaFree(p.d_split_rows); cudaFree(p.d_csr_scratch);
   p = Plan();
+}
+
+// Cuts the rows of the gather-CSR slices (in list order) into work items of bounded nonzero count.
+// Rows of >= kCsrLongRow nonzeros get CTAs of their own; beyond kCsrSegment they are split into segments
+// whose partial sums meet again, in order, in a fix-up kernel (deterministic, no atomics).
+int build_csr_items(cask_b200_ctx* ctx) {
+  Plan& p = ctx->plan;
+  cudaFree(p.d_csr_items); cudaFree(p.d_split_rows); cudaFree(p.d_csr_scratch);
+  p.d_csr_items = nullptr; p.d_split_rows = nullptr; p.d_csr_scratch = nullptr;
+  p.h_item_begin.assign(1, 0);
+  p.h_split_begin.assign(1, 0);
+  if (p.n_csr == 0) return CASK_B200_OK;
+  cudaStream_t s = ctx->stream;
+  std::vector<int32_t> rp((size_t)p.n + 1);
+  CB_CUDA(cudaMemcpyAsync(rp.data(), p.d_row_ptr, sizeof(int32_t) * (p.n + 1), cudaMemcpyDeviceToHost, s));
+  CB_CUDA(cudaStreamSynchronize(s));
+  std::vector<CsrItem> items;
+  std::vector<SplitRow> splits;
+  int32_t n_scratch = 0;
+  auto pick_vec = [&](int64_t nnz, int32_t rows) {
+    if (ctx->force_csr_vec) return ctx->force_csr_vec;
+    int32_t v = 2;
+    const double mean = rows ? (double)nnz / rows : 0.0;
+    while (v < 32 && v * 2 <= mean) v <<= 1;
+    return v;
+  };
+  for (int32_t pos = 0; pos < p.n_csr; pos++) {
+    const SliceDesc& sd = p.h_slices[p.h_list_csr[pos]];
+    int32_t start = sd.row0;
+    auto flush = [&](int32_t end) {
+      if (end > start) {
+        CsrItem it{start, end - start, rp[start], rp[end], -1, pick_vec(rp[end] - rp[start], end - start), {0, 0}};
+        items.push_back(it);
+      }
+      start = end;
+    };
+    for (int32_t r = sd.row0; r < sd.row0 + sd.nrows; r++) {
+      const int32_t len = rp[r + 1] - rp[r];
+      if (len >= kCsrLongRow) {
+        flush(r);
+        if (len <= kCsrSegment) {
+          items.push_back(CsrItem{r, 1, rp[r], rp[r + 1], -1, 0, {0, 0}});
+        } else {
+          const int32_t nseg = (len + kCsrSegment - 1) / kCsrSegment;
+          splits.push_back(SplitRow{r, n_scratch, nseg, 0});
+          for (int32_t g = 0; g < nseg; g++)
+            items.push_back(CsrItem{r, 1, rp[r] + g * kCsrSegment, std::min(rp[r + 1], rp[r] + (g + 1) * kCsrSegment),
+                                    n_scratch++, 0, {0, 0}});
+        }
+        start = r + 1;
+      } else if (rp[r + 1] - rp[start] >= kCsrItemNnz) {
+        flush(r + 1);
+      }
+    }
+    flush(sd.row0 + sd.nrows);
+    p.h_item_begin.push_back((int32_t)items.size());
+    p.h_split_begin.push_back((int32_t)splits.size());
+  }
+  CB_CUDA(cudaMalloc(&p.d_csr_items, sizeof(CsrItem) * std::max<size_t>(items.size(), 1)));
+  CB_CUDA(cudaMemcpyAsync(p.d_csr_items, items.data(), sizeof(CsrItem) * items.size(), cudaMemcpyHostToDevice, s));
+  CB_CUDA(cudaMalloc(&p.d_split_rows, sizeof(SplitRow) * std::max<size_t>(splits.size(), 1)));
+  if (!splits.empty())
+    CB_CUDA(cudaMemcpyAsync(p.d_split_rows, splits.data(), sizeof(SplitRow) * splits.size(), cudaMemcpyHostToDevice, s));
+  CB_CUDA(cudaMalloc(&p.d_csr_scratch, sizeof(double) * std::max(n_scratch, 1)));
+  CB_CUDA(cudaStreamSynchronize(s));
+  return CASK_B200_OK;
 }
 
 int build_plan(cask_b200_ctx* ctx) {
@@ -386,6 +453,7 @@ int build_plan(cask_b200_ctx* ctx) {
   cudaFree(d_row0); cudaFree(d_nrows); cudaFree(d_counts); cudaFree(d_hist); cudaFree(d_maxlen);
 
   CB_TRY(configure_persistent(ctx));
+  CB_TRY(build_csr_items(ctx));
   p.stats.slices_staged_ell = p.n_ell;
   p.stats.slices_gather_csr = p.n_csr;
   p.stats.csr_lanes_per_row = vec;

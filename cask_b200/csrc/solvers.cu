@@ -33,7 +33,7 @@ enum {
 enum { F_DONE = 0, F_CONVERGED = 1, F_ITERATIONS = 2, F_TRIPS = 3, F_RESTART = 4, F_RESTARTS = 5, F_I = 6, F_MAXIT = 7, F_COUNT = 8 };
 
 constexpr int kVecThreads = 256;
-constexpr int kVecItems = 4;
+constexpr int kVecItems = 8;  // 8 coalesced 8-byte elements per thread and array: enough loads in flight to stream HBM
 
 __device__ __forceinline__ double cta_sum(double v, double* red) {
 #pragma unroll
@@ -68,13 +68,13 @@ cg_init_kernel(int64_t n, const double* __restrict__ b, double* __restrict__ r, 
                double* __restrict__ partials) {
   __shared__ double red[kVecThreads / 32];
   double acc = 0.0;
-  const int64_t base = ((int64_t)blockIdx.x * kVecThreads + threadIdx.x) * kVecItems;
+  const int64_t base = (int64_t)blockIdx.x * (kVecThreads * kVecItems) + threadIdx.x;
 #pragma unroll
   for (int i = 0; i < kVecItems; i++)
-    if (base + i < n) {
-      const double rv = b[base + i] - r[base + i];
-      r[base + i] = rv;
-      p[base + i] = rv;
+    if (base + (int64_t)i * kVecThreads < n) {
+      const double rv = b[base + (int64_t)i * kVecThreads] - r[base + (int64_t)i * kVecThreads];
+      r[base + (int64_t)i * kVecThreads] = rv;
+      p[base + (int64_t)i * kVecThreads] = rv;
       acc += rv * rv;
     }
   const double t = cta_sum(acc, red);
@@ -90,13 +90,13 @@ cg_update_xr_kernel(int64_t n, int it, const double* __restrict__ scal, const in
   __shared__ double red[kVecThreads / 32];
   const double alpha = scal[S_RS0 + (it & 1)] / scal[S_PAP];
   double acc = 0.0;
-  const int64_t base = ((int64_t)blockIdx.x * kVecThreads + threadIdx.x) * kVecItems;
+  const int64_t base = (int64_t)blockIdx.x * (kVecThreads * kVecItems) + threadIdx.x;
 #pragma unroll
   for (int i = 0; i < kVecItems; i++)
-    if (base + i < n) {
-      x[base + i] += alpha * p[base + i];
-      const double rv = r[base + i] - alpha * Ap[base + i];
-      r[base + i] = rv;
+    if (base + (int64_t)i * kVecThreads < n) {
+      x[base + (int64_t)i * kVecThreads] += alpha * p[base + (int64_t)i * kVecThreads];
+      const double rv = r[base + (int64_t)i * kVecThreads] - alpha * Ap[base + (int64_t)i * kVecThreads];
+      r[base + (int64_t)i * kVecThreads] = rv;
       acc += rv * rv;
     }
   const double t = cta_sum(acc, red);
@@ -112,10 +112,10 @@ cg_update_p_kernel(int64_t n, int it, double* __restrict__ scal, int32_t* __rest
   const bool converged = rsnew <= scal[S_TOL2];
   const double beta = rsnew / rsold;
   if (!converged) {
-    const int64_t base = ((int64_t)blockIdx.x * kVecThreads + threadIdx.x) * kVecItems;
+    const int64_t base = (int64_t)blockIdx.x * (kVecThreads * kVecItems) + threadIdx.x;
 #pragma unroll
     for (int i = 0; i < kVecItems; i++)
-      if (base + i < n) p[base + i] = r[base + i] + beta * p[base + i];
+      if (base + (int64_t)i * kVecThreads < n) p[base + (int64_t)i * kVecThreads] = r[base + (int64_t)i * kVecThreads] + beta * p[base + (int64_t)i * kVecThreads];
   }
   // flags are only written by the grid's LAST CTA to finish, after every CTA has read them
   __shared__ bool last;
@@ -157,13 +157,13 @@ bicg_residual_kernel(int64_t n, const int32_t* __restrict__ flags, int only_on_r
   if (only_on_restart && !flags[F_RESTART]) return;
   __shared__ double red[kVecThreads / 32];
   double acc = 0.0;
-  const int64_t base = ((int64_t)blockIdx.x * kVecThreads + threadIdx.x) * kVecItems;
+  const int64_t base = (int64_t)blockIdx.x * (kVecThreads * kVecItems) + threadIdx.x;
 #pragma unroll
   for (int i = 0; i < kVecItems; i++)
-    if (base + i < n) {
-      const double rv = b[base + i] - Ax[base + i];
-      r[base + i] = rv;
-      r0[base + i] = rv;
+    if (base + (int64_t)i * kVecThreads < n) {
+      const double rv = b[base + (int64_t)i * kVecThreads] - Ax[base + (int64_t)i * kVecThreads];
+      r[base + (int64_t)i * kVecThreads] = rv;
+      r0[base + (int64_t)i * kVecThreads] = rv;
       acc += rv * rv;
     }
   const double t = cta_sum(acc, red);
@@ -177,12 +177,12 @@ dot2_kernel(int64_t n, const int32_t* __restrict__ flags, const double* __restri
   if (flags && (flags[F_DONE] || flags[F_RESTART])) return;
   __shared__ double red[kVecThreads / 32];
   double s0 = 0.0, s1 = 0.0;
-  const int64_t base = ((int64_t)blockIdx.x * kVecThreads + threadIdx.x) * kVecItems;
+  const int64_t base = (int64_t)blockIdx.x * (kVecThreads * kVecItems) + threadIdx.x;
 #pragma unroll
   for (int i = 0; i < kVecItems; i++)
-    if (base + i < n) {
-      s0 += a[base + i] * b[base + i];
-      if (c) s1 += c[base + i] * d[base + i];
+    if (base + (int64_t)i * kVecThreads < n) {
+      s0 += a[base + (int64_t)i * kVecThreads] * b[base + (int64_t)i * kVecThreads];
+      if (c) s1 += c[base + (int64_t)i * kVecThreads] * d[base + (int64_t)i * kVecThreads];
     }
   const double t0 = cta_sum(s0, red);
   if (threadIdx.x == 0) partials[blockIdx.x] = t0;
@@ -219,13 +219,13 @@ bicg_p_kernel(int64_t n, const double* __restrict__ scal, const int32_t* __restr
   if (flags[F_DONE] || flags[F_RESTART]) return;
   const double beta = (scal[B_RHO] / scal[B_RHO_OLD]) * (scal[B_ALPHA] / scal[B_W]);
   const double w = scal[B_W];
-  const int64_t base = ((int64_t)blockIdx.x * kVecThreads + threadIdx.x) * kVecItems;
+  const int64_t base = (int64_t)blockIdx.x * (kVecThreads * kVecItems) + threadIdx.x;
 #pragma unroll
   for (int i = 0; i < kVecItems; i++)
-    if (base + i < n) {
-      const double pv = r[base + i] + beta * (p[base + i] - w * v[base + i]);
-      p[base + i] = pv;
-      y[base + i] = invd[base + i] * pv;
+    if (base + (int64_t)i * kVecThreads < n) {
+      const double pv = r[base + (int64_t)i * kVecThreads] + beta * (p[base + (int64_t)i * kVecThreads] - w * v[base + (int64_t)i * kVecThreads]);
+      p[base + (int64_t)i * kVecThreads] = pv;
+      y[base + (int64_t)i * kVecThreads] = invd[base + (int64_t)i * kVecThreads] * pv;
     }
 }
 
@@ -241,13 +241,13 @@ bicg_s_kernel(int64_t n, const double* __restrict__ scal, const int32_t* __restr
               double* __restrict__ s, double* __restrict__ z) {
   if (flags[F_DONE] || flags[F_RESTART]) return;
   const double alpha = scal[B_ALPHA];
-  const int64_t base = ((int64_t)blockIdx.x * kVecThreads + threadIdx.x) * kVecItems;
+  const int64_t base = (int64_t)blockIdx.x * (kVecThreads * kVecItems) + threadIdx.x;
 #pragma unroll
   for (int i = 0; i < kVecItems; i++)
-    if (base + i < n) {
-      const double sv = r[base + i] - alpha * v[base + i];
-      s[base + i] = sv;
-      z[base + i] = invd[base + i] * sv;
+    if (base + (int64_t)i * kVecThreads < n) {
+      const double sv = r[base + (int64_t)i * kVecThreads] - alpha * v[base + (int64_t)i * kVecThreads];
+      s[base + (int64_t)i * kVecThreads] = sv;
+      z[base + (int64_t)i * kVecThreads] = invd[base + (int64_t)i * kVecThreads] * sv;
     }
 }
 
@@ -263,15 +263,15 @@ bicg_xr_kernel(int64_t n, const double* __restrict__ scal, const int32_t* __rest
   const double w = tt > 0.0 ? scal[B_TS] / tt : 0.0;
   const double alpha = scal[B_ALPHA];
   double a0 = 0.0, a1 = 0.0;
-  const int64_t base = ((int64_t)blockIdx.x * kVecThreads + threadIdx.x) * kVecItems;
+  const int64_t base = (int64_t)blockIdx.x * (kVecThreads * kVecItems) + threadIdx.x;
 #pragma unroll
   for (int i = 0; i < kVecItems; i++)
-    if (base + i < n) {
-      x[base + i] += alpha * y[base + i] + w * z[base + i];
-      const double rv = s[base + i] - w * t[base + i];
-      r[base + i] = rv;
+    if (base + (int64_t)i * kVecThreads < n) {
+      x[base + (int64_t)i * kVecThreads] += alpha * y[base + (int64_t)i * kVecThreads] + w * z[base + (int64_t)i * kVecThreads];
+      const double rv = s[base + (int64_t)i * kVecThreads] - w * t[base + (int64_t)i * kVecThreads];
+      r[base + (int64_t)i * kVecThreads] = rv;
       a0 += rv * rv;
-      a1 += r0[base + i] * rv;
+      a1 += r0[base + (int64_t)i * kVecThreads] * rv;
     }
   const double t0 = cta_sum(a0, red);
   if (threadIdx.x == 0) partials[blockIdx.x] = t0;

@@ -9,8 +9,10 @@
 //                          with 64-bit loads, double-buffered in registers, and sums every row in
 //                          ascending column order with separate multiply and add — bit-identical to
 //                          the reference's CsrMatrix::dot.
-//  spmv_csr_vec_kernel     one CTA per gather-CSR slice, VEC lanes per row (2..32 from the row-length
-//                          histogram), x gathered through the read-only path, warp-shuffle reduction.
+//  spmv_csr_items_kernel   gather-CSR slices cut into work items of ~8K nonzeros: lanes per row (2..32) from
+//                          the item's mean row length, x gathered through the read-only path, warp-shuffle
+//                          reduction; long rows get a CTA each and rows beyond 16K nonzeros are split into
+//                          segments that a fix-up kernel sums in order (R-MAT hubs).
 //
 // Both can fuse the per-CTA partial of dot(y, w) (CG's p.Ap) into their epilogue.
 #include <algorithm>
@@ -323,29 +325,54 @@ spmv_ell_persistent_kernel(const SliceDesc* __restrict__ slices, const int32_t* 
   }
 }
 
-template <int VEC, bool kDot>
+// ---- gather-CSR path: irregular rows, x gathered through the read-only path / L2 -----------------------
+// One CTA per CsrItem.  Multi-row items: `vec` lanes per row (chosen per item from its mean row length),
+// warp-shuffle reduction.  Single-row items (long rows and segments of split rows): the whole CTA strides
+// over the row with four independent accumulators per thread, then a CTA reduction.
+template <bool kDot>
 __global__ void __launch_bounds__(256)
-spmv_csr_vec_kernel(const SliceDesc* __restrict__ slices, const int32_t* __restrict__ list,
-                    const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
-                    const double* __restrict__ val, const double* __restrict__ x, double* __restrict__ y,
-                    const double* __restrict__ dot_with, double* __restrict__ partials) {
+spmv_csr_items_kernel(const CsrItem* __restrict__ items, const int32_t* __restrict__ row_ptr,
+                      const int32_t* __restrict__ col, const double* __restrict__ val, const double* __restrict__ x,
+                      double* __restrict__ y, const double* __restrict__ dot_with, double* __restrict__ partials,
+                      double* __restrict__ scratch) {
   __shared__ double red[8];
-  const SliceDesc sd = slices[list[blockIdx.x]];
-  const int lane = threadIdx.x % VEC, sub = threadIdx.x / VEC;
-  constexpr int kRowsPerPass = 256 / VEC;
+  const CsrItem it = items[blockIdx.x];
   double dot = 0.0;
-  for (int rb = 0; rb < sd.nrows; rb += kRowsPerPass) {
+  if (it.vec == 0) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int32_t k = it.k_lo + threadIdx.x;
+    for (; k + 768 < it.k_hi; k += 1024) {
+      a0 += __ldcs(val + k) * __ldg(x + __ldcs(col + k));
+      a1 += __ldcs(val + k + 256) * __ldg(x + __ldcs(col + k + 256));
+      a2 += __ldcs(val + k + 512) * __ldg(x + __ldcs(col + k + 512));
+      a3 += __ldcs(val + k + 768) * __ldg(x + __ldcs(col + k + 768));
+    }
+    for (; k < it.k_hi; k += 256) a0 += __ldcs(val + k) * __ldg(x + __ldcs(col + k));
+    const double t = cta_sum_d((a0 + a1) + (a2 + a3), red);
+    if (threadIdx.x == 0) {
+      if (it.scratch >= 0) scratch[it.scratch] = t;
+      else {
+        y[it.row0] = t;
+        if (kDot) dot = t * dot_with[it.row0];
+      }
+      if (kDot) partials[blockIdx.x] = dot;
+    }
+    return;
+  }
+  const int vec = it.vec;
+  const int lane = threadIdx.x & (vec - 1), sub = threadIdx.x / vec;
+  const int rows_per_pass = 256 / vec;
+  for (int rb = 0; rb < it.nrows; rb += rows_per_pass) {
     const int r = rb + sub;
     double acc = 0.0;
-    if (r < sd.nrows) {
-      const int32_t kb = row_ptr[sd.row0 + r], ke = row_ptr[sd.row0 + r + 1];
-      for (int32_t k = kb + lane; k < ke; k += VEC) acc += __ldcs(val + k) * __ldg(x + __ldcs(col + k));
+    if (r < it.nrows) {
+      const int32_t kb = row_ptr[it.row0 + r], ke = row_ptr[it.row0 + r + 1];
+      for (int32_t k = kb + lane; k < ke; k += vec) acc += __ldcs(val + k) * __ldg(x + __ldcs(col + k));
     }
-#pragma unroll
-    for (int d = VEC / 2; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-    if (lane == 0 && r < sd.nrows) {
-      y[sd.row0 + r] = acc;
-      if (kDot) dot += acc * dot_with[sd.row0 + r];
+    for (int d = vec >> 1; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if (lane == 0 && r < it.nrows) {
+      y[it.row0 + r] = acc;
+      if (kDot) dot += acc * dot_with[it.row0 + r];
     }
   }
   if (kDot) {
@@ -354,19 +381,24 @@ spmv_csr_vec_kernel(const SliceDesc* __restrict__ slices, const int32_t* __restr
   }
 }
 
+// split rows: partial sums of the segments meet here, in segment order
 template <bool kDot>
-void launch_csr(int vec, int grid, cudaStream_t s, const SliceDesc* sl, const int32_t* list, const Plan& p,
-                const double* x, double* y, const double* w, double* partials) {
-#define CB_CSR(V)                                                                                         \
-  spmv_csr_vec_kernel<V, kDot><<<grid, 256, 0, s>>>(sl, list, p.d_row_ptr, p.d_col, p.d_val, x, y, w, partials)
-  switch (vec) {
-    case 2: CB_CSR(2); break;
-    case 4: CB_CSR(4); break;
-    case 8: CB_CSR(8); break;
-    case 16: CB_CSR(16); break;
-    default: CB_CSR(32); break;
+__global__ void __launch_bounds__(256)
+spmv_csr_fixup_kernel(const SplitRow* __restrict__ rows, int count, const double* __restrict__ scratch,
+                      double* __restrict__ y, const double* __restrict__ dot_with, double* __restrict__ partial) {
+  __shared__ double red[8];
+  double dot = 0.0;
+  for (int i = threadIdx.x; i < count; i += blockDim.x) {
+    const SplitRow r = rows[i];
+    double acc = 0.0;
+    for (int g = 0; g < r.nseg; g++) acc += scratch[r.first + g];
+    y[r.row] = acc;
+    if (kDot) dot += acc * dot_with[r.row];
   }
-#undef CB_CSR
+  if (kDot) {
+    const double t = cta_sum_d(dot, red);
+    if (threadIdx.x == 0) *partial = t;
+  }
 }
 
 }  // namespace
@@ -377,12 +409,19 @@ static int ell_grid(const cask_b200_ctx* ctx, int n_slices) {
   return n_slices;
 }
 
+// partial dots written by the gather-CSR part of a launch over list positions [lo, hi): one per item, plus one
+// for the fix-up kernel when split rows are involved
+static int csr_partials(const Plan& p, int lo, int hi) {
+  if (hi <= lo || p.h_item_begin.size() <= (size_t)hi) return 0;
+  return (p.h_item_begin[hi] - p.h_item_begin[lo]) + (p.h_split_begin[hi] > p.h_split_begin[lo] ? 1 : 0);
+}
+
 // number of per-CTA partial dots a fused launch over `part` writes
 int spmv_num_ctas(cask_b200_ctx* ctx, int part) {
   const Plan& p = ctx->plan;
-  if (part == 1) return ell_grid(ctx, p.n_ell_interior) + p.n_csr_interior;
-  if (part == 2) return ell_grid(ctx, p.n_ell - p.n_ell_interior) + (p.n_csr - p.n_csr_interior);
-  return ell_grid(ctx, p.n_ell) + p.n_csr;
+  if (part == 1) return ell_grid(ctx, p.n_ell_interior) + csr_partials(p, 0, p.n_csr_interior);
+  if (part == 2) return ell_grid(ctx, p.n_ell - p.n_ell_interior) + csr_partials(p, p.n_csr_interior, p.n_csr);
+  return ell_grid(ctx, p.n_ell) + csr_partials(p, 0, p.n_csr);
 }
 
 // Picks KU (ELL columns per ring stage), the ring depth and the CTAs per SM of the persistent kernel from
@@ -470,10 +509,21 @@ int launch_spmv_range(cask_b200_ctx* ctx, const double* d_x, double* d_y, int el
     if (partials) partials += ell_hi - ell_lo;
   }
   if (csr_hi > csr_lo) {
-    double* pp = partials;
-    if (dot) launch_csr<true>(p.csr_vec, csr_hi - csr_lo, s, p.d_slices, p.d_list_csr + csr_lo, p, d_x, d_y, w, pp);
-    else launch_csr<false>(p.csr_vec, csr_hi - csr_lo, s, p.d_slices, p.d_list_csr + csr_lo, p, d_x, d_y, nullptr, nullptr);
-    ctx->launches++;
+    const int i_lo = p.h_item_begin[csr_lo], i_hi = p.h_item_begin[csr_hi];
+    const int s_lo = p.h_split_begin[csr_lo], s_hi = p.h_split_begin[csr_hi];
+    if (i_hi > i_lo) {
+      if (dot) spmv_csr_items_kernel<true><<<i_hi - i_lo, 256, 0, s>>>(p.d_csr_items + i_lo, p.d_row_ptr, p.d_col, p.d_val,
+                                                                       d_x, d_y, w, partials, p.d_csr_scratch);
+      else spmv_csr_items_kernel<false><<<i_hi - i_lo, 256, 0, s>>>(p.d_csr_items + i_lo, p.d_row_ptr, p.d_col, p.d_val,
+                                                                     d_x, d_y, nullptr, nullptr, p.d_csr_scratch);
+      ctx->launches++;
+    }
+    if (s_hi > s_lo) {
+      if (dot) spmv_csr_fixup_kernel<true><<<1, 256, 0, s>>>(p.d_split_rows + s_lo, s_hi - s_lo, p.d_csr_scratch, d_y, w,
+                                                             partials + (i_hi - i_lo));
+      else spmv_csr_fixup_kernel<false><<<1, 256, 0, s>>>(p.d_split_rows + s_lo, s_hi - s_lo, p.d_csr_scratch, d_y, nullptr, nullptr);
+      ctx->launches++;
+    }
   }
   CB_CUDA(cudaGetLastError());
   return CASK_B200_OK;
