@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = (
     "cask_b200_partition_export", "cask_b200_spmv", "cask_b200_spmv_device", "cask_b200_spmv_refformat",
     "cask_b200_cg", "cask_b200_cg_device", "cask_b200_bicgstab", "cask_b200_bicgstab_device",
     "cask_b200_nccl_unique_id", "cask_b200_dist_init", "cask_b200_shard_rows",
-    "cask_b200_preprocess_shard_device", "cask_b200_dist_halo_counts", "cask_b200_synth_rows",
+    "cask_b200_preprocess_shard_device", "cask_b200_dist_halo_counts", "cask_b200_dist_peer_active", "cask_b200_synth_rows",
     "cask_b200_synth_nnz", "cask_b200_synth_device", "cask_b200_launch_count", "cask_b200_legacy_write",
     "cask_b200_legacy_read", "cask_b200_legacy_run", "cask_b200_legacy_reset", "cask_b200_legacy_launch_count",
 )
@@ -101,6 +101,7 @@ def lib():
         L.cask_b200_dist_init.argtypes = [vp, i32, i32, vp]
         L.cask_b200_shard_rows.argtypes = [i64, i32, i32, vp, vp]
         L.cask_b200_dist_halo_counts.argtypes = [vp, vp]
+        L.cask_b200_dist_peer_active.argtypes = [vp, vp]
         L.cask_b200_synth_rows.argtypes = [i32, i32, vp]
         L.cask_b200_synth_nnz.argtypes = [i32, i32, i64, i64, vp]
         L.cask_b200_synth_device.argtypes = [i32, i32, i64, i64, vp, vp, vp, vp]
@@ -266,6 +267,11 @@ class Context:
         out = np.zeros(world, np.int64)
         check(lib().cask_b200_dist_halo_counts(self.h, _p(out)))
         return out
+
+    def peer_active(self):
+        a = C.c_int32()
+        check(lib().cask_b200_dist_peer_active(self.h, C.byref(a)))
+        return bool(a.value)
 
     def launch_count(self):
         c = C.c_int64()

@@ -99,6 +99,7 @@ int cask_b200_create(cask_b200_ctx** out, int device) {
   if (const char* e = getenv("CASK_B200_ELL_KERNEL")) ctx->ell_kernel = atoi(e);
   if (const char* e = getenv("CASK_B200_PERSIST_KU")) ctx->persist_ku = atoi(e);
   if (const char* e = getenv("CASK_B200_HOST_CHUNKS")) ctx->host_pipeline_chunks = atoi(e);
+  if (const char* e = getenv("CASK_B200_PEER")) ctx->peer_mode = atoi(e);
   *out = ctx;
   return CASK_B200_OK;
 }
@@ -153,6 +154,7 @@ int cask_b200_set_option(cask_b200_ctx* ctx, const char* name, double value) {
   else if (k == "ell_kernel") ctx->ell_kernel = (int32_t)value;
   else if (k == "host_pipeline_chunks") ctx->host_pipeline_chunks = (int32_t)value;
   else if (k == "persist_ku") ctx->persist_ku = (int32_t)value;
+  else if (k == "peer_mode") ctx->peer_mode = (int32_t)value;
   else return fail(CASK_B200_ERR_INVALID_ARGUMENT, "set_option: unknown option " + k);
   return CASK_B200_OK;
 }

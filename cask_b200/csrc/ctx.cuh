@@ -125,6 +125,48 @@ struct Plan {
 
 struct DistState;  // dist.cu
 
+// ---- peer-memory layer (dist.cu) --------------------------------------------------
+// Every rank owns one "symmetric arena" (one cudaMalloc, exported with cudaIpcGetMemHandle and mapped by all
+// peers over NVLink): a control block followed by the full-layout vectors the solvers feed to the SpMV.
+// Kernels store halo entries and reduction scalars straight into the peers' arenas.
+constexpr int kMaxPeers = 8;       // one NVSwitch box
+constexpr int kMaxPush = 8;        // contiguous row ranges a rank pushes per vector (stencils: 2)
+constexpr int kHaloChannels = 2;   // full-layout vectors living in the arena (CG: p; BiCGStab: y, z)
+
+struct PeerCtrl {
+  // written by peers (slot = sequence number & 3; a rank can be at most one collective ahead of another)
+  unsigned long long ar_flag[4][kMaxPeers];
+  double ar_val[4][kMaxPeers][2];
+  unsigned long long halo_flag[kHaloChannels][kMaxPeers];  // [channel][source rank] = epoch whose halo has landed
+  // local
+  unsigned long long ar_seq;                    // all-reduces performed
+  unsigned long long push_seq[kHaloChannels];   // halo epochs pushed per channel (== the epoch the next SpMV expects)
+  unsigned int push_ticket[kHaloChannels];      // last-CTA detection of the pushing kernels
+  int error;                                    // a wait on a peer flag timed out
+};
+
+struct PushDesc {       // by-value kernel argument of every kernel that produces a full-layout vector
+  int32_t nsend = 0;    // ranges to push; the peer path is in use iff ctrl != nullptr
+  int32_t channel = 0;
+  int32_t me = 0;
+  int32_t pad_ = 0;
+  int64_t lo[kMaxPush], hi[kMaxPush];  // local row range [lo, hi) that a peer stages
+  double* dst[kMaxPush];               // peer's copy of the vector, rebased: dst[i] is its entry for local row i
+  PeerCtrl* peer_ctrl[kMaxPush];       // that peer's control block
+  PeerCtrl* ctrl = nullptr;            // this rank's control block
+};
+
+struct HaloWait {       // by-value kernel argument of the persistent SpMV kernel
+  const PeerCtrl* ctrl = nullptr;  // nullptr: nothing to wait for
+  PeerCtrl* ctrl_rw = nullptr;     // for the timeout flag
+  int32_t channel = 0;
+  int32_t first_item = 0;          // list position of the first slice that stages remote x
+  uint32_t peer_mask = 0;          // ranks this rank receives halo entries from
+  int32_t pad_ = 0;
+  const int32_t* skip0 = nullptr;  // the kernel returns at once if *skip0 or *skip1 is set (solver flags:
+  const int32_t* skip1 = nullptr;  // converged / restart pending) - the producer of x skipped its push as well
+};
+
 struct SolverWork {  // device scratch of the CG / BiCGStab loops
   double* d_vec[8] = {nullptr};
   int64_t vec_len = 0;
@@ -158,6 +200,7 @@ struct cask_b200_ctx {
   int32_t force_csr_vec = 0;
   int32_t ell_kernel = 1;    // 1 persistent warp-specialised kernel, 0 one CTA per slice
   int32_t persist_ku = 0;    // 0 auto, else 2 or 4
+  int32_t peer_mode = 1;     // 1: halo pushes and scalar all-reduces by own kernels over mapped peer memory; 0: NCCL
 
   // host-call staging buffers
   double* d_x = nullptr; int64_t d_x_len = 0;
@@ -193,9 +236,9 @@ struct SpmvFusion {           // optional fused epilogue: partial dot products p
   int fuse_self_dot = 0;               // also accumulate y[r]*y[r]
 };
 int launch_spmv(cask_b200_ctx* ctx, const double* d_x_full, double* d_y, int part /*0 all,1 interior,2 boundary*/,
-                cudaStream_t stream, const SpmvFusion* fusion);
+                cudaStream_t stream, const SpmvFusion* fusion, const HaloWait* wait = nullptr);
 int launch_spmv_range(cask_b200_ctx* ctx, const double* d_x, double* d_y, int ell_lo, int ell_hi, int csr_lo, int csr_hi,
-                      cudaStream_t stream, const SpmvFusion* fusion);
+                      cudaStream_t stream, const SpmvFusion* fusion, const HaloWait* wait = nullptr);
 int spmv_num_ctas(cask_b200_ctx* ctx, int part);
 int configure_persistent(cask_b200_ctx* ctx);
 
@@ -206,6 +249,16 @@ int dist_allreduce_sum(cask_b200_ctx* ctx, const double* d_local, double* d_glob
 void dist_free(cask_b200_ctx* ctx);
 bool dist_active(const cask_b200_ctx* ctx);
 int dist_plan_halo(cask_b200_ctx* ctx);
+// peer-memory path: usable once the arena is mapped and the halo plan is a handful of contiguous ranges
+bool peer_ready(const cask_b200_ctx* ctx);
+int peer_ensure_arena(cask_b200_ctx* ctx, int64_t len_full);         // collective
+double* peer_vector(cask_b200_ctx* ctx, int channel);                // full-layout vector `channel` of the arena
+PushDesc peer_push_desc(cask_b200_ctx* ctx, int channel);            // nsend == 0 when the peer path is off
+HaloWait peer_halo_wait(cask_b200_ctx* ctx, int channel);
+int peer_push(cask_b200_ctx* ctx, int channel, cudaStream_t stream); // standalone push of the channel's own slice
+int peer_allreduce_partials(cask_b200_ctx* ctx, const double* d_partials, int count, int stride, int nq, double* d_scal,
+                            int slot0, const int32_t* d_skip0, const int32_t* d_skip1, cudaStream_t stream);
+int peer_check_error(cask_b200_ctx* ctx);
 
 // solvers.cu
 void free_solver_work(cask_b200_ctx* ctx);

@@ -18,6 +18,7 @@
 #include <cstring>
 
 #include "ctx.cuh"
+#include "peer.cuh"
 
 namespace caskb200 {
 
@@ -25,7 +26,7 @@ namespace {
 
 typedef struct { char internal[128]; } NcclUniqueId;
 typedef void* NcclComm;
-enum { kNcclInt64 = 4, kNcclFloat64 = 8, kNcclSum = 0 };
+enum { kNcclInt8 = 0, kNcclInt64 = 4, kNcclFloat64 = 8, kNcclSum = 0 };
 
 struct NcclApi {
   void* lib = nullptr;
@@ -86,13 +87,38 @@ struct DistState {
   std::vector<std::vector<Range>> recv_from;  // [peer] ranges of x this rank receives
   std::vector<std::vector<Range>> send_to;    // [peer] ranges of its own slice this rank sends
   int64_t n_global = 0;
+  // peer-memory layer
+  bool peer_mapped = false;      // arenas of all ranks are mapped into this process
+  bool peer_failed = false;      // IPC mapping was tried and is not available on this machine: NCCL from now on
+  bool peer_plan_ok = false;     // every rank's halo plan fits a PushDesc and runs on the persistent kernel
+  unsigned char* arena = nullptr;
+  size_t arena_bytes = 0, vec_stride = 0;
+  int64_t arena_len = 0;         // doubles per full-layout vector
+  unsigned char* peer_base[kMaxPeers] = {nullptr};
+  uint32_t recv_mask = 0;
 };
+
+constexpr size_t kCtrlBytes = 4096;
+static_assert(sizeof(PeerCtrl) <= kCtrlBytes, "control block must fit its reservation");
+
+static void peer_unmap(DistState* d) {
+  for (int q = 0; q < kMaxPeers; q++) {
+    if (d->peer_base[q] && q != d->rank) cudaIpcCloseMemHandle(d->peer_base[q]);
+    d->peer_base[q] = nullptr;
+  }
+  if (d->arena) cudaFree(d->arena);
+  d->arena = nullptr;
+  d->arena_bytes = 0;
+  d->arena_len = 0;
+  d->peer_mapped = false;
+}
 
 bool dist_active(const cask_b200_ctx* ctx) { return ctx->dist && ctx->dist->world > 1; }
 
 void dist_free(cask_b200_ctx* ctx) {
   if (!ctx->dist) return;
   DistState* d = ctx->dist;
+  peer_unmap(d);
   if (d->comm_red && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm_red);
   if (d->comm_halo && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm_halo);
   if (d->ev_ready) cudaEventDestroy(d->ev_ready);
@@ -223,6 +249,230 @@ int dist_plan_halo(cask_b200_ctx* ctx) {
   p.h_list_ell = ell;
   p.h_list_csr = csr;
   CB_TRY(build_csr_items(ctx));  // items follow the (re-ordered) slice list
+
+  // Peer-memory path: every rank's sends must fit one PushDesc and every rank must run the persistent staged-ELL
+  // kernel on all its slices; the ranks agree through one all-reduce.
+  size_t nsend = 0;
+  d->recv_mask = 0;
+  for (int q = 0; q < W; q++) {
+    nsend += d->send_to[q].size();
+    if (!d->recv_from[q].empty()) d->recv_mask |= 1u << q;
+  }
+  const bool mine_ok = !d->allgather && W <= kMaxPeers && nsend <= (size_t)kMaxPush && p.n_csr == 0 &&
+                       ctx->ell_kernel == 1 && p.persist_ku != 0 && ctx->peer_mode != 0;
+  int64_t* d_ok = nullptr;
+  CB_CUDA(cudaMalloc(&d_ok, sizeof(int64_t)));
+  const int64_t bad = mine_ok ? 0 : 1;
+  int64_t bad_all = 1;
+  CB_CUDA(cudaMemcpyAsync(d_ok, &bad, sizeof(bad), cudaMemcpyHostToDevice, s));
+  CB_NCCL(g_nccl.AllReduce(d_ok, d_ok, 1, kNcclInt64, kNcclSum, d->comm_halo, s));
+  CB_CUDA(cudaMemcpyAsync(&bad_all, d_ok, sizeof(bad_all), cudaMemcpyDeviceToHost, s));
+  CB_CUDA(cudaStreamSynchronize(s));
+  cudaFree(d_ok);
+  d->peer_plan_ok = bad_all == 0;
+  return CASK_B200_OK;
+}
+
+// ---- peer-memory layer: arena, halo push, scalar all-reduce --------------------------------------------------
+bool peer_ready(const cask_b200_ctx* ctx) {
+  return dist_active(ctx) && ctx->peer_mode != 0 && ctx->dist->peer_mapped && ctx->dist->peer_plan_ok;
+}
+
+// Collective.  (Re)allocates the symmetric arena so that each of its kHaloChannels vectors holds len_full doubles,
+// exchanges the IPC handles over NCCL and maps every peer's arena.  If the machine does not allow the mapping the
+// ranks agree to stay on NCCL (peer_failed).
+int peer_ensure_arena(cask_b200_ctx* ctx, int64_t len_full) {
+  if (!dist_active(ctx) || ctx->peer_mode == 0) return CASK_B200_OK;
+  DistState* d = ctx->dist;
+  if (d->peer_failed || d->world > kMaxPeers) return CASK_B200_OK;
+  if (d->peer_mapped && d->arena_len >= len_full) return CASK_B200_OK;
+  cudaStream_t s = ctx->stream;
+  const int W = d->world, me = d->rank;
+  CB_CUDA(cudaStreamSynchronize(s));
+  CB_CUDA(cudaStreamSynchronize(ctx->comm_stream));
+  peer_unmap(d);
+  d->vec_stride = (sizeof(double) * (size_t)std::max<int64_t>(len_full, 2) + 255) & ~(size_t)255;
+  d->arena_bytes = kCtrlBytes + kHaloChannels * d->vec_stride;
+  CB_CUDA(cudaMalloc(&d->arena, d->arena_bytes));
+  CB_CUDA(cudaMemsetAsync(d->arena, 0, d->arena_bytes, s));
+  cudaIpcMemHandle_t mine;
+  int64_t bad = cudaIpcGetMemHandle(&mine, d->arena) == cudaSuccess ? 0 : 1;
+  if (bad) cudaGetLastError();
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  unsigned char* d_h = nullptr;
+  CB_CUDA(cudaMalloc(&d_h, 64 * (size_t)(W + 1) + 8));
+  std::vector<cudaIpcMemHandle_t> all(W);
+  CB_CUDA(cudaMemcpyAsync(d_h + 64 * (size_t)W, &mine, 64, cudaMemcpyHostToDevice, s));
+  CB_NCCL(g_nccl.AllGather(d_h + 64 * (size_t)W, d_h, 64, kNcclInt8, d->comm_halo, s));
+  CB_CUDA(cudaMemcpyAsync(all.data(), d_h, 64 * (size_t)W, cudaMemcpyDeviceToHost, s));
+  CB_CUDA(cudaStreamSynchronize(s));
+  d->peer_base[me] = d->arena;
+  for (int q = 0; q < W && !bad; q++) {
+    if (q == me) continue;
+    void* ptr = nullptr;
+    if (cudaIpcOpenMemHandle(&ptr, all[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      bad = 1;
+    } else {
+      d->peer_base[q] = static_cast<unsigned char*>(ptr);
+    }
+  }
+  int64_t* d_bad = reinterpret_cast<int64_t*>(d_h + 64 * (size_t)(W + 1));
+  int64_t bad_all = 1;
+  CB_CUDA(cudaMemcpyAsync(d_bad, &bad, sizeof(bad), cudaMemcpyHostToDevice, s));
+  CB_NCCL(g_nccl.AllReduce(d_bad, d_bad, 1, kNcclInt64, kNcclSum, d->comm_halo, s));
+  CB_CUDA(cudaMemcpyAsync(&bad_all, d_bad, sizeof(bad_all), cudaMemcpyDeviceToHost, s));
+  CB_CUDA(cudaStreamSynchronize(s));
+  cudaFree(d_h);
+  if (bad_all) {
+    peer_unmap(d);
+    d->peer_failed = true;
+    return CASK_B200_OK;
+  }
+  d->arena_len = len_full;
+  d->peer_mapped = true;
+  return CASK_B200_OK;
+}
+
+double* peer_vector(cask_b200_ctx* ctx, int channel) {
+  DistState* d = ctx->dist;
+  return reinterpret_cast<double*>(d->arena + kCtrlBytes + (size_t)channel * d->vec_stride);
+}
+
+PushDesc peer_push_desc(cask_b200_ctx* ctx, int channel) {
+  PushDesc pd;
+  for (int i = 0; i < kMaxPush; i++) { pd.lo[i] = pd.hi[i] = 0; pd.dst[i] = nullptr; pd.peer_ctrl[i] = nullptr; }
+  if (!peer_ready(ctx)) return pd;
+  DistState* d = ctx->dist;
+  const int64_t own_lo = ctx->plan.row0_global;
+  pd.channel = channel;
+  pd.me = d->rank;
+  pd.ctrl = reinterpret_cast<PeerCtrl*>(d->arena);
+  int k = 0;
+  for (int q = 0; q < d->world; q++)
+    for (auto& r : d->send_to[q]) {
+      pd.lo[k] = r.col0 - own_lo;
+      pd.hi[k] = r.col0 + r.len - own_lo;
+      pd.dst[k] = reinterpret_cast<double*>(d->peer_base[q] + kCtrlBytes + (size_t)channel * d->vec_stride) + own_lo;
+      pd.peer_ctrl[k] = reinterpret_cast<PeerCtrl*>(d->peer_base[q]);
+      k++;
+    }
+  pd.nsend = k;
+  return pd;
+}
+
+HaloWait peer_halo_wait(cask_b200_ctx* ctx, int channel) {
+  HaloWait w;
+  if (!peer_ready(ctx)) return w;
+  DistState* d = ctx->dist;
+  if (d->recv_mask == 0) return w;
+  w.ctrl = reinterpret_cast<const PeerCtrl*>(d->arena);
+  w.ctrl_rw = reinterpret_cast<PeerCtrl*>(d->arena);
+  w.channel = channel;
+  w.first_item = ctx->plan.n_ell_interior;
+  w.peer_mask = d->recv_mask;
+  return w;
+}
+
+namespace {
+
+// standalone push: copies the pushed ranges of the channel's own slice into the peers' vectors, then signals
+__global__ void __launch_bounds__(256) halo_push_kernel(const double* __restrict__ own, const PushDesc pd) {
+  // blockIdx.y = range, blockIdx.x strides over it
+  const int s = blockIdx.y;
+  if (s < pd.nsend) {
+    double* dst = pd.dst[s];
+    for (int64_t i = pd.lo[s] + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pd.hi[s]; i += (int64_t)gridDim.x * blockDim.x)
+      dst[i] = own[i];
+  }
+  push_signal(pd);
+}
+
+struct PeerCtrlPtrs { PeerCtrl* p[kMaxPeers]; };
+
+// Deterministic sum of per-CTA partials (index order) followed by a one-shot all-reduce over peer memory: every
+// rank stores its local sums into slot [seq & 3][me] of every rank's control block, publishes the sequence number
+// with a release store, acquires the W flags of its own block and adds the W contributions in rank order - the
+// same order on every rank, so all ranks hold bit-identical scalars and take identical convergence decisions.
+__global__ void __launch_bounds__(1024)
+peer_allreduce_kernel(const double* __restrict__ partials, int count, int stride, int nq, double* __restrict__ scal,
+                      int slot0, const int32_t* __restrict__ skip0, const int32_t* __restrict__ skip1, PeerCtrl* ctrl,
+                      const PeerCtrlPtrs peers, int me, int world) {
+  if ((skip0 && *skip0) || (skip1 && *skip1)) return;
+  __shared__ double red[32];
+  __shared__ double local[2];
+  __shared__ double contrib[kMaxPeers][2];
+  __shared__ unsigned long long seq_s;
+  const int tid = threadIdx.x;
+  for (int q = 0; q < nq; q++) {
+    double v = 0.0;
+    for (int i = tid; i < count; i += blockDim.x) v += partials[(size_t)q * stride + i];
+#pragma unroll
+    for (int dlt = 16; dlt; dlt >>= 1) v += __shfl_xor_sync(0xffffffffu, v, dlt);
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += red[w];
+      local[q] = t;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    seq_s = ctrl->ar_seq + 1;
+    ctrl->ar_seq = seq_s;
+  }
+  __syncthreads();
+  const unsigned long long seq = seq_s;
+  const int slot = (int)(seq & 3ull);
+  if (tid < world) {
+    PeerCtrl* pc = peers.p[tid];
+    for (int q = 0; q < nq; q++) pc->ar_val[slot][me][q] = local[q];
+    __threadfence_system();
+    st_release_sys_u64(&pc->ar_flag[slot][me], seq);
+    peer_wait_ge(&ctrl->ar_flag[slot][tid], seq, &ctrl->error);
+    for (int q = 0; q < nq; q++) contrib[tid][q] = *reinterpret_cast<volatile double*>(&ctrl->ar_val[slot][tid][q]);
+  }
+  __syncthreads();
+  if (tid < nq) {
+    double t = 0.0;
+    for (int r = 0; r < world; r++) t += contrib[r][tid];
+    scal[slot0 + tid] = t;
+  }
+}
+
+}  // namespace
+
+int peer_push(cask_b200_ctx* ctx, int channel, cudaStream_t stream) {
+  const PushDesc pd = peer_push_desc(ctx, channel);
+  if (pd.ctrl == nullptr) return CASK_B200_OK;
+  int64_t longest = 1;
+  for (int i = 0; i < pd.nsend; i++) longest = std::max(longest, pd.hi[i] - pd.lo[i]);
+  const dim3 grid((unsigned)std::min<int64_t>((longest + 255) / 256, 64), (unsigned)std::max(pd.nsend, 1));
+  halo_push_kernel<<<grid, 256, 0, stream>>>(peer_vector(ctx, channel) + ctx->plan.row0_global, pd);
+  ctx->launches++;
+  CB_CUDA(cudaGetLastError());
+  return CASK_B200_OK;
+}
+
+int peer_allreduce_partials(cask_b200_ctx* ctx, const double* d_partials, int count, int stride, int nq, double* d_scal,
+                            int slot0, const int32_t* d_skip0, const int32_t* d_skip1, cudaStream_t stream) {
+  DistState* d = ctx->dist;
+  PeerCtrlPtrs pp;
+  for (int q = 0; q < kMaxPeers; q++) pp.p[q] = q < d->world ? reinterpret_cast<PeerCtrl*>(d->peer_base[q]) : nullptr;
+  peer_allreduce_kernel<<<1, 1024, 0, stream>>>(d_partials, count, stride, nq, d_scal, slot0, d_skip0, d_skip1,
+                                                reinterpret_cast<PeerCtrl*>(d->arena), pp, d->rank, d->world);
+  ctx->launches++;
+  CB_CUDA(cudaGetLastError());
+  return CASK_B200_OK;
+}
+
+// after a solve: did any wait on a peer time out?
+int peer_check_error(cask_b200_ctx* ctx) {
+  if (!peer_ready(ctx)) return CASK_B200_OK;
+  int err = 0;
+  CB_CUDA(cudaMemcpy(&err, ctx->dist->arena + offsetof(PeerCtrl, error), sizeof(int), cudaMemcpyDeviceToHost));
+  if (err) return fail(CASK_B200_ERR_RUNTIME, "peer-memory wait timed out: a rank stopped participating");
   return CASK_B200_OK;
 }
 
@@ -307,6 +557,12 @@ extern "C" int cask_b200_shard_rows(int64_t n, int32_t world, int32_t rank, int6
   if (world < 1 || rank < 0 || rank >= world || n < 0 || !row0 || !nrows)
     return fail(CASK_B200_ERR_INVALID_ARGUMENT, "shard_rows: bad arguments");
   stripe_of(n, world, rank, row0, nrows);
+  return CASK_B200_OK;
+}
+
+extern "C" int cask_b200_dist_peer_active(cask_b200_ctx* ctx, int32_t* active) {
+  if (!ctx || !active) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "dist_peer_active: null");
+  *active = peer_ready(ctx) ? 1 : 0;
   return CASK_B200_OK;
 }
 

@@ -13,6 +13,7 @@
 #include <cstring>
 
 #include "ctx.cuh"
+#include "peer.cuh"
 
 namespace caskb200 {
 
@@ -106,16 +107,23 @@ cg_update_xr_kernel(int64_t n, int it, const double* __restrict__ scal, const in
 // convergence test + p = r + (rsnew/rsold) p                        SparseLinearSolvers.hpp:220-231
 __global__ void __launch_bounds__(kVecThreads)
 cg_update_p_kernel(int64_t n, int it, double* __restrict__ scal, int32_t* __restrict__ flags,
-                   const double* __restrict__ r, double* __restrict__ p) {
+                   const double* __restrict__ r, double* __restrict__ p, const PushDesc pd) {
   if (flags[F_DONE]) return;
   const double rsold = scal[S_RS0 + (it & 1)], rsnew = scal[S_RS0 + ((it + 1) & 1)];
   const bool converged = rsnew <= scal[S_TOL2];
   const double beta = rsnew / rsold;
   if (!converged) {
     const int64_t base = (int64_t)blockIdx.x * (kVecThreads * kVecItems) + threadIdx.x;
+    // row-sharded: entries of the new p that a neighbour stages are stored into its copy of p as they are produced
+    const bool push = pd.nsend && push_overlaps(pd, base - threadIdx.x, base - threadIdx.x + kVecThreads * kVecItems);
 #pragma unroll
     for (int i = 0; i < kVecItems; i++)
-      if (base + (int64_t)i * kVecThreads < n) p[base + (int64_t)i * kVecThreads] = r[base + (int64_t)i * kVecThreads] + beta * p[base + (int64_t)i * kVecThreads];
+      if (base + (int64_t)i * kVecThreads < n) {
+        const double pv = r[base + (int64_t)i * kVecThreads] + beta * p[base + (int64_t)i * kVecThreads];
+        p[base + (int64_t)i * kVecThreads] = pv;
+        if (push) push_store(pd, base + (int64_t)i * kVecThreads, pv);
+      }
+    push_signal(pd);  // the grid's last CTA publishes the new halo epoch to the peers
   }
   // flags are only written by the grid's LAST CTA to finish, after every CTA has read them
   __shared__ bool last;
@@ -215,18 +223,22 @@ __global__ void bicg_restart_scalars_kernel(double* scal, int32_t* flags) {
 __global__ void __launch_bounds__(kVecThreads)
 bicg_p_kernel(int64_t n, const double* __restrict__ scal, const int32_t* __restrict__ flags,
               const double* __restrict__ r, const double* __restrict__ v, const double* __restrict__ invd,
-              double* __restrict__ p, double* __restrict__ y) {
+              double* __restrict__ p, double* __restrict__ y, const PushDesc pd) {
   if (flags[F_DONE] || flags[F_RESTART]) return;
   const double beta = (scal[B_RHO] / scal[B_RHO_OLD]) * (scal[B_ALPHA] / scal[B_W]);
   const double w = scal[B_W];
   const int64_t base = (int64_t)blockIdx.x * (kVecThreads * kVecItems) + threadIdx.x;
+  const bool push = pd.nsend && push_overlaps(pd, base - threadIdx.x, base - threadIdx.x + kVecThreads * kVecItems);
 #pragma unroll
   for (int i = 0; i < kVecItems; i++)
     if (base + (int64_t)i * kVecThreads < n) {
       const double pv = r[base + (int64_t)i * kVecThreads] + beta * (p[base + (int64_t)i * kVecThreads] - w * v[base + (int64_t)i * kVecThreads]);
       p[base + (int64_t)i * kVecThreads] = pv;
-      y[base + (int64_t)i * kVecThreads] = invd[base + (int64_t)i * kVecThreads] * pv;
+      const double yv = invd[base + (int64_t)i * kVecThreads] * pv;
+      y[base + (int64_t)i * kVecThreads] = yv;
+      if (push) push_store(pd, base + (int64_t)i * kVecThreads, yv);
     }
+  push_signal(pd);
 }
 
 __global__ void bicg_alpha_kernel(double* scal, const int32_t* flags) {
@@ -238,17 +250,21 @@ __global__ void bicg_alpha_kernel(double* scal, const int32_t* flags) {
 __global__ void __launch_bounds__(kVecThreads)
 bicg_s_kernel(int64_t n, const double* __restrict__ scal, const int32_t* __restrict__ flags,
               const double* __restrict__ r, const double* __restrict__ v, const double* __restrict__ invd,
-              double* __restrict__ s, double* __restrict__ z) {
+              double* __restrict__ s, double* __restrict__ z, const PushDesc pd) {
   if (flags[F_DONE] || flags[F_RESTART]) return;
   const double alpha = scal[B_ALPHA];
   const int64_t base = (int64_t)blockIdx.x * (kVecThreads * kVecItems) + threadIdx.x;
+  const bool push = pd.nsend && push_overlaps(pd, base - threadIdx.x, base - threadIdx.x + kVecThreads * kVecItems);
 #pragma unroll
   for (int i = 0; i < kVecItems; i++)
     if (base + (int64_t)i * kVecThreads < n) {
       const double sv = r[base + (int64_t)i * kVecThreads] - alpha * v[base + (int64_t)i * kVecThreads];
       s[base + (int64_t)i * kVecThreads] = sv;
-      z[base + (int64_t)i * kVecThreads] = invd[base + (int64_t)i * kVecThreads] * sv;
+      const double zv = invd[base + (int64_t)i * kVecThreads] * sv;
+      z[base + (int64_t)i * kVecThreads] = zv;
+      if (push) push_store(pd, base + (int64_t)i * kVecThreads, zv);
     }
+  push_signal(pd);
 }
 
 // w = t.s / t.t (0 if t.t == 0); x += alpha y + w z; r = s - w t; partials r.r and r0.r
@@ -289,7 +305,7 @@ __global__ void bicg_tail_kernel(double* scal, int32_t* flags) {
 
 // partial dots written by one fused SpMV: interior and halo-dependent launches are sized separately when sharded
 int spmv_partials(cask_b200_ctx* ctx) {
-  return dist_active(ctx) ? spmv_num_ctas(ctx, 1) + spmv_num_ctas(ctx, 2) : spmv_num_ctas(ctx, 0);
+  return dist_active(ctx) && !peer_ready(ctx) ? spmv_num_ctas(ctx, 1) + spmv_num_ctas(ctx, 2) : spmv_num_ctas(ctx, 0);
 }
 
 int vec_grid(int64_t n) { return (int)((n + (int64_t)kVecThreads * kVecItems - 1) / ((int64_t)kVecThreads * kVecItems)); }
@@ -320,9 +336,16 @@ int ensure_work(cask_b200_ctx* ctx, int nvec, int64_t len_full) {
 
 // y = A x for a vector held in "full" layout (global length, own slice at row0_global): halo exchange
 // overlapped with the interior slices when row-sharded.
-int spmv_full(cask_b200_ctx* ctx, double* d_full, double* d_y, const SpmvFusion* f) {
+// Peer-memory path (channel >= 0: d_full is vector `channel` of the symmetric arena and its producer has pushed
+// this epoch's halo): ONE launch over all slices, interior first; the kernel's producer warp acquires the peers'
+// epoch flags when it reaches the first halo-dependent slice.  flags != nullptr: the launch does nothing once the
+// solver's DONE / RESTART flag is up (its producer skipped the push under the same condition).
+int spmv_full(cask_b200_ctx* ctx, double* d_full, double* d_y, const SpmvFusion* f, int channel, const int32_t* flags) {
   cudaStream_t s = ctx->stream;
-  if (!dist_active(ctx)) return launch_spmv(ctx, d_full, d_y, 0, s, f);
+  HaloWait hw;
+  if (channel >= 0 && peer_ready(ctx)) hw = peer_halo_wait(ctx, channel);
+  if (flags) { hw.skip0 = flags + F_DONE; hw.skip1 = flags + F_RESTART; }
+  if (!dist_active(ctx) || (channel >= 0 && peer_ready(ctx))) return launch_spmv(ctx, d_full, d_y, 0, s, f, &hw);
   CB_TRY(dist_exchange_begin(ctx, d_full, s));
   SpmvFusion fi, fb;
   const int n_int = spmv_num_ctas(ctx, 1);
@@ -339,6 +362,9 @@ int reduce_dots(cask_b200_ctx* ctx, int count, int stride, int nq, int slot0, co
   SolverWork& w = ctx->work;
   cudaStream_t s = ctx->stream;
   const bool dist = dist_active(ctx);
+  if (peer_ready(ctx))
+    return peer_allreduce_partials(ctx, w.d_partials, count, stride, nq, w.d_scalars, slot0, flags ? flags + F_DONE : nullptr,
+                                   flags ? flags + F_RESTART : nullptr, s);
   double* dst = w.d_scalars + (dist ? S_COUNT : 0);
   reduce_partials_kernel<<<1, 1024, 0, s>>>(w.d_partials, count, stride, nq, dst, slot0, slot0 + 1, flags);
   ctx->launches++;
@@ -370,10 +396,14 @@ extern "C" int cask_b200_cg_device(cask_b200_ctx* ctx, const double* d_rhs, doub
   if (pl.n_global != pl.m) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "cg: matrix must be square");
   const int64_t n = pl.n, off = pl.row0_global;
   cudaStream_t s = ctx->stream;
+  CB_TRY(peer_ensure_arena(ctx, pl.m));  // collective; no-op unless row-sharded with the peer-memory path on
   CB_TRY(ensure_work(ctx, 3, pl.m));
   SolverWork& w = ctx->work;
+  const bool peer = peer_ready(ctx);
+  const int ch = peer ? 0 : -1;                       // p is vector 0 of the symmetric arena
+  const PushDesc pd = peer_push_desc(ctx, 0);
   double* r = w.d_vec[0];
-  double* p_full = w.d_vec[1];
+  double* p_full = peer ? peer_vector(ctx, 0) : w.d_vec[1];
   double* Ap = w.d_vec[2];
   double* p = p_full + off;
   double* scal = w.d_scalars;
@@ -390,10 +420,12 @@ extern "C" int cask_b200_cg_device(cask_b200_ctx* ctx, const double* d_rhs, doub
 
   // r = A x (x staged through p's full-layout buffer), r = b - r, p = r, rsold = r.r   (:189-198)
   CB_CUDA(cudaMemcpyAsync(p, d_x, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
-  CB_TRY(spmv_full(ctx, p_full, r, nullptr));
+  CB_TRY(peer_push(ctx, 0, s));
+  CB_TRY(spmv_full(ctx, p_full, r, nullptr, ch, nullptr));
   cg_init_kernel<<<vg, kVecThreads, 0, s>>>(n, d_rhs, r, p, w.d_partials);
   ctx->launches++;
   CB_TRY(reduce_dots(ctx, vg, 0, 1, S_RS0, nullptr));
+  CB_TRY(peer_push(ctx, 0, s));   // p = r; after the all-reduce, so no peer is still reading the previous epoch
 
   // Enqueue batches of iterations; poll the device's done flag one batch behind so the host never
   // stalls the stream.  Kernels of iterations enqueued past convergence see F_DONE and do nothing.
@@ -407,11 +439,11 @@ extern "C" int cask_b200_cg_device(cask_b200_ctx* ctx, const double* d_rhs, doub
       SpmvFusion f;
       f.d_dot_with = p;
       f.d_partials = w.d_partials;
-      CB_TRY(spmv_full(ctx, p_full, Ap, &f));                                        // :206
+      CB_TRY(spmv_full(ctx, p_full, Ap, &f, ch, flags));                             // :206
       CB_TRY(reduce_dots(ctx, spmv_partials(ctx), 0, 1, S_PAP, flags));
       cg_update_xr_kernel<<<vg, kVecThreads, 0, s>>>(n, it, scal, flags, p, Ap, d_x, r, w.d_partials);   // :208-218
       CB_TRY(reduce_dots(ctx, vg, 0, 1, S_RS0 + ((it + 1) & 1), flags));
-      cg_update_p_kernel<<<vg, kVecThreads, 0, s>>>(n, it, scal, flags, r, p);         // :220-231
+      cg_update_p_kernel<<<vg, kVecThreads, 0, s>>>(n, it, scal, flags, r, p, pd);     // :220-231 (+ halo push)
       ctx->launches += 2;
     }
     enq = hi;
@@ -432,7 +464,7 @@ extern "C" int cask_b200_cg_device(cask_b200_ctx* ctx, const double* d_rhs, doub
   if (converged) *converged = hf[F_CONVERGED];
   if (loop_trips) *loop_trips = hf[F_TRIPS];
   if (rs_final) *rs_final = w.h_scalars[S_RS_FINAL];
-  return CASK_B200_OK;
+  return peer_check_error(ctx);
 }
 
 extern "C" int cask_b200_bicgstab_device(cask_b200_ctx* ctx, const double* d_b, double* d_x, int32_t* iters,
@@ -444,10 +476,15 @@ extern "C" int cask_b200_bicgstab_device(cask_b200_ctx* ctx, const double* d_b, 
   if (pl.n_global != pl.m) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "bicgstab: matrix must be square");
   const int64_t n = pl.n, off = pl.row0_global;
   cudaStream_t st = ctx->stream;
+  CB_TRY(peer_ensure_arena(ctx, pl.m));
   CB_TRY(ensure_work(ctx, 8, pl.m));
   SolverWork& w = ctx->work;
+  const bool peer = peer_ready(ctx);
+  const int ch_y = peer ? 0 : -1, ch_z = peer ? 1 : -1;   // y and z are vectors 0 and 1 of the symmetric arena
+  const PushDesc pd_y = peer_push_desc(ctx, 0), pd_z = peer_push_desc(ctx, 1);
   double *r = w.d_vec[0], *r0 = w.d_vec[1], *v = w.d_vec[2], *p = w.d_vec[3];
-  double *y_full = w.d_vec[4], *z_full = w.d_vec[5], *s = w.d_vec[6], *t = w.d_vec[7];
+  double *y_full = peer ? peer_vector(ctx, 0) : w.d_vec[4], *z_full = peer ? peer_vector(ctx, 1) : w.d_vec[5];
+  double *s = w.d_vec[6], *t = w.d_vec[7];
   double *y = y_full + off, *z = z_full + off;
   // invdiag shares the tail of the partials allocation? keep it simple: own buffer
   double* invd = nullptr;
@@ -474,7 +511,8 @@ extern "C" int cask_b200_bicgstab_device(cask_b200_ctx* ctx, const double* d_b, 
   CB_CUDA(cudaMemsetAsync(p, 0, sizeof(double) * n, st));
   CB_CUDA(cudaMemsetAsync(y_full, 0, sizeof(double) * pl.m, st));
   // r = b - A x ; r0 = r ; r0_sq = r.r ; rhs_sq = b.b
-  CB_TRY(spmv_full(ctx, y_full, t, nullptr));
+  CB_TRY(peer_push(ctx, 0, st));
+  CB_TRY(spmv_full(ctx, y_full, t, nullptr, ch_y, nullptr));
   bicg_residual_kernel<<<vg, kVecThreads, 0, st>>>(n, flags, 0, d_b, r, r0, t, w.d_partials);
   CB_TRY(reduce_dots(ctx, vg, 0, 1, B_R0SQ, nullptr));
   dot2_kernel<<<vg, kVecThreads, 0, st>>>(n, nullptr, d_b, d_b, nullptr, nullptr, w.d_partials, stride);
@@ -497,13 +535,13 @@ extern "C" int cask_b200_bicgstab_device(cask_b200_ctx* ctx, const double* d_b, 
 
   // body of one iteration after the loop head; every kernel no-ops while F_DONE or F_RESTART is up
   auto enqueue_body = [&]() -> int {
-    bicg_p_kernel<<<vg, kVecThreads, 0, st>>>(n, scal, flags, r, v, invd, p, y);
+    bicg_p_kernel<<<vg, kVecThreads, 0, st>>>(n, scal, flags, r, v, invd, p, y, pd_y);
     SpmvFusion f1; f1.d_dot_with = r0; f1.d_partials = w.d_partials;
-    CB_TRY(spmv_full(ctx, y_full, v, &f1));                                  // v = A y, partials of r0.v
+    CB_TRY(spmv_full(ctx, y_full, v, &f1, ch_y, flags));                     // v = A y, partials of r0.v
     CB_TRY(reduce_dots(ctx, spmv_partials(ctx), 0, 1, B_R0V, flags));
     bicg_alpha_kernel<<<1, 1, 0, st>>>(scal, flags);
-    bicg_s_kernel<<<vg, kVecThreads, 0, st>>>(n, scal, flags, r, v, invd, s, z);
-    CB_TRY(spmv_full(ctx, z_full, t, nullptr));                               // t = A z
+    bicg_s_kernel<<<vg, kVecThreads, 0, st>>>(n, scal, flags, r, v, invd, s, z, pd_z);
+    CB_TRY(spmv_full(ctx, z_full, t, nullptr, ch_z, flags));                  // t = A z
     dot2_kernel<<<vg, kVecThreads, 0, st>>>(n, flags, t, s, t, t, w.d_partials, stride);
     CB_TRY(reduce_dots(ctx, vg, stride, 2, B_TS, flags));
     bicg_xr_kernel<<<vg, kVecThreads, 0, st>>>(n, scal, flags, y, z, s, t, r0, d_x, r, w.d_partials, stride);
@@ -535,7 +573,8 @@ extern "C" int cask_b200_bicgstab_device(cask_b200_ctx* ctx, const double* d_b, 
         // rare: r became orthogonal to r0.  Everything enqueued since is idle; restart on the host's cue:
         // r = b - A x; r0 = r; rho = r0_sq = r.r; the interrupted iteration then continues.
         CB_CUDA(cudaMemcpyAsync(z, d_x, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
-        CB_TRY(spmv_full(ctx, z_full, t, nullptr));
+        CB_TRY(peer_push(ctx, 1, st));
+        CB_TRY(spmv_full(ctx, z_full, t, nullptr, ch_z, nullptr));
         bicg_residual_kernel<<<vg, kVecThreads, 0, st>>>(n, flags, 1, d_b, r, r0, t, w.d_partials);
         CB_TRY(reduce_dots(ctx, vg, 0, 1, B_TMP, nullptr));
         bicg_restart_scalars_kernel<<<1, 1, 0, st>>>(scal, flags);
@@ -557,5 +596,5 @@ extern "C" int cask_b200_bicgstab_device(cask_b200_ctx* ctx, const double* d_b, 
   cudaFree(invd);
   *iters = hf[F_I];
   *tol_error = std::sqrt(w.h_scalars[B_RR] / rhs_sq);
-  return CASK_B200_OK;
+  return peer_check_error(ctx);
 }

@@ -18,6 +18,7 @@
 #include <algorithm>
 
 #include "ctx.cuh"
+#include "peer.cuh"
 
 namespace caskb200 {
 
@@ -205,7 +206,9 @@ spmv_ell_persistent_kernel(const SliceDesc* __restrict__ slices, const int32_t* 
                            const Run* __restrict__ runs, const double* __restrict__ ell_vals,
                            const uint16_t* __restrict__ ell_idx, const double* __restrict__ x, double* __restrict__ y,
                            const double* __restrict__ dot_with, double* __restrict__ partials, int xbuf_doubles,
-                           int stages) {
+                           int stages, const HaloWait hw) {
+  // solver loops enqueue iterations ahead of the convergence test: once the device-side flag is up nothing runs
+  if ((hw.skip0 && *hw.skip0) || (hw.skip1 && *hw.skip1)) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   PersistHeader* hdr = reinterpret_cast<PersistHeader*>(smem_raw);
   double* xbuf = reinterpret_cast<double*>(smem_raw + kPersistHeaderBytes);
@@ -234,7 +237,14 @@ spmv_ell_persistent_kernel(const SliceDesc* __restrict__ slices, const int32_t* 
     // ===== producer warp =====
     int chunk_no = 0;
     int it = 0;
+    bool halo_landed = hw.ctrl == nullptr;
     for (int item = blockIdx.x; item < count; item += gridDim.x, it++) {
+      if (!halo_landed && item >= hw.first_item) {
+        // first slice that stages x entries owned by a peer: wait until the peers' pushes of this epoch have landed
+        if (lane == 0) halo_wait(hw);
+        __syncwarp();
+        halo_landed = true;
+      }
       const SliceDesc* sdp = slices + list[item];
       const int L = sdp->width, nruns = sdp->nruns;
       const int64_t val_off = sdp->val_off;
@@ -459,18 +469,21 @@ int configure_persistent(cask_b200_ctx* ctx) {
 // part: 0 = every slice, 1 = slices that read only this rank's own x (interior), 2 = the rest.
 // With fusion, partials[0 .. spmv_num_ctas(part)) receives one partial dot per CTA.
 int launch_spmv(cask_b200_ctx* ctx, const double* d_x, double* d_y, int part, cudaStream_t s,
-                const SpmvFusion* fusion) {
+                const SpmvFusion* fusion, const HaloWait* wait) {
   const Plan& p = ctx->plan;
   int ell_lo = 0, ell_hi = p.n_ell, csr_lo = 0, csr_hi = p.n_csr;
   if (part == 1) { ell_hi = p.n_ell_interior; csr_hi = p.n_csr_interior; }
   if (part == 2) { ell_lo = p.n_ell_interior; csr_lo = p.n_csr_interior; }
-  return launch_spmv_range(ctx, d_x, d_y, ell_lo, ell_hi, csr_lo, csr_hi, s, fusion);
+  return launch_spmv_range(ctx, d_x, d_y, ell_lo, ell_hi, csr_lo, csr_hi, s, fusion, wait);
 }
 
 // entries [ell_lo, ell_hi) of the staged-ELL list and [csr_lo, csr_hi) of the gather-CSR list
 int launch_spmv_range(cask_b200_ctx* ctx, const double* d_x, double* d_y, int ell_lo, int ell_hi, int csr_lo, int csr_hi,
-                      cudaStream_t s, const SpmvFusion* fusion) {
+                      cudaStream_t s, const SpmvFusion* fusion, const HaloWait* wait) {
   const Plan& p = ctx->plan;
+  const HaloWait hw = wait ? *wait : HaloWait();
+  if (hw.ctrl && !(ctx->ell_kernel == 1 && p.persist_ku && csr_hi == csr_lo))
+    return fail(CASK_B200_ERR_RUNTIME, "peer halo wait needs the persistent staged-ELL kernel");
   if ((reinterpret_cast<uintptr_t>(d_x) & 15u) != 0)
     return fail(CASK_B200_ERR_INVALID_ARGUMENT, "x must be 16-byte aligned (TMA bulk copies)");
   const bool dot = fusion && fusion->d_dot_with;
@@ -484,7 +497,7 @@ int launch_spmv_range(cask_b200_ctx* ctx, const double* d_x, double* d_y, int el
                                  (int)p.persist_smem));                                                              \
     spmv_ell_persistent_kernel<KU, DOT><<<grid, kPersistThreads, p.persist_smem, s>>>(                               \
         p.d_slices, p.d_list_ell + ell_lo, ell_hi - ell_lo, p.d_runs, p.d_ell_vals, p.d_ell_idx, d_x, d_y, w,        \
-        partials, p.persist_xbuf, p.persist_stages);                                                                 \
+        partials, p.persist_xbuf, p.persist_stages, hw);                                                             \
   } while (0)
     if (p.persist_ku == 2) { if (dot) CB_PERSIST(2, true); else CB_PERSIST(2, false); }
     else { if (dot) CB_PERSIST(4, true); else CB_PERSIST(4, false); }

@@ -95,7 +95,9 @@ int cask_b200_use_own_stream(cask_b200_ctx* ctx);
 int cask_b200_synchronize(cask_b200_ctx* ctx);
 /* Tuning knobs of the kernel selector (tests and sweeps): "ell_min_fill" (default 0.75),
  * "force_kind" (-1 auto, 0 staged ELL wherever the x windows fit, 1 gather CSR everywhere),
- * "force_csr_vec" (0 auto, else 2/4/8/16/32 lanes per row).  Takes effect at the next preprocess. */
+ * "force_csr_vec" (0 auto, else 2/4/8/16/32 lanes per row), "peer_mode" (row-sharded solvers: 1 = halo pushes
+ * and scalar all-reduces by the library's own kernels over IPC-mapped peer memory, 0 = NCCL send/recv and
+ * all-reduce; every rank must use the same value).  Takes effect at the next preprocess. */
 int cask_b200_set_option(cask_b200_ctx* ctx, const char* name, double value);
 
 /* ---- preprocess: replaces Spmv::preprocess(const CsrMatrix&), src/runtime/Spmv.cpp:329-365 ---- */
@@ -160,6 +162,11 @@ int cask_b200_preprocess_shard_device(cask_b200_ctx* ctx, const cask_b200_design
 /* Host-side halo plan of the last preprocess_shard: for each peer, the number of x doubles this
  * rank receives from it per SpMV. counts has `world` entries. */
 int cask_b200_dist_halo_counts(cask_b200_ctx* ctx, int64_t* recv_counts);
+/* 1 if the row-sharded solvers of this context run on the peer-memory path (halo entries stored into the
+ * neighbours' vectors by the producing kernel, scalar all-reduces by a kernel over IPC-mapped control blocks),
+ * 0 if they use NCCL send/recv + all-reduce (option peer_mode = 0, irregular halo, or no IPC on this machine).
+ * Meaningful after the first solver call that followed a preprocess_shard. */
+int cask_b200_dist_peer_active(cask_b200_ctx* ctx, int32_t* active);
 
 /* ---- synthetic matrices of BASELINE.json, generated on the device ----------------------------- */
 #define CASK_B200_SYNTH_POISSON2D 0   /* 5-point, N x N grid  */

@@ -40,7 +40,9 @@ for name, gen, N in (("poisson2d", O.gen_poisson2d, 96), ("poisson3d27", O.gen_p
     lrp = torch.tensor(rp[r0:r0 + nr + 1] - rp[r0], dtype=torch.int32, device=dev)
     lci = torch.tensor(ci[rp[r0]:rp[r0 + nr]], dtype=torch.int32, device=dev)
     lva = torch.tensor(va[rp[r0]:rp[r0 + nr]], dtype=torch.float64, device=dev)
-    ctx.preprocess_shard_device(cb.design(1, 8192, 16), n, n, r0, nr, len(lva), lrp.data_ptr(), lci.data_ptr(), lva.data_ptr())
+    # cache 2560: the 24^3 twin's slices then stage a few planes each (real halos) and the x windows leave room for
+    # the persistent kernel's ring, which the peer-memory path needs
+    ctx.preprocess_shard_device(cb.design(1, 2560 if name == "poisson3d27" else 8192, 16), n, n, r0, nr, len(lva), lrp.data_ptr(), lci.data_ptr(), lva.data_ptr())
     halo = ctx.halo_counts(world).tolist()
     x = np.random.default_rng(5).random(n)
     xf = torch.zeros(n, dtype=torch.float64, device=dev)
@@ -58,7 +60,12 @@ for name, gen, N in (("poisson2d", O.gen_poisson2d, 96), ("poisson3d27", O.gen_p
         db = torch.tensor(b[r0:r0 + nr], device=dev)
         dx = torch.zeros(nr, dtype=torch.float64, device=dev)
         conv, it, rs, trips = ctx.cg_device(db.data_ptr(), dx.data_ptr())
-        out[name].update({"cg_conv": conv, "cg_it": it, "oracle_it": oi, "cg_err": float(np.abs(dx.cpu().numpy() - ox[r0:r0 + nr]).max())})
+        out[name].update({"cg_conv": conv, "cg_it": it, "oracle_it": oi, "cg_err": float(np.abs(dx.cpu().numpy() - ox[r0:r0 + nr]).max()),
+                          "peer": ctx.peer_active()})
+        # a second solve on the same context: epochs and sequence numbers carry over
+        dx.zero_()
+        conv2, it2, rs2, trips2 = ctx.cg_device(db.data_ptr(), dx.data_ptr())
+        out[name]["cg_repeat_same"] = bool(conv2 == conv and it2 == it and rs2 == rs)
         if name == "poisson2d":
             n2, rp2, ci2, va2 = O.gen_convdiff3d7(16)
 n, rp, ci, va = O.gen_convdiff3d7(16)
@@ -72,7 +79,8 @@ ox, oit, oerr = O.bicgstab(n, rp, ci, va, b, tol=1e-10)
 db = torch.tensor(b[r0:r0 + nr], device=dev)
 dx = torch.zeros(nr, dtype=torch.float64, device=dev)
 it, err = ctx.bicgstab_device(db.data_ptr(), dx.data_ptr(), tol=1e-10)
-out["bicgstab"] = {"it": it, "oracle_it": oit, "err": err, "sol_err": float(np.abs(dx.cpu().numpy() - 1.0).max())}
+out["bicgstab"] = {"it": it, "oracle_it": oit, "err": err, "sol_err": float(np.abs(dx.cpu().numpy() - 1.0).max()),
+                   "peer": ctx.peer_active()}
 if rank == 0:
     print("RESULT " + json.dumps(out))
 ctx.close()
@@ -80,15 +88,18 @@ dist.destroy_process_group()
 '''
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_sharded_spmv_and_solvers(world, tmp_path):
+@pytest.mark.parametrize("world,peer", [(2, 1), (2, 0), (4, 1), (8, 1)])
+def test_sharded_spmv_and_solvers(world, peer, tmp_path):
+    """peer=1: halo entries pushed into the neighbours' vectors by the producing kernels + all-reduce kernel over
+    IPC-mapped memory; peer=0: NCCL send/recv + ncclAllReduce.  Same parity bars for both."""
     if _ngpus() < world:
         pytest.skip("needs %d GPUs" % world)
     script = tmp_path / "worker.py"
     script.write_text(WORKER % ROOT)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(29500 + world), str(script)]
-    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    env = dict(os.environ, CASK_B200_PEER=str(peer))
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900, env=env)
     assert p.returncode == 0, p.stdout[-6000:]
     line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")][-1]
     res = json.loads(line[7:])
@@ -97,6 +108,8 @@ def test_sharded_spmv_and_solvers(world, tmp_path):
         assert r["bitexact"], r                      # stencils: staged-ELL rows, reference summation order
         assert sum(r["halo"]) > 0 and r["halo"][0] == 0   # rank 0 receives only from its neighbour(s)
         assert r["cg_conv"] and abs(r["cg_it"] - r["oracle_it"]) <= 1 and r["cg_err"] < 1e-6, r
+        assert r["peer"] == bool(peer) and r["cg_repeat_same"], r
+    assert res["bicgstab"]["peer"] == bool(peer), res["bicgstab"]
     assert res["rmat"]["spmv_max_rel"] < 1e-12, res["rmat"]
     bi = res["bicgstab"]
     assert bi["err"] <= 1e-10 and bi["sol_err"] < 1e-7 and abs(bi["it"] - bi["oracle_it"]) <= max(2, bi["oracle_it"] // 10), bi
