@@ -156,6 +156,16 @@ struct PushDesc {       // by-value kernel argument of every kernel that produce
   PeerCtrl* ctrl = nullptr;            // this rank's control block
 };
 
+struct ReduceDesc {     // by-value kernel argument: the grid's last CTA finishes a dot product (and its all-reduce)
+  double* partials = nullptr;      // [nq][stride] per-CTA partial sums; nullptr: no reduction in this launch
+  int32_t stride = 0, nq = 0;
+  unsigned int* ticket = nullptr;  // zero between launches
+  double* out = nullptr;           // out[0 .. nq) receives the sums
+  PeerCtrl* ctrl = nullptr;        // non-null: one-shot all-reduce over the peers' control blocks before writing out
+  PeerCtrl* peers[kMaxPeers] = {nullptr};
+  int32_t me = 0, world = 1;
+};
+
 struct HaloWait {       // by-value kernel argument of the persistent SpMV kernel
   const PeerCtrl* ctrl = nullptr;  // nullptr: nothing to wait for
   PeerCtrl* ctrl_rw = nullptr;     // for the timeout flag
@@ -173,6 +183,7 @@ struct SolverWork {  // device scratch of the CG / BiCGStab loops
   double* d_scalars = nullptr;   // see solvers.cu
   double* d_partials = nullptr;
   unsigned int* d_counters = nullptr;
+  unsigned int* d_tickets = nullptr;  // last-CTA tickets of the in-kernel reductions
   int32_t* h_flags = nullptr;    // pinned
   double* h_scalars = nullptr;   // pinned
 };
@@ -234,7 +245,11 @@ struct SpmvFusion {           // optional fused epilogue: partial dot products p
   const double* d_dot_with = nullptr;  // if set: partial sum of y[r] * dot_with[r] (local rows)
   double* d_partials = nullptr;        // one partial per CTA of the launch (+offset)
   int fuse_self_dot = 0;               // also accumulate y[r]*y[r]
+  ReduceDesc reduce;                   // persistent kernel only: the last CTA sums the partials (and all-reduces them)
+  bool pdl = false;                    // launch with programmatic stream serialization (solver loops)
 };
+// true if one persistent staged-ELL launch covers the whole SpMV (in-kernel reduction / peer halo wait possible)
+bool spmv_single_launch(const cask_b200_ctx* ctx);
 int launch_spmv(cask_b200_ctx* ctx, const double* d_x_full, double* d_y, int part /*0 all,1 interior,2 boundary*/,
                 cudaStream_t stream, const SpmvFusion* fusion, const HaloWait* wait = nullptr);
 int launch_spmv_range(cask_b200_ctx* ctx, const double* d_x, double* d_y, int ell_lo, int ell_hi, int csr_lo, int csr_hi,
@@ -253,7 +268,8 @@ int dist_plan_halo(cask_b200_ctx* ctx);
 bool peer_ready(const cask_b200_ctx* ctx);
 int peer_ensure_arena(cask_b200_ctx* ctx, int64_t len_full);         // collective
 double* peer_vector(cask_b200_ctx* ctx, int channel);                // full-layout vector `channel` of the arena
-PushDesc peer_push_desc(cask_b200_ctx* ctx, int channel);            // nsend == 0 when the peer path is off
+PushDesc peer_push_desc(cask_b200_ctx* ctx, int channel);            // ctrl == nullptr when the peer path is off
+void peer_fill_reduce(cask_b200_ctx* ctx, ReduceDesc* rd);           // adds the all-reduce part when the peer path is on
 HaloWait peer_halo_wait(cask_b200_ctx* ctx, int channel);
 int peer_push(cask_b200_ctx* ctx, int channel, cudaStream_t stream); // standalone push of the channel's own slice
 int peer_allreduce_partials(cask_b200_ctx* ctx, const double* d_partials, int count, int stride, int nq, double* d_scal,

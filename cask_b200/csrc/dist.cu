@@ -361,6 +361,15 @@ PushDesc peer_push_desc(cask_b200_ctx* ctx, int channel) {
   return pd;
 }
 
+void peer_fill_reduce(cask_b200_ctx* ctx, ReduceDesc* rd) {
+  if (!peer_ready(ctx)) return;
+  DistState* d = ctx->dist;
+  rd->ctrl = reinterpret_cast<PeerCtrl*>(d->arena);
+  for (int q = 0; q < kMaxPeers; q++) rd->peers[q] = q < d->world ? reinterpret_cast<PeerCtrl*>(d->peer_base[q]) : nullptr;
+  rd->me = d->rank;
+  rd->world = d->world;
+}
+
 HaloWait peer_halo_wait(cask_b200_ctx* ctx, int channel) {
   HaloWait w;
   if (!peer_ready(ctx)) return w;

@@ -43,6 +43,79 @@ __device__ __forceinline__ bool peer_wait_ge(const unsigned long long* flag, uns
   }
 }
 
+// Programmatic dependent launch: kernels of the solver loops are launched with the stream-serialization attribute,
+// trigger their dependents at once and wait for their predecessor before touching memory - the launch latency of
+// kernel i+1 hides behind the tail of kernel i.  Both instructions are no-ops in a plain launch.
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// Finishes a grid-wide dot product inside the producing kernel.  Called by ALL threads of EVERY CTA; t0 / t1 are
+// the CTA's partial sums (valid in thread 0).  The last CTA to arrive adds the partials in a fixed order
+// (deterministic) and, when row-sharded on the peer path, performs the one-shot all-reduce: it stores the local
+// sums into slot [seq & 3][me] of every rank's control block, publishes seq with a release store, acquires the W
+// flags of its own block and adds the W contributions in rank order - the same order on every rank, so all ranks
+// hold bit-identical scalars and take identical convergence decisions.
+__device__ __forceinline__ void grid_finish_reduce(const ReduceDesc& rd, double t0, double t1, int cta, int ncta) {
+  __shared__ int s_last;
+  __shared__ double s_red[2][32];
+  __shared__ double s_tot[2];
+  __shared__ double s_contrib[kMaxPeers][2];
+  __shared__ unsigned long long s_seq;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    rd.partials[cta] = t0;
+    if (rd.nq > 1) rd.partials[rd.stride + cta] = t1;
+    __threadfence();
+    s_last = atomicAdd(rd.ticket, 1u) == (unsigned)(ncta - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int q = 0; q < rd.nq; q++) {
+    double v = 0.0;
+    for (int i = tid; i < ncta; i += blockDim.x) v += __ldcg(rd.partials + (size_t)q * rd.stride + i);
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if ((tid & 31) == 0) s_red[q][tid >> 5] = v;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int q = 0; q < rd.nq; q++) {
+      double t = 0.0;
+      for (int w = 0; w < (int)((blockDim.x + 31) >> 5); w++) t += s_red[q][w];
+      s_tot[q] = t;
+    }
+    *rd.ticket = 0;
+    if (rd.ctrl) {
+      s_seq = rd.ctrl->ar_seq + 1;
+      rd.ctrl->ar_seq = s_seq;
+    }
+  }
+  __syncthreads();
+  if (rd.ctrl == nullptr) {
+    if (tid < rd.nq) rd.out[tid] = s_tot[tid];
+    return;
+  }
+  const unsigned long long seq = s_seq;
+  const int slot = (int)(seq & 3ull);
+  if (tid < rd.world) {
+    PeerCtrl* pc = rd.peers[tid];
+    for (int q = 0; q < rd.nq; q++) pc->ar_val[slot][rd.me][q] = s_tot[q];
+    __threadfence_system();
+    st_release_sys_u64(&pc->ar_flag[slot][rd.me], seq);
+    peer_wait_ge(&rd.ctrl->ar_flag[slot][tid], seq, &rd.ctrl->error);
+    for (int q = 0; q < rd.nq; q++) s_contrib[tid][q] = *reinterpret_cast<volatile double*>(&rd.ctrl->ar_val[slot][tid][q]);
+  }
+  __syncthreads();
+  if (tid < rd.nq) {
+    double t = 0.0;
+    for (int r = 0; r < rd.world; r++) t += s_contrib[r][tid];
+    rd.out[tid] = t;
+  }
+}
+
 // true if some pushed range intersects local rows [lo, hi)
 __device__ __forceinline__ bool push_overlaps(const PushDesc& d, int64_t lo, int64_t hi) {
   bool any = false;

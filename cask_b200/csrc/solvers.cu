@@ -35,6 +35,24 @@ enum { F_DONE = 0, F_CONVERGED = 1, F_ITERATIONS = 2, F_TRIPS = 3, F_RESTART = 4
 
 constexpr int kVecThreads = 256;
 constexpr int kVecItems = 8;  // 8 coalesced 8-byte elements per thread and array: enough loads in flight to stream HBM
+constexpr int kVecTile = kVecThreads * kVecItems;
+constexpr int kVecCtasPerSm = 2;  // vector kernels run as ONE wave of 2 x SMs CTAs, each owning a contiguous chunk
+
+// Launch with programmatic stream serialization: the kernel may be scheduled while its predecessor drains; every
+// kernel launched this way starts with pdl_enter() (griddepcontrol.wait) before it touches memory.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 __device__ __forceinline__ double cta_sum(double v, double* red) {
 #pragma unroll
@@ -48,7 +66,21 @@ __device__ __forceinline__ double cta_sum(double v, double* red) {
   return t;
 }
 
-// out[q] = sum_i partials[q*stride + i], i < count, in index order (deterministic). One CTA.
+// Every vector kernel walks tiles of kVecTile elements grid-stride; a thread owns kVecItems elements of a tile,
+// kVecThreads apart (coalesced), loads all its operands into registers first and only then computes and stores,
+// so kVecItems x (number of operand arrays) loads are in flight per thread whatever the compiler can prove about
+// aliasing.
+// CTA c owns the contiguous chunk [lo_, hi_) of the vector (chunks are multiples of kVecThreads elements, so every
+// access is 2 KB aligned and the CTAs of the single wave are balanced to within 256 elements).
+#define CB_TILE_LOOP(n)                                                                                             \
+  const int64_t chunk_ = (((n) + gridDim.x - 1) / gridDim.x + kVecThreads - 1) / kVecThreads * kVecThreads;         \
+  const int64_t lo_ = (int64_t)blockIdx.x * chunk_, hi_ = lo_ + chunk_ < (n) ? lo_ + chunk_ : (n);                  \
+  for (int64_t tile = lo_; tile < hi_; tile += kVecTile)
+#define CB_ITEMS for (int i = 0; i < kVecItems; i++)
+#define CB_IDX(tile) ((tile) + threadIdx.x + (int64_t)i * kVecThreads)
+
+// out[q] = sum_i partials[q*stride + i], i < count, in index order (deterministic). One CTA.  Used after kernels
+// that cannot finish their reduction themselves (gather-CSR / two-part SpMV launches).
 __global__ void __launch_bounds__(1024)
 reduce_partials_kernel(const double* __restrict__ partials, int count, int stride, int nq, double* __restrict__ scal,
                        int slot0, int slot1, const int32_t* __restrict__ flags) {
@@ -63,67 +95,93 @@ reduce_partials_kernel(const double* __restrict__ partials, int count, int strid
 }
 
 // ---- CG -------------------------------------------------------------------------------------
-// r = b - Ax (Ax arrives in r), p = r, partial r.r            SparseLinearSolvers.hpp:189-198
-__global__ void __launch_bounds__(kVecThreads)
+// r = b - Ax (Ax arrives in r), p = r, r.r            SparseLinearSolvers.hpp:189-198
+__global__ void __launch_bounds__(kVecThreads, kVecCtasPerSm)
 cg_init_kernel(int64_t n, const double* __restrict__ b, double* __restrict__ r, double* __restrict__ p,
-               double* __restrict__ partials) {
+               const ReduceDesc rd) {
   __shared__ double red[kVecThreads / 32];
   double acc = 0.0;
-  const int64_t base = (int64_t)blockIdx.x * (kVecThreads * kVecItems) + threadIdx.x;
+  CB_TILE_LOOP(n) {
+    double bv[kVecItems], rv[kVecItems];
 #pragma unroll
-  for (int i = 0; i < kVecItems; i++)
-    if (base + (int64_t)i * kVecThreads < n) {
-      const double rv = b[base + (int64_t)i * kVecThreads] - r[base + (int64_t)i * kVecThreads];
-      r[base + (int64_t)i * kVecThreads] = rv;
-      p[base + (int64_t)i * kVecThreads] = rv;
-      acc += rv * rv;
+    CB_ITEMS { const int64_t k = CB_IDX(tile); bv[i] = k < hi_ ? b[k] : 0.0; rv[i] = k < hi_ ? r[k] : 0.0; }
+#pragma unroll
+    CB_ITEMS {
+      const int64_t k = CB_IDX(tile);
+      if (k < hi_) {
+        const double v = bv[i] - rv[i];
+        r[k] = v;
+        p[k] = v;
+        acc += v * v;
+      }
     }
+  }
   const double t = cta_sum(acc, red);
-  if (threadIdx.x == 0) partials[blockIdx.x] = t;
+  grid_finish_reduce(rd, t, 0.0, blockIdx.x, gridDim.x);
 }
 
-// alpha = rsold / p.Ap; x += alpha p; r -= alpha Ap; partial r.r    SparseLinearSolvers.hpp:208-218
-__global__ void __launch_bounds__(kVecThreads)
+// alpha = rsold / p.Ap; x += alpha p; r -= alpha Ap; r.r (summed, and all-reduced, by the grid's last CTA)
+// SparseLinearSolvers.hpp:208-218
+__global__ void __launch_bounds__(kVecThreads, kVecCtasPerSm)
 cg_update_xr_kernel(int64_t n, int it, const double* __restrict__ scal, const int32_t* __restrict__ flags,
                     const double* __restrict__ p, const double* __restrict__ Ap, double* __restrict__ x,
-                    double* __restrict__ r, double* __restrict__ partials) {
+                    double* __restrict__ r, const ReduceDesc rd) {
+  pdl_enter();
   if (flags[F_DONE]) return;
   __shared__ double red[kVecThreads / 32];
   const double alpha = scal[S_RS0 + (it & 1)] / scal[S_PAP];
   double acc = 0.0;
-  const int64_t base = (int64_t)blockIdx.x * (kVecThreads * kVecItems) + threadIdx.x;
+  CB_TILE_LOOP(n) {
+    double pv[kVecItems], av[kVecItems], xv[kVecItems], rv[kVecItems];
 #pragma unroll
-  for (int i = 0; i < kVecItems; i++)
-    if (base + (int64_t)i * kVecThreads < n) {
-      x[base + (int64_t)i * kVecThreads] += alpha * p[base + (int64_t)i * kVecThreads];
-      const double rv = r[base + (int64_t)i * kVecThreads] - alpha * Ap[base + (int64_t)i * kVecThreads];
-      r[base + (int64_t)i * kVecThreads] = rv;
-      acc += rv * rv;
+    CB_ITEMS {
+      const int64_t k = CB_IDX(tile);
+      const bool ok = k < hi_;
+      pv[i] = ok ? p[k] : 0.0; av[i] = ok ? Ap[k] : 0.0; xv[i] = ok ? x[k] : 0.0; rv[i] = ok ? r[k] : 0.0;
     }
+#pragma unroll
+    CB_ITEMS {
+      const int64_t k = CB_IDX(tile);
+      if (k < hi_) {
+        x[k] = xv[i] + alpha * pv[i];
+        const double v = rv[i] - alpha * av[i];
+        r[k] = v;
+        acc += v * v;
+      }
+    }
+  }
   const double t = cta_sum(acc, red);
-  if (threadIdx.x == 0) partials[blockIdx.x] = t;
+  grid_finish_reduce(rd, t, 0.0, blockIdx.x, gridDim.x);
 }
 
 // convergence test + p = r + (rsnew/rsold) p                        SparseLinearSolvers.hpp:220-231
-__global__ void __launch_bounds__(kVecThreads)
+// Row-sharded on the peer path: entries of the new p that a neighbour stages are stored straight into its copy of p
+// as they are produced, and the grid's last CTA publishes the new halo epoch.
+__global__ void __launch_bounds__(kVecThreads, kVecCtasPerSm)
 cg_update_p_kernel(int64_t n, int it, double* __restrict__ scal, int32_t* __restrict__ flags,
                    const double* __restrict__ r, double* __restrict__ p, const PushDesc pd) {
+  pdl_enter();
   if (flags[F_DONE]) return;
   const double rsold = scal[S_RS0 + (it & 1)], rsnew = scal[S_RS0 + ((it + 1) & 1)];
   const bool converged = rsnew <= scal[S_TOL2];
   const double beta = rsnew / rsold;
   if (!converged) {
-    const int64_t base = (int64_t)blockIdx.x * (kVecThreads * kVecItems) + threadIdx.x;
-    // row-sharded: entries of the new p that a neighbour stages are stored into its copy of p as they are produced
-    const bool push = pd.nsend && push_overlaps(pd, base - threadIdx.x, base - threadIdx.x + kVecThreads * kVecItems);
+    CB_TILE_LOOP(n) {
+      const bool push = pd.nsend && push_overlaps(pd, tile, tile + kVecTile);
+      double rv[kVecItems], pv[kVecItems];
 #pragma unroll
-    for (int i = 0; i < kVecItems; i++)
-      if (base + (int64_t)i * kVecThreads < n) {
-        const double pv = r[base + (int64_t)i * kVecThreads] + beta * p[base + (int64_t)i * kVecThreads];
-        p[base + (int64_t)i * kVecThreads] = pv;
-        if (push) push_store(pd, base + (int64_t)i * kVecThreads, pv);
+      CB_ITEMS { const int64_t k = CB_IDX(tile); rv[i] = k < hi_ ? r[k] : 0.0; pv[i] = k < hi_ ? p[k] : 0.0; }
+#pragma unroll
+      CB_ITEMS {
+        const int64_t k = CB_IDX(tile);
+        if (k < hi_) {
+          const double v = rv[i] + beta * pv[i];
+          p[k] = v;
+          if (push) push_store(pd, k, v);
+        }
       }
-    push_signal(pd);  // the grid's last CTA publishes the new halo epoch to the peers
+    }
+    push_signal(pd);
   }
   // flags are only written by the grid's LAST CTA to finish, after every CTA has read them
   __shared__ bool last;
@@ -156,52 +214,62 @@ __global__ void jacobi_diag_kernel(int64_t n, int64_t row0_global, const int32_t
   invdiag[i] = d != 0.0 ? 1.0 / d : 1.0;   // Eigen DiagonalPreconditioner
 }
 
-// r = b - r(=Ax); r0 = r; partial r.r
-__global__ void __launch_bounds__(kVecThreads)
+// r = b - r(=Ax); r0 = r; r.r
+__global__ void __launch_bounds__(kVecThreads, kVecCtasPerSm)
 bicg_residual_kernel(int64_t n, const int32_t* __restrict__ flags, int only_on_restart, const double* __restrict__ b,
                      double* __restrict__ r, double* __restrict__ r0, const double* __restrict__ Ax,
-                     double* __restrict__ partials) {
+                     const ReduceDesc rd) {
   if (flags[F_DONE]) return;
   if (only_on_restart && !flags[F_RESTART]) return;
   __shared__ double red[kVecThreads / 32];
   double acc = 0.0;
-  const int64_t base = (int64_t)blockIdx.x * (kVecThreads * kVecItems) + threadIdx.x;
+  CB_TILE_LOOP(n) {
+    double bv[kVecItems], av[kVecItems];
 #pragma unroll
-  for (int i = 0; i < kVecItems; i++)
-    if (base + (int64_t)i * kVecThreads < n) {
-      const double rv = b[base + (int64_t)i * kVecThreads] - Ax[base + (int64_t)i * kVecThreads];
-      r[base + (int64_t)i * kVecThreads] = rv;
-      r0[base + (int64_t)i * kVecThreads] = rv;
-      acc += rv * rv;
+    CB_ITEMS { const int64_t k = CB_IDX(tile); bv[i] = k < hi_ ? b[k] : 0.0; av[i] = k < hi_ ? Ax[k] : 0.0; }
+#pragma unroll
+    CB_ITEMS {
+      const int64_t k = CB_IDX(tile);
+      if (k < hi_) {
+        const double v = bv[i] - av[i];
+        r[k] = v;
+        r0[k] = v;
+        acc += v * v;
+      }
     }
+  }
   const double t = cta_sum(acc, red);
-  if (threadIdx.x == 0) partials[blockIdx.x] = t;
+  grid_finish_reduce(rd, t, 0.0, blockIdx.x, gridDim.x);
 }
 
-// generic partial dot(s): partials[0][cta] = a.b ; partials[1][cta] = c.d (optional)
-__global__ void __launch_bounds__(kVecThreads)
+// dot(s): out[0] = a.b ; out[1] = c.d (optional)
+__global__ void __launch_bounds__(kVecThreads, kVecCtasPerSm)
 dot2_kernel(int64_t n, const int32_t* __restrict__ flags, const double* __restrict__ a, const double* __restrict__ b,
-            const double* __restrict__ c, const double* __restrict__ d, double* __restrict__ partials, int stride) {
+            const double* __restrict__ c, const double* __restrict__ d, const ReduceDesc rd) {
+  pdl_enter();
   if (flags && (flags[F_DONE] || flags[F_RESTART])) return;
   __shared__ double red[kVecThreads / 32];
   double s0 = 0.0, s1 = 0.0;
-  const int64_t base = (int64_t)blockIdx.x * (kVecThreads * kVecItems) + threadIdx.x;
+  CB_TILE_LOOP(n) {
+    double av[kVecItems], bv[kVecItems], cv[kVecItems], dv[kVecItems];
 #pragma unroll
-  for (int i = 0; i < kVecItems; i++)
-    if (base + (int64_t)i * kVecThreads < n) {
-      s0 += a[base + (int64_t)i * kVecThreads] * b[base + (int64_t)i * kVecThreads];
-      if (c) s1 += c[base + (int64_t)i * kVecThreads] * d[base + (int64_t)i * kVecThreads];
+    CB_ITEMS {
+      const int64_t k = CB_IDX(tile);
+      const bool ok = k < hi_;
+      av[i] = ok ? a[k] : 0.0; bv[i] = ok ? b[k] : 0.0;
+      cv[i] = ok && c ? c[k] : 0.0; dv[i] = ok && c ? d[k] : 0.0;
     }
-  const double t0 = cta_sum(s0, red);
-  if (threadIdx.x == 0) partials[blockIdx.x] = t0;
-  if (c) {
-    const double t1 = cta_sum(s1, red);
-    if (threadIdx.x == 0) partials[stride + blockIdx.x] = t1;
+#pragma unroll
+    CB_ITEMS { s0 += av[i] * bv[i]; s1 += cv[i] * dv[i]; }
   }
+  const double t0 = cta_sum(s0, red);
+  const double t1 = cta_sum(s1, red);
+  grid_finish_reduce(rd, t0, t1, blockIdx.x, gridDim.x);
 }
 
 // One thread: the scalar part of the loop head (Eigen BiCGSTAB.h: while-test, rho, restart test).
 __global__ void bicg_head_kernel(double* scal, int32_t* flags) {
+  pdl_enter();
   if (flags[F_DONE] || flags[F_RESTART]) return;
   const bool go = scal[B_RR] > scal[B_TOL2] && flags[F_I] < flags[F_MAXIT];
   if (!go) { flags[F_DONE] = 1; return; }
@@ -219,83 +287,113 @@ __global__ void bicg_restart_scalars_kernel(double* scal, int32_t* flags) {
   flags[F_RESTART] = 0;
 }
 
-// beta = (rho/rho_old)(alpha/w); p = r + beta (p - w v); y = invdiag * p
-__global__ void __launch_bounds__(kVecThreads)
+// beta = (rho/rho_old)(alpha/w); p = r + beta (p - w v); y = invdiag * p   (+ halo push of y)
+__global__ void __launch_bounds__(kVecThreads, kVecCtasPerSm)
 bicg_p_kernel(int64_t n, const double* __restrict__ scal, const int32_t* __restrict__ flags,
               const double* __restrict__ r, const double* __restrict__ v, const double* __restrict__ invd,
               double* __restrict__ p, double* __restrict__ y, const PushDesc pd) {
+  pdl_enter();
   if (flags[F_DONE] || flags[F_RESTART]) return;
   const double beta = (scal[B_RHO] / scal[B_RHO_OLD]) * (scal[B_ALPHA] / scal[B_W]);
   const double w = scal[B_W];
-  const int64_t base = (int64_t)blockIdx.x * (kVecThreads * kVecItems) + threadIdx.x;
-  const bool push = pd.nsend && push_overlaps(pd, base - threadIdx.x, base - threadIdx.x + kVecThreads * kVecItems);
+  CB_TILE_LOOP(n) {
+    const bool push = pd.nsend && push_overlaps(pd, tile, tile + kVecTile);
+    double rv[kVecItems], pv[kVecItems], vv[kVecItems], dv[kVecItems];
 #pragma unroll
-  for (int i = 0; i < kVecItems; i++)
-    if (base + (int64_t)i * kVecThreads < n) {
-      const double pv = r[base + (int64_t)i * kVecThreads] + beta * (p[base + (int64_t)i * kVecThreads] - w * v[base + (int64_t)i * kVecThreads]);
-      p[base + (int64_t)i * kVecThreads] = pv;
-      const double yv = invd[base + (int64_t)i * kVecThreads] * pv;
-      y[base + (int64_t)i * kVecThreads] = yv;
-      if (push) push_store(pd, base + (int64_t)i * kVecThreads, yv);
+    CB_ITEMS {
+      const int64_t k = CB_IDX(tile);
+      const bool ok = k < hi_;
+      rv[i] = ok ? r[k] : 0.0; pv[i] = ok ? p[k] : 0.0; vv[i] = ok ? v[k] : 0.0; dv[i] = ok ? invd[k] : 0.0;
     }
+#pragma unroll
+    CB_ITEMS {
+      const int64_t k = CB_IDX(tile);
+      if (k < hi_) {
+        const double np = rv[i] + beta * (pv[i] - w * vv[i]);
+        p[k] = np;
+        const double yv = dv[i] * np;
+        y[k] = yv;
+        if (push) push_store(pd, k, yv);
+      }
+    }
+  }
   push_signal(pd);
 }
 
-__global__ void bicg_alpha_kernel(double* scal, const int32_t* flags) {
-  if (flags[F_DONE] || flags[F_RESTART]) return;
-  scal[B_ALPHA] = scal[B_RHO] / scal[B_R0V];
-}
-
-// s = r - alpha v; z = invdiag * s
-__global__ void __launch_bounds__(kVecThreads)
-bicg_s_kernel(int64_t n, const double* __restrict__ scal, const int32_t* __restrict__ flags,
+// alpha = rho / r0.v; s = r - alpha v; z = invdiag * s   (+ halo push of z)
+__global__ void __launch_bounds__(kVecThreads, kVecCtasPerSm)
+bicg_s_kernel(int64_t n, double* __restrict__ scal, const int32_t* __restrict__ flags,
               const double* __restrict__ r, const double* __restrict__ v, const double* __restrict__ invd,
               double* __restrict__ s, double* __restrict__ z, const PushDesc pd) {
+  pdl_enter();
   if (flags[F_DONE] || flags[F_RESTART]) return;
-  const double alpha = scal[B_ALPHA];
-  const int64_t base = (int64_t)blockIdx.x * (kVecThreads * kVecItems) + threadIdx.x;
-  const bool push = pd.nsend && push_overlaps(pd, base - threadIdx.x, base - threadIdx.x + kVecThreads * kVecItems);
+  const double alpha = scal[B_RHO] / scal[B_R0V];
+  if (blockIdx.x == 0 && threadIdx.x == 0) scal[B_ALPHA] = alpha;  // read again by bicg_xr and the next bicg_p
+  CB_TILE_LOOP(n) {
+    const bool push = pd.nsend && push_overlaps(pd, tile, tile + kVecTile);
+    double rv[kVecItems], vv[kVecItems], dv[kVecItems];
 #pragma unroll
-  for (int i = 0; i < kVecItems; i++)
-    if (base + (int64_t)i * kVecThreads < n) {
-      const double sv = r[base + (int64_t)i * kVecThreads] - alpha * v[base + (int64_t)i * kVecThreads];
-      s[base + (int64_t)i * kVecThreads] = sv;
-      const double zv = invd[base + (int64_t)i * kVecThreads] * sv;
-      z[base + (int64_t)i * kVecThreads] = zv;
-      if (push) push_store(pd, base + (int64_t)i * kVecThreads, zv);
+    CB_ITEMS {
+      const int64_t k = CB_IDX(tile);
+      const bool ok = k < hi_;
+      rv[i] = ok ? r[k] : 0.0; vv[i] = ok ? v[k] : 0.0; dv[i] = ok ? invd[k] : 0.0;
     }
+#pragma unroll
+    CB_ITEMS {
+      const int64_t k = CB_IDX(tile);
+      if (k < hi_) {
+        const double sv = rv[i] - alpha * vv[i];
+        s[k] = sv;
+        const double zv = dv[i] * sv;
+        z[k] = zv;
+        if (push) push_store(pd, k, zv);
+      }
+    }
+  }
   push_signal(pd);
 }
 
-// w = t.s / t.t (0 if t.t == 0); x += alpha y + w z; r = s - w t; partials r.r and r0.r
-__global__ void __launch_bounds__(kVecThreads)
+// w = t.s / t.t (0 if t.t == 0); x += alpha y + w z; r = s - w t; r.r and r0.r
+__global__ void __launch_bounds__(kVecThreads, kVecCtasPerSm)
 bicg_xr_kernel(int64_t n, const double* __restrict__ scal, const int32_t* __restrict__ flags,
                const double* __restrict__ y, const double* __restrict__ z, const double* __restrict__ s,
                const double* __restrict__ t, const double* __restrict__ r0, double* __restrict__ x,
-               double* __restrict__ r, double* __restrict__ partials, int stride) {
+               double* __restrict__ r, const ReduceDesc rd) {
+  pdl_enter();
   if (flags[F_DONE] || flags[F_RESTART]) return;
   __shared__ double red[kVecThreads / 32];
   const double tt = scal[B_TT];
   const double w = tt > 0.0 ? scal[B_TS] / tt : 0.0;
   const double alpha = scal[B_ALPHA];
   double a0 = 0.0, a1 = 0.0;
-  const int64_t base = (int64_t)blockIdx.x * (kVecThreads * kVecItems) + threadIdx.x;
+  CB_TILE_LOOP(n) {
+    double yv[kVecItems], zv[kVecItems], sv[kVecItems], tv[kVecItems], qv[kVecItems], xv[kVecItems];
 #pragma unroll
-  for (int i = 0; i < kVecItems; i++)
-    if (base + (int64_t)i * kVecThreads < n) {
-      x[base + (int64_t)i * kVecThreads] += alpha * y[base + (int64_t)i * kVecThreads] + w * z[base + (int64_t)i * kVecThreads];
-      const double rv = s[base + (int64_t)i * kVecThreads] - w * t[base + (int64_t)i * kVecThreads];
-      r[base + (int64_t)i * kVecThreads] = rv;
-      a0 += rv * rv;
-      a1 += r0[base + (int64_t)i * kVecThreads] * rv;
+    CB_ITEMS {
+      const int64_t k = CB_IDX(tile);
+      const bool ok = k < hi_;
+      yv[i] = ok ? y[k] : 0.0; zv[i] = ok ? z[k] : 0.0; sv[i] = ok ? s[k] : 0.0;
+      tv[i] = ok ? t[k] : 0.0; qv[i] = ok ? r0[k] : 0.0; xv[i] = ok ? x[k] : 0.0;
     }
+#pragma unroll
+    CB_ITEMS {
+      const int64_t k = CB_IDX(tile);
+      if (k < hi_) {
+        x[k] = xv[i] + (alpha * yv[i] + w * zv[i]);
+        const double nr = sv[i] - w * tv[i];
+        r[k] = nr;
+        a0 += nr * nr;
+        a1 += qv[i] * nr;
+      }
+    }
+  }
   const double t0 = cta_sum(a0, red);
-  if (threadIdx.x == 0) partials[blockIdx.x] = t0;
   const double t1 = cta_sum(a1, red);
-  if (threadIdx.x == 0) partials[stride + blockIdx.x] = t1;
+  grid_finish_reduce(rd, t0, t1, blockIdx.x, gridDim.x);
 }
 
 __global__ void bicg_tail_kernel(double* scal, int32_t* flags) {
+  pdl_enter();
   if (flags[F_DONE] || flags[F_RESTART]) return;
   const double tt = scal[B_TT];
   scal[B_W] = tt > 0.0 ? scal[B_TS] / tt : 0.0;
@@ -303,12 +401,21 @@ __global__ void bicg_tail_kernel(double* scal, int32_t* flags) {
   flags[F_TRIPS] += 1;
 }
 
+#undef CB_TILE_LOOP
+#undef CB_ITEMS
+#undef CB_IDX
+
 // partial dots written by one fused SpMV: interior and halo-dependent launches are sized separately when sharded
 int spmv_partials(cask_b200_ctx* ctx) {
   return dist_active(ctx) && !peer_ready(ctx) ? spmv_num_ctas(ctx, 1) + spmv_num_ctas(ctx, 2) : spmv_num_ctas(ctx, 0);
 }
 
-int vec_grid(int64_t n) { return (int)((n + (int64_t)kVecThreads * kVecItems - 1) / ((int64_t)kVecThreads * kVecItems)); }
+int vec_grid(const cask_b200_ctx* ctx, int64_t n) {
+  const int64_t units = (n + kVecThreads - 1) / kVecThreads;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(units, (int64_t)ctx->sm_count * kVecCtasPerSm));
+}
+
+enum { T_SPMV = 0, T_VEC = 1, T_COUNT = 4 };  // tickets of the in-kernel reductions
 
 int ensure_work(cask_b200_ctx* ctx, int nvec, int64_t len_full) {
   SolverWork& w = ctx->work;
@@ -324,40 +431,40 @@ int ensure_work(cask_b200_ctx* ctx, int nvec, int64_t len_full) {
   w.vec_len = std::max(w.vec_len, len_full);
   if (!w.d_scalars) CB_CUDA(cudaMalloc(&w.d_scalars, sizeof(double) * 2 * S_COUNT));
   if (!w.d_counters) CB_CUDA(cudaMalloc(&w.d_counters, sizeof(int32_t) * (F_COUNT + 1)));
+  if (!w.d_tickets) {
+    CB_CUDA(cudaMalloc(&w.d_tickets, sizeof(unsigned int) * T_COUNT));
+    CB_CUDA(cudaMemsetAsync(w.d_tickets, 0, sizeof(unsigned int) * T_COUNT, ctx->stream));
+  }
   if (!w.h_flags) CB_CUDA(cudaMallocHost(&w.h_flags, sizeof(int32_t) * (F_COUNT + 1) * 4));
   if (!w.h_scalars) CB_CUDA(cudaMallocHost(&w.h_scalars, sizeof(double) * S_COUNT));
-  const int64_t np = 2 * (int64_t)std::max(std::max(spmv_partials(ctx), vec_grid(ctx->plan.n)), 1);
-  static_assert(sizeof(int64_t) == 8, "");
+  const int64_t np = 2 * (int64_t)std::max(std::max(spmv_partials(ctx), vec_grid(ctx, ctx->plan.n)), 1);
   cudaFree(w.d_partials);
   w.d_partials = nullptr;
   CB_CUDA(cudaMalloc(&w.d_partials, sizeof(double) * np));
   return CASK_B200_OK;
 }
 
-// y = A x for a vector held in "full" layout (global length, own slice at row0_global): halo exchange
-// overlapped with the interior slices when row-sharded.
-// Peer-memory path (channel >= 0: d_full is vector `channel` of the symmetric arena and its producer has pushed
-// this epoch's halo): ONE launch over all slices, interior first; the kernel's producer warp acquires the peers'
-// epoch flags when it reaches the first halo-dependent slice.  flags != nullptr: the launch does nothing once the
-// solver's DONE / RESTART flag is up (its producer skipped the push under the same condition).
-int spmv_full(cask_b200_ctx* ctx, double* d_full, double* d_y, const SpmvFusion* f, int channel, const int32_t* flags) {
-  cudaStream_t s = ctx->stream;
-  HaloWait hw;
-  if (channel >= 0 && peer_ready(ctx)) hw = peer_halo_wait(ctx, channel);
-  if (flags) { hw.skip0 = flags + F_DONE; hw.skip1 = flags + F_RESTART; }
-  if (!dist_active(ctx) || (channel >= 0 && peer_ready(ctx))) return launch_spmv(ctx, d_full, d_y, 0, s, f, &hw);
-  CB_TRY(dist_exchange_begin(ctx, d_full, s));
-  SpmvFusion fi, fb;
-  const int n_int = spmv_num_ctas(ctx, 1);
-  if (f) { fi = *f; fb = *f; fb.d_partials = f->d_partials + n_int; }
-  CB_TRY(launch_spmv(ctx, d_full, d_y, 1, s, f ? &fi : nullptr));   // interior rows: no remote x
-  CB_TRY(dist_exchange_wait(ctx, s));
-  CB_TRY(launch_spmv(ctx, d_full, d_y, 2, s, f ? &fb : nullptr));   // rows that read the halo
-  return CASK_B200_OK;
+// Descriptor of an in-kernel reduction of nq dot products into scal[slot0 ..): single rank -> the sums; peer path ->
+// the all-reduced sums; NCCL path -> the local sums go to the staging slots and finish_reduce() adds the all-reduce.
+ReduceDesc make_reduce(cask_b200_ctx* ctx, int ticket, int stride, int nq, int slot0) {
+  SolverWork& w = ctx->work;
+  ReduceDesc rd;
+  rd.partials = w.d_partials;
+  rd.stride = stride;
+  rd.nq = nq;
+  rd.ticket = w.d_tickets + ticket;
+  const bool nccl = dist_active(ctx) && !peer_ready(ctx);
+  rd.out = w.d_scalars + (nccl ? S_COUNT : 0) + slot0;
+  peer_fill_reduce(ctx, &rd);
+  return rd;
+}
+int finish_reduce(cask_b200_ctx* ctx, int nq, int slot0) {
+  if (!dist_active(ctx) || peer_ready(ctx)) return CASK_B200_OK;
+  SolverWork& w = ctx->work;
+  return dist_allreduce_sum(ctx, w.d_scalars + S_COUNT + slot0, w.d_scalars + slot0, nq, ctx->stream);
 }
 
-// sums `count` per-CTA partials (nq = 1 or 2 quantities, `stride` apart) into scal[slot0], scal[slot0 + 1];
-// across ranks too when sharded
+// sums `count` per-CTA partials written by a launch that could not reduce in-kernel; across ranks too when sharded
 int reduce_dots(cask_b200_ctx* ctx, int count, int stride, int nq, int slot0, const int32_t* flags) {
   SolverWork& w = ctx->work;
   cudaStream_t s = ctx->stream;
@@ -372,12 +479,50 @@ int reduce_dots(cask_b200_ctx* ctx, int count, int stride, int nq, int slot0, co
   return CASK_B200_OK;
 }
 
+// y = A x for a vector held in "full" layout (global length, own slice at row0_global).
+//  * single rank, or row-sharded on the peer path (channel >= 0: d_full is vector `channel` of the symmetric arena
+//    and its producer has pushed this epoch's halo): ONE persistent launch over all slices, interior first; the
+//    kernel's producer warp acquires the peers' epoch flags when it reaches the first halo-dependent slice, and with
+//    a fused dot the grid's last CTA finishes the reduction (and the all-reduce) in place -> scal[dot_slot];
+//  * row-sharded over NCCL: grouped send/recv on the communication stream overlapped with the interior slices,
+//    halo-dependent slices after the event, then a reduction kernel + ncclAllReduce.
+// flags != nullptr: the launches do nothing once the solver's DONE / RESTART flag is up.
+int spmv_full(cask_b200_ctx* ctx, double* d_full, double* d_y, const double* d_dot_with, int dot_slot, int channel,
+              const int32_t* flags) {
+  cudaStream_t s = ctx->stream;
+  SolverWork& w = ctx->work;
+  const bool peer = channel >= 0 && peer_ready(ctx);
+  SpmvFusion f;
+  f.d_dot_with = d_dot_with;
+  f.d_partials = w.d_partials;
+  f.pdl = true;
+  HaloWait hw;
+  if (peer) hw = peer_halo_wait(ctx, channel);
+  if (flags) { hw.skip0 = flags + F_DONE; hw.skip1 = flags + F_RESTART; }
+  if (!dist_active(ctx) || peer) {
+    const bool in_kernel = d_dot_with && spmv_single_launch(ctx);
+    if (in_kernel) f.reduce = make_reduce(ctx, T_SPMV, 0, 1, dot_slot);
+    CB_TRY(launch_spmv(ctx, d_full, d_y, 0, s, &f, &hw));
+    if (d_dot_with && !in_kernel) CB_TRY(reduce_dots(ctx, spmv_partials(ctx), 0, 1, dot_slot, flags));
+    return CASK_B200_OK;
+  }
+  f.pdl = false;
+  CB_TRY(dist_exchange_begin(ctx, d_full, s));
+  SpmvFusion fb = f;
+  fb.d_partials = f.d_partials + spmv_num_ctas(ctx, 1);
+  CB_TRY(launch_spmv(ctx, d_full, d_y, 1, s, &f));    // interior rows: no remote x
+  CB_TRY(dist_exchange_wait(ctx, s));
+  CB_TRY(launch_spmv(ctx, d_full, d_y, 2, s, &fb));   // rows that read the halo
+  if (d_dot_with) CB_TRY(reduce_dots(ctx, spmv_partials(ctx), 0, 1, dot_slot, flags));
+  return CASK_B200_OK;
+}
+
 }  // namespace
 
 void free_solver_work(cask_b200_ctx* ctx) {
   SolverWork& w = ctx->work;
   for (auto& v : w.d_vec) { cudaFree(v); v = nullptr; }
-  cudaFree(w.d_scalars); cudaFree(w.d_partials); cudaFree(w.d_counters);
+  cudaFree(w.d_scalars); cudaFree(w.d_partials); cudaFree(w.d_counters); cudaFree(w.d_tickets);
   if (w.h_flags) cudaFreeHost(w.h_flags);
   if (w.h_scalars) cudaFreeHost(w.h_scalars);
   w = SolverWork();
@@ -408,8 +553,7 @@ extern "C" int cask_b200_cg_device(cask_b200_ctx* ctx, const double* d_rhs, doub
   double* p = p_full + off;
   double* scal = w.d_scalars;
   int32_t* flags = reinterpret_cast<int32_t*>(w.d_counters);
-  const int vg = vec_grid(n);
-  const bool dist = dist_active(ctx);
+  const int vg = vec_grid(ctx, n);
 
   double h_scal[S_COUNT] = {0};
   h_scal[S_TOL2] = tol * tol;
@@ -421,10 +565,10 @@ extern "C" int cask_b200_cg_device(cask_b200_ctx* ctx, const double* d_rhs, doub
   // r = A x (x staged through p's full-layout buffer), r = b - r, p = r, rsold = r.r   (:189-198)
   CB_CUDA(cudaMemcpyAsync(p, d_x, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
   CB_TRY(peer_push(ctx, 0, s));
-  CB_TRY(spmv_full(ctx, p_full, r, nullptr, ch, nullptr));
-  cg_init_kernel<<<vg, kVecThreads, 0, s>>>(n, d_rhs, r, p, w.d_partials);
+  CB_TRY(spmv_full(ctx, p_full, r, nullptr, 0, ch, nullptr));
+  cg_init_kernel<<<vg, kVecThreads, 0, s>>>(n, d_rhs, r, p, make_reduce(ctx, T_VEC, 0, 1, S_RS0));
   ctx->launches++;
-  CB_TRY(reduce_dots(ctx, vg, 0, 1, S_RS0, nullptr));
+  CB_TRY(finish_reduce(ctx, 1, S_RS0));
   CB_TRY(peer_push(ctx, 0, s));   // p = r; after the all-reduce, so no peer is still reading the previous epoch
 
   // Enqueue batches of iterations; poll the device's done flag one batch behind so the host never
@@ -436,14 +580,14 @@ extern "C" int cask_b200_cg_device(cask_b200_ctx* ctx, const double* d_rhs, doub
   for (int batch = 0;; batch++) {
     const int hi = std::min(maxiters, enq + kBatch);
     for (int it = enq; it < hi; it++) {
-      SpmvFusion f;
-      f.d_dot_with = p;
-      f.d_partials = w.d_partials;
-      CB_TRY(spmv_full(ctx, p_full, Ap, &f, ch, flags));                             // :206
-      CB_TRY(reduce_dots(ctx, spmv_partials(ctx), 0, 1, S_PAP, flags));
-      cg_update_xr_kernel<<<vg, kVecThreads, 0, s>>>(n, it, scal, flags, p, Ap, d_x, r, w.d_partials);   // :208-218
-      CB_TRY(reduce_dots(ctx, vg, 0, 1, S_RS0 + ((it + 1) & 1), flags));
-      cg_update_p_kernel<<<vg, kVecThreads, 0, s>>>(n, it, scal, flags, r, p, pd);     // :220-231 (+ halo push)
+      // three launches per iteration, chained by programmatic dependent launch; dots are finished (and all-reduced
+      // over peer memory when sharded) by the last CTA of the kernel that produces them
+      CB_TRY(spmv_full(ctx, p_full, Ap, p, S_PAP, ch, flags));                                          // :206
+      const int rs_new = S_RS0 + ((it + 1) & 1);
+      CB_CUDA(launch_pdl(cg_update_xr_kernel, vg, kVecThreads, s, n, it, scal, flags, p, Ap, d_x, r,   // :208-218
+                         make_reduce(ctx, T_VEC, 0, 1, rs_new)));
+      CB_TRY(finish_reduce(ctx, 1, rs_new));
+      CB_CUDA(launch_pdl(cg_update_p_kernel, vg, kVecThreads, s, n, it, scal, flags, r, p, pd));       // :220-231 (+ halo push)
       ctx->launches += 2;
     }
     enq = hi;
@@ -491,9 +635,8 @@ extern "C" int cask_b200_bicgstab_device(cask_b200_ctx* ctx, const double* d_b, 
   CB_CUDA(cudaMalloc(&invd, sizeof(double) * std::max<int64_t>(n, 1)));
   double* scal = w.d_scalars;
   int32_t* flags = reinterpret_cast<int32_t*>(w.d_counters);
-  const int vg = vec_grid(n);
+  const int vg = vec_grid(ctx, n);
   const int stride = std::max(std::max(spmv_partials(ctx), vg), 1);
-  const bool dist = dist_active(ctx);
   const double tol = *tol_error > 0 ? *tol_error : DBL_EPSILON;
   const int64_t maxit64 = *iters > 0 ? *iters : 2 * pl.n_global;
   const int32_t maxit = (int32_t)std::min<int64_t>(maxit64, INT32_MAX);
@@ -512,11 +655,11 @@ extern "C" int cask_b200_bicgstab_device(cask_b200_ctx* ctx, const double* d_b, 
   CB_CUDA(cudaMemsetAsync(y_full, 0, sizeof(double) * pl.m, st));
   // r = b - A x ; r0 = r ; r0_sq = r.r ; rhs_sq = b.b
   CB_TRY(peer_push(ctx, 0, st));
-  CB_TRY(spmv_full(ctx, y_full, t, nullptr, ch_y, nullptr));
-  bicg_residual_kernel<<<vg, kVecThreads, 0, st>>>(n, flags, 0, d_b, r, r0, t, w.d_partials);
-  CB_TRY(reduce_dots(ctx, vg, 0, 1, B_R0SQ, nullptr));
-  dot2_kernel<<<vg, kVecThreads, 0, st>>>(n, nullptr, d_b, d_b, nullptr, nullptr, w.d_partials, stride);
-  CB_TRY(reduce_dots(ctx, vg, 0, 1, B_RHSSQ, nullptr));
+  CB_TRY(spmv_full(ctx, y_full, t, nullptr, 0, ch_y, nullptr));
+  bicg_residual_kernel<<<vg, kVecThreads, 0, st>>>(n, flags, 0, d_b, r, r0, t, make_reduce(ctx, T_VEC, 0, 1, B_R0SQ));
+  CB_TRY(finish_reduce(ctx, 1, B_R0SQ));
+  dot2_kernel<<<vg, kVecThreads, 0, st>>>(n, nullptr, d_b, d_b, nullptr, nullptr, make_reduce(ctx, T_VEC, 0, 1, B_RHSSQ));
+  CB_TRY(finish_reduce(ctx, 1, B_RHSSQ));
   ctx->launches += 3;
   CB_CUDA(cudaMemcpyAsync(w.h_scalars, scal, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, st));
   CB_CUDA(cudaStreamSynchronize(st));
@@ -535,19 +678,17 @@ extern "C" int cask_b200_bicgstab_device(cask_b200_ctx* ctx, const double* d_b, 
 
   // body of one iteration after the loop head; every kernel no-ops while F_DONE or F_RESTART is up
   auto enqueue_body = [&]() -> int {
-    bicg_p_kernel<<<vg, kVecThreads, 0, st>>>(n, scal, flags, r, v, invd, p, y, pd_y);
-    SpmvFusion f1; f1.d_dot_with = r0; f1.d_partials = w.d_partials;
-    CB_TRY(spmv_full(ctx, y_full, v, &f1, ch_y, flags));                     // v = A y, partials of r0.v
-    CB_TRY(reduce_dots(ctx, spmv_partials(ctx), 0, 1, B_R0V, flags));
-    bicg_alpha_kernel<<<1, 1, 0, st>>>(scal, flags);
-    bicg_s_kernel<<<vg, kVecThreads, 0, st>>>(n, scal, flags, r, v, invd, s, z, pd_z);
-    CB_TRY(spmv_full(ctx, z_full, t, nullptr, ch_z, flags));                  // t = A z
-    dot2_kernel<<<vg, kVecThreads, 0, st>>>(n, flags, t, s, t, t, w.d_partials, stride);
-    CB_TRY(reduce_dots(ctx, vg, stride, 2, B_TS, flags));
-    bicg_xr_kernel<<<vg, kVecThreads, 0, st>>>(n, scal, flags, y, z, s, t, r0, d_x, r, w.d_partials, stride);
-    CB_TRY(reduce_dots(ctx, vg, stride, 2, B_RR, flags));
-    bicg_tail_kernel<<<1, 1, 0, st>>>(scal, flags);
-    ctx->launches += 6;
+    CB_CUDA(launch_pdl(bicg_p_kernel, vg, kVecThreads, st, n, scal, flags, r, v, invd, p, y, pd_y));
+    CB_TRY(spmv_full(ctx, y_full, v, r0, B_R0V, ch_y, flags));               // v = A y, r0.v finished in-kernel
+    CB_CUDA(launch_pdl(bicg_s_kernel, vg, kVecThreads, st, n, scal, flags, r, v, invd, s, z, pd_z));   // alpha, s, z
+    CB_TRY(spmv_full(ctx, z_full, t, nullptr, 0, ch_z, flags));              // t = A z
+    CB_CUDA(launch_pdl(dot2_kernel, vg, kVecThreads, st, n, flags, t, s, t, t, make_reduce(ctx, T_VEC, stride, 2, B_TS)));
+    CB_TRY(finish_reduce(ctx, 2, B_TS));
+    CB_CUDA(launch_pdl(bicg_xr_kernel, vg, kVecThreads, st, n, scal, flags, y, z, s, t, r0, d_x, r,
+                       make_reduce(ctx, T_VEC, stride, 2, B_RR)));
+    CB_TRY(finish_reduce(ctx, 2, B_RR));
+    CB_CUDA(launch_pdl(bicg_tail_kernel, 1, 1, st, scal, flags));
+    ctx->launches += 5;
     return CASK_B200_OK;
   };
   const int kBatch = 4;
@@ -558,7 +699,7 @@ extern "C" int cask_b200_bicgstab_device(cask_b200_ctx* ctx, const double* d_b, 
   bool skip_check = true;
   for (int batch = 0;; batch++) {
     for (int b = 0; b < kBatch && enq < enq_cap; b++, enq++) {
-      bicg_head_kernel<<<1, 1, 0, st>>>(scal, flags);
+      CB_CUDA(launch_pdl(bicg_head_kernel, 1, 1, st, scal, flags));
       ctx->launches++;
       CB_TRY(enqueue_body());
     }
@@ -574,9 +715,9 @@ extern "C" int cask_b200_bicgstab_device(cask_b200_ctx* ctx, const double* d_b, 
         // r = b - A x; r0 = r; rho = r0_sq = r.r; the interrupted iteration then continues.
         CB_CUDA(cudaMemcpyAsync(z, d_x, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
         CB_TRY(peer_push(ctx, 1, st));
-        CB_TRY(spmv_full(ctx, z_full, t, nullptr, ch_z, nullptr));
-        bicg_residual_kernel<<<vg, kVecThreads, 0, st>>>(n, flags, 1, d_b, r, r0, t, w.d_partials);
-        CB_TRY(reduce_dots(ctx, vg, 0, 1, B_TMP, nullptr));
+        CB_TRY(spmv_full(ctx, z_full, t, nullptr, 0, ch_z, nullptr));
+        bicg_residual_kernel<<<vg, kVecThreads, 0, st>>>(n, flags, 1, d_b, r, r0, t, make_reduce(ctx, T_VEC, 0, 1, B_TMP));
+        CB_TRY(finish_reduce(ctx, 1, B_TMP));
         bicg_restart_scalars_kernel<<<1, 1, 0, st>>>(scal, flags);
         ctx->launches += 2;
         CB_TRY(enqueue_body());

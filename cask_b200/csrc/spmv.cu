@@ -206,7 +206,8 @@ spmv_ell_persistent_kernel(const SliceDesc* __restrict__ slices, const int32_t* 
                            const Run* __restrict__ runs, const double* __restrict__ ell_vals,
                            const uint16_t* __restrict__ ell_idx, const double* __restrict__ x, double* __restrict__ y,
                            const double* __restrict__ dot_with, double* __restrict__ partials, int xbuf_doubles,
-                           int stages, const HaloWait hw) {
+                           int stages, const HaloWait hw, const ReduceDesc rd) {
+  pdl_enter();
   // solver loops enqueue iterations ahead of the convergence test: once the device-side flag is up nothing runs
   if ((hw.skip0 && *hw.skip0) || (hw.skip1 && *hw.skip1)) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -331,7 +332,8 @@ spmv_ell_persistent_kernel(const SliceDesc* __restrict__ slices, const int32_t* 
   }
   if (kDot) {
     const double t = cta_sum_d(dot, red);  // deterministic: fixed slice->CTA map, fixed order inside the CTA
-    if (tid == 0) partials[blockIdx.x] = t;
+    if (rd.partials) grid_finish_reduce(rd, t, 0.0, blockIdx.x, gridDim.x);  // last CTA: sum (+ all-reduce) in place
+    else if (tid == 0) partials[blockIdx.x] = t;
   }
 }
 
@@ -412,6 +414,11 @@ spmv_csr_fixup_kernel(const SplitRow* __restrict__ rows, int count, const double
 }
 
 }  // namespace
+
+bool spmv_single_launch(const cask_b200_ctx* ctx) {
+  const Plan& p = ctx->plan;
+  return p.n_csr == 0 && p.n_ell > 0 && ctx->ell_kernel == 1 && p.persist_ku != 0 && (!dist_active(ctx) || peer_ready(ctx));
+}
 
 static int ell_grid(const cask_b200_ctx* ctx, int n_slices) {
   const Plan& p = ctx->plan;
@@ -495,10 +502,23 @@ int launch_spmv_range(cask_b200_ctx* ctx, const double* d_x, double* d_y, int el
   do {                                                                                                               \
     CB_CUDA(cudaFuncSetAttribute(spmv_ell_persistent_kernel<KU, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                  (int)p.persist_smem));                                                              \
-    spmv_ell_persistent_kernel<KU, DOT><<<grid, kPersistThreads, p.persist_smem, s>>>(                               \
-        p.d_slices, p.d_list_ell + ell_lo, ell_hi - ell_lo, p.d_runs, p.d_ell_vals, p.d_ell_idx, d_x, d_y, w,        \
-        partials, p.persist_xbuf, p.persist_stages, hw);                                                             \
+    CB_CUDA(cudaLaunchKernelEx(&cfg, spmv_ell_persistent_kernel<KU, DOT>, (const SliceDesc*)p.d_slices,              \
+                               (const int32_t*)(p.d_list_ell + ell_lo), ell_hi - ell_lo, (const Run*)p.d_runs,       \
+                               (const double*)p.d_ell_vals, (const uint16_t*)p.d_ell_idx, d_x, d_y, w, partials,     \
+                               (int)p.persist_xbuf, (int)p.persist_stages, hw, rd));                                 \
   } while (0)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kPersistThreads);
+    cfg.dynamicSmemBytes = p.persist_smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = fusion && fusion->pdl ? 1 : 0;
+    const ReduceDesc rd = dot && fusion->reduce.partials && ell_lo == 0 && ell_hi == p.n_ell && csr_hi == csr_lo
+                              ? fusion->reduce : ReduceDesc();
     if (p.persist_ku == 2) { if (dot) CB_PERSIST(2, true); else CB_PERSIST(2, false); }
     else { if (dot) CB_PERSIST(4, true); else CB_PERSIST(4, false); }
 #undef CB_PERSIST

@@ -41,7 +41,9 @@ for name, gen, N in (("poisson2d", O.gen_poisson2d, 96), ("poisson3d27", O.gen_p
     lci = torch.tensor(ci[rp[r0]:rp[r0 + nr]], dtype=torch.int32, device=dev)
     lva = torch.tensor(va[rp[r0]:rp[r0 + nr]], dtype=torch.float64, device=dev)
     # cache 2560: the 24^3 twin's slices then stage a few planes each (real halos) and the x windows leave room for
-    # the persistent kernel's ring, which the peer-memory path needs
+    # the persistent kernel's ring, which the peer-memory path needs; on so small a grid the slices holding the
+    # z = 0 / z = N-1 planes have an ELL fill just below the default 0.75, so the threshold is lowered
+    ctx.set_option("ell_min_fill", 0.5 if name == "poisson3d27" else 0.75)
     ctx.preprocess_shard_device(cb.design(1, 2560 if name == "poisson3d27" else 8192, 16), n, n, r0, nr, len(lva), lrp.data_ptr(), lci.data_ptr(), lva.data_ptr())
     halo = ctx.halo_counts(world).tolist()
     x = np.random.default_rng(5).random(n)
