@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--no-extra", action="store_true", help="skip the C3 (R-MAT SpMV) and C5 (BiCGStab) side measurements")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cache", type=int, default=8192)
+    ap.add_argument("--cg-maxiters", type=int, default=2000, help="cap on CG iterations (profiling runs)")
     return ap.parse_args()
 
 
@@ -363,7 +364,7 @@ def main():
     del x_full, y, cols, vals, rp
     torch.cuda.empty_cache()
     if not args.no_cg:
-        cg = bench_cg(ctx, cb, torch, dist, dev, rank, world, barrier)
+        cg = bench_cg(ctx, cb, torch, dist, dev, rank, world, barrier, args.cg_maxiters)
         torch.cuda.empty_cache()
     if not args.no_extra:
         bicg = bench_bicgstab(ctx, cb, torch, dist, dev, rank, world, barrier)
@@ -406,7 +407,7 @@ def main():
         dist.destroy_process_group()
 
 
-def bench_cg(ctx, cb, torch, dist, dev, rank, world, barrier):
+def bench_cg(ctx, cb, torch, dist, dev, rank, world, barrier, maxiters=2000):
     """BASELINE configs[3]: CG (the reference's pcg loop, identity preconditioner) on the 3D 27-point
     256^3 Poisson system, row-sharded over the ranks; b = A x_true, x_true[k] = 1 + 0.25 (k mod 4)."""
     N = CG_GRID
@@ -433,14 +434,25 @@ def bench_cg(ctx, cb, torch, dist, dev, rank, world, barrier):
     barrier()
     l0 = ctx.launch_count()
     t0 = time.perf_counter()
-    conv, iters, rs, trips = ctx.cg_device(b.data_ptr(), x.data_ptr(), maxiters=2000, tol=1e-5)
+    conv, iters, rs, trips = ctx.cg_device(b.data_ptr(), x.data_ptr(), maxiters=maxiters, tol=1e-5)
     barrier()
     dt = time.perf_counter() - t0
     tt = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     dt = float(tt.item())
+    launches = ctx.launch_count() - l0
     err = float((x - xt[r0:r0 + nr]).abs().max().item())
+    # marginal cost of an iteration (solve set-up and the final synchronisation excluded): two capped solves
+    tm = []
+    for cap in (50, 250):
+        x.zero_()
+        barrier()
+        t1 = time.perf_counter()
+        ctx.cg_device(b.data_ptr(), x.data_ptr(), maxiters=cap, tol=1e-5)
+        barrier()
+        tm.append(time.perf_counter() - t1)
+    marginal_us = (tm[1] - tm[0]) / 200.0 * 1e6
     et = torch.tensor([err], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(et, op=dist.ReduceOp.MAX)
@@ -448,7 +460,8 @@ def bench_cg(ctx, cb, torch, dist, dev, rank, world, barrier):
     return {"workload": "C4: CG on 3D 27-pt Poisson %d^3 (%d rows, %d nnz), row-sharded over %d GPU(s)" % (N, n, nnz_total, world),
             "scaling": "strong", "iters_per_s": trips / dt, "loop_trips": trips, "iterations_reported": iters,
             "converged": conv, "rs_final": rs, "seconds": dt, "max_abs_err_vs_x_true": float(et.item()),
-            "gpu_launches": int(ctx.launch_count() - l0),
+            "gpu_launches": int(launches), "us_per_iteration_marginal": marginal_us,
+            "peer_memory_path": bool(ctx.peer_active()) if world > 1 else None,
             "traffic_bound_iters_per_s_1gpu": 1.0 / ((algorithmic_bytes(nnz_total, n, n) + 72 * n) / (measured_peak()[0] * 1e9))}
 
 

@@ -182,8 +182,10 @@ struct SolverWork {  // device scratch of the CG / BiCGStab loops
   int64_t vec_len = 0;
   double* d_scalars = nullptr;   // see solvers.cu
   double* d_partials = nullptr;
+  int64_t partials_len = 0;
   unsigned int* d_counters = nullptr;
   unsigned int* d_tickets = nullptr;  // last-CTA tickets of the in-kernel reductions
+  unsigned long long* d_trace = nullptr;  // CASK_B200_TRACE: kTraceIters x 3 kernels x 3 timestamps
   int32_t* h_flags = nullptr;    // pinned
   double* h_scalars = nullptr;   // pinned
 };
@@ -246,6 +248,7 @@ struct SpmvFusion {           // optional fused epilogue: partial dot products p
   double* d_partials = nullptr;        // one partial per CTA of the launch (+offset)
   int fuse_self_dot = 0;               // also accumulate y[r]*y[r]
   ReduceDesc reduce;                   // persistent kernel only: the last CTA sums the partials (and all-reduces them)
+  unsigned long long* trace = nullptr; // persistent kernel only: 3 timeline slots (peer.cuh: trace_min / trace_max)
   bool pdl = false;                    // launch with programmatic stream serialization (solver loops)
 };
 // true if one persistent staged-ELL launch covers the whole SpMV (in-kernel reduction / peer halo wait possible)

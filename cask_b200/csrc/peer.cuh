@@ -46,9 +46,14 @@ __device__ __forceinline__ bool peer_wait_ge(const unsigned long long* flag, uns
 // Programmatic dependent launch: kernels of the solver loops are launched with the stream-serialization attribute,
 // trigger their dependents at once and wait for their predecessor before touching memory - the launch latency of
 // kernel i+1 hides behind the tail of kernel i.  Both instructions are no-ops in a plain launch.
+// Order: wait, THEN trigger - when a kernel releases its dependents its own predecessor is complete, so at most
+// two consecutive kernels overlap and a dependent may pre-load, before its own wait, anything its immediate
+// predecessor does not write.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_enter() {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  pdl_wait();
+  pdl_trigger();
 }
 
 // Finishes a grid-wide dot product inside the producing kernel.  Called by ALL threads of EVERY CTA; t0 / t1 are
@@ -116,12 +121,31 @@ __device__ __forceinline__ void grid_finish_reduce(const ReduceDesc& rd, double 
   }
 }
 
+// In-situ timeline (profiling runs: CASK_B200_TRACE=<file>): per kernel, the earliest CTA entry, the earliest CTA
+// past its dependency wait and the latest CTA exit, in globaltimer nanoseconds.  ncu cannot profile a multi-rank
+// job and serialises kernels; this shows the real gaps between the kernels of a solver iteration on every rank.
+__device__ __forceinline__ void trace_min(unsigned long long* slot) {
+  if (slot && threadIdx.x == 0) atomicMin(slot, globaltimer_ns());
+}
+__device__ __forceinline__ void trace_max(unsigned long long* slot) {
+  if (slot && threadIdx.x == 0) atomicMax(slot, globaltimer_ns());
+}
+
 // true if some pushed range intersects local rows [lo, hi)
 __device__ __forceinline__ bool push_overlaps(const PushDesc& d, int64_t lo, int64_t hi) {
   bool any = false;
 #pragma unroll
   for (int s = 0; s < kMaxPush; s++)
     if (s < d.nsend) any |= (lo < d.hi[s]) & (hi > d.lo[s]);
+  return any;
+}
+
+// true if local row i lies inside a pushed range
+__device__ __forceinline__ bool push_contains(const PushDesc& d, int64_t i) {
+  bool any = false;
+#pragma unroll
+  for (int s = 0; s < kMaxPush; s++)
+    if (s < d.nsend) any |= (i >= d.lo[s]) & (i < d.hi[s]);
   return any;
 }
 

@@ -10,6 +10,8 @@
 // index order by a single CTA (and by NCCL across ranks when row-sharded).
 #include <cfloat>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "ctx.cuh"
@@ -125,8 +127,10 @@ cg_init_kernel(int64_t n, const double* __restrict__ b, double* __restrict__ r, 
 __global__ void __launch_bounds__(kVecThreads, kVecCtasPerSm)
 cg_update_xr_kernel(int64_t n, int it, const double* __restrict__ scal, const int32_t* __restrict__ flags,
                     const double* __restrict__ p, const double* __restrict__ Ap, double* __restrict__ x,
-                    double* __restrict__ r, const ReduceDesc rd) {
+                    double* __restrict__ r, const ReduceDesc rd, unsigned long long* trace) {
+  trace_min(trace);
   pdl_enter();
+  trace_min(trace ? trace + 1 : nullptr);
   if (flags[F_DONE]) return;
   __shared__ double red[kVecThreads / 32];
   const double alpha = scal[S_RS0 + (it & 1)] / scal[S_PAP];
@@ -152,6 +156,7 @@ cg_update_xr_kernel(int64_t n, int it, const double* __restrict__ scal, const in
   }
   const double t = cta_sum(acc, red);
   grid_finish_reduce(rd, t, 0.0, blockIdx.x, gridDim.x);
+  trace_max(trace ? trace + 2 : nullptr);
 }
 
 // convergence test + p = r + (rsnew/rsold) p                        SparseLinearSolvers.hpp:220-231
@@ -159,26 +164,40 @@ cg_update_xr_kernel(int64_t n, int it, const double* __restrict__ scal, const in
 // as they are produced, and the grid's last CTA publishes the new halo epoch.
 __global__ void __launch_bounds__(kVecThreads, kVecCtasPerSm)
 cg_update_p_kernel(int64_t n, int it, double* __restrict__ scal, int32_t* __restrict__ flags,
-                   const double* __restrict__ r, double* __restrict__ p, const PushDesc pd) {
+                   const double* __restrict__ r, double* __restrict__ p, const PushDesc pd, unsigned long long* trace) {
+  trace_min(trace);
   pdl_enter();
+  trace_min(trace ? trace + 1 : nullptr);
   if (flags[F_DONE]) return;
   const double rsold = scal[S_RS0 + (it & 1)], rsnew = scal[S_RS0 + ((it + 1) & 1)];
   const bool converged = rsnew <= scal[S_TOL2];
   const double beta = rsnew / rsold;
   if (!converged) {
+    // Row-sharded: the pushed ranges (the planes a neighbour stages) are updated FIRST and by ALL CTAs, 256-element
+    // pieces each, so the NVLink stores leave from every SM at the start of the kernel instead of from the two or
+    // three CTAs whose chunk happens to hold a plane; the chunk loop below then skips those rows.
+    for (int sidx = 0; sidx < pd.nsend; sidx++) {
+      const int64_t lo = pd.lo[sidx], hi = pd.hi[sidx];
+      const int64_t piece = ((hi - lo + gridDim.x - 1) / gridDim.x + kVecThreads - 1) / kVecThreads * kVecThreads;
+      const int64_t a = lo + (int64_t)blockIdx.x * piece, b = a + piece < hi ? a + piece : hi;
+      for (int64_t k = a + threadIdx.x; k < b; k += kVecThreads) {
+        bool seen = false;  // a row staged by two peers lies in two ranges: updated (and pushed to both) only once
+        for (int e = 0; e < sidx; e++) seen |= (k >= pd.lo[e]) & (k < pd.hi[e]);
+        if (seen) continue;
+        const double v = r[k] + beta * p[k];
+        p[k] = v;
+        push_store(pd, k, v);
+      }
+    }
     CB_TILE_LOOP(n) {
-      const bool push = pd.nsend && push_overlaps(pd, tile, tile + kVecTile);
+      const bool halo = pd.nsend && push_overlaps(pd, tile, tile + kVecTile);
       double rv[kVecItems], pv[kVecItems];
 #pragma unroll
       CB_ITEMS { const int64_t k = CB_IDX(tile); rv[i] = k < hi_ ? r[k] : 0.0; pv[i] = k < hi_ ? p[k] : 0.0; }
 #pragma unroll
       CB_ITEMS {
         const int64_t k = CB_IDX(tile);
-        if (k < hi_) {
-          const double v = rv[i] + beta * pv[i];
-          p[k] = v;
-          if (push) push_store(pd, k, v);
-        }
+        if (k < hi_ && !(halo && push_contains(pd, k))) p[k] = rv[i] + beta * pv[i];
       }
     }
     push_signal(pd);
@@ -200,6 +219,7 @@ cg_update_p_kernel(int64_t n, int it, double* __restrict__ scal, int32_t* __rest
     else flags[F_ITERATIONS] = it;   // :231 — assigned only at the end of a non-converged iteration
     __threadfence();
   }
+  trace_max(trace ? trace + 2 : nullptr);
 }
 
 // ---- BiCGStab ---------------------------------------------------------------------------------
@@ -416,9 +436,29 @@ int vec_grid(const cask_b200_ctx* ctx, int64_t n) {
 }
 
 enum { T_SPMV = 0, T_VEC = 1, T_COUNT = 4 };  // tickets of the in-kernel reductions
+constexpr int kTraceFirst = 40, kTraceIters = 32;  // iterations covered by the CASK_B200_TRACE timeline
+
+// The persistent SpMV kernel runs with the maximum shared-memory carve-out.  The vector kernels stream and gain
+// nothing from L1, so they ask for the same carve-out: the SMs are not reconfigured between the kernels of an
+// iteration and a dependent kernel can become resident while its predecessor drains.
+int prefer_max_shared() {
+  static thread_local int done_for_device = -1;
+  int dev = -1;
+  CB_CUDA(cudaGetDevice(&dev));
+  if (done_for_device == dev) return CASK_B200_OK;
+#define CB_CARVE(k) CB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))
+  CB_CARVE(cg_init_kernel); CB_CARVE(cg_update_xr_kernel); CB_CARVE(cg_update_p_kernel);
+  CB_CARVE(bicg_residual_kernel); CB_CARVE(dot2_kernel); CB_CARVE(bicg_head_kernel); CB_CARVE(bicg_p_kernel);
+  CB_CARVE(bicg_s_kernel); CB_CARVE(bicg_xr_kernel); CB_CARVE(bicg_tail_kernel); CB_CARVE(bicg_restart_scalars_kernel);
+  CB_CARVE(reduce_partials_kernel); CB_CARVE(jacobi_diag_kernel);
+#undef CB_CARVE
+  done_for_device = dev;
+  return CASK_B200_OK;
+}
 
 int ensure_work(cask_b200_ctx* ctx, int nvec, int64_t len_full) {
   SolverWork& w = ctx->work;
+  CB_TRY(prefer_max_shared());
   if (w.vec_len < len_full) {
     for (auto& v : w.d_vec) { cudaFree(v); v = nullptr; }
     w.vec_len = 0;
@@ -438,9 +478,13 @@ int ensure_work(cask_b200_ctx* ctx, int nvec, int64_t len_full) {
   if (!w.h_flags) CB_CUDA(cudaMallocHost(&w.h_flags, sizeof(int32_t) * (F_COUNT + 1) * 4));
   if (!w.h_scalars) CB_CUDA(cudaMallocHost(&w.h_scalars, sizeof(double) * S_COUNT));
   const int64_t np = 2 * (int64_t)std::max(std::max(spmv_partials(ctx), vec_grid(ctx, ctx->plan.n)), 1);
-  cudaFree(w.d_partials);
-  w.d_partials = nullptr;
-  CB_CUDA(cudaMalloc(&w.d_partials, sizeof(double) * np));
+  if (w.partials_len < np) {
+    cudaFree(w.d_partials);
+    w.d_partials = nullptr;
+    w.partials_len = 0;
+    CB_CUDA(cudaMalloc(&w.d_partials, sizeof(double) * np));
+    w.partials_len = np;
+  }
   return CASK_B200_OK;
 }
 
@@ -488,7 +532,7 @@ int reduce_dots(cask_b200_ctx* ctx, int count, int stride, int nq, int slot0, co
 //    halo-dependent slices after the event, then a reduction kernel + ncclAllReduce.
 // flags != nullptr: the launches do nothing once the solver's DONE / RESTART flag is up.
 int spmv_full(cask_b200_ctx* ctx, double* d_full, double* d_y, const double* d_dot_with, int dot_slot, int channel,
-              const int32_t* flags) {
+              const int32_t* flags, unsigned long long* trace = nullptr) {
   cudaStream_t s = ctx->stream;
   SolverWork& w = ctx->work;
   const bool peer = channel >= 0 && peer_ready(ctx);
@@ -496,6 +540,7 @@ int spmv_full(cask_b200_ctx* ctx, double* d_full, double* d_y, const double* d_d
   f.d_dot_with = d_dot_with;
   f.d_partials = w.d_partials;
   f.pdl = true;
+  f.trace = trace;
   HaloWait hw;
   if (peer) hw = peer_halo_wait(ctx, channel);
   if (flags) { hw.skip0 = flags + F_DONE; hw.skip1 = flags + F_RESTART; }
@@ -522,7 +567,7 @@ int spmv_full(cask_b200_ctx* ctx, double* d_full, double* d_y, const double* d_d
 void free_solver_work(cask_b200_ctx* ctx) {
   SolverWork& w = ctx->work;
   for (auto& v : w.d_vec) { cudaFree(v); v = nullptr; }
-  cudaFree(w.d_scalars); cudaFree(w.d_partials); cudaFree(w.d_counters); cudaFree(w.d_tickets);
+  cudaFree(w.d_scalars); cudaFree(w.d_partials); cudaFree(w.d_counters); cudaFree(w.d_tickets); cudaFree(w.d_trace);
   if (w.h_flags) cudaFreeHost(w.h_flags);
   if (w.h_scalars) cudaFreeHost(w.h_scalars);
   w = SolverWork();
@@ -571,6 +616,19 @@ extern "C" int cask_b200_cg_device(cask_b200_ctx* ctx, const double* d_rhs, doub
   CB_TRY(finish_reduce(ctx, 1, S_RS0));
   CB_TRY(peer_push(ctx, 0, s));   // p = r; after the all-reduce, so no peer is still reading the previous epoch
 
+  // CASK_B200_TRACE=<file>: in-situ timeline of iterations [kTraceFirst, kTraceFirst + kTraceIters)
+  const char* trace_path = getenv("CASK_B200_TRACE");
+  std::vector<unsigned long long> h_trace;
+  if (trace_path) {
+    h_trace.assign((size_t)kTraceIters * 9, 0ull);
+    for (size_t i = 0; i < h_trace.size(); i++) h_trace[i] = (i % 3) == 2 ? 0ull : ~0ull;
+    if (!w.d_trace) CB_CUDA(cudaMalloc(&w.d_trace, sizeof(unsigned long long) * h_trace.size()));
+    CB_CUDA(cudaMemcpyAsync(w.d_trace, h_trace.data(), sizeof(unsigned long long) * h_trace.size(), cudaMemcpyHostToDevice, s));
+  } else if (w.d_trace) {
+    cudaFree(w.d_trace);
+    w.d_trace = nullptr;
+  }
+
   // Enqueue batches of iterations; poll the device's done flag one batch behind so the host never
   // stalls the stream.  Kernels of iterations enqueued past convergence see F_DONE and do nothing.
   const int kBatch = 8;
@@ -582,12 +640,15 @@ extern "C" int cask_b200_cg_device(cask_b200_ctx* ctx, const double* d_rhs, doub
     for (int it = enq; it < hi; it++) {
       // three launches per iteration, chained by programmatic dependent launch; dots are finished (and all-reduced
       // over peer memory when sharded) by the last CTA of the kernel that produces them
-      CB_TRY(spmv_full(ctx, p_full, Ap, p, S_PAP, ch, flags));                                          // :206
+      unsigned long long* tr = w.d_trace && it >= kTraceFirst && it < kTraceFirst + kTraceIters
+                                   ? w.d_trace + (size_t)(it - kTraceFirst) * 9 : nullptr;
+      CB_TRY(spmv_full(ctx, p_full, Ap, p, S_PAP, ch, flags, tr));                                      // :206
       const int rs_new = S_RS0 + ((it + 1) & 1);
       CB_CUDA(launch_pdl(cg_update_xr_kernel, vg, kVecThreads, s, n, it, scal, flags, p, Ap, d_x, r,   // :208-218
-                         make_reduce(ctx, T_VEC, 0, 1, rs_new)));
+                         make_reduce(ctx, T_VEC, 0, 1, rs_new), tr ? tr + 3 : nullptr));
       CB_TRY(finish_reduce(ctx, 1, rs_new));
-      CB_CUDA(launch_pdl(cg_update_p_kernel, vg, kVecThreads, s, n, it, scal, flags, r, p, pd));       // :220-231 (+ halo push)
+      CB_CUDA(launch_pdl(cg_update_p_kernel, vg, kVecThreads, s, n, it, scal, flags, r, p, pd,         // :220-231 (+ halo push)
+                         tr ? tr + 6 : nullptr));
       ctx->launches += 2;
     }
     enq = hi;
@@ -604,6 +665,21 @@ extern "C" int cask_b200_cg_device(cask_b200_ctx* ctx, const double* d_rhs, doub
   CB_CUDA(cudaMemcpyAsync(w.h_scalars, scal, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, s));
   CB_CUDA(cudaStreamSynchronize(s));
   CB_CUDA(cudaGetLastError());
+  if (trace_path && w.d_trace) {
+    CB_CUDA(cudaMemcpy(h_trace.data(), w.d_trace, sizeof(unsigned long long) * h_trace.size(), cudaMemcpyDeviceToHost));
+    std::string path = std::string(trace_path) + "." + std::to_string((long long)pl.row0_global);
+    if (FILE* fp = fopen(path.c_str(), "w")) {
+      fprintf(fp, "iteration,kernel,entry_ns,start_ns,end_ns\n");
+      static const char* names[3] = {"spmv_dot", "update_xr", "update_p"};
+      for (int i = 0; i < kTraceIters; i++)
+        for (int k = 0; k < 3; k++) {
+          const unsigned long long* q = h_trace.data() + (size_t)i * 9 + k * 3;
+          if (q[2] == 0ull) continue;
+          fprintf(fp, "%d,%s,%llu,%llu,%llu\n", kTraceFirst + i, names[k], q[0], q[1], q[2]);
+        }
+      fclose(fp);
+    }
+  }
   if (iterations) *iterations = hf[F_ITERATIONS];
   if (converged) *converged = hf[F_CONVERGED];
   if (loop_trips) *loop_trips = hf[F_TRIPS];

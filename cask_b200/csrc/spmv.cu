@@ -53,6 +53,18 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+// same, with an L2 eviction-priority hint: the matrix is streamed once per SpMV and must not push the vectors
+// (x, y and the solver's r, p) out of the 126 MB L2
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
   for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
@@ -206,10 +218,8 @@ spmv_ell_persistent_kernel(const SliceDesc* __restrict__ slices, const int32_t* 
                            const Run* __restrict__ runs, const double* __restrict__ ell_vals,
                            const uint16_t* __restrict__ ell_idx, const double* __restrict__ x, double* __restrict__ y,
                            const double* __restrict__ dot_with, double* __restrict__ partials, int xbuf_doubles,
-                           int stages, const HaloWait hw, const ReduceDesc rd) {
-  pdl_enter();
-  // solver loops enqueue iterations ahead of the convergence test: once the device-side flag is up nothing runs
-  if ((hw.skip0 && *hw.skip0) || (hw.skip1 && *hw.skip1)) return;
+                           int stages, const HaloWait hw, const ReduceDesc rd, unsigned long long* trace) {
+  trace_min(trace);
   extern __shared__ __align__(128) unsigned char smem_raw[];
   PersistHeader* hdr = reinterpret_cast<PersistHeader*>(smem_raw);
   double* xbuf = reinterpret_cast<double*>(smem_raw + kPersistHeaderBytes);
@@ -233,8 +243,40 @@ spmv_ell_persistent_kernel(const SliceDesc* __restrict__ slices, const int32_t* 
   }
   __syncthreads();
 
+  const bool is_producer = warp == kConsumerThreads / 32;
+  const uint64_t stream_policy = l2_evict_first_policy();
+  auto issue_chunk = [&](const SliceDesc* sdp, int c, int chunk_no) {  // lane 0 of the producer warp
+    const int L = sdp->width;
+    const int s = chunk_no % stages;
+    const int cols = min(KU, L - c * KU);
+    const uint32_t fc = smem_u32(&hdr->full_c[s]);
+    mbar_expect_tx(fc, (uint32_t)cols * kSliceRows * 10u);
+    const size_t src = (size_t)sdp->val_off + (size_t)c * KU * kSliceRows;
+    bulk_g2s_hint(smem_u32(cvals + (size_t)s * KU * kSliceRows), ell_vals + src, (uint32_t)cols * kSliceRows * 8u, fc, stream_policy);
+    bulk_g2s_hint(smem_u32(cidx + (size_t)s * KU * kSliceRows), ell_idx + src, (uint32_t)cols * kSliceRows * 2u, fc, stream_policy);
+  };
+  // Programmatic dependent launch: this CTA may be resident while the kernel that produces x is still running.
+  // The matrix is static, so the producer warp fills the ring with the first chunks of its first slice BEFORE it
+  // waits for the predecessor; only then are x, the solver flags and the peers' halo epochs looked at.
+  int prefetched = 0;
+  if (is_producer && blockIdx.x < count) {
+    const SliceDesc* sdp = slices + list[blockIdx.x];
+    prefetched = min((sdp->width + KU - 1) / KU, stages);
+    if (lane == 0)
+      for (int c = 0; c < prefetched; c++) issue_chunk(sdp, c, c);
+  }
+  pdl_wait();
+  pdl_trigger();
+  trace_min(trace ? trace + 1 : nullptr);
+  // solver loops enqueue iterations ahead of the convergence test: once the device-side flag is up nothing runs
+  if ((hw.skip0 && *hw.skip0) || (hw.skip1 && *hw.skip1)) {
+    if (is_producer)
+      for (int c = 0; c < prefetched; c++) mbar_wait(smem_u32(&hdr->full_c[c]), 0);  // drain the copies in flight
+    return;
+  }
+
   double dot = 0.0;
-  if (warp == kConsumerThreads / 32) {
+  if (is_producer) {
     // ===== producer warp =====
     int chunk_no = 0;
     int it = 0;
@@ -248,7 +290,6 @@ spmv_ell_persistent_kernel(const SliceDesc* __restrict__ slices, const int32_t* 
       }
       const SliceDesc* sdp = slices + list[item];
       const int L = sdp->width, nruns = sdp->nruns;
-      const int64_t val_off = sdp->val_off;
       const int xb = it & 1;
       mbar_wait(smem_u32(&hdr->empty_x[xb]), ((it >> 1) & 1) ^ 1);
       double* xs = xbuf + (size_t)xb * xbuf_doubles;
@@ -273,16 +314,10 @@ spmv_ell_persistent_kernel(const SliceDesc* __restrict__ slices, const int32_t* 
       if (lane == 0) mbar_expect_tx(fx, bytes);  // arrive (release): meta and odd tails become visible with it
       const int nchunks = (L + KU - 1) / KU;
       for (int c = 0; c < nchunks; c++, chunk_no++) {
+        if (chunk_no < prefetched) continue;  // already in flight (first slice)
         const int s = chunk_no % stages;
         mbar_wait(smem_u32(&hdr->empty_c[s]), ((chunk_no / stages) & 1) ^ 1);
-        if (lane == 0) {
-          const int cols = min(KU, L - c * KU);
-          const uint32_t fc = smem_u32(&hdr->full_c[s]);
-          mbar_expect_tx(fc, (uint32_t)cols * kSliceRows * 10u);
-          const size_t src = (size_t)val_off + (size_t)c * KU * kSliceRows;
-          bulk_g2s(smem_u32(cvals + (size_t)s * KU * kSliceRows), ell_vals + src, (uint32_t)cols * kSliceRows * 8u, fc);
-          bulk_g2s(smem_u32(cidx + (size_t)s * KU * kSliceRows), ell_idx + src, (uint32_t)cols * kSliceRows * 2u, fc);
-        }
+        if (lane == 0) issue_chunk(sdp, c, chunk_no);
       }
     }
   } else {
@@ -335,6 +370,7 @@ spmv_ell_persistent_kernel(const SliceDesc* __restrict__ slices, const int32_t* 
     if (rd.partials) grid_finish_reduce(rd, t, 0.0, blockIdx.x, gridDim.x);  // last CTA: sum (+ all-reduce) in place
     else if (tid == 0) partials[blockIdx.x] = t;
   }
+  trace_max(trace ? trace + 2 : nullptr);
 }
 
 // ---- gather-CSR path: irregular rows, x gathered through the read-only path / L2 -----------------------
@@ -505,7 +541,8 @@ int launch_spmv_range(cask_b200_ctx* ctx, const double* d_x, double* d_y, int el
     CB_CUDA(cudaLaunchKernelEx(&cfg, spmv_ell_persistent_kernel<KU, DOT>, (const SliceDesc*)p.d_slices,              \
                                (const int32_t*)(p.d_list_ell + ell_lo), ell_hi - ell_lo, (const Run*)p.d_runs,       \
                                (const double*)p.d_ell_vals, (const uint16_t*)p.d_ell_idx, d_x, d_y, w, partials,     \
-                               (int)p.persist_xbuf, (int)p.persist_stages, hw, rd));                                 \
+                               (int)p.persist_xbuf, (int)p.persist_stages, hw, rd,                                   \
+                               fusion ? fusion->trace : (unsigned long long*)nullptr));                              \
   } while (0)
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
