@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cache", type=int, default=8192)
     ap.add_argument("--cg-maxiters", type=int, default=2000, help="cap on CG iterations (profiling runs)")
+    ap.add_argument("--cg-emulate-shard", type=int, default=0,
+                    help="profiling: on ONE GPU, run CG on the stripe that rank W/2 of a W-way sharded C4 system owns "
+                         "(principal submatrix, halo columns read zeros): the per-rank work of the W-GPU job under ncu")
     return ap.parse_args()
 
 
@@ -364,7 +367,7 @@ def main():
     del x_full, y, cols, vals, rp
     torch.cuda.empty_cache()
     if not args.no_cg:
-        cg = bench_cg(ctx, cb, torch, dist, dev, rank, world, barrier, args.cg_maxiters)
+        cg = bench_cg(ctx, cb, torch, dist, dev, rank, world, barrier, args.cg_maxiters, args.cg_emulate_shard)
         torch.cuda.empty_cache()
     if not args.no_extra:
         bicg = bench_bicgstab(ctx, cb, torch, dist, dev, rank, world, barrier)
@@ -407,20 +410,22 @@ def main():
         dist.destroy_process_group()
 
 
-def bench_cg(ctx, cb, torch, dist, dev, rank, world, barrier, maxiters=2000):
+def bench_cg(ctx, cb, torch, dist, dev, rank, world, barrier, maxiters=2000, emulate=0):
     """BASELINE configs[3]: CG (the reference's pcg loop, identity preconditioner) on the 3D 27-point
     256^3 Poisson system, row-sharded over the ranks; b = A x_true, x_true[k] = 1 + 0.25 (k mod 4)."""
     N = CG_GRID
     kind = cb.SYNTH_POISSON3D27
     n = cb.synth_rows(kind, N)
     r0, nr = cb.shard_rows(n, world, rank)
+    if emulate > 1 and world == 1:
+        r0, nr = cb.shard_rows(n, emulate, emulate // 2)
     nnz = cb.synth_nnz(kind, N, r0, nr)
     rp = torch.empty(nr + 1, dtype=torch.int32, device=dev)
     ci = torch.empty(nnz, dtype=torch.int32, device=dev)
     va = torch.empty(nnz, dtype=torch.float64, device=dev)
     cb.synth_device(kind, N, r0, nr, rp.data_ptr(), ci.data_ptr(), va.data_ptr(), torch.cuda.current_stream().cuda_stream)
     dsg = cb.design(num_pipes=1, cache_size=8192, input_width=16)
-    if world > 1:
+    if world > 1 or emulate > 1:
         ctx.preprocess_shard_device(dsg, n, n, r0, nr, nnz, rp.data_ptr(), ci.data_ptr(), va.data_ptr())
     else:
         ctx.preprocess_device(dsg, n, n, nnz, rp.data_ptr(), ci.data_ptr(), va.data_ptr())
@@ -472,13 +477,15 @@ def bench_bicgstab(ctx, cb, torch, dist, dev, rank, world, barrier):
     kind = cb.SYNTH_CONVDIFF3D7
     n = cb.synth_rows(kind, N)
     r0, nr = cb.shard_rows(n, world, rank)
+    if emulate > 1 and world == 1:
+        r0, nr = cb.shard_rows(n, emulate, emulate // 2)
     nnz = cb.synth_nnz(kind, N, r0, nr)
     rp = torch.empty(nr + 1, dtype=torch.int32, device=dev)
     ci = torch.empty(nnz, dtype=torch.int32, device=dev)
     va = torch.empty(nnz, dtype=torch.float64, device=dev)
     cb.synth_device(kind, N, r0, nr, rp.data_ptr(), ci.data_ptr(), va.data_ptr(), torch.cuda.current_stream().cuda_stream)
     dsg = cb.design(num_pipes=1, cache_size=8192, input_width=16)
-    if world > 1:
+    if world > 1 or emulate > 1:
         ctx.preprocess_shard_device(dsg, n, n, r0, nr, nnz, rp.data_ptr(), ci.data_ptr(), va.data_ptr())
     else:
         ctx.preprocess_device(dsg, n, n, nnz, rp.data_ptr(), ci.data_ptr(), va.data_ptr())

@@ -164,6 +164,24 @@ struct ReduceDesc {     // by-value kernel argument: the grid's last CTA finishe
   PeerCtrl* ctrl = nullptr;        // non-null: one-shot all-reduce over the peers' control blocks before writing out
   PeerCtrl* peers[kMaxPeers] = {nullptr};
   int32_t me = 0, world = 1;
+  unsigned int* gen = nullptr;     // non-null: grid barrier - no CTA returns before out[] is written (all CTAs resident)
+  int32_t publish_only = 0;        // peer path: store the local sums into the peers' slots and return; the CONSUMER
+  int32_t pad_ = 0;                // kernel gathers the W contributions (peer_gather_sum) - hides the NVLink round trip
+};
+
+struct GatherDesc {     // by-value kernel argument of the consumer of a publish-only reduction
+  PeerCtrl* ctrl = nullptr;        // nullptr: the value is in the scalar slot already
+  int32_t world = 1;
+  int32_t pad_ = 0;
+};
+
+struct HaloUpdate {     // by-value kernel argument: halo rows of a full-layout vector that this rank recomputes itself
+  int32_t nrecv = 0;               // from halo entries of ANOTHER vector that the peers pushed (CG: p_halo = r_halo + beta p_halo)
+  int32_t channel = 0;             // channel of the pushed vector
+  uint32_t peer_mask = 0;
+  int32_t pad_ = 0;
+  int64_t lo[kMaxPush], hi[kMaxPush];  // ranges as offsets from the LOCAL base pointer (negative / >= n: outside the own slice)
+  PeerCtrl* ctrl = nullptr;
 };
 
 struct HaloWait {       // by-value kernel argument of the persistent SpMV kernel
@@ -274,6 +292,7 @@ double* peer_vector(cask_b200_ctx* ctx, int channel);                // full-lay
 PushDesc peer_push_desc(cask_b200_ctx* ctx, int channel);            // ctrl == nullptr when the peer path is off
 void peer_fill_reduce(cask_b200_ctx* ctx, ReduceDesc* rd);           // adds the all-reduce part when the peer path is on
 HaloWait peer_halo_wait(cask_b200_ctx* ctx, int channel);
+HaloUpdate peer_halo_update(cask_b200_ctx* ctx, int channel);
 int peer_push(cask_b200_ctx* ctx, int channel, cudaStream_t stream); // standalone push of the channel's own slice
 int peer_allreduce_partials(cask_b200_ctx* ctx, const double* d_partials, int count, int stride, int nq, double* d_scal,
                             int slot0, const int32_t* d_skip0, const int32_t* d_skip1, cudaStream_t stream);

@@ -252,13 +252,14 @@ int dist_plan_halo(cask_b200_ctx* ctx) {
 
   // Peer-memory path: every rank's sends must fit one PushDesc and every rank must run the persistent staged-ELL
   // kernel on all its slices; the ranks agree through one all-reduce.
-  size_t nsend = 0;
+  size_t nsend = 0, nrecv = 0;
   d->recv_mask = 0;
   for (int q = 0; q < W; q++) {
     nsend += d->send_to[q].size();
+    nrecv += d->recv_from[q].size();
     if (!d->recv_from[q].empty()) d->recv_mask |= 1u << q;
   }
-  const bool mine_ok = !d->allgather && W <= kMaxPeers && nsend <= (size_t)kMaxPush && p.n_csr == 0 &&
+  const bool mine_ok = !d->allgather && W <= kMaxPeers && nsend <= (size_t)kMaxPush && nrecv <= (size_t)kMaxPush && p.n_csr == 0 &&
                        ctx->ell_kernel == 1 && p.persist_ku != 0 && ctx->peer_mode != 0;
   int64_t* d_ok = nullptr;
   CB_CUDA(cudaMalloc(&d_ok, sizeof(int64_t)));
@@ -381,6 +382,27 @@ HaloWait peer_halo_wait(cask_b200_ctx* ctx, int channel) {
   w.first_item = ctx->plan.n_ell_interior;
   w.peer_mask = d->recv_mask;
   return w;
+}
+
+HaloUpdate peer_halo_update(cask_b200_ctx* ctx, int channel) {
+  HaloUpdate h;
+  for (int i = 0; i < kMaxPush; i++) h.lo[i] = h.hi[i] = 0;
+  if (!peer_ready(ctx)) return h;
+  DistState* d = ctx->dist;
+  const int64_t own_lo = ctx->plan.row0_global;
+  int k = 0;
+  for (int q = 0; q < d->world; q++)
+    for (auto& r : d->recv_from[q]) {
+      if (k == kMaxPush) break;
+      h.lo[k] = r.col0 - own_lo;
+      h.hi[k] = r.col0 + r.len - own_lo;
+      k++;
+    }
+  h.nrecv = k;
+  h.channel = channel;
+  h.peer_mask = d->recv_mask;
+  h.ctrl = reinterpret_cast<PeerCtrl*>(d->arena);
+  return h;
 }
 
 namespace {

@@ -62,7 +62,8 @@ __device__ __forceinline__ void pdl_enter() {
 // sums into slot [seq & 3][me] of every rank's control block, publishes seq with a release store, acquires the W
 // flags of its own block and adds the W contributions in rank order - the same order on every rank, so all ranks
 // hold bit-identical scalars and take identical convergence decisions.
-__device__ __forceinline__ void grid_finish_reduce(const ReduceDesc& rd, double t0, double t1, int cta, int ncta) {
+__device__ __forceinline__ void grid_finish_reduce(const ReduceDesc& rd, double t0, double t1, int cta, int ncta,
+                                                   unsigned int gen0 = 0u) {
   __shared__ int s_last;
   __shared__ double s_red[2][32];
   __shared__ double s_tot[2];
@@ -76,7 +77,15 @@ __device__ __forceinline__ void grid_finish_reduce(const ReduceDesc& rd, double 
     s_last = atomicAdd(rd.ticket, 1u) == (unsigned)(ncta - 1);
   }
   __syncthreads();
-  if (!s_last) return;
+  if (!s_last) {
+    if (rd.gen) {  // grid barrier: wait until the last CTA has published the result (gen0 was read at kernel entry)
+      if (tid == 0)
+        while (*reinterpret_cast<volatile unsigned int*>(rd.gen) == gen0) {}
+      __syncthreads();
+      __threadfence();
+    }
+    return;
+  }
   __threadfence();
   for (int q = 0; q < rd.nq; q++) {
     double v = 0.0;
@@ -101,10 +110,23 @@ __device__ __forceinline__ void grid_finish_reduce(const ReduceDesc& rd, double 
   __syncthreads();
   if (rd.ctrl == nullptr) {
     if (tid < rd.nq) rd.out[tid] = s_tot[tid];
+    if (rd.gen) {
+      __syncthreads();
+      if (tid == 0) { __threadfence(); atomicExch(rd.gen, gen0 + 1u); }
+    }
     return;
   }
   const unsigned long long seq = s_seq;
   const int slot = (int)(seq & 3ull);
+  if (rd.publish_only) {
+    if (tid < rd.world) {
+      PeerCtrl* pc = rd.peers[tid];
+      for (int q = 0; q < rd.nq; q++) pc->ar_val[slot][rd.me][q] = s_tot[q];
+      __threadfence_system();
+      st_release_sys_u64(&pc->ar_flag[slot][rd.me], seq);
+    }
+    return;
+  }
   if (tid < rd.world) {
     PeerCtrl* pc = rd.peers[tid];
     for (int q = 0; q < rd.nq; q++) pc->ar_val[slot][rd.me][q] = s_tot[q];
@@ -119,6 +141,10 @@ __device__ __forceinline__ void grid_finish_reduce(const ReduceDesc& rd, double 
     for (int r = 0; r < rd.world; r++) t += s_contrib[r][tid];
     rd.out[tid] = t;
   }
+  if (rd.gen) {
+    __syncthreads();
+    if (tid == 0) { __threadfence(); atomicExch(rd.gen, gen0 + 1u); }
+  }
 }
 
 // In-situ timeline (profiling runs: CASK_B200_TRACE=<file>): per kernel, the earliest CTA entry, the earliest CTA
@@ -129,6 +155,22 @@ __device__ __forceinline__ void trace_min(unsigned long long* slot) {
 }
 __device__ __forceinline__ void trace_max(unsigned long long* slot) {
   if (slot && threadIdx.x == 0) atomicMax(slot, globaltimer_ns());
+}
+
+// Consumer side of a publish-only reduction (first quantity): every CTA gathers the W contributions of the latest
+// collective from its own control block and adds them in rank order.  Called by all threads; s_c is CTA scratch.
+__device__ __forceinline__ double peer_gather_sum(const GatherDesc& g, double* s_c) {
+  const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(&g.ctrl->ar_seq);
+  const int slot = (int)(seq & 3ull);
+  if ((int)threadIdx.x < g.world) {
+    peer_wait_ge(&g.ctrl->ar_flag[slot][threadIdx.x], seq, &g.ctrl->error);
+    s_c[threadIdx.x] = *reinterpret_cast<volatile double*>(&g.ctrl->ar_val[slot][threadIdx.x][0]);
+  }
+  __syncthreads();
+  double t = 0.0;
+  for (int r = 0; r < g.world; r++) t += s_c[r];
+  __syncthreads();
+  return t;
 }
 
 // true if some pushed range intersects local rows [lo, hi)

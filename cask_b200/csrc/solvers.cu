@@ -222,6 +222,138 @@ cg_update_p_kernel(int64_t n, int it, double* __restrict__ scal, int32_t* __rest
   trace_max(trace ? trace + 2 : nullptr);
 }
 
+// One kernel per iteration for everything after the SpMV (single rank, or row-sharded on the peer path):
+//   phase 1   alpha = rsold / p.Ap; x += alpha p; r -= alpha Ap; r.r                        (:208-218)
+//   barrier   the grid's last CTA sums the partials (+ all-reduce over peer memory) -> rsnew; all CTAs wait for it
+//   phase 2   convergence test; p = r + (rsnew / rsold) p                                   (:220-231)
+// Row-sharded: the rows of the new r that a neighbour stages are updated first, by all CTAs, and stored straight
+// into the neighbour's copy of r; in phase 2 every rank recomputes the halo rows of p ITSELF from the halo rows of
+// r it received and the old halo rows of p (same arithmetic as the owner, bit-identical).  The NVLink transfer is
+// thereby off the critical path: it overlaps the all-reduce, and the following SpMV needs no halo wait at all.
+// The grid (<= 2 CTAs per SM) is resident as a whole, which the barrier relies on.
+__global__ void __launch_bounds__(kVecThreads, kVecCtasPerSm)
+cg_update_fused_kernel(int64_t n, int it, double* __restrict__ scal, int32_t* __restrict__ flags, double* p,
+                       const double* __restrict__ Ap, double* __restrict__ x, double* r, const ReduceDesc rd,
+                       const PushDesc pd, const HaloUpdate hu, const GatherDesc pap, unsigned long long* trace) {
+  trace_min(trace);
+  pdl_enter();
+  trace_min(trace ? trace + 1 : nullptr);
+  if (flags[F_DONE]) return;
+  __shared__ double red[kVecThreads / 32];
+  const unsigned int gen0 = *reinterpret_cast<volatile unsigned int*>(rd.gen);
+  const double rsold = scal[S_RS0 + (it & 1)];
+  // row-sharded: the SpMV's last CTA only PUBLISHED this rank's p.Ap to the peers; the W contributions are gathered here
+  const double alpha = rsold / (pap.ctrl ? peer_gather_sum(pap, red) : scal[S_PAP]);
+  double acc = 0.0;
+  // ---- phase 1 ----
+  for (int sidx = 0; sidx < pd.nsend; sidx++) {
+    const int64_t lo = pd.lo[sidx], hi = pd.hi[sidx];
+    const int64_t piece = ((hi - lo + gridDim.x - 1) / gridDim.x + kVecThreads - 1) / kVecThreads * kVecThreads;
+    const int64_t a = lo + (int64_t)blockIdx.x * piece, b = a + piece < hi ? a + piece : hi;
+    for (int64_t k = a + threadIdx.x; k < b; k += kVecThreads) {
+      bool seen = false;  // a row staged by two peers lies in two ranges: updated (and pushed to both) only once
+      for (int e = 0; e < sidx; e++) seen |= (k >= pd.lo[e]) & (k < pd.hi[e]);
+      if (seen) continue;
+      x[k] += alpha * p[k];
+      const double v = r[k] - alpha * Ap[k];
+      r[k] = v;
+      push_store(pd, k, v);
+      acc += v * v;
+    }
+  }
+  {
+    CB_TILE_LOOP(n) {
+      const bool halo = pd.nsend && push_overlaps(pd, tile, tile + kVecTile);
+      double pv[kVecItems], av[kVecItems], xv[kVecItems], rv[kVecItems];
+#pragma unroll
+      CB_ITEMS {
+        const int64_t k = CB_IDX(tile);
+        const bool ok = k < hi_;
+        pv[i] = ok ? p[k] : 0.0; av[i] = ok ? Ap[k] : 0.0; xv[i] = ok ? x[k] : 0.0; rv[i] = ok ? r[k] : 0.0;
+      }
+#pragma unroll
+      CB_ITEMS {
+        const int64_t k = CB_IDX(tile);
+        if (k < hi_ && !(halo && push_contains(pd, k))) {
+          x[k] = xv[i] + alpha * pv[i];
+          const double v = rv[i] - alpha * av[i];
+          r[k] = v;
+          acc += v * v;
+        }
+      }
+    }
+  }
+  push_signal(pd);  // the grid's last CTA publishes this epoch of r to the peers
+  const double t = cta_sum(acc, red);
+  grid_finish_reduce(rd, t, 0.0, blockIdx.x, gridDim.x, gen0);  // returns everywhere once scal[rs_new] is final
+  // ---- phase 2 ----
+  const double rsnew = *reinterpret_cast<volatile double*>(&scal[S_RS0 + ((it + 1) & 1)]);
+  const bool converged = rsnew <= scal[S_TOL2];
+  const double beta = rsnew / rsold;
+  if (!converged) {
+    for (int sidx = 0; sidx < pd.nsend; sidx++) {  // same thread <-> row map as in phase 1: each thread reads its own r
+      const int64_t lo = pd.lo[sidx], hi = pd.hi[sidx];
+      const int64_t piece = ((hi - lo + gridDim.x - 1) / gridDim.x + kVecThreads - 1) / kVecThreads * kVecThreads;
+      const int64_t a = lo + (int64_t)blockIdx.x * piece, b = a + piece < hi ? a + piece : hi;
+      for (int64_t k = a + threadIdx.x; k < b; k += kVecThreads) {
+        bool seen = false;
+        for (int e = 0; e < sidx; e++) seen |= (k >= pd.lo[e]) & (k < pd.hi[e]);
+        if (!seen) p[k] = r[k] + beta * p[k];
+      }
+    }
+    {
+      CB_TILE_LOOP(n) {
+        const bool halo = pd.nsend && push_overlaps(pd, tile, tile + kVecTile);
+        double rv[kVecItems], pv[kVecItems];
+#pragma unroll
+        CB_ITEMS { const int64_t k = CB_IDX(tile); rv[i] = k < hi_ ? r[k] : 0.0; pv[i] = k < hi_ ? p[k] : 0.0; }
+#pragma unroll
+        CB_ITEMS {
+          const int64_t k = CB_IDX(tile);
+          if (k < hi_ && !(halo && push_contains(pd, k))) p[k] = rv[i] + beta * pv[i];
+        }
+      }
+    }
+    if (hu.nrecv) {
+      // halo rows of p: the peers' r entries of this epoch (pushed in their phase 1) must have landed
+      if (threadIdx.x == 0) {
+        const unsigned long long want = *reinterpret_cast<volatile unsigned long long*>(&hu.ctrl->push_seq[hu.channel]);
+        for (int q = 0; q < kMaxPeers; q++)
+          if (hu.peer_mask & (1u << q)) peer_wait_ge(&hu.ctrl->halo_flag[hu.channel][q], want, &hu.ctrl->error);
+      }
+      __syncthreads();
+      for (int sidx = 0; sidx < hu.nrecv; sidx++) {
+        const int64_t lo = hu.lo[sidx], hi = hu.hi[sidx];
+        const int64_t piece = ((hi - lo + gridDim.x - 1) / gridDim.x + kVecThreads - 1) / kVecThreads * kVecThreads;
+        const int64_t a = lo + (int64_t)blockIdx.x * piece, b = a + piece < hi ? a + piece : hi;
+        for (int64_t g = a + threadIdx.x; g < b; g += kVecThreads) {
+          bool seen = false;
+          for (int e = 0; e < sidx; e++) seen |= (g >= hu.lo[e]) & (g < hu.hi[e]);
+          if (!seen) p[g] = __ldcg(r + g) + beta * p[g];  // written by a peer over NVLink: read past L1
+        }
+      }
+    }
+  }
+  // flags are only written by the grid's LAST CTA to finish, after every CTA has read them
+  __shared__ bool last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned ticket = atomicAdd(reinterpret_cast<unsigned*>(&flags[F_COUNT]), 1u);
+    last = ticket == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    flags[F_COUNT] = 0;
+    flags[F_TRIPS] = it + 1;
+    scal[S_RS_FINAL] = rsnew;
+    if (converged) { flags[F_CONVERGED] = 1; flags[F_DONE] = 1; }
+    else flags[F_ITERATIONS] = it;   // :231 — assigned only at the end of a non-converged iteration
+    __threadfence();
+  }
+  trace_max(trace ? trace + 2 : nullptr);
+}
+
 // ---- BiCGStab ---------------------------------------------------------------------------------
 __global__ void jacobi_diag_kernel(int64_t n, int64_t row0_global, const int32_t* __restrict__ row_ptr,
                                    const int32_t* __restrict__ col, const double* __restrict__ val,
@@ -435,7 +567,7 @@ int vec_grid(const cask_b200_ctx* ctx, int64_t n) {
   return (int)std::max<int64_t>(1, std::min<int64_t>(units, (int64_t)ctx->sm_count * kVecCtasPerSm));
 }
 
-enum { T_SPMV = 0, T_VEC = 1, T_COUNT = 4 };  // tickets of the in-kernel reductions
+enum { T_SPMV = 0, T_VEC = 1, T_GEN = 2, T_COUNT = 4 };  // tickets of the in-kernel reductions
 constexpr int kTraceFirst = 40, kTraceIters = 32;  // iterations covered by the CASK_B200_TRACE timeline
 
 // The persistent SpMV kernel runs with the maximum shared-memory carve-out.  The vector kernels stream and gain
@@ -447,7 +579,7 @@ int prefer_max_shared() {
   CB_CUDA(cudaGetDevice(&dev));
   if (done_for_device == dev) return CASK_B200_OK;
 #define CB_CARVE(k) CB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))
-  CB_CARVE(cg_init_kernel); CB_CARVE(cg_update_xr_kernel); CB_CARVE(cg_update_p_kernel);
+  CB_CARVE(cg_init_kernel); CB_CARVE(cg_update_xr_kernel); CB_CARVE(cg_update_p_kernel); CB_CARVE(cg_update_fused_kernel);
   CB_CARVE(bicg_residual_kernel); CB_CARVE(dot2_kernel); CB_CARVE(bicg_head_kernel); CB_CARVE(bicg_p_kernel);
   CB_CARVE(bicg_s_kernel); CB_CARVE(bicg_xr_kernel); CB_CARVE(bicg_tail_kernel); CB_CARVE(bicg_restart_scalars_kernel);
   CB_CARVE(reduce_partials_kernel); CB_CARVE(jacobi_diag_kernel);
@@ -532,7 +664,7 @@ int reduce_dots(cask_b200_ctx* ctx, int count, int stride, int nq, int slot0, co
 //    halo-dependent slices after the event, then a reduction kernel + ncclAllReduce.
 // flags != nullptr: the launches do nothing once the solver's DONE / RESTART flag is up.
 int spmv_full(cask_b200_ctx* ctx, double* d_full, double* d_y, const double* d_dot_with, int dot_slot, int channel,
-              const int32_t* flags, unsigned long long* trace = nullptr) {
+              const int32_t* flags, unsigned long long* trace = nullptr, bool publish_only = false) {
   cudaStream_t s = ctx->stream;
   SolverWork& w = ctx->work;
   const bool peer = channel >= 0 && peer_ready(ctx);
@@ -547,6 +679,10 @@ int spmv_full(cask_b200_ctx* ctx, double* d_full, double* d_y, const double* d_d
   if (!dist_active(ctx) || peer) {
     const bool in_kernel = d_dot_with && spmv_single_launch(ctx);
     if (in_kernel) f.reduce = make_reduce(ctx, T_SPMV, 0, 1, dot_slot);
+    if (publish_only) {
+      if (!(in_kernel && peer)) return fail(CASK_B200_ERR_RUNTIME, "publish-only reduction needs the in-kernel peer path");
+      f.reduce.publish_only = 1;
+    }
     CB_TRY(launch_spmv(ctx, d_full, d_y, 0, s, &f, &hw));
     if (d_dot_with && !in_kernel) CB_TRY(reduce_dots(ctx, spmv_partials(ctx), 0, 1, dot_slot, flags));
     return CASK_B200_OK;
@@ -592,7 +728,12 @@ extern "C" int cask_b200_cg_device(cask_b200_ctx* ctx, const double* d_rhs, doub
   const bool peer = peer_ready(ctx);
   const int ch = peer ? 0 : -1;                       // p is vector 0 of the symmetric arena
   const PushDesc pd = peer_push_desc(ctx, 0);
-  double* r = w.d_vec[0];
+  // fused update kernel (single rank / peer path): r lives in the arena too (vector 1) - its boundary rows are what
+  // travels every iteration, and each rank recomputes the halo rows of p from them
+  const bool fused = !dist_active(ctx) || peer;
+  const PushDesc pd_r = peer_push_desc(ctx, 1);
+  const HaloUpdate hu = peer_halo_update(ctx, 1);
+  double* r = peer ? peer_vector(ctx, 1) + off : w.d_vec[0];
   double* p_full = peer ? peer_vector(ctx, 0) : w.d_vec[1];
   double* Ap = w.d_vec[2];
   double* p = p_full + off;
@@ -642,14 +783,25 @@ extern "C" int cask_b200_cg_device(cask_b200_ctx* ctx, const double* d_rhs, doub
       // over peer memory when sharded) by the last CTA of the kernel that produces them
       unsigned long long* tr = w.d_trace && it >= kTraceFirst && it < kTraceFirst + kTraceIters
                                    ? w.d_trace + (size_t)(it - kTraceFirst) * 9 : nullptr;
-      CB_TRY(spmv_full(ctx, p_full, Ap, p, S_PAP, ch, flags, tr));                                      // :206
+      const bool publish = fused && peer && spmv_single_launch(ctx);  // p.Ap gathered by the consumer kernel
+      CB_TRY(spmv_full(ctx, p_full, Ap, p, S_PAP, ch, flags, tr, publish));                             // :206
       const int rs_new = S_RS0 + ((it + 1) & 1);
-      CB_CUDA(launch_pdl(cg_update_xr_kernel, vg, kVecThreads, s, n, it, scal, flags, p, Ap, d_x, r,   // :208-218
-                         make_reduce(ctx, T_VEC, 0, 1, rs_new), tr ? tr + 3 : nullptr));
-      CB_TRY(finish_reduce(ctx, 1, rs_new));
-      CB_CUDA(launch_pdl(cg_update_p_kernel, vg, kVecThreads, s, n, it, scal, flags, r, p, pd,         // :220-231 (+ halo push)
-                         tr ? tr + 6 : nullptr));
-      ctx->launches += 2;
+      if (fused) {
+        ReduceDesc rd = make_reduce(ctx, T_VEC, 0, 1, rs_new);
+        rd.gen = w.d_tickets + T_GEN;
+        GatherDesc gd;
+        if (publish) { gd.ctrl = rd.ctrl; gd.world = rd.world; }
+        CB_CUDA(launch_pdl(cg_update_fused_kernel, vg, kVecThreads, s, n, it, scal, flags, p, Ap, d_x, r, rd, pd_r, hu, gd,   // :208-231
+                           tr ? tr + 3 : nullptr));
+        ctx->launches += 1;
+      } else {  // NCCL between the two halves
+        CB_CUDA(launch_pdl(cg_update_xr_kernel, vg, kVecThreads, s, n, it, scal, flags, p, Ap, d_x, r,   // :208-218
+                           make_reduce(ctx, T_VEC, 0, 1, rs_new), tr ? tr + 3 : nullptr));
+        CB_TRY(finish_reduce(ctx, 1, rs_new));
+        CB_CUDA(launch_pdl(cg_update_p_kernel, vg, kVecThreads, s, n, it, scal, flags, r, p, pd,         // :220-231 (+ halo push)
+                           tr ? tr + 6 : nullptr));
+        ctx->launches += 2;
+      }
     }
     enq = hi;
     CB_CUDA(cudaMemcpyAsync(hf + (batch & 1) * (F_COUNT + 1), flags, sizeof(int32_t) * (F_COUNT + 1),
@@ -670,7 +822,7 @@ extern "C" int cask_b200_cg_device(cask_b200_ctx* ctx, const double* d_rhs, doub
     std::string path = std::string(trace_path) + "." + std::to_string((long long)pl.row0_global);
     if (FILE* fp = fopen(path.c_str(), "w")) {
       fprintf(fp, "iteration,kernel,entry_ns,start_ns,end_ns\n");
-      static const char* names[3] = {"spmv_dot", "update_xr", "update_p"};
+      static const char* names[3] = {"spmv_dot", "update_xr", "update_p"};  // fused path: update_xr = the fused kernel
       for (int i = 0; i < kTraceIters; i++)
         for (int k = 0; k < 3; k++) {
           const unsigned long long* q = h_trace.data() + (size_t)i * 9 + k * 3;
