@@ -477,15 +477,13 @@ def bench_bicgstab(ctx, cb, torch, dist, dev, rank, world, barrier):
     kind = cb.SYNTH_CONVDIFF3D7
     n = cb.synth_rows(kind, N)
     r0, nr = cb.shard_rows(n, world, rank)
-    if emulate > 1 and world == 1:
-        r0, nr = cb.shard_rows(n, emulate, emulate // 2)
     nnz = cb.synth_nnz(kind, N, r0, nr)
     rp = torch.empty(nr + 1, dtype=torch.int32, device=dev)
     ci = torch.empty(nnz, dtype=torch.int32, device=dev)
     va = torch.empty(nnz, dtype=torch.float64, device=dev)
     cb.synth_device(kind, N, r0, nr, rp.data_ptr(), ci.data_ptr(), va.data_ptr(), torch.cuda.current_stream().cuda_stream)
     dsg = cb.design(num_pipes=1, cache_size=8192, input_width=16)
-    if world > 1 or emulate > 1:
+    if world > 1:
         ctx.preprocess_shard_device(dsg, n, n, r0, nr, nnz, rp.data_ptr(), ci.data_ptr(), va.data_ptr())
     else:
         ctx.preprocess_device(dsg, n, n, nnz, rp.data_ptr(), ci.data_ptr(), va.data_ptr())

@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = (
     "cask_b200_partition_export", "cask_b200_spmv", "cask_b200_spmv_device", "cask_b200_spmv_refformat",
     "cask_b200_cg", "cask_b200_cg_device", "cask_b200_bicgstab", "cask_b200_bicgstab_device",
     "cask_b200_nccl_unique_id", "cask_b200_dist_init", "cask_b200_shard_rows",
-    "cask_b200_preprocess_shard_device", "cask_b200_dist_halo_counts", "cask_b200_dist_peer_active", "cask_b200_synth_rows",
+    "cask_b200_preprocess_shard_device", "cask_b200_dist_halo_counts", "cask_b200_dist_peer_active", "cask_b200_halo_plan_host", "cask_b200_synth_rows",
     "cask_b200_synth_nnz", "cask_b200_synth_device", "cask_b200_launch_count", "cask_b200_legacy_write",
     "cask_b200_legacy_read", "cask_b200_legacy_run", "cask_b200_legacy_reset", "cask_b200_legacy_launch_count",
 )
@@ -102,6 +102,7 @@ def lib():
         L.cask_b200_shard_rows.argtypes = [i64, i32, i32, vp, vp]
         L.cask_b200_dist_halo_counts.argtypes = [vp, vp]
         L.cask_b200_dist_peer_active.argtypes = [vp, vp]
+        L.cask_b200_halo_plan_host.argtypes = [i64, i32, i32, i64, vp, vp, i64, vp, vp, vp, vp]
         L.cask_b200_synth_rows.argtypes = [i32, i32, vp]
         L.cask_b200_synth_nnz.argtypes = [i32, i32, i64, i64, vp]
         L.cask_b200_synth_device.argtypes = [i32, i32, i64, i64, vp, vp, vp, vp]
@@ -133,6 +134,18 @@ def shard_rows(n, world, rank):
     r0, nr = C.c_int64(), C.c_int64()
     check(lib().cask_b200_shard_rows(n, world, rank, C.byref(r0), C.byref(nr)))
     return r0.value, nr.value
+
+
+def halo_plan_host(n_global, world, rank, run_col0, run_len):
+    """[(peer, col0, len)] this rank must receive, from the x windows it stages (host arithmetic only)."""
+    c0 = np.ascontiguousarray(run_col0, np.int64)
+    ln = np.ascontiguousarray(run_len, np.int64)
+    cap = 2 * len(c0) * max(world, 1) + 8
+    peer, col0, length = np.zeros(cap, np.int32), np.zeros(cap, np.int64), np.zeros(cap, np.int64)
+    cnt = C.c_int64()
+    check(lib().cask_b200_halo_plan_host(n_global, world, rank, len(c0), _p(c0), _p(ln), cap, _p(peer), _p(col0), _p(length),
+                                         C.byref(cnt)))
+    return [(int(peer[i]), int(col0[i]), int(length[i])) for i in range(cnt.value)]
 
 
 def synth_rows(kind, N):

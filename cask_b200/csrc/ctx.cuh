@@ -138,6 +138,9 @@ struct PeerCtrl {
   unsigned long long ar_flag[4][kMaxPeers];
   double ar_val[4][kMaxPeers][2];
   unsigned long long halo_flag[kHaloChannels][kMaxPeers];  // [channel][source rank] = epoch whose halo has landed
+  // low-latency slots of the in-kernel all-reduce: [slot][source rank][quantity][half] = {32 data bits, 32-bit
+  // sequence number} in ONE 8-byte store - data and flag arrive together, no fence, one NVLink traversal
+  unsigned long long ar_ll[4][kMaxPeers][2][2];
   // local
   unsigned long long ar_seq;                    // all-reduces performed
   unsigned long long push_seq[kHaloChannels];   // halo epochs pushed per channel (== the epoch the next SpMV expects)

@@ -133,6 +133,42 @@ static void stripe_of(int64_t n, int world, int r, int64_t* row0, int64_t* nrows
   *nrows = r == world - 1 ? n - rpp * (world - 1) : rpp;  // Spmv.cpp:362-364: remainder to the last
 }
 
+// Pure host arithmetic (no CUDA, no NCCL; exported as cask_b200_halo_plan_host and exercised by the world-size-2
+// gloo tests on CPU): the x windows (runs) this rank stages, clipped to the columns it does NOT own, merged, and
+// split by owner according to the reference's row striping.  Returns the number of (peer, range) pairs.
+static int64_t halo_ranges_from_runs(int64_t n_global, int world, int me, const int64_t* run_col0, const int64_t* run_len,
+                                     int64_t nruns, std::vector<std::vector<Range>>* recv_from) {
+  int64_t own_lo, own_n;
+  stripe_of(n_global, world, me, &own_lo, &own_n);
+  const int64_t own_hi = own_lo + own_n;
+  std::vector<Range> remote;
+  for (int64_t i = 0; i < nruns; i++) {
+    const int64_t lo = run_col0[i], hi = run_col0[i] + run_len[i];
+    if (lo < own_lo) remote.push_back({lo, std::min(hi, own_lo) - lo});
+    if (hi > own_hi) { const int64_t b = std::max(lo, own_hi); remote.push_back({b, hi - b}); }
+  }
+  std::sort(remote.begin(), remote.end(), [](const Range& a, const Range& b) { return a.col0 < b.col0; });
+  std::vector<Range> merged;
+  for (auto& r : remote) {
+    if (r.len <= 0) continue;
+    if (!merged.empty() && r.col0 <= merged.back().col0 + merged.back().len) {
+      merged.back().len = std::max(merged.back().len, r.col0 + r.len - merged.back().col0);
+    } else merged.push_back(r);
+  }
+  recv_from->assign(world, {});
+  int64_t nranges = 0;
+  for (auto& r : merged) {
+    int64_t lo = r.col0, hi = r.col0 + r.len;
+    for (int q = 0; q < world && lo < hi; q++) {
+      int64_t q0, qn;
+      stripe_of(n_global, world, q, &q0, &qn);
+      const int64_t a = std::max(lo, q0), b = std::min(hi, q0 + qn);
+      if (a < b && q != me) { (*recv_from)[q].push_back({a, b - a}); nranges++; }
+    }
+  }
+  return nranges;
+}
+
 // Derives, from the plan's staged runs, which x ranges come from which peer; exchanges the requests so
 // every rank also knows what to send; splits the slice lists into interior / halo-dependent.
 int dist_plan_halo(cask_b200_ctx* ctx) {
@@ -153,37 +189,18 @@ int dist_plan_halo(cask_b200_ctx* ctx) {
   if (total_runs) CB_CUDA(cudaMemcpyAsync(runs.data(), p.d_runs, sizeof(Run) * total_runs, cudaMemcpyDeviceToHost, s));
   CB_CUDA(cudaStreamSynchronize(s));
 
-  std::vector<Range> remote;
   for (auto& sd : p.h_slices) {
     sd.remote = 0;
     if (sd.kind != kSliceStagedEll) { sd.remote = 1; continue; }
     for (int i = 0; i < sd.nruns; i++) {
       const Run& r = runs[sd.run_off + i];
-      const int64_t lo = r.col0, hi = (int64_t)r.col0 + r.len;
-      if (lo < own_lo) { remote.push_back({lo, std::min(hi, own_lo) - lo}); sd.remote = 1; }
-      if (hi > own_hi) { const int64_t b = std::max(lo, own_hi); remote.push_back({b, hi - b}); sd.remote = 1; }
+      if (r.col0 < own_lo || (int64_t)r.col0 + r.len > own_hi) sd.remote = 1;
     }
   }
-  // merge
-  std::sort(remote.begin(), remote.end(), [](const Range& a, const Range& b) { return a.col0 < b.col0; });
-  std::vector<Range> merged;
-  for (auto& r : remote) {
-    if (r.len <= 0) continue;
-    if (!merged.empty() && r.col0 <= merged.back().col0 + merged.back().len) {
-      merged.back().len = std::max(merged.back().len, r.col0 + r.len - merged.back().col0);
-    } else merged.push_back(r);
-  }
-  // split by owner
-  int64_t nranges = 0;
-  for (auto& r : merged) {
-    int64_t lo = r.col0, hi = r.col0 + r.len;
-    for (int q = 0; q < W && lo < hi; q++) {
-      int64_t q0, qn;
-      stripe_of(p.n_global, W, q, &q0, &qn);
-      const int64_t a = std::max(lo, q0), b = std::min(hi, q0 + qn);
-      if (a < b && q != me) { d->recv_from[q].push_back({a, b - a}); nranges++; }
-    }
-  }
+  std::vector<int64_t> run_col0(runs.size()), run_len(runs.size());
+  for (size_t i = 0; i < runs.size(); i++) { run_col0[i] = runs[i].col0; run_len[i] = runs[i].len; }
+  const int64_t nranges = halo_ranges_from_runs(p.n_global, W, me, run_col0.data(), run_len.data(), (int64_t)runs.size(),
+                                                &d->recv_from);
   bool want_allgather = p.n_csr > 0 || nranges > 512;
   // agree on the mode and exchange the request lists through NCCL itself
   int64_t* d_buf = nullptr;
@@ -588,6 +605,26 @@ extern "C" int cask_b200_shard_rows(int64_t n, int32_t world, int32_t rank, int6
   if (world < 1 || rank < 0 || rank >= world || n < 0 || !row0 || !nrows)
     return fail(CASK_B200_ERR_INVALID_ARGUMENT, "shard_rows: bad arguments");
   stripe_of(n, world, rank, row0, nrows);
+  return CASK_B200_OK;
+}
+
+extern "C" int cask_b200_halo_plan_host(int64_t n_global, int32_t world, int32_t rank, int64_t nruns, const int64_t* run_col0,
+                                        const int64_t* run_len, int64_t capacity, int32_t* out_peer, int64_t* out_col0,
+                                        int64_t* out_len, int64_t* out_count) {
+  if (world < 1 || rank < 0 || rank >= world || n_global < 0 || nruns < 0 || (nruns && (!run_col0 || !run_len)) || !out_count)
+    return fail(CASK_B200_ERR_INVALID_ARGUMENT, "halo_plan_host: bad arguments");
+  std::vector<std::vector<Range>> recv;
+  const int64_t total = halo_ranges_from_runs(n_global, world, rank, run_col0, run_len, nruns, &recv);
+  *out_count = total;
+  if (total > capacity) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "halo_plan_host: output capacity too small");
+  int64_t k = 0;
+  for (int q = 0; q < world; q++)
+    for (auto& r : recv[q]) {
+      if (out_peer) out_peer[k] = q;
+      if (out_col0) out_col0[k] = r.col0;
+      if (out_len) out_len[k] = r.len;
+      k++;
+    }
   return CASK_B200_OK;
 }
 

@@ -25,6 +25,15 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 constexpr unsigned long long kPeerTimeoutNs = 8000000000ull;  // a peer that stays silent for 8 s is gone: report, never hang
 
 // Spins until *flag >= want.  Returns false (and raises *err) on timeout so that a lost peer surfaces as an error
@@ -43,6 +52,30 @@ __device__ __forceinline__ bool peer_wait_ge(const unsigned long long* flag, uns
   }
 }
 
+// Low-latency exchange of a double (the "LL" idea of NCCL): each half of the value travels with the 32-bit sequence
+// number in a single 8-byte store, which is atomic, so the receiver needs no separate flag and the sender no fence.
+__device__ __forceinline__ void ll_send(unsigned long long* slot2, double v, unsigned int seq32) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+  st_volatile_u64(slot2, ((unsigned long long)seq32 << 32) | (bits & 0xffffffffull));
+  st_volatile_u64(slot2 + 1, ((unsigned long long)seq32 << 32) | (bits >> 32));
+}
+__device__ __forceinline__ double ll_recv(const unsigned long long* slot2, unsigned int seq32, int* err) {
+  unsigned long long a = ld_volatile_u64(slot2), b = ld_volatile_u64(slot2 + 1);
+  if ((unsigned int)(a >> 32) != seq32 || (unsigned int)(b >> 32) != seq32) {
+    const unsigned long long t0 = globaltimer_ns();
+    for (;;) {
+      a = ld_volatile_u64(slot2);
+      b = ld_volatile_u64(slot2 + 1);
+      if ((unsigned int)(a >> 32) == seq32 && (unsigned int)(b >> 32) == seq32) break;
+      if (globaltimer_ns() - t0 > kPeerTimeoutNs) {
+        if (err) *err = 1;
+        break;
+      }
+    }
+  }
+  return __longlong_as_double((long long)((b << 32) | (a & 0xffffffffull)));
+}
+
 // Programmatic dependent launch: kernels of the solver loops are launched with the stream-serialization attribute,
 // trigger their dependents at once and wait for their predecessor before touching memory - the launch latency of
 // kernel i+1 hides behind the tail of kernel i.  Both instructions are no-ops in a plain launch.
@@ -59,9 +92,9 @@ __device__ __forceinline__ void pdl_enter() {
 // Finishes a grid-wide dot product inside the producing kernel.  Called by ALL threads of EVERY CTA; t0 / t1 are
 // the CTA's partial sums (valid in thread 0).  The last CTA to arrive adds the partials in a fixed order
 // (deterministic) and, when row-sharded on the peer path, performs the one-shot all-reduce: it stores the local
-// sums into slot [seq & 3][me] of every rank's control block, publishes seq with a release store, acquires the W
-// flags of its own block and adds the W contributions in rank order - the same order on every rank, so all ranks
-// hold bit-identical scalars and take identical convergence decisions.
+// sums into slot [seq & 3][me] of every rank's control block (low-latency 8-byte {data, sequence} stores), polls
+// the W slots of its own block and adds the W contributions in rank order - the same order on every rank, so all
+// ranks hold bit-identical scalars and take identical convergence decisions.
 __device__ __forceinline__ void grid_finish_reduce(const ReduceDesc& rd, double t0, double t1, int cta, int ncta,
                                                    unsigned int gen0 = 0u) {
   __shared__ int s_last;
@@ -118,23 +151,14 @@ __device__ __forceinline__ void grid_finish_reduce(const ReduceDesc& rd, double 
   }
   const unsigned long long seq = s_seq;
   const int slot = (int)(seq & 3ull);
-  if (rd.publish_only) {
-    if (tid < rd.world) {
-      PeerCtrl* pc = rd.peers[tid];
-      for (int q = 0; q < rd.nq; q++) pc->ar_val[slot][rd.me][q] = s_tot[q];
-      __threadfence_system();
-      st_release_sys_u64(&pc->ar_flag[slot][rd.me], seq);
-    }
-    return;
-  }
+  const unsigned int seq32 = (unsigned int)seq;
   if (tid < rd.world) {
     PeerCtrl* pc = rd.peers[tid];
-    for (int q = 0; q < rd.nq; q++) pc->ar_val[slot][rd.me][q] = s_tot[q];
-    __threadfence_system();
-    st_release_sys_u64(&pc->ar_flag[slot][rd.me], seq);
-    peer_wait_ge(&rd.ctrl->ar_flag[slot][tid], seq, &rd.ctrl->error);
-    for (int q = 0; q < rd.nq; q++) s_contrib[tid][q] = *reinterpret_cast<volatile double*>(&rd.ctrl->ar_val[slot][tid][q]);
+    for (int q = 0; q < rd.nq; q++) ll_send(&pc->ar_ll[slot][rd.me][q][0], s_tot[q], seq32);
   }
+  if (rd.publish_only) return;
+  if (tid < rd.world)
+    for (int q = 0; q < rd.nq; q++) s_contrib[tid][q] = ll_recv(&rd.ctrl->ar_ll[slot][tid][q][0], seq32, &rd.ctrl->error);
   __syncthreads();
   if (tid < rd.nq) {
     double t = 0.0;
@@ -162,10 +186,8 @@ __device__ __forceinline__ void trace_max(unsigned long long* slot) {
 __device__ __forceinline__ double peer_gather_sum(const GatherDesc& g, double* s_c) {
   const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(&g.ctrl->ar_seq);
   const int slot = (int)(seq & 3ull);
-  if ((int)threadIdx.x < g.world) {
-    peer_wait_ge(&g.ctrl->ar_flag[slot][threadIdx.x], seq, &g.ctrl->error);
-    s_c[threadIdx.x] = *reinterpret_cast<volatile double*>(&g.ctrl->ar_val[slot][threadIdx.x][0]);
-  }
+  if ((int)threadIdx.x < g.world)
+    s_c[threadIdx.x] = ll_recv(&g.ctrl->ar_ll[slot][threadIdx.x][0][0], (unsigned int)seq, &g.ctrl->error);
   __syncthreads();
   double t = 0.0;
   for (int r = 0; r < g.world; r++) t += s_c[r];

@@ -153,6 +153,13 @@ int cask_b200_nccl_unique_id(void* out_128_bytes);
 int cask_b200_dist_init(cask_b200_ctx* ctx, int32_t rank, int32_t world, const void* unique_id_128_bytes);
 /* Host-side shard arithmetic (no GPU needed): rows [row0, row0+nrows) owned by `rank`. */
 int cask_b200_shard_rows(int64_t n, int32_t world, int32_t rank, int64_t* row0, int64_t* nrows);
+/* Host-side halo plan (no GPU needed; the same routine the GPU path runs after it has built a stripe's x windows):
+ * given the contiguous x windows [run_col0[i], run_col0[i] + run_len[i]) that `rank` stages, returns the column
+ * ranges it must receive per peer, ranges merged and split by owner under the striping above.  *out_count
+ * receives the number of (peer, col0, len) triples; the call fails if it exceeds `capacity`. */
+int cask_b200_halo_plan_host(int64_t n_global, int32_t world, int32_t rank, int64_t nruns, const int64_t* run_col0,
+                             const int64_t* run_len, int64_t capacity, int32_t* out_peer, int64_t* out_col0,
+                             int64_t* out_len, int64_t* out_count);
 /* Local stripe of the global n x m matrix: d_row_ptr has nrows+1 entries rebased to 0 (exactly
  * CsrMatrix::sliceRows, SparseMatrix.hpp:426-443), column indices stay global. */
 int cask_b200_preprocess_shard_device(cask_b200_ctx* ctx, const cask_b200_design* design,
