@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--no-extra", action="store_true", help="skip the C3 (R-MAT SpMV) and C5 (BiCGStab) side measurements")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cache", type=int, default=8192)
+    ap.add_argument("--only-rmat", action="store_true", help="profiling: run only the C3 R-MAT SpMV side measurement")
     ap.add_argument("--cg-maxiters", type=int, default=2000, help="cap on CG iterations (profiling runs)")
     ap.add_argument("--cg-emulate-shard", type=int, default=0,
                     help="profiling: on ONE GPU, run CG on the stripe that rank W/2 of a W-way sharded C4 system owns "
@@ -115,7 +116,7 @@ def ncu_traffic():
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(p):
         with open(p) as f:
-            return json.load(f).get("spmv_ell_staged_kernel_bytes_per_launch")
+            return json.load(f).get("spmv_ell_persistent_kernel_bytes_per_launch")
     return None
 
 
@@ -370,8 +371,9 @@ def main():
         cg = bench_cg(ctx, cb, torch, dist, dev, rank, world, barrier, args.cg_maxiters, args.cg_emulate_shard)
         torch.cuda.empty_cache()
     if not args.no_extra:
-        bicg = bench_bicgstab(ctx, cb, torch, dist, dev, rank, world, barrier)
-        torch.cuda.empty_cache()
+        if not args.only_rmat:
+            bicg = bench_bicgstab(ctx, cb, torch, dist, dev, rank, world, barrier)
+            torch.cuda.empty_cache()
         rmat = bench_rmat(ctx, cb, torch, dist, dev, rank, world, barrier)
         torch.cuda.empty_cache()
 
@@ -389,7 +391,7 @@ def main():
                        "preprocess_s": preprocess_s, "plan": stats},
             "hbm_gbs": achieved, "frac_of_nominal_8tbs": achieved / 8000.0,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "spmv_ell_staged_kernel",
+                         "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "spmv_ell_persistent_kernel<2,false>",
                          "algorithmic_bytes_per_launch": bytes_per_launch},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
@@ -449,15 +451,16 @@ def bench_cg(ctx, cb, torch, dist, dev, rank, world, barrier, maxiters=2000, emu
     launches = ctx.launch_count() - l0
     err = float((x - xt[r0:r0 + nr]).abs().max().item())
     # marginal cost of an iteration (solve set-up and the final synchronisation excluded): two capped solves
-    tm = []
-    for cap in (50, 250):
-        x.zero_()
-        barrier()
-        t1 = time.perf_counter()
-        ctx.cg_device(b.data_ptr(), x.data_ptr(), maxiters=cap, tol=1e-5)
-        barrier()
-        tm.append(time.perf_counter() - t1)
-    marginal_us = (tm[1] - tm[0]) / 200.0 * 1e6
+    tm, caps, marginal_us = [], (50, 250), None
+    if maxiters >= caps[1] and trips >= caps[1]:
+        for cap in caps:
+            x.zero_()
+            barrier()
+            t1 = time.perf_counter()
+            ctx.cg_device(b.data_ptr(), x.data_ptr(), maxiters=cap, tol=1e-5)
+            barrier()
+            tm.append(time.perf_counter() - t1)
+        marginal_us = (tm[1] - tm[0]) / float(caps[1] - caps[0]) * 1e6
     et = torch.tensor([err], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(et, op=dist.ReduceOp.MAX)

@@ -100,6 +100,9 @@ int cask_b200_create(cask_b200_ctx** out, int device) {
   if (const char* e = getenv("CASK_B200_PERSIST_KU")) ctx->persist_ku = atoi(e);
   if (const char* e = getenv("CASK_B200_HOST_CHUNKS")) ctx->host_pipeline_chunks = atoi(e);
   if (const char* e = getenv("CASK_B200_PEER")) ctx->peer_mode = atoi(e);
+  if (const char* e = getenv("CASK_B200_L2_KEEP")) ctx->l2_keep = atoi(e);
+  if (const char* e = getenv("CASK_B200_CSR_STREAM")) ctx->csr_stream = atoi(e);
+  if (const char* e = getenv("CASK_B200_CSR_ITEM_NNZ")) ctx->csr_item_nnz = atoi(e);
   *out = ctx;
   return CASK_B200_OK;
 }
@@ -155,6 +158,9 @@ int cask_b200_set_option(cask_b200_ctx* ctx, const char* name, double value) {
   else if (k == "host_pipeline_chunks") ctx->host_pipeline_chunks = (int32_t)value;
   else if (k == "persist_ku") ctx->persist_ku = (int32_t)value;
   else if (k == "peer_mode") ctx->peer_mode = (int32_t)value;
+  else if (k == "l2_keep") ctx->l2_keep = (int32_t)value;
+  else if (k == "csr_stream") ctx->csr_stream = (int32_t)value;
+  else if (k == "csr_item_nnz") ctx->csr_item_nnz = (int32_t)value;
   else return fail(CASK_B200_ERR_INVALID_ARGUMENT, "set_option: unknown option " + k);
   return CASK_B200_OK;
 }

@@ -107,6 +107,8 @@ struct Plan {
   int32_t n_ell = 0, n_ell_interior = 0;
   int32_t n_csr = 0, n_csr_interior = 0;
   int32_t csr_vec = 4;
+  bool csr_stream = false;        // gather-CSR items run the CSR-stream variant (products staged in shared memory)
+  int32_t csr_item_nnz = kCsrItemNnz;
   CsrItem* d_csr_items = nullptr;
   SplitRow* d_split_rows = nullptr;
   double* d_csr_scratch = nullptr;
@@ -234,6 +236,10 @@ struct cask_b200_ctx {
   int32_t force_csr_vec = 0;
   int32_t ell_kernel = 1;    // 1 persistent warp-specialised kernel, 0 one CTA per slice
   int32_t persist_ku = 0;    // 0 auto, else 2 or 4
+  int64_t l2_persist_bytes = -1;  // persisting L2 set-aside claimed for evict-last vector accesses (-1: not asked yet)
+  int32_t csr_stream = 0;    // 1: CSR-stream variant of the gather-CSR kernel (products staged in shared memory)
+  int32_t csr_item_nnz = 4096;  // nonzeros per work item of the CSR-stream variant (its shared-memory footprint)
+  int32_t l2_keep = -1;      // -1 auto (vectors of a solver iteration fit L2), 0 never, 1 always: evict-last on vector accesses
   int32_t peer_mode = 1;     // 1: halo pushes and scalar all-reduces by own kernels over mapped peer memory; 0: NCCL
 
   // host-call staging buffers
@@ -271,6 +277,7 @@ struct SpmvFusion {           // optional fused epilogue: partial dot products p
   ReduceDesc reduce;                   // persistent kernel only: the last CTA sums the partials (and all-reduces them)
   unsigned long long* trace = nullptr; // persistent kernel only: 3 timeline slots (peer.cuh: trace_min / trace_max)
   bool pdl = false;                    // launch with programmatic stream serialization (solver loops)
+  int keep_vectors = 0;                // persistent kernel only: x windows, y and dot_with with an L2 evict-last policy
 };
 // true if one persistent staged-ELL launch covers the whole SpMV (in-kernel reduction / peer halo wait possible)
 bool spmv_single_launch(const cask_b200_ctx* ctx);

@@ -34,6 +34,25 @@ __device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned 
   asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// L2 residency control.  When the vectors a solver touches per iteration fit the 126 MB L2 (row-sharded runs: the
+// per-rank slices of x, r, p, Ap), they are loaded and stored with an evict-last policy while the matrix streams
+// through with evict-first: the vector kernels and the SpMV's x windows then run out of L2 instead of HBM.
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ double ld_keep(const double* p, unsigned long long pol, bool keep) {
+  double v;
+  if (keep) asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol) : "memory");
+  else v = *p;
+  return v;
+}
+__device__ __forceinline__ void st_keep(double* p, double v, unsigned long long pol, bool keep) {
+  if (keep) asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+  else *p = v;
+}
+
 constexpr unsigned long long kPeerTimeoutNs = 8000000000ull;  // a peer that stays silent for 8 s is gone: report, never hang
 
 // Spins until *flag >= want.  Returns false (and raises *err) on timeout so that a lost peer surfaces as an error

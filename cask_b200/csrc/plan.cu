@@ -275,6 +275,9 @@ int build_csr_items(cask_b200_ctx* ctx) {
     while (v < 32 && v * 2 <= mean) v <<= 1;
     return v;
   };
+  p.csr_stream = ctx->csr_stream != 0;
+  p.csr_item_nnz = p.csr_stream ? std::max(1024, std::min(ctx->csr_item_nnz, 16384)) : kCsrItemNnz;
+  const int32_t item_target = p.csr_item_nnz;
   for (int32_t pos = 0; pos < p.n_csr; pos++) {
     const SliceDesc& sd = p.h_slices[p.h_list_csr[pos]];
     int32_t start = sd.row0;
@@ -299,7 +302,7 @@ int build_csr_items(cask_b200_ctx* ctx) {
                                     n_scratch++, 0, {0, 0}});
         }
         start = r + 1;
-      } else if (rp[r + 1] - rp[start] >= kCsrItemNnz) {
+      } else if (rp[r + 1] - rp[start] >= item_target) {
         flush(r + 1);
       }
     }

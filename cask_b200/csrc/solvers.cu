@@ -234,12 +234,14 @@ cg_update_p_kernel(int64_t n, int it, double* __restrict__ scal, int32_t* __rest
 __global__ void __launch_bounds__(kVecThreads, kVecCtasPerSm)
 cg_update_fused_kernel(int64_t n, int it, double* __restrict__ scal, int32_t* __restrict__ flags, double* p,
                        const double* __restrict__ Ap, double* __restrict__ x, double* r, const ReduceDesc rd,
-                       const PushDesc pd, const HaloUpdate hu, const GatherDesc pap, unsigned long long* trace) {
+                       const PushDesc pd, const HaloUpdate hu, const GatherDesc pap, int keep_i, unsigned long long* trace) {
   trace_min(trace);
   pdl_enter();
   trace_min(trace ? trace + 1 : nullptr);
   if (flags[F_DONE]) return;
   __shared__ double red[kVecThreads / 32];
+  const bool keep = keep_i != 0;  // the vectors fit L2: evict-last on every access (peer.cuh: L2 residency control)
+  const unsigned long long pol = l2_policy_evict_last();
   const unsigned int gen0 = *reinterpret_cast<volatile unsigned int*>(rd.gen);
   const double rsold = scal[S_RS0 + (it & 1)];
   // row-sharded: the SpMV's last CTA only PUBLISHED this rank's p.Ap to the peers; the W contributions are gathered here
@@ -254,9 +256,9 @@ cg_update_fused_kernel(int64_t n, int it, double* __restrict__ scal, int32_t* __
       bool seen = false;  // a row staged by two peers lies in two ranges: updated (and pushed to both) only once
       for (int e = 0; e < sidx; e++) seen |= (k >= pd.lo[e]) & (k < pd.hi[e]);
       if (seen) continue;
-      x[k] += alpha * p[k];
-      const double v = r[k] - alpha * Ap[k];
-      r[k] = v;
+      st_keep(x + k, ld_keep(x + k, pol, keep) + alpha * ld_keep(p + k, pol, keep), pol, keep);
+      const double v = ld_keep(r + k, pol, keep) - alpha * ld_keep(Ap + k, pol, keep);
+      st_keep(r + k, v, pol, keep);
       push_store(pd, k, v);
       acc += v * v;
     }
@@ -269,15 +271,16 @@ cg_update_fused_kernel(int64_t n, int it, double* __restrict__ scal, int32_t* __
       CB_ITEMS {
         const int64_t k = CB_IDX(tile);
         const bool ok = k < hi_;
-        pv[i] = ok ? p[k] : 0.0; av[i] = ok ? Ap[k] : 0.0; xv[i] = ok ? x[k] : 0.0; rv[i] = ok ? r[k] : 0.0;
+        pv[i] = ok ? ld_keep(p + k, pol, keep) : 0.0; av[i] = ok ? ld_keep(Ap + k, pol, keep) : 0.0;
+        xv[i] = ok ? ld_keep(x + k, pol, keep) : 0.0; rv[i] = ok ? ld_keep(r + k, pol, keep) : 0.0;
       }
 #pragma unroll
       CB_ITEMS {
         const int64_t k = CB_IDX(tile);
         if (k < hi_ && !(halo && push_contains(pd, k))) {
-          x[k] = xv[i] + alpha * pv[i];
+          st_keep(x + k, xv[i] + alpha * pv[i], pol, keep);
           const double v = rv[i] - alpha * av[i];
-          r[k] = v;
+          st_keep(r + k, v, pol, keep);
           acc += v * v;
         }
       }
@@ -298,7 +301,7 @@ cg_update_fused_kernel(int64_t n, int it, double* __restrict__ scal, int32_t* __
       for (int64_t k = a + threadIdx.x; k < b; k += kVecThreads) {
         bool seen = false;
         for (int e = 0; e < sidx; e++) seen |= (k >= pd.lo[e]) & (k < pd.hi[e]);
-        if (!seen) p[k] = r[k] + beta * p[k];
+        if (!seen) st_keep(p + k, ld_keep(r + k, pol, keep) + beta * ld_keep(p + k, pol, keep), pol, keep);
       }
     }
     {
@@ -306,11 +309,14 @@ cg_update_fused_kernel(int64_t n, int it, double* __restrict__ scal, int32_t* __
         const bool halo = pd.nsend && push_overlaps(pd, tile, tile + kVecTile);
         double rv[kVecItems], pv[kVecItems];
 #pragma unroll
-        CB_ITEMS { const int64_t k = CB_IDX(tile); rv[i] = k < hi_ ? r[k] : 0.0; pv[i] = k < hi_ ? p[k] : 0.0; }
+        CB_ITEMS {
+          const int64_t k = CB_IDX(tile);
+          rv[i] = k < hi_ ? ld_keep(r + k, pol, keep) : 0.0; pv[i] = k < hi_ ? ld_keep(p + k, pol, keep) : 0.0;
+        }
 #pragma unroll
         CB_ITEMS {
           const int64_t k = CB_IDX(tile);
-          if (k < hi_ && !(halo && push_contains(pd, k))) p[k] = rv[i] + beta * pv[i];
+          if (k < hi_ && !(halo && push_contains(pd, k))) st_keep(p + k, rv[i] + beta * pv[i], pol, keep);
         }
       }
     }
@@ -664,7 +670,7 @@ int reduce_dots(cask_b200_ctx* ctx, int count, int stride, int nq, int slot0, co
 //    halo-dependent slices after the event, then a reduction kernel + ncclAllReduce.
 // flags != nullptr: the launches do nothing once the solver's DONE / RESTART flag is up.
 int spmv_full(cask_b200_ctx* ctx, double* d_full, double* d_y, const double* d_dot_with, int dot_slot, int channel,
-              const int32_t* flags, unsigned long long* trace = nullptr, bool publish_only = false) {
+              const int32_t* flags, unsigned long long* trace = nullptr, bool publish_only = false, int keep = 0) {
   cudaStream_t s = ctx->stream;
   SolverWork& w = ctx->work;
   const bool peer = channel >= 0 && peer_ready(ctx);
@@ -673,6 +679,7 @@ int spmv_full(cask_b200_ctx* ctx, double* d_full, double* d_y, const double* d_d
   f.d_partials = w.d_partials;
   f.pdl = true;
   f.trace = trace;
+  f.keep_vectors = keep;
   HaloWait hw;
   if (peer) hw = peer_halo_wait(ctx, channel);
   if (flags) { hw.skip0 = flags + F_DONE; hw.skip1 = flags + F_RESTART; }
@@ -731,6 +738,19 @@ extern "C" int cask_b200_cg_device(cask_b200_ctx* ctx, const double* d_rhs, doub
   // fused update kernel (single rank / peer path): r lives in the arena too (vector 1) - its boundary rows are what
   // travels every iteration, and each rank recomputes the halo rows of p from them
   const bool fused = !dist_active(ctx) || peer;
+  // x, r, p, Ap of this rank fit L2 (with room for the matrix stream): keep them there (peer.cuh: L2 residency control)
+  // evict-last lines live in the persisting set-aside of L2, which is 0 by default: claim the device maximum once
+  if (ctx->l2_persist_bytes < 0) {
+    int max_persist = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+    if (max_persist > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist) != cudaSuccess) {
+      cudaGetLastError();
+      max_persist = 0;
+    }
+    ctx->l2_persist_bytes = max_persist;
+  }
+  const int keep = ctx->l2_keep < 0 ? (4 * sizeof(double) * (size_t)n <= (size_t)ctx->l2_persist_bytes ? 1 : 0) : ctx->l2_keep;
+  if (getenv("CASK_B200_TRACE")) fprintf(stderr, "cask_b200: L2 persisting set-aside %lld bytes, keep=%d\n", (long long)ctx->l2_persist_bytes, keep);
   const PushDesc pd_r = peer_push_desc(ctx, 1);
   const HaloUpdate hu = peer_halo_update(ctx, 1);
   double* r = peer ? peer_vector(ctx, 1) + off : w.d_vec[0];
@@ -784,7 +804,7 @@ extern "C" int cask_b200_cg_device(cask_b200_ctx* ctx, const double* d_rhs, doub
       unsigned long long* tr = w.d_trace && it >= kTraceFirst && it < kTraceFirst + kTraceIters
                                    ? w.d_trace + (size_t)(it - kTraceFirst) * 9 : nullptr;
       const bool publish = fused && peer && spmv_single_launch(ctx);  // p.Ap gathered by the consumer kernel
-      CB_TRY(spmv_full(ctx, p_full, Ap, p, S_PAP, ch, flags, tr, publish));                             // :206
+      CB_TRY(spmv_full(ctx, p_full, Ap, p, S_PAP, ch, flags, tr, publish, keep));                       // :206
       const int rs_new = S_RS0 + ((it + 1) & 1);
       if (fused) {
         ReduceDesc rd = make_reduce(ctx, T_VEC, 0, 1, rs_new);
@@ -792,7 +812,7 @@ extern "C" int cask_b200_cg_device(cask_b200_ctx* ctx, const double* d_rhs, doub
         GatherDesc gd;
         if (publish) { gd.ctrl = rd.ctrl; gd.world = rd.world; }
         CB_CUDA(launch_pdl(cg_update_fused_kernel, vg, kVecThreads, s, n, it, scal, flags, p, Ap, d_x, r, rd, pd_r, hu, gd,   // :208-231
-                           tr ? tr + 3 : nullptr));
+                           keep, tr ? tr + 3 : nullptr));
         ctx->launches += 1;
       } else {  // NCCL between the two halves
         CB_CUDA(launch_pdl(cg_update_xr_kernel, vg, kVecThreads, s, n, it, scal, flags, p, Ap, d_x, r,   // :208-218

@@ -218,8 +218,10 @@ spmv_ell_persistent_kernel(const SliceDesc* __restrict__ slices, const int32_t* 
                            const Run* __restrict__ runs, const double* __restrict__ ell_vals,
                            const uint16_t* __restrict__ ell_idx, const double* __restrict__ x, double* __restrict__ y,
                            const double* __restrict__ dot_with, double* __restrict__ partials, int xbuf_doubles,
-                           int stages, const HaloWait hw, const ReduceDesc rd, unsigned long long* trace) {
+                           int stages, const HaloWait hw, const ReduceDesc rd, int keep_i, unsigned long long* trace) {
   trace_min(trace);
+  const bool keep = keep_i != 0;  // vectors fit L2: x windows, y and dot_with are accessed with evict-last
+  const unsigned long long keep_policy = l2_policy_evict_last();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   PersistHeader* hdr = reinterpret_cast<PersistHeader*>(smem_raw);
   double* xbuf = reinterpret_cast<double*>(smem_raw + kPersistHeaderBytes);
@@ -300,7 +302,10 @@ spmv_ell_persistent_kernel(const SliceDesc* __restrict__ slices, const int32_t* 
         const Run r = rr[i];
         const uint32_t b = (uint32_t)(r.len & ~1) * 8u;
         bytes += b;
-        if (b) bulk_g2s(smem_u32(xs + r.local_base), x + r.col0, b, fx);
+        if (b) {
+          if (keep) bulk_g2s_hint(smem_u32(xs + r.local_base), x + r.col0, b, fx, keep_policy);
+          else bulk_g2s(smem_u32(xs + r.local_base), x + r.col0, b, fx);
+        }
         if (r.len & 1) xs[r.local_base + r.len - 1] = x[r.col0 + r.len - 1];  // odd tail at column m-1
       }
 #pragma unroll
@@ -359,8 +364,8 @@ spmv_ell_persistent_kernel(const SliceDesc* __restrict__ slices, const int32_t* 
       for (int j = 0; j < RPT; j++) {
         const int row = j * kConsumerThreads + tid;
         if (row < nrows) {
-          y[row0 + row] = acc[j];
-          if (kDot) dot += acc[j] * dot_with[row0 + row];
+          st_keep(y + row0 + row, acc[j], keep_policy, keep);
+          if (kDot) dot += acc[j] * ld_keep(dot_with + row0 + row, keep_policy, keep);
         }
       }
     }
@@ -377,13 +382,18 @@ spmv_ell_persistent_kernel(const SliceDesc* __restrict__ slices, const int32_t* 
 // One CTA per CsrItem.  Multi-row items: `vec` lanes per row (chosen per item from its mean row length),
 // warp-shuffle reduction.  Single-row items (long rows and segments of split rows): the whole CTA strides
 // over the row with four independent accumulators per thread, then a CTA reduction.
-template <bool kDot>
+// kStream ("CSR-stream"): the multi-row branch first turns the item's contiguous nonzero range into products -
+// values and column indices read with perfectly coalesced streaming loads, eight independent x gathers in flight per
+// thread whatever the row structure - parks them in shared memory, and only then reduces row by row out of shared
+// memory.  The gather, which bounds power-law matrices, no longer waits on the row-length distribution.
+template <bool kDot, bool kStream>
 __global__ void __launch_bounds__(256)
 spmv_csr_items_kernel(const CsrItem* __restrict__ items, const int32_t* __restrict__ row_ptr,
                       const int32_t* __restrict__ col, const double* __restrict__ val, const double* __restrict__ x,
                       double* __restrict__ y, const double* __restrict__ dot_with, double* __restrict__ partials,
                       double* __restrict__ scratch) {
   __shared__ double red[8];
+  extern __shared__ __align__(16) double prod[];  // kStream: products of the item's nonzeros
   const CsrItem it = items[blockIdx.x];
   double dot = 0.0;
   if (it.vec == 0) {
@@ -410,17 +420,62 @@ spmv_csr_items_kernel(const CsrItem* __restrict__ items, const int32_t* __restri
   const int vec = it.vec;
   const int lane = threadIdx.x & (vec - 1), sub = threadIdx.x / vec;
   const int rows_per_pass = 256 / vec;
-  for (int rb = 0; rb < it.nrows; rb += rows_per_pass) {
-    const int r = rb + sub;
-    double acc = 0.0;
-    if (r < it.nrows) {
-      const int32_t kb = row_ptr[it.row0 + r], ke = row_ptr[it.row0 + r + 1];
-      for (int32_t k = kb + lane; k < ke; k += vec) acc += __ldcs(val + k) * __ldg(x + __ldcs(col + k));
+  if (kStream) {
+    const int32_t k_lo = it.k_lo, cnt = it.k_hi - it.k_lo;
+    int32_t* rps = reinterpret_cast<int32_t*>(prod + cnt + (cnt & 1));  // the item's row pointers, rebased
+    for (int r = threadIdx.x; r <= it.nrows; r += 256) rps[r] = row_ptr[it.row0 + r] - k_lo;
+    for (int32_t j0 = 0; j0 < cnt; j0 += 256 * 8) {
+      int32_t c[8];
+      double v[8], xv[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int32_t j = j0 + u * 256 + (int32_t)threadIdx.x;
+        c[u] = j < cnt ? __ldcs(col + k_lo + j) : 0;
+        v[u] = j < cnt ? __ldcs(val + k_lo + j) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) xv[u] = __ldg(x + c[u]);
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int32_t j = j0 + u * 256 + (int32_t)threadIdx.x;
+        if (j < cnt) prod[j] = v[u] * xv[u];
+      }
     }
-    for (int d = vec >> 1; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-    if (lane == 0 && r < it.nrows) {
-      y[it.row0 + r] = acc;
-      if (kDot) dot += acc * dot_with[it.row0 + r];
+    __syncthreads();
+    if (vec <= 8) {
+      // short rows (and the many empty ones of a power-law matrix): a thread per row, no global loads left
+      for (int r = threadIdx.x; r < it.nrows; r += 256) {
+        double acc = 0.0;
+        for (int32_t k = rps[r]; k < rps[r + 1]; k++) acc += prod[k];
+        y[it.row0 + r] = acc;
+        if (kDot) dot += acc * dot_with[it.row0 + r];
+      }
+    } else {
+      for (int rb = 0; rb < it.nrows; rb += rows_per_pass) {
+        const int r = rb + sub;
+        double acc = 0.0;
+        if (r < it.nrows)
+          for (int32_t k = rps[r] + lane; k < rps[r + 1]; k += vec) acc += prod[k];
+        for (int d = vec >> 1; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+        if (lane == 0 && r < it.nrows) {
+          y[it.row0 + r] = acc;
+          if (kDot) dot += acc * dot_with[it.row0 + r];
+        }
+      }
+    }
+  } else {
+    for (int rb = 0; rb < it.nrows; rb += rows_per_pass) {
+      const int r = rb + sub;
+      double acc = 0.0;
+      if (r < it.nrows) {
+        const int32_t kb = row_ptr[it.row0 + r], ke = row_ptr[it.row0 + r + 1];
+        for (int32_t k = kb + lane; k < ke; k += vec) acc += __ldcs(val + k) * __ldg(x + __ldcs(col + k));
+      }
+      for (int d = vec >> 1; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+      if (lane == 0 && r < it.nrows) {
+        y[it.row0 + r] = acc;
+        if (kDot) dot += acc * dot_with[it.row0 + r];
+      }
     }
   }
   if (kDot) {
@@ -542,6 +597,7 @@ int launch_spmv_range(cask_b200_ctx* ctx, const double* d_x, double* d_y, int el
                                (const int32_t*)(p.d_list_ell + ell_lo), ell_hi - ell_lo, (const Run*)p.d_runs,       \
                                (const double*)p.d_ell_vals, (const uint16_t*)p.d_ell_idx, d_x, d_y, w, partials,     \
                                (int)p.persist_xbuf, (int)p.persist_stages, hw, rd,                                   \
+                               fusion ? fusion->keep_vectors : 0,                                                    \
                                fusion ? fusion->trace : (unsigned long long*)nullptr));                              \
   } while (0)
     cudaLaunchConfig_t cfg = {};
@@ -582,10 +638,27 @@ int launch_spmv_range(cask_b200_ctx* ctx, const double* d_x, double* d_y, int el
     const int i_lo = p.h_item_begin[csr_lo], i_hi = p.h_item_begin[csr_hi];
     const int s_lo = p.h_split_begin[csr_lo], s_hi = p.h_split_begin[csr_hi];
     if (i_hi > i_lo) {
-      if (dot) spmv_csr_items_kernel<true><<<i_hi - i_lo, 256, 0, s>>>(p.d_csr_items + i_lo, p.d_row_ptr, p.d_col, p.d_val,
-                                                                       d_x, d_y, w, partials, p.d_csr_scratch);
-      else spmv_csr_items_kernel<false><<<i_hi - i_lo, 256, 0, s>>>(p.d_csr_items + i_lo, p.d_row_ptr, p.d_col, p.d_val,
-                                                                     d_x, d_y, nullptr, nullptr, p.d_csr_scratch);
+      if (p.csr_stream) {
+        // products of one item in shared memory: item target + one row short of the long-row threshold
+        const size_t smem = sizeof(double) * (size_t)(p.csr_item_nnz + kCsrLongRow + 2) + sizeof(int32_t) * (kSliceRows + 2);
+        if (dot) {
+          CB_CUDA(cudaFuncSetAttribute(spmv_csr_items_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          CB_CUDA(cudaFuncSetAttribute(spmv_csr_items_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+          spmv_csr_items_kernel<true, true><<<i_hi - i_lo, 256, smem, s>>>(p.d_csr_items + i_lo, p.d_row_ptr, p.d_col, p.d_val,
+                                                                             d_x, d_y, w, partials, p.d_csr_scratch);
+        } else {
+          CB_CUDA(cudaFuncSetAttribute(spmv_csr_items_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          CB_CUDA(cudaFuncSetAttribute(spmv_csr_items_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+          spmv_csr_items_kernel<false, true><<<i_hi - i_lo, 256, smem, s>>>(p.d_csr_items + i_lo, p.d_row_ptr, p.d_col, p.d_val,
+                                                                              d_x, d_y, nullptr, nullptr, p.d_csr_scratch);
+        }
+      } else if (dot) {
+        spmv_csr_items_kernel<true, false><<<i_hi - i_lo, 256, 0, s>>>(p.d_csr_items + i_lo, p.d_row_ptr, p.d_col, p.d_val,
+                                                                        d_x, d_y, w, partials, p.d_csr_scratch);
+      } else {
+        spmv_csr_items_kernel<false, false><<<i_hi - i_lo, 256, 0, s>>>(p.d_csr_items + i_lo, p.d_row_ptr, p.d_col, p.d_val,
+                                                                         d_x, d_y, nullptr, nullptr, p.d_csr_scratch);
+      }
       ctx->launches++;
     }
     if (s_hi > s_lo) {

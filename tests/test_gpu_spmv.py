@@ -38,10 +38,15 @@ def test_staged_ell_is_bit_identical_to_reference_dot(golden, gpu_lib, ctx):
             assert (got == exp).mean() > 0.5, (name, st)
 
 
+@pytest.mark.parametrize("stream", [0, 1])
 @pytest.mark.parametrize("vec", [2, 4, 8, 16, 32])
-def test_gather_csr_vector_per_row(golden, gpu_lib, ctx, vec):
+def test_gather_csr_vector_per_row(golden, gpu_lib, ctx, vec, stream):
+    """stream=1: the CSR-stream variant (products staged in shared memory, then reduced row by row)."""
     ctx.set_option("force_kind", 1)
     ctx.set_option("force_csr_vec", vec)
+    ctx.set_option("csr_stream", stream)
+    if stream:
+        ctx.set_option("csr_item_nnz", 1024 if vec == 2 else 4096)
     _check_all(golden, gpu_lib, ctx, gpu_lib.design(3, 2048, 16), exact=False)
     assert ctx.plan_stats()["slices_staged_ell"] == 0
 
