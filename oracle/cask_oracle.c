@@ -528,3 +528,134 @@ int oracle_csr_spmv_omp32(int32_t n, const int32_t* rp, const int32_t* ci, const
   }
   return oracle_num_threads();
 }
+
+/* ---- preconditioners ---------------------------------------------- */
+/* position of (i, j) in row i, or -1 (DokMatrix::dok[i].count(j)) */
+static int32_t find_entry(const int32_t* rp, const int32_t* ci, int32_t i, int32_t j) {
+  for (int32_t k = rp[i]; k < rp[i + 1]; k++)
+    if (ci[k] == j) return k;
+  return -1;
+}
+
+/* ILUPreconditioner::ILUPreconditioner, src/runtime/SparseLinearSolvers.hpp:89-140: ILU(0) in IKJ order on
+ * the pattern of `a` (rows in ascending column order, as CsrMatrix::toDok's std::map iterates them).
+ * pc receives the factors in the pattern of `a`: strictly-lower entries = multipliers, the rest = U.
+ * isNnz(k, j) is "entry exists AND its current value != 0" (SparseMatrix.hpp:209-215).
+ * NB the reference's pcg hands the constructor whatever `a` it was given - in test/LinearSolvers.cpp:54-77
+ * that is the LOWER TRIANGLE ONLY, for which no row update ever fires (row k has no column > k). */
+int oracle_ilu0(int32_t n, const int32_t* rp, const int32_t* ci, const double* va, double* pc) {
+  memcpy(pc, va, sizeof(double) * (size_t)rp[n]);
+  for (int32_t i = 1; i < n; i++) {                               /* :93 */
+    for (int32_t a = rp[i]; a < rp[i + 1]; a++) {                 /* :97  for (auto& p : pc.dok[i]) */
+      const int32_t k = ci[a];
+      if (k >= i) break;                                          /* :99-100 */
+      const int32_t dk = find_entry(rp, ci, k, k);
+      if (dk < 0 || pc[dk] == 0.0) continue;                      /* :101-102 !isNnz(k, k) */
+      pc[a] = pc[a] / pc[dk];                                     /* :103 */
+      const double beta = pc[a];                                  /* :104 */
+      for (int32_t b = rp[i]; b < rp[i + 1]; b++) {               /* :106 */
+        const int32_t j = ci[b];
+        if (j < k + 1) continue;                                  /* :108-109 */
+        const int32_t kj = find_entry(rp, ci, k, j);
+        if (kj >= 0 && pc[kj] != 0.0) pc[b] = pc[b] - pc[kj] * beta; /* :111-113 */
+      }
+    }
+  }
+  return 0;
+}
+
+/* ILUPreconditioner::apply, SparseLinearSolvers.hpp:142-150: L y = x then U z = y with
+ * mkl_dcsrtrsv(uplo, 'N', diag = 'N') (MklLayer.hpp:66-84) - NON-unit diagonal in BOTH solves: L is
+ * getLowerTriangular() (j <= i, so it carries U's diagonal), U is getUpperTriangular() (i <= j).
+ * MKL's internal summation order is unknowable; restated in ascending column order.
+ * Returns 1 if a diagonal entry is missing or zero (MKL's behaviour is then undefined). */
+int oracle_ilu_apply_mode(int32_t n, const int32_t* rp, const int32_t* ci, const double* pc, const double* x,
+                          double* z, int unit_lower) {
+  double* y = (double*)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+  int rc = 0;
+  for (int32_t i = 0; i < n; i++) {
+    double acc = x[i], d = 0.0;
+    for (int32_t k = rp[i]; k < rp[i + 1]; k++) {
+      if (ci[k] < i) acc -= pc[k] * y[ci[k]];
+      else if (ci[k] == i) d = pc[k];
+    }
+    if (unit_lower) d = 1.0;
+    if (d == 0.0) rc = 1;
+    y[i] = acc / d;
+  }
+  for (int32_t i = n - 1; i >= 0; i--) {
+    double acc = y[i], d = 0.0;
+    for (int32_t k = rp[i]; k < rp[i + 1]; k++) {
+      if (ci[k] > i) acc -= pc[k] * z[ci[k]];
+      else if (ci[k] == i) d = pc[k];
+    }
+    if (d == 0.0) rc = 1;
+    z[i] = acc / d;
+  }
+  free(y);
+  return rc;
+}
+
+int oracle_ilu_apply(int32_t n, const int32_t* rp, const int32_t* ci, const double* pc, const double* x,
+                     double* z) {
+  return oracle_ilu_apply_mode(n, rp, ci, pc, x, z, 0);
+}
+
+/* pcg<double, Precon>, SparseLinearSolvers.hpp:162-239, with the preconditioner left in:
+ *   precon 0  IdentityPreconditioner (:64-73)
+ *   precon 1  ILUPreconditioner (:77-156), built from the SAME arrays the product is taken from
+ *   precon 2  Jacobi, z = r / a_ii (1 where a_ii is absent or 0) - NOT in the reference; SURVEY 8(f) rank 4
+ *             proposes it as the first GPU preconditioner (it is what Eigen's BiCGSTAB defaults to)
+ *   precon 3  the same ILU(0) factors applied with a UNIT lower solve, M = (I + L)(D + U) - the textbook ILU(0)
+ *             preconditioner, symmetric for symmetric A.  NOT the reference: its non-unit lower solve makes M
+ *             non-symmetric and its PCG stalls on every SPD stencil tried (tests/test_oracle_precond.py)
+ * lower != 0: `a` is the stored lower triangle and the product is mkl_dcsrsymv('l') (the reference's call);
+ * lower == 0: `a` is the full matrix (what the GPU path multiplies with). */
+int oracle_pcg_precond(int32_t n, const int32_t* rp, const int32_t* ci, const double* va, const double* rhs,
+                       double* x, int32_t* iterations, int32_t maxiters, double tol, int precon, int lower,
+                       double* rs_final) {
+  matvec_fn mv = lower ? symv_lower : gemv_full;
+  const size_t nb = sizeof(double) * (size_t)(n > 0 ? n : 1);
+  double *r = (double*)malloc(nb), *p = (double*)malloc(nb), *Ap = (double*)malloc(nb), *z = (double*)malloc(nb);
+  double* pc = NULL;
+  double* invd = NULL;
+  int converged = 0, bad = 0;
+  if (precon == 1 || precon == 3) {
+    pc = (double*)malloc(sizeof(double) * (size_t)(rp[n] > 0 ? rp[n] : 1));
+    oracle_ilu0(n, rp, ci, va, pc);
+  } else if (precon == 2) {
+    invd = (double*)malloc(nb);
+    for (int32_t i = 0; i < n; i++) {
+      const int32_t d = find_entry(rp, ci, i, i);
+      invd[i] = (d >= 0 && va[d] != 0.0) ? 1.0 / va[d] : 1.0;
+    }
+  }
+#define ORACLE_APPLY()                                                          \
+  do {                                                                          \
+    if (precon == 1 || precon == 3) bad |= oracle_ilu_apply_mode(n, rp, ci, pc, r, z, precon == 3); \
+    else if (precon == 2) for (int32_t i_ = 0; i_ < n; i_++) z[i_] = invd[i_] * r[i_]; \
+    else memcpy(z, r, nb);                                                      \
+  } while (0)
+  mv(n, rp, ci, va, x, r);                                        /* :189 */
+  for (int32_t i = 0; i < n; i++) r[i] = rhs[i] - r[i];           /* :190 */
+  ORACLE_APPLY();                                                 /* :193 */
+  memcpy(p, z, nb);                                               /* :195 */
+  double rsold = ddot(n, r, z), rsnew = rsold;                    /* :198 */
+  for (int32_t it = 0; it < maxiters; it++) {                     /* :200 */
+    mv(n, rp, ci, va, p, Ap);                                     /* :206 */
+    const double alpha = rsold / ddot(n, p, Ap);                  /* :208 */
+    for (int32_t i = 0; i < n; i++) x[i] += alpha * p[i];         /* :210 */
+    for (int32_t i = 0; i < n; i++) r[i] = -alpha * Ap[i] + r[i]; /* :212 */
+    ORACLE_APPLY();                                               /* :215 */
+    rsnew = ddot(n, r, z);                                        /* :218 */
+    if (rsnew <= tol * tol) { converged = 1; break; }             /* :220-226 */
+    const double beta = rsnew / rsold;
+    for (int32_t i = 0; i < n; i++) p[i] = z[i] + beta * p[i];    /* :229 daxpby(1, z, beta, p) */
+    rsold = rsnew;                                                /* :230 */
+    *iterations = it;                                             /* :231 */
+  }
+#undef ORACLE_APPLY
+  if (rs_final) *rs_final = rsnew;
+  free(r); free(p); free(Ap); free(z); free(pc); free(invd);
+  return bad ? -1 : converged;
+}

@@ -80,6 +80,24 @@ int oracle_pcg_full(int32_t n, const int32_t* row_ptr, const int32_t* col_ind, c
                     const double* rhs, double* x, int32_t* iterations, int32_t maxiters, double tol,
                     double* rs_final);
 
+/* ---- preconditioners ----
+ * ILUPreconditioner's constructor (SparseLinearSolvers.hpp:89-140): ILU(0), IKJ order, on the pattern of the
+ * CSR it is given (rows in ascending column order); pc has rp[n] entries in that pattern. */
+int oracle_ilu0(int32_t n, const int32_t* row_ptr, const int32_t* col_ind, const double* values, double* pc);
+/* ILUPreconditioner::apply (:142-150): L y = x, U z = y, both NON-unit (MklLayer.hpp:66-84). Returns 1 if a
+ * diagonal entry is missing or zero. */
+int oracle_ilu_apply(int32_t n, const int32_t* row_ptr, const int32_t* col_ind, const double* pc,
+                     const double* x, double* z);
+/* unit_lower != 0: the textbook variant (unit diagonal in the lower solve) - not the reference's arithmetic */
+int oracle_ilu_apply_mode(int32_t n, const int32_t* row_ptr, const int32_t* col_ind, const double* pc,
+                          const double* x, double* z, int unit_lower);
+/* pcg<double, Precon> (:162-239). precon: 0 identity, 1 ILU (built from the same arrays), 2 Jacobi (not in the
+ * reference), 3 ILU(0) with a unit lower solve (not in the reference).  lower != 0: stored lower triangle + symmetric product (the reference's call); 0: full matrix.
+ * Returns 1 converged, 0 not, -1 if the ILU solve met a zero pivot. */
+int oracle_pcg_precond(int32_t n, const int32_t* row_ptr, const int32_t* col_ind, const double* values,
+                       const double* rhs, double* x, int32_t* iterations, int32_t maxiters, double tol,
+                       int precon, int lower, double* rs_final);
+
 /* Eigen 3.3.1 bicgstab() with DiagonalPreconditioner, as called at SparseLinearSolvers.cpp:18-26.
  * In: *iters = max iterations, *tol_error = tolerance.  Out: iterations done, relative residual. */
 int oracle_bicgstab(int32_t n, const int32_t* row_ptr, const int32_t* col_ind, const double* values,

@@ -51,6 +51,10 @@ def lib():
         L.oracle_pcg.argtypes = [i32, vp, vp, vp, vp, vp, vp, i32, dbl]
         L.oracle_pcg_full.argtypes = [i32, vp, vp, vp, vp, vp, vp, i32, dbl, vp]
         L.oracle_bicgstab.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp]
+        L.oracle_ilu0.argtypes = [i32, vp, vp, vp, vp]
+        L.oracle_ilu_apply.argtypes = [i32, vp, vp, vp, vp, vp]
+        L.oracle_ilu_apply_mode.argtypes = [i32, vp, vp, vp, vp, vp, C.c_int]
+        L.oracle_pcg_precond.argtypes = [i32, vp, vp, vp, vp, vp, vp, i32, dbl, C.c_int, C.c_int, vp]
         for g in ("poisson2d", "poisson3d27", "convdiff3d7"):
             f = getattr(L, "oracle_gen_" + g)
             f.restype = i64
@@ -146,6 +150,41 @@ def pcg(n, row_ptr, col_ind, values, rhs, x0=None, maxiters=2000, tol=1e-5, lowe
     ok = lib().oracle_pcg_full(n, _p(rp), _p(ci), _p(va), _p(rhs), _p(x), C.byref(it), maxiters, tol,
                                C.byref(rs))
     return bool(ok), it.value, x, rs.value
+
+
+def ilu0(n, row_ptr, col_ind, values):
+    """ILUPreconditioner's pc in the pattern of the given CSR (SparseLinearSolvers.hpp:89-140)."""
+    rp, ci, va = _csr(row_ptr, col_ind, values)
+    pc = np.zeros(len(va), np.float64)
+    lib().oracle_ilu0(n, _p(rp), _p(ci), _p(va), _p(pc))
+    return pc
+
+
+def ilu_apply(n, row_ptr, col_ind, pc, x, unit_lower=False):
+    """ILUPreconditioner::apply (:142-150). Returns (z, zero_pivot)."""
+    rp, ci, pc = _csr(row_ptr, col_ind, pc)
+    x = np.ascontiguousarray(x, np.float64)
+    z = np.zeros(n, np.float64)
+    rc = lib().oracle_ilu_apply_mode(n, _p(rp), _p(ci), _p(pc), _p(x), _p(z), 1 if unit_lower else 0)
+    return z, bool(rc)
+
+
+PRECON = {"identity": 0, "ilu": 1, "jacobi": 2, "ilu_unit": 3}
+
+
+def pcg_precond(n, row_ptr, col_ind, values, rhs, precon, x0=None, maxiters=2000, tol=1e-5, lower=True,
+                iterations=0):
+    """pcg<double, Precon> with the preconditioner left in. Returns (converged, iterations, x, rs_final);
+    converged is None if the ILU solve met a zero pivot."""
+    rp, ci, va = _csr(row_ptr, col_ind, values)
+    rhs = np.ascontiguousarray(rhs, np.float64)
+    x = np.zeros(n, np.float64) if x0 is None else np.array(x0, np.float64)
+    it = C.c_int32(iterations)
+    rs = C.c_double(0)
+    ok = lib().oracle_pcg_precond(n, _p(rp), _p(ci), _p(va), _p(rhs), _p(x), C.byref(it), maxiters, tol,
+                                  PRECON[precon] if isinstance(precon, str) else precon, 1 if lower else 0,
+                                  C.byref(rs))
+    return (None if ok < 0 else bool(ok)), it.value, x, rs.value
 
 
 def bicgstab(n, row_ptr, col_ind, values, b, tol=np.finfo(np.float64).eps, maxit=None):

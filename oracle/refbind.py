@@ -52,6 +52,12 @@ def lib():
         L.ref_spmv_mock.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.ref_slice_rows.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 3
         L.ref_slice_columns.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 3
+        # reference solvers (ref_solvers.cpp: pcg<> / ILUPreconditioner compiled with ref_shim/mkl.h)
+        if hasattr(L, "ref_pcg"):
+            L.ref_solvers_last_error.restype = C.c_char_p
+            L.ref_pcg.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.POINTER(C.c_int), C.c_int]
+            L.ref_ilu.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.POINTER(C.c_int)]
+            L.ref_ilu_apply.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 5
         assert L.ref_sizeof_pair() == 12
         _lib = L
     return _lib
@@ -148,3 +154,44 @@ def read_vector(path):
     out = np.zeros(n, np.float64)
     lib().ref_read_vector(path.encode(), _p(out), n)
     return out
+
+
+def _csr3(row_ptr, col_ind, values):
+    return (np.ascontiguousarray(row_ptr, np.int32), np.ascontiguousarray(col_ind, np.int32),
+            np.ascontiguousarray(values, np.float64))
+
+
+def solvers_available():
+    return available() and hasattr(lib(), "ref_pcg")
+
+
+def pcg(n, row_ptr, col_ind, values, rhs, x0=None, precon=0, iterations=0):
+    """The reference's own pcg<double, Precon> (SparseLinearSolvers.hpp:162-239) on the CSR as given
+    (its tests pass the stored lower triangle). precon: 0 identity, 1 ILU. Returns (converged, iterations, x)."""
+    rp, ci, va = _csr3(row_ptr, col_ind, values)
+    rhs = np.ascontiguousarray(rhs, np.float64)
+    x = np.zeros(n, np.float64) if x0 is None else np.array(x0, np.float64)
+    it = C.c_int(iterations)
+    rc = lib().ref_pcg(n, len(va), _p(rp), _p(ci), _p(va), _p(rhs), _p(x), C.byref(it), precon)
+    if rc < 0:
+        raise RuntimeError(lib().ref_solvers_last_error().decode())
+    return bool(rc), it.value, x
+
+
+def ilu(n, row_ptr, col_ind, values):
+    """ILUPreconditioner{a}.pc in the pattern of a, and its nnzs field."""
+    rp, ci, va = _csr3(row_ptr, col_ind, values)
+    pc = np.zeros(len(va), np.float64)
+    nn = C.c_int(0)
+    if lib().ref_ilu(n, len(va), _p(rp), _p(ci), _p(va), _p(pc), C.byref(nn)) < 0:
+        raise RuntimeError(lib().ref_solvers_last_error().decode())
+    return pc, nn.value
+
+
+def ilu_apply(n, row_ptr, col_ind, values, x):
+    rp, ci, va = _csr3(row_ptr, col_ind, values)
+    x = np.ascontiguousarray(x, np.float64)
+    z = np.zeros(n, np.float64)
+    if lib().ref_ilu_apply(n, len(va), _p(rp), _p(ci), _p(va), _p(x), _p(z)) < 0:
+        raise RuntimeError(lib().ref_solvers_last_error().decode())
+    return z
