@@ -29,7 +29,11 @@ EXPORTED_SYMBOLS = (
     "cask_b200_preprocess_shard_device", "cask_b200_dist_halo_counts", "cask_b200_dist_peer_active", "cask_b200_halo_plan_host", "cask_b200_synth_rows",
     "cask_b200_synth_nnz", "cask_b200_synth_device", "cask_b200_launch_count", "cask_b200_legacy_write",
     "cask_b200_legacy_read", "cask_b200_legacy_run", "cask_b200_legacy_reset", "cask_b200_legacy_launch_count",
+    "cask_b200_mm_read_info", "cask_b200_mm_read_coo", "cask_b200_mm_read_vector", "cask_b200_ingest_coo",
+    "cask_b200_ingest_coo_device", "cask_b200_read_matrix", "cask_b200_csr_get_info", "cask_b200_csr_export",
+    "cask_b200_csr_device_arrays", "cask_b200_csr_free", "cask_b200_preprocess_csr",
 )
+INGEST_ONE_BASED, INGEST_SYMMETRIC, INGEST_DROP_UPPER = 1, 2, 4
 
 
 class Design(C.Structure):
@@ -56,6 +60,16 @@ class PlanStats(C.Structure):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k != "row_length_histogram"}
         d["row_length_histogram"] = list(self.row_length_histogram)
         return d
+
+
+class MmInfo(C.Structure):
+    """cask_b200_mm_info == struct MmInfo (IO.hpp:39-58) + the size line."""
+    _fields_ = [("type", C.c_char * 16), ("format", C.c_char * 16), ("data_type", C.c_char * 16),
+                ("symmetry", C.c_char * 16), ("n", C.c_int64), ("m", C.c_int64), ("entries", C.c_int64)]
+
+    def as_dict(self):
+        return {"type": self.type.decode(), "format": self.format.decode(), "data_type": self.data_type.decode(),
+                "symmetry": self.symmetry.decode(), "n": self.n, "m": self.m, "entries": self.entries}
 
 
 class CaskError(RuntimeError):
@@ -108,6 +122,17 @@ def lib():
         L.cask_b200_synth_device.argtypes = [i32, i32, i64, i64, vp, vp, vp, vp]
         L.cask_b200_launch_count.argtypes = [vp, vp]
         L.cask_b200_device_count.argtypes = [vp]
+        L.cask_b200_mm_read_info.argtypes = [C.c_char_p, C.POINTER(MmInfo)]
+        L.cask_b200_mm_read_coo.argtypes = [C.c_char_p, i64, vp, vp, vp, vp]
+        L.cask_b200_mm_read_vector.argtypes = [C.c_char_p, i64, vp, vp]
+        L.cask_b200_ingest_coo.argtypes = [vp, i64, i64, i64, vp, vp, vp, i32, C.POINTER(vp)]
+        L.cask_b200_ingest_coo_device.argtypes = [vp, i64, i64, i64, vp, vp, vp, i32, C.POINTER(vp)]
+        L.cask_b200_read_matrix.argtypes = [vp, C.c_char_p, i32, C.POINTER(vp)]
+        L.cask_b200_csr_get_info.argtypes = [vp, vp, vp, vp, vp]
+        L.cask_b200_csr_export.argtypes = [vp, vp, vp, vp, vp]
+        L.cask_b200_csr_device_arrays.argtypes = [vp, vp, vp, vp]
+        L.cask_b200_csr_free.argtypes = [vp]
+        L.cask_b200_preprocess_csr.argtypes = [vp, C.POINTER(Design), vp]
         _lib = L
     return _lib
 
@@ -160,6 +185,63 @@ def synth_nnz(kind, N, row0, nrows):
     return z.value
 
 
+def mm_read_info(path):
+    """io::readHeader + the size line (host only, no GPU needed)."""
+    info = MmInfo()
+    check(lib().cask_b200_mm_read_info(os.fsencode(path), C.byref(info)))
+    return info.as_dict()
+
+
+def mm_read_coo(path):
+    """(info, rows, cols, vals): the entries of a coordinate file in file order, 1-based (host only)."""
+    info = mm_read_info(path)
+    L = info["entries"]
+    rows, cols, vals = np.zeros(L, np.int32), np.zeros(L, np.int32), np.zeros(L, np.float64)
+    cnt = C.c_int64()
+    check(lib().cask_b200_mm_read_coo(os.fsencode(path), L, _p(rows), _p(cols), _p(vals), C.byref(cnt)))
+    return info, rows, cols, vals
+
+
+def mm_read_vector(path):
+    """io::readVector (host only)."""
+    n = mm_read_info(path)["n"]
+    out = np.zeros(n, np.float64)
+    cnt = C.c_int64()
+    check(lib().cask_b200_mm_read_vector(os.fsencode(path), n, _p(out), C.byref(cnt)))
+    return out
+
+
+class DeviceCsr:
+    """cask_b200_csr: a CSR matrix built on (and resident on) the GPU by the ingest path."""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self.h = ctx, handle
+        n, m, nnz, field = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        check(lib().cask_b200_csr_get_info(self.h, C.byref(n), C.byref(m), C.byref(nnz), C.byref(field)))
+        self.n, self.m, self.nnz, self.nnzs_field = n.value, m.value, nnz.value, field.value
+
+    def export(self):
+        rp, ci, va = np.zeros(self.n + 1, np.int32), np.zeros(self.nnz, np.int32), np.zeros(self.nnz, np.float64)
+        check(lib().cask_b200_csr_export(self.ctx.h, self.h, _p(rp), _p(ci), _p(va)))
+        return rp, ci, va
+
+    def device_arrays(self):
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(lib().cask_b200_csr_device_arrays(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def free(self):
+        if self.h:
+            lib().cask_b200_csr_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 class Context:
     """One cask_b200_ctx: one GPU, one stream."""
 
@@ -208,6 +290,31 @@ class Context:
         check(lib().cask_b200_preprocess_shard_device(self.h, C.byref(dsg), n_global, m, row0, nrows, nnz,
                                                       _p(d_row_ptr), _p(d_col_ind), _p(d_values)))
         self.n, self.m = nrows, m
+
+    def ingest_coo(self, n, m, rows, cols, vals, flags):
+        """COO (host arrays, file order) -> DeviceCsr with the reference's DokMatrix semantics."""
+        rows = np.ascontiguousarray(rows, np.int32)
+        cols = np.ascontiguousarray(cols, np.int32)
+        vals = np.ascontiguousarray(vals, np.float64)
+        h = C.c_void_p()
+        check(lib().cask_b200_ingest_coo(self.h, n, m, len(vals), _p(rows), _p(cols), _p(vals), flags, C.byref(h)))
+        return DeviceCsr(self, h)
+
+    def ingest_coo_device(self, n, m, count, d_rows, d_cols, d_vals, flags):
+        h = C.c_void_p()
+        check(lib().cask_b200_ingest_coo_device(self.h, n, m, count, _p(d_rows), _p(d_cols), _p(d_vals), flags, C.byref(h)))
+        return DeviceCsr(self, h)
+
+    def read_matrix(self, path, sym_lower=False):
+        """io::readMatrix (sym_lower=False) / io::readSymMatrix().matrix (True), built on the GPU."""
+        h = C.c_void_p()
+        check(lib().cask_b200_read_matrix(self.h, os.fsencode(path), 1 if sym_lower else 0, C.byref(h)))
+        return DeviceCsr(self, h)
+
+    def preprocess_csr(self, dsg, csr):
+        check(lib().cask_b200_preprocess_csr(self.h, C.byref(dsg), csr.h))
+        self.n, self.m = csr.n, csr.m
+        self._csr_keepalive = csr
 
     def plan_stats(self):
         st = PlanStats()

@@ -10,7 +10,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcask_b200.so")
-SOURCES = ["capi.cu", "refformat.cu", "plan.cu", "spmv.cu", "solvers.cu", "dist.cu", "synth.cu", "legacy.cu"]
+SOURCES = ["capi.cu", "refformat.cu", "plan.cu", "spmv.cu", "solvers.cu", "dist.cu", "synth.cu", "legacy.cu", "ingest.cu",
+           "mmio.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -32,7 +33,7 @@ def build(force=False, verbose=False):
     objs = []
     procs = []
     for src in SOURCES:
-        obj = os.path.join(CSRC, src[:-3] + ".o")
+        obj = os.path.join(CSRC, os.path.splitext(src)[0] + ".o")
         cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)

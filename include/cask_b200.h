@@ -175,6 +175,49 @@ int cask_b200_dist_halo_counts(cask_b200_ctx* ctx, int64_t* recv_counts);
  * Meaningful after the first solver call that followed a preprocess_shard. */
 int cask_b200_dist_peer_active(cask_b200_ctx* ctx, int32_t* active);
 
+/* ---- Matrix Market ingest: file -> CSR on the device ------------------------- */
+/* Replaces io::readHeader / readDokMatrix / readMatrix / readSymMatrix / readVector (src/runtime/IO.hpp:60-176) and
+ * the DokMatrix -> CsrMatrix conversion behind them (SparseMatrix.hpp:156-189, 289-305).  The text is tokenised on
+ * the host by all cores (mm_* below: no GPU needed); the dictionary-of-keys build - last value wins for a repeated
+ * key, explicitSymmetric mirroring with its "Matrix is not symmetric" check, rows in ascending column order - is a
+ * radix sort and four data-parallel passes on the GPU (ingest_*), and the result can be handed to preprocess
+ * without ever visiting the host. */
+typedef struct {
+  char type[16], format[16], data_type[16], symmetry[16]; /* the header words, struct MmInfo IO.hpp:39-58 */
+  int64_t n, m, entries;                                  /* the size line: N M L (coordinate) or N M (array) */
+} cask_b200_mm_info;
+/* io::readHeader (IO.hpp:60-71) + the size line.  Same acceptance rule and messages as the reference. */
+int cask_b200_mm_read_info(const char* path, cask_b200_mm_info* info);
+/* The entries of a coordinate file in file order, indices 1-based as stored.  *count receives L. */
+int cask_b200_mm_read_coo(const char* path, int64_t capacity, int32_t* rows, int32_t* cols, double* vals, int64_t* count);
+/* io::readVector (IO.hpp:73-115), including its quirk: coordinate vectors are not rebased (v[a] = val). */
+int cask_b200_mm_read_vector(const char* path, int64_t capacity, double* out, int64_t* n);
+
+typedef struct cask_b200_csr cask_b200_csr; /* a CSR matrix resident on the device of the context that built it */
+#define CASK_B200_INGEST_ONE_BASED 1  /* indices are 1-based (Matrix Market) */
+#define CASK_B200_INGEST_SYMMETRIC 2  /* DokMatrix::explicitSymmetric: every (i, j, v) also gives (j, i, v) */
+#define CASK_B200_INGEST_DROP_UPPER 4 /* ignore entries above the diagonal (what mkl_dcsrsymv('l') reads); with
+                                         SYMMETRIC this expands a stored lower triangle to the full matrix */
+/* COO (host or device arrays, `count` entries in file order) -> CSR.  Fails with CASK_B200_ERR_INVALID_ARGUMENT and
+ * the reference's message "Matrix is not symmetric" when SYMMETRIC meets a stored transpose pair with different
+ * values, or when an index lies outside the n x m matrix. */
+int cask_b200_ingest_coo(cask_b200_ctx* ctx, int64_t n, int64_t m, int64_t count, const int32_t* rows,
+                         const int32_t* cols, const double* vals, int32_t flags, cask_b200_csr** out);
+int cask_b200_ingest_coo_device(cask_b200_ctx* ctx, int64_t n, int64_t m, int64_t count, const int32_t* d_rows,
+                                const int32_t* d_cols, const double* d_vals, int32_t flags, cask_b200_csr** out);
+/* mode 0: io::readMatrix (IO.hpp:151-163; symmetric files are expanded).  mode 1: io::readSymMatrix (IO.hpp:165-176;
+ * the stored triangle is kept as it is; fails with the reference's message if the file is not symmetric). */
+int cask_b200_read_matrix(cask_b200_ctx* ctx, const char* path, int32_t mode, cask_b200_csr** out);
+/* nnz = entries stored; nnzs_field = what the reference's CsrMatrix::nnzs / row_ptr[n] holds (it counts every
+ * DokMatrix::set call, so it exceeds nnz when a file repeats a key or stores both (i, j) and (j, i)). */
+int cask_b200_csr_get_info(const cask_b200_csr* csr, int64_t* n, int64_t* m, int64_t* nnz, int64_t* nnzs_field);
+int cask_b200_csr_export(cask_b200_ctx* ctx, const cask_b200_csr* csr, int32_t* row_ptr, int32_t* col_ind, double* values);
+int cask_b200_csr_device_arrays(const cask_b200_csr* csr, const int32_t** d_row_ptr, const int32_t** d_col_ind,
+                                const double** d_values);
+int cask_b200_csr_free(cask_b200_csr* csr);
+/* Spmv::preprocess on an ingested matrix; the CSR stays owned by `csr`, which must outlive the next preprocess. */
+int cask_b200_preprocess_csr(cask_b200_ctx* ctx, const cask_b200_design* design, const cask_b200_csr* csr);
+
 /* ---- synthetic matrices of BASELINE.json, generated on the device ----------------------------- */
 #define CASK_B200_SYNTH_POISSON2D 0   /* 5-point, N x N grid  */
 #define CASK_B200_SYNTH_POISSON3D27 1 /* 27-point, N^3 grid   */
