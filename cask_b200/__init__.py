@@ -32,7 +32,9 @@ EXPORTED_SYMBOLS = (
     "cask_b200_mm_read_info", "cask_b200_mm_read_coo", "cask_b200_mm_read_vector", "cask_b200_ingest_coo",
     "cask_b200_ingest_coo_device", "cask_b200_read_matrix", "cask_b200_csr_get_info", "cask_b200_csr_export",
     "cask_b200_csr_device_arrays", "cask_b200_csr_free", "cask_b200_preprocess_csr",
+    "cask_b200_pcg", "cask_b200_pcg_device", "cask_b200_precond_set_matrix", "cask_b200_ilu_factor", "cask_b200_ilu_apply",
 )
+PRECON_IDENTITY, PRECON_ILU, PRECON_JACOBI, PRECON_ILU_UNIT = range(4)
 INGEST_ONE_BASED, INGEST_SYMMETRIC, INGEST_DROP_UPPER = 1, 2, 4
 
 
@@ -133,6 +135,11 @@ def lib():
         L.cask_b200_csr_device_arrays.argtypes = [vp, vp, vp, vp]
         L.cask_b200_csr_free.argtypes = [vp]
         L.cask_b200_preprocess_csr.argtypes = [vp, C.POINTER(Design), vp]
+        L.cask_b200_pcg.argtypes = [vp, vp, vp, i32, dbl, i32, vp, vp, vp]
+        L.cask_b200_pcg_device.argtypes = [vp, vp, vp, i32, dbl, i32, vp, vp, vp]
+        L.cask_b200_precond_set_matrix.argtypes = [vp, vp]
+        L.cask_b200_ilu_factor.argtypes = [vp, vp, vp, vp]
+        L.cask_b200_ilu_apply.argtypes = [vp, i32, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -366,6 +373,39 @@ class Context:
         check(lib().cask_b200_cg_device(self.h, _p(d_rhs), _p(d_x), maxiters, tol, C.byref(it), C.byref(conv),
                                         C.byref(rs), C.byref(trips)))
         return bool(conv.value), it.value, rs.value, trips.value
+
+    def pcg(self, rhs, precon, x0=None, maxiters=2000, tol=1e-5, iterations=0):
+        """pcg<double, Precon>: returns (converged, iterations, x, rs_final); x is returned even when an ILU solve met a
+        zero pivot (CaskError is raised after the download in that case)."""
+        rhs = np.ascontiguousarray(rhs, np.float64)
+        x = np.zeros(self.n, np.float64) if x0 is None else np.array(x0, np.float64)
+        it, conv, rs = C.c_int32(iterations), C.c_int32(0), C.c_double(0)
+        check(lib().cask_b200_pcg(self.h, _p(rhs), _p(x), maxiters, tol, precon, C.byref(it), C.byref(conv), C.byref(rs)))
+        return bool(conv.value), it.value, x, rs.value
+
+    def pcg_device(self, d_rhs, d_x, precon, maxiters=2000, tol=1e-5, iterations=0):
+        it, conv, rs = C.c_int32(iterations), C.c_int32(0), C.c_double(0)
+        check(lib().cask_b200_pcg_device(self.h, _p(d_rhs), _p(d_x), maxiters, tol, precon, C.byref(it), C.byref(conv),
+                                         C.byref(rs)))
+        return bool(conv.value), it.value, rs.value
+
+    def precond_set_matrix(self, csr):
+        check(lib().cask_b200_precond_set_matrix(self.h, csr.h if csr is not None else None))
+        self._precond_keepalive = csr
+
+    def ilu_factor(self, nnz):
+        """(pc in the pattern of the matrix, lower levels, upper levels): ILUPreconditioner's factors from the GPU."""
+        pc = np.zeros(max(nnz, 1), np.float64)
+        ll, lu = C.c_int32(), C.c_int32()
+        check(lib().cask_b200_ilu_factor(self.h, _p(pc), C.byref(ll), C.byref(lu)))
+        return pc[:nnz], ll.value, lu.value
+
+    def ilu_apply(self, x, unit_lower=False):
+        x = np.ascontiguousarray(x, np.float64)
+        z = np.zeros(len(x), np.float64)
+        zp = C.c_int32()
+        check(lib().cask_b200_ilu_apply(self.h, 1 if unit_lower else 0, _p(x), _p(z), C.byref(zp)))
+        return z, bool(zp.value)
 
     def bicgstab(self, b, tol=0.0, maxit=0):
         b = np.ascontiguousarray(b, np.float64)

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcask_b200.so")
 SOURCES = ["capi.cu", "refformat.cu", "plan.cu", "spmv.cu", "solvers.cu", "dist.cu", "synth.cu", "legacy.cu", "ingest.cu",
-           "mmio.cpp"]
+           "precond.cu", "mmio.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

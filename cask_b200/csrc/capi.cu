@@ -33,6 +33,7 @@ int check_design(const cask_b200_design* d) {
 }
 
 void reset_matrix(cask_b200_ctx* ctx) {
+  free_precond(ctx);
   free_ref_partitions(ctx);
   free_plan(ctx);
   ctx->have_design = false;

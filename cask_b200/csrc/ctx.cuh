@@ -125,7 +125,8 @@ struct Plan {
   std::vector<int32_t> h_list_ell, h_list_csr;  // host copies of the slice lists (ascending slice id unless sharded)
 };
 
-struct DistState;  // dist.cu
+struct DistState;     // dist.cu
+struct PrecondState;  // precond.cu
 
 // ---- peer-memory layer (dist.cu) --------------------------------------------------
 // Every rank owns one "symmetric arena" (one cudaMalloc, exported with cudaIpcGetMemHandle and mapped by all
@@ -253,6 +254,7 @@ struct cask_b200_ctx {
 
   caskb200::SolverWork work;
   caskb200::DistState* dist = nullptr;
+  caskb200::PrecondState* precond = nullptr;  // preconditioners + work vectors of cask_b200_pcg (precond.cu)
 };
 
 namespace caskb200 {
@@ -310,6 +312,9 @@ int peer_check_error(cask_b200_ctx* ctx);
 
 // solvers.cu
 void free_solver_work(cask_b200_ctx* ctx);
+
+// precond.cu: everything derived from the current matrix (factors, levels, the override set by precond_set_matrix)
+void free_precond(cask_b200_ctx* ctx);
 
 // helpers
 int ensure_device(cask_b200_ctx* ctx);

@@ -112,6 +112,10 @@ inline int inclusive_sum_i32(Exec& ex, const int32_t* in, int32_t* out, int64_t 
   return CASK_B200_OK;
 }
 
+// IEEE multiply / subtract that the compiler may not contract into an FMA (the oracle is built with -ffp-contract=off)
+CB_DEV double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+CB_DEV double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+
 CB_DEV void atomic_or_i32(int32_t* p, int32_t v) { atomicOr(reinterpret_cast<int*>(p), (int)v); }
 CB_DEV void atomic_add_i64(int64_t* p, int64_t v) {
   atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);

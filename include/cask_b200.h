@@ -218,6 +218,39 @@ int cask_b200_csr_free(cask_b200_csr* csr);
 /* Spmv::preprocess on an ingested matrix; the CSR stays owned by `csr`, which must outlive the next preprocess. */
 int cask_b200_preprocess_csr(cask_b200_ctx* ctx, const cask_b200_design* design, const cask_b200_csr* csr);
 
+/* ---- preconditioned CG --------------------------------------------------------- */
+/* pcg<double, Precon>, src/runtime/SparseLinearSolvers.hpp:162-239, with the preconditioner left in.  Single rank.
+ *   IDENTITY  IdentityPreconditioner (:64-73); cask_b200_cg is the tuned loop for this case
+ *   ILU       ILUPreconditioner (:77-156): ILU(0) in IKJ order on the pattern of the matrix, applied as the reference
+ *             applies it - mkl_dcsrtrsv with diag = 'N' for BOTH factors (MklLayer.hpp:66-84), i.e. the lower solve
+ *             divides by U's diagonal.  M = (D + L)(D + U) is then not symmetric and the reference's PCG stalls on
+ *             SPD stencils; reproduced because it is what the reference computes (test/LinearSolvers.cpp:54-77)
+ *   JACOBI    z = r / a_ii (1 where a_ii is absent or 0).  Not in the reference
+ *   ILU_UNIT  the same ILU(0) factors with a unit lower solve, M = (I + L)(D + U): the textbook preconditioner.
+ *             Not in the reference
+ * ILU needs rows in strictly ascending column order (CsrMatrix(DokMatrix) / the ingest path give that); the
+ * factorisation and both triangular solves are level-scheduled on the GPU, bit-identical to the sequential loops.
+ * Arguments as cask_b200_cg; x holds the iterate the loop stopped at, converged or not.  A zero or missing pivot
+ * met by an ILU solve is reported as CASK_B200_ERR_RUNTIME after the loop. */
+#define CASK_B200_PRECON_IDENTITY 0
+#define CASK_B200_PRECON_ILU 1
+#define CASK_B200_PRECON_JACOBI 2
+#define CASK_B200_PRECON_ILU_UNIT 3
+int cask_b200_pcg(cask_b200_ctx* ctx, const double* rhs, double* x, int32_t maxiters, double tol, int32_t precon,
+                  int32_t* iterations, int32_t* converged, double* rs_final);
+int cask_b200_pcg_device(cask_b200_ctx* ctx, const double* d_rhs, double* d_x, int32_t maxiters, double tol,
+                         int32_t precon, int32_t* iterations, int32_t* converged, double* rs_final);
+/* Build the preconditioner from `csr` instead of the matrix given to preprocess (NULL: back to that matrix).  The
+ * reference's pcg constructs Precon{a} from the array it was handed - the stored LOWER TRIANGLE in its tests - while
+ * the product uses the implied symmetric matrix; this call reproduces that pairing.  Same dimensions as A; `csr` is
+ * borrowed until the next preprocess (which clears the override) or cask_b200_destroy. */
+int cask_b200_precond_set_matrix(cask_b200_ctx* ctx, const cask_b200_csr* csr);
+/* Parity hooks.  ilu_factor: ILUPreconditioner's `pc` (:89-140) in the pattern of the matrix, nnz doubles (pc may be
+ * NULL), and the number of dependency levels of the lower / upper solve.  ilu_apply: ILUPreconditioner::apply
+ * (:142-150) on host vectors; unit_lower selects the ILU_UNIT variant. */
+int cask_b200_ilu_factor(cask_b200_ctx* ctx, double* pc, int32_t* levels_lower, int32_t* levels_upper);
+int cask_b200_ilu_apply(cask_b200_ctx* ctx, int32_t unit_lower, const double* x, double* z, int32_t* zero_pivot);
+
 /* ---- synthetic matrices of BASELINE.json, generated on the device ----------------------------- */
 #define CASK_B200_SYNTH_POISSON2D 0   /* 5-point, N x N grid  */
 #define CASK_B200_SYNTH_POISSON3D27 1 /* 27-point, N^3 grid   */

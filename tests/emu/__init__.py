@@ -33,6 +33,8 @@ def lib():
         L.emu_live_allocations.restype = C.c_int64
         vp, i64 = C.c_void_p, C.c_int64
         L.emu_coo_to_csr.argtypes = [i64, i64, i64, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, i64, vp]
+        L.emu_ilu.argtypes = [i64, i64, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp]
+        L.emu_inv_diag.argtypes = [i64, vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -60,3 +62,27 @@ def coo_to_csr(n, m, rows, cols, vals, flags, order=1):
     return {"rc": rc, "err": int(info[2]), "first_bad": int(info[3]), "nnz": nnz, "nnzs_field": int(info[1]),
             "row_ptr": rp, "col": ci[:nnz].copy(), "val": va[:nnz].copy(), "launches": int(info[4]),
             "message": lib().emu_error().decode()}
+
+
+def ilu(n, row_ptr, col_ind, values, x=None, unit_lower=False, order=1):
+    """Returns dict(rc, pc, z, levels_lower, levels_upper, zero_pivot, launches, message)."""
+    rp = np.ascontiguousarray(row_ptr, np.int32)
+    ci = np.ascontiguousarray(col_ind, np.int32)
+    va = np.ascontiguousarray(values, np.float64)
+    pc = np.zeros(max(len(va), 1), np.float64)
+    info = np.zeros(4, np.int64)
+    xx = None if x is None else np.ascontiguousarray(x, np.float64)
+    z = np.zeros(max(n, 1), np.float64)
+    rc = lib().emu_ilu(n, len(va), _p(rp), _p(ci), _p(va), order, 1 if unit_lower else 0, _p(pc),
+                       None if xx is None else _p(xx), _p(z), _p(info))
+    return {"rc": rc, "pc": pc[:len(va)], "z": z[:n], "levels_lower": int(info[0]), "levels_upper": int(info[1]),
+            "zero_pivot": bool(info[2]), "launches": int(info[3]), "message": lib().emu_error().decode()}
+
+
+def inv_diag(n, row_ptr, col_ind, values):
+    rp = np.ascontiguousarray(row_ptr, np.int32)
+    ci = np.ascontiguousarray(col_ind, np.int32)
+    va = np.ascontiguousarray(values, np.float64)
+    out = np.zeros(max(n, 1), np.float64)
+    lib().emu_inv_diag(n, _p(rp), _p(ci), _p(va), _p(out))
+    return out[:n]

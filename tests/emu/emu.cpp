@@ -35,3 +35,35 @@ int emu_coo_to_csr(int64_t n, int64_t m, int64_t L, const int32_t* rows, const i
 }
 
 }  // extern "C"
+
+// ---- ILU(0) ------------------------------------------------------------------------------------------------
+#include "../../cask_b200/csrc/precond_logic.inl"
+
+extern "C" {
+
+// Factorises (pc_out: nnz values in the pattern) and, if x != NULL, applies z = M^-1 x.
+// info[0] = lower levels, info[1] = upper levels, info[2] = zero-pivot flag, info[3] = launches
+int emu_ilu(int64_t n, int64_t nnz, const int32_t* rp, const int32_t* ci, const double* va, int order, int unit_lower,
+            double* pc_out, const double* x, double* z, int64_t* info) {
+  dev::Exec ex;
+  int64_t launches = 0;
+  ex.launches = &launches;
+  ex.order = order;
+  precond::IluState st;
+  int rc = precond::ilu_analyse(ex, n, nnz, rp, ci, &st);
+  if (rc == CASK_B200_OK) rc = precond::ilu_factor(ex, va, &st);
+  int32_t zp = 0;
+  if (rc == CASK_B200_OK && pc_out) std::memcpy(pc_out, st.pc, sizeof(double) * (size_t)nnz);
+  if (rc == CASK_B200_OK && x) rc = precond::ilu_apply(ex, &st, unit_lower, x, z, &zp);
+  info[0] = (int64_t)st.ptr_l.size() - 1; info[1] = (int64_t)st.ptr_u.size() - 1; info[2] = zp; info[3] = launches;
+  precond::ilu_free(&st);
+  return rc;
+}
+
+int emu_inv_diag(int64_t n, const int32_t* rp, const int32_t* ci, const double* va, double* invd) {
+  dev::Exec ex;
+  precond::InvDiag f{rp, ci, va, invd};
+  return dev::for_each(ex, n, f);
+}
+
+}  // extern "C"
