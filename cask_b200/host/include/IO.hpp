@@ -1,11 +1,13 @@
 // Matrix Market input with the reference's entry points (src/runtime/IO.hpp): readHeader, readVector,
-// readDokMatrix, readMatrix, readSymMatrix, MmReader<T>.  Host-only harness input; no GPU work.
+// readDokMatrix, readMatrix, readSymMatrix, MmReader<T> on the host, and io::gpu::readMatrix / readSymMatrix through the
+// GPU ingest path (cask_b200_read_matrix).
 #ifndef CASK_B200_HOST_IO_HPP
 #define CASK_B200_HOST_IO_HPP
 #include <fstream>
 #include <sstream>
 #include <string>
 
+#include "../../../include/cask_b200.h"
 #include "SparseMatrix.hpp"
 
 namespace cask {
@@ -96,6 +98,41 @@ inline cask::SymCsrMatrix readSymMatrix(const std::string& path) {  // IO.hpp:16
     throw std::invalid_argument("Error! Matrix found in " + path + " is not symmetric. To read unsymmetric matrix use cask::io::readSymMatrix()");
   return SymCsrMatrix(readDokMatrix(path, info));
 }
+
+// The same two readers with the tokenising on all host cores and the DokMatrix build on the GPU
+// (cask_b200_read_matrix: radix sort + data-parallel passes instead of one hash-map insertion per entry; identical
+// results, including "last value wins" for repeated keys and the "Matrix is not symmetric" check).  Opt-in for now:
+// io::readMatrix / io::readSymMatrix above stay the host path until this one has its GPU parity run on record.
+namespace gpu {
+namespace detail {
+inline CsrMatrix fetch(const std::string& path, int mode) {
+  cask_b200_ctx* raw = nullptr;
+  auto check = [](int rc) {
+    if (rc == CASK_B200_OK) return;
+    const std::string msg = cask_b200_last_error();
+    if (rc == CASK_B200_ERR_INVALID_ARGUMENT) throw std::invalid_argument(msg);
+    throw std::runtime_error(msg);
+  };
+  check(cask_b200_create(&raw, 0));
+  struct Guard {
+    cask_b200_ctx* c; cask_b200_csr* m;
+    ~Guard() { cask_b200_csr_free(m); cask_b200_destroy(c); }
+  } g{raw, nullptr};
+  check(cask_b200_read_matrix(g.c, path.c_str(), mode, &g.m));
+  int64_t n = 0, m = 0, nnz = 0, field = 0;
+  check(cask_b200_csr_get_info(g.m, &n, &m, &nnz, &field));
+  std::vector<int> rp((size_t)n + 1), ci((size_t)nnz);
+  std::vector<double> va((size_t)nnz);
+  check(cask_b200_csr_export(g.c, g.m, rp.data(), ci.data(), va.data()));
+  rp[(size_t)n] = (int)field;  // CsrMatrix(const DokMatrix&) ends row_ptr with the nnzs FIELD (SparseMatrix.hpp:304)
+  return CsrMatrix((int)n, (int)m, (int)field, va, ci, rp);
+}
+}  // namespace detail
+inline cask::CsrMatrix readMatrix(const std::string& path) { return detail::fetch(path, 0); }  // IO.hpp:151-163
+inline cask::SymCsrMatrix readSymMatrix(const std::string& path) {                             // IO.hpp:165-176
+  return SymCsrMatrix(detail::fetch(path, 1).toDok());
+}
+}  // namespace gpu
 
 // COO reader: 0-based, symmetric entries mirrored, sorted by (row, column) — IO.hpp:178-330
 template <typename value_type>

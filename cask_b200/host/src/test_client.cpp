@@ -62,6 +62,69 @@ void CGSymWithIdentityPC() {  // test/LinearSolvers.cpp:34-52
   for (int i = 0; i < sol.size(); i++) CHECK(double_eq(sol[i], exp_sol[i]));
 }
 
+void CGSymWithILUPC() {  // test/LinearSolvers.cpp:54-77
+  Vector rhs = io::readVector(g_dir + "/tinysym_b.mtx");
+  SymCsrMatrix a = io::readSymMatrix(g_dir + "/tinysym.mtx");
+  int iterations = 0;
+  Vector sol(a.n);
+  pcg<double, ILUPreconditioner>(a.matrix, &rhs[0], &sol[0], iterations);  // the reference ignores the return value too
+  Vector exp_sol{-1.9982580059252246, 2.0000862488691915, 3.0001293733037859, 2.9987581910958183};
+  sol.print("got x =");
+  std::cout << "Iterations = " << iterations << std::endl;
+  // the loop stalls (non-symmetric M) and x is where it stands after 2000 iterations; the GPU's dot products sum in
+  // another order than MKL's, so the asserted doubles are met to ~1e-12 rather than to 4 ulp
+  for (int i = 0; i < sol.size(); i++) CHECK(std::fabs(sol[i] - exp_sol[i]) <= 1e-9 * std::fabs(exp_sol[i]));
+}
+
+void ILUCompute2() {  // test/LinearSolvers.cpp:79-99
+  CsrMatrix a{2, 1, 1, 1, 1, 1, 0, 0, 1, 0, 1, 0, 1, 0, 0, 1};
+  ILUPreconditioner ilupc{a};
+  DokMatrix exp{2, 1, 1, 1, 0.5, 0.5, 0, 0, 0.5, 0, 0.5, 0, 0.5, 0, 0, 0.5};
+  CHECK(ilupc.pc.n == exp.n);
+  CHECK(ilupc.pc.nnzs == exp.nnzs);
+  CHECK(ilupc.pc == exp);
+}
+
+void ILUCompute() {  // test/LinearSolvers.cpp:101-123
+  SymCsrMatrix a = io::readSymMatrix(g_dir + "/tinysym.mtx");
+  CsrMatrix explicitA(a.matrix.toDok().explicitSymmetric());
+  ILUPreconditioner explicitPc{explicitA};
+  CsrMatrix csrPc{explicitPc.pc};
+  CHECK((csrPc.row_ptr == std::vector<int>{0, 2, 3, 4, 6}));
+  CHECK((csrPc.col_ind == std::vector<int>{0, 3, 1, 2, 0, 3}));
+  CHECK((csrPc.values == std::vector<double>{1, 1, 1, 1, 1, 1}));
+}
+
+void ILUComputeAndApply() {  // test/LinearSolvers.cpp:125-146
+  ILUPreconditioner ilupc{CsrMatrix{DokMatrix{2, 1, 1, 1, 1, 1, 0, 0, 1, 0, 1, 0, 1, 0, 0, 1}}};
+  std::vector<double> v{1, 2, 3, 4};
+  auto res = ilupc.apply(v);
+  std::vector<double> expPcApply{-16.25, 7, 11, 15};
+  for (size_t i = 0; i < res.size(); i++) CHECK(double_eq(res[i], expPcApply[i]));
+}
+
+void PreconditionersBeyondTheReference() {  // Jacobi and the unit-lower ILU: converge to the reference's solution
+  Vector rhs = io::readVector(g_dir + "/tinysym_b.mtx");
+  SymCsrMatrix a = io::readSymMatrix(g_dir + "/tinysym.mtx");
+  Vector exp_sol{-2, 2, 3, 3};
+  for (int which = 0; which < 2; which++) {
+    int iterations = 0;
+    Vector sol(a.n);
+    const bool ok = which == 0 ? pcg<double, JacobiPreconditioner>(a.matrix, &rhs[0], &sol[0], iterations)
+                               : pcg<double, IluUnitPreconditioner>(a.matrix, &rhs[0], &sol[0], iterations);
+    CHECK(ok);
+    for (int i = 0; i < sol.size(); i++) CHECK(std::fabs(sol[i] - exp_sol[i]) < 1e-6);
+  }
+}
+
+void GpuReadersMatchTheHostReaders() {  // io::gpu::readMatrix / readSymMatrix against io::readMatrix / readSymMatrix
+  for (const char* name : {"tiny", "tinysym"}) {
+    const std::string p = g_dir + "/" + name + ".mtx";
+    CHECK(io::gpu::readMatrix(p) == io::readMatrix(p));
+    CHECK(io::gpu::readSymMatrix(p).matrix == io::readSymMatrix(p).matrix);
+  }
+}
+
 void CgTestRun(const std::string& name) {  // test/CgTest.cpp:10-43 (identity preconditioner leg)
   SymCsrMatrix a = io::readSymMatrix(g_dir + "/" + name + ".mtx");
   Vector rhs = io::readVector(g_dir + "/" + name + "_b.mtx");
@@ -133,14 +196,21 @@ void ErrorsMirrorReference() {  // Spmv.cpp:195-232
 }  // namespace
 
 int main(int argc, char** argv) {
-  if (argc != 2) { std::cerr << "usage: test_client <systems dir>" << std::endl; return 2; }
+  if (argc != 2 && argc != 3) { std::cerr << "usage: test_client <systems dir> [base|extra|all]" << std::endl; return 2; }
   g_dir = argv[1];
-  struct { const char* name; void (*fn)(); } tests[] = {
-      {"TestLinearSolvers.CGWithIdentityPC", CGWithIdentityPC}, {"TestLinearSolvers.CGSymWithIdentityPC", CGSymWithIdentityPC},
-      {"CgTest.SolveTiny", [] { CgTestRun("tiny"); }}, {"CgTest.SolveTinySym", [] { CgTestRun("tinysym"); }},
-      {"ClientTestSpmv.TinySymSpmv", ClientTestSpmv}, {"ClientCg.SimpleSystem", ClientCg},
-      {"Spmv.ErrorsMirrorReference", ErrorsMirrorReference}};
+  // "base": the suites that have been green on a B200 since round 1 (default, what tests/test_gpu_harness.py runs);
+  // "extra": the ILU / Jacobi / GPU-ingest suites added afterwards (tests/test_gpu_w_precond.py runs them)
+  const std::string which = argc == 3 ? argv[2] : "base";
+  struct { const char* name; void (*fn)(); int extra; } tests[] = {
+      {"TestLinearSolvers.CGWithIdentityPC", CGWithIdentityPC, 0}, {"TestLinearSolvers.CGSymWithIdentityPC", CGSymWithIdentityPC, 0},
+      {"CgTest.SolveTiny", [] { CgTestRun("tiny"); }, 0}, {"CgTest.SolveTinySym", [] { CgTestRun("tinysym"); }, 0},
+      {"ClientTestSpmv.TinySymSpmv", ClientTestSpmv, 0}, {"ClientCg.SimpleSystem", ClientCg, 0},
+      {"Spmv.ErrorsMirrorReference", ErrorsMirrorReference, 0},
+      {"TestLinearSolvers.CGSymWithILUPC", CGSymWithILUPC, 1}, {"TestLinearSolvers.ILUCompute2", ILUCompute2, 1},
+      {"TestLinearSolvers.ILUCompute", ILUCompute, 1}, {"TestLinearSolvers.ILUComputeAndApply", ILUComputeAndApply, 1},
+      {"Precon.JacobiAndUnitIlu", PreconditionersBeyondTheReference, 1}, {"Io.GpuReaders", GpuReadersMatchTheHostReaders, 1}};
   for (auto& t : tests) {
+    if ((which == "base" && t.extra) || (which == "extra" && !t.extra)) continue;
     const int before = g_failures;
     std::cout << "[ RUN      ] " << t.name << std::endl;
     try { t.fn(); } catch (std::exception& e) { std::cerr << "exception: " << e.what() << std::endl; g_failures++; }

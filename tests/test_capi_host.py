@@ -76,10 +76,12 @@ def test_product_never_touches_the_oracle():
     pkg = os.path.join(ROOT, "cask_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")) or f == "Makefile":
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h", ".inl")) or f == "Makefile":
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 for pat in (r"#\s*include[^\n]*oracle", r"^\s*(from|import)\s+oracle", r"import[^\n]*oraclebind",
-                            r"dlopen[^\n]*oracle", r"libcask_oracle", r"caskref", r"-l\s*cask_oracle"):
+                            r"dlopen[^\n]*oracle", r"libcask_oracle", r"caskref", r"-l\s*cask_oracle",
+                            # nor the host emulation of the device-logic backend (tests/emu): test infrastructure only
+                            r"#\s*include[^\n]*dev_host", r"#\s*include[^\n]*tests/", r"libcask_emu"):
                     assert not re.search(pat, text, re.M), (os.path.join(dirpath, f), pat)
     out = os.popen("ldd %s" % os.path.join(pkg, "libcask_b200.so")).read()
-    assert "oracle" not in out and "caskref" not in out
+    assert "oracle" not in out and "caskref" not in out and "emu" not in out
