@@ -58,6 +58,17 @@ def algorithmic_bytes(nnz, rows, cols):
     return 12 * nnz + 8 * (rows + cols)
 
 
+def workload_name(G, world, nnz_rank0=None):
+    """config.workload, identical in both arms.  Rank 0's stripe of the (G*world) x G five-point grid: every row has
+    5 entries minus the missing neighbours (left/right edges: 2G; top edge: G; bottom edge: G only when world == 1);
+    the measuring arm passes the count of the stripe it actually generated."""
+    n_local = G * G
+    if nnz_rank0 is None:
+        nnz_rank0 = 5 * n_local - 2 * G - G - (G if world == 1 else 0)
+    return ("C2: 2D 5-pt Poisson %dx%d grid per GPU (%d rows, %d nnz per GPU), y = A x" % (G, G, n_local, nnz_rank0),
+            n_local, nnz_rank0)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -158,7 +169,7 @@ def reference_arm(args):
     line = {"impl": "reference", "metric": "fp64 SpMV GFLOP/s", "unit": "GFLOP/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C2 2D 5-pt Poisson %dx%d grid per GPU" % (args.grid, args.grid),
+            "config": {"workload": workload_name(args.grid, args.gpus)[0],
                        "sample": "same operator on a %dx%d grid" % (sample_grid, sample_grid)}}
     steps = max(1, min(args.steps, 20))
     warm = max(1, min(args.warmup, 2))
@@ -383,8 +394,7 @@ def main():
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": kernel_ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": "C2: 2D 5-pt Poisson %dx%d grid per GPU (%d rows, %d nnz per GPU), y = A x"
-                                   % (G, G, n_local, nnz_local),
+            "config": {"workload": workload_name(G, world, nnz_local)[0],
                        "global_rows": n_global, "sharding": "row stripes over ranks (Spmv.cpp:334-364), NCCL x halo",
                        "l2": "inputs (%.2f GB per launch) larger than L2 (126 MB); no flush needed" % (bytes_per_launch / 1e9),
                        "design": {"num_pipes": 1, "cache_size": args.cache, "input_width": 16},
