@@ -2,8 +2,9 @@
 //
 // C-callable driver around the reference's OWN solver code, compiled where it lies: pcg<T, Precon>,
 // IdentityPreconditioner and ILUPreconditioner (src/runtime/SparseLinearSolvers.hpp:62-239) with -DUSEMKL and
-// the six MKL routines they call supplied by ref_shim/mkl.h (MKL itself is absent).  Part of
-// oracle/_ref/libcaskref.so (oracle/Makefile, target `ref`).  No reference source is copied into the repository.
+// the six MKL routines they call supplied by ref_shim/mkl.h (sequential stand-in; part of oracle/_ref/libcaskref.so,
+// oracle/Makefile target `ref`) or by ref_shim_mkl/mkl.h (adapters over the real oneMKL that libtorch_cpu.so exports;
+// oracle/_ref/libcaskref_mkl.so, target `ref_mkl`).  No reference source is copied into the repository.
 #include <algorithm>
 #include <cassert>
 #include <cmath>
@@ -31,16 +32,33 @@ const char* ref_solvers_last_error() { return g_serr.c_str(); }
 
 // pcg<double, Precon>(a, rhs, x, iterations): precon 0 = IdentityPreconditioner, 1 = ILUPreconditioner.
 // `a` is handed over exactly as given (the reference's tests pass the stored lower triangle, readSymMatrix().matrix).
-// Returns 1 converged / 0 not / -1 exception.
-int ref_pcg(int n, int nnz, const int* rp, const int* ci, const double* va, const double* rhs, double* x,
-            int* iterations, int precon) {
+// Returns 1 converged / 0 not / -1 exception.  *solve_seconds (optional) receives the reference's own "cg:solve"
+// timer (cask::utils::Timer, Utils.hpp:15-50): the loop without the set-up copies, as CgTest / sparse-bench report it.
+int ref_pcg_timed(int n, int nnz, const int* rp, const int* ci, const double* va, const double* rhs, double* x,
+                  int* iterations, int precon, double* solve_seconds) {
   try {
     CsrMatrix a = make(n, n, nnz, rp, ci, va);
     std::vector<double> b(rhs, rhs + n);
-    const bool ok = precon == 1 ? sls::pcg<double, sls::ILUPreconditioner>(a, b.data(), x, *iterations)
-                                : sls::pcg<double, sls::IdentityPreconditioner>(a, b.data(), x, *iterations);
+    cask::utils::Timer t;
+    const bool ok = precon == 1 ? sls::pcg<double, sls::ILUPreconditioner>(a, b.data(), x, *iterations, false, &t)
+                                : sls::pcg<double, sls::IdentityPreconditioner>(a, b.data(), x, *iterations, false, &t);
+    if (solve_seconds) *solve_seconds = t.get("cg:solve").count();
     return ok ? 1 : 0;
   } catch (std::exception& e) { g_serr = e.what(); return -1; }
+}
+
+int ref_pcg(int n, int nnz, const int* rp, const int* ci, const double* va, const double* rhs, double* x,
+            int* iterations, int precon) {
+  return ref_pcg_timed(n, nnz, rp, ci, va, rhs, x, iterations, precon, nullptr);
+}
+
+// 1 when this build runs on Intel MKL's arithmetic (ref_shim_mkl/mkl.h), 0 with the sequential stand-in (ref_shim/mkl.h)
+int ref_solvers_real_mkl() {
+#ifdef CASK_REF_REAL_MKL
+  return 1;
+#else
+  return 0;
+#endif
 }
 
 // ILUPreconditioner{a}: pc_out receives pc in the pattern of `a` (entries of `a`'s pattern, row-major ascending
