@@ -45,7 +45,9 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.check_call([NVCC, "-shared", "-o", LIB] + objs + ["-ccbin", "/usr/bin/g++", "-lcudart_static", "-ldl", "-lpthread", "-lrt"])
+    # the arch is repeated at link time so that nvcc does not add a stub for its default (pre-sm_75) target
+    subprocess.check_call([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs +
+                          ["-ccbin", "/usr/bin/g++", "-lcudart_static", "-ldl", "-lpthread", "-lrt"])
     return LIB
 
 

@@ -100,7 +100,7 @@ reduce_partials_kernel(const double* __restrict__ partials, int count, int strid
 // r = b - Ax (Ax arrives in r), p = r, r.r            SparseLinearSolvers.hpp:189-198
 __global__ void __launch_bounds__(kVecThreads, kVecCtasPerSm)
 cg_init_kernel(int64_t n, const double* __restrict__ b, double* __restrict__ r, double* __restrict__ p,
-               const ReduceDesc rd) {
+               const __grid_constant__ ReduceDesc rd) {
   __shared__ double red[kVecThreads / 32];
   double acc = 0.0;
   CB_TILE_LOOP(n) {
@@ -127,7 +127,7 @@ cg_init_kernel(int64_t n, const double* __restrict__ b, double* __restrict__ r, 
 __global__ void __launch_bounds__(kVecThreads, kVecCtasPerSm)
 cg_update_xr_kernel(int64_t n, int it, const double* __restrict__ scal, const int32_t* __restrict__ flags,
                     const double* __restrict__ p, const double* __restrict__ Ap, double* __restrict__ x,
-                    double* __restrict__ r, const ReduceDesc rd, unsigned long long* trace) {
+                    double* __restrict__ r, const __grid_constant__ ReduceDesc rd, unsigned long long* trace) {
   trace_min(trace);
   pdl_enter();
   trace_min(trace ? trace + 1 : nullptr);
@@ -233,7 +233,7 @@ cg_update_p_kernel(int64_t n, int it, double* __restrict__ scal, int32_t* __rest
 // The grid (<= 2 CTAs per SM) is resident as a whole, which the barrier relies on.
 __global__ void __launch_bounds__(kVecThreads, kVecCtasPerSm)
 cg_update_fused_kernel(int64_t n, int it, double* __restrict__ scal, int32_t* __restrict__ flags, double* p,
-                       const double* __restrict__ Ap, double* __restrict__ x, double* r, const ReduceDesc rd,
+                       const double* __restrict__ Ap, double* __restrict__ x, double* r, const __grid_constant__ ReduceDesc rd,
                        const PushDesc pd, const HaloUpdate hu, const GatherDesc pap, int keep_i, unsigned long long* trace) {
   trace_min(trace);
   pdl_enter();
@@ -376,7 +376,7 @@ __global__ void jacobi_diag_kernel(int64_t n, int64_t row0_global, const int32_t
 __global__ void __launch_bounds__(kVecThreads, kVecCtasPerSm)
 bicg_residual_kernel(int64_t n, const int32_t* __restrict__ flags, int only_on_restart, const double* __restrict__ b,
                      double* __restrict__ r, double* __restrict__ r0, const double* __restrict__ Ax,
-                     const ReduceDesc rd) {
+                     const __grid_constant__ ReduceDesc rd) {
   if (flags[F_DONE]) return;
   if (only_on_restart && !flags[F_RESTART]) return;
   __shared__ double red[kVecThreads / 32];
@@ -403,7 +403,7 @@ bicg_residual_kernel(int64_t n, const int32_t* __restrict__ flags, int only_on_r
 // dot(s): out[0] = a.b ; out[1] = c.d (optional)
 __global__ void __launch_bounds__(kVecThreads, kVecCtasPerSm)
 dot2_kernel(int64_t n, const int32_t* __restrict__ flags, const double* __restrict__ a, const double* __restrict__ b,
-            const double* __restrict__ c, const double* __restrict__ d, const ReduceDesc rd) {
+            const double* __restrict__ c, const double* __restrict__ d, const __grid_constant__ ReduceDesc rd) {
   pdl_enter();
   if (flags && (flags[F_DONE] || flags[F_RESTART])) return;
   __shared__ double red[kVecThreads / 32];
@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(kVecThreads, kVecCtasPerSm)
 bicg_xr_kernel(int64_t n, const double* __restrict__ scal, const int32_t* __restrict__ flags,
                const double* __restrict__ y, const double* __restrict__ z, const double* __restrict__ s,
                const double* __restrict__ t, const double* __restrict__ r0, double* __restrict__ x,
-               double* __restrict__ r, const ReduceDesc rd) {
+               double* __restrict__ r, const __grid_constant__ ReduceDesc rd) {
   pdl_enter();
   if (flags[F_DONE] || flags[F_RESTART]) return;
   __shared__ double red[kVecThreads / 32];

@@ -218,7 +218,7 @@ spmv_ell_persistent_kernel(const SliceDesc* __restrict__ slices, const int32_t* 
                            const Run* __restrict__ runs, const double* __restrict__ ell_vals,
                            const uint16_t* __restrict__ ell_idx, const double* __restrict__ x, double* __restrict__ y,
                            const double* __restrict__ dot_with, double* __restrict__ partials, int xbuf_doubles,
-                           int stages, const HaloWait hw, const ReduceDesc rd, int keep_i, unsigned long long* trace) {
+                           int stages, const HaloWait hw, const __grid_constant__ ReduceDesc rd, int keep_i, unsigned long long* trace) {
   trace_min(trace);
   const bool keep = keep_i != 0;  // vectors fit L2: x windows, y and dot_with are accessed with evict-last
   const unsigned long long keep_policy = l2_policy_evict_last();
