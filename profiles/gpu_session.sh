@@ -1,0 +1,58 @@
+#!/bin/bash
+# One-GPU evidence session: everything the judge reads from one `gpurun` call.
+#
+#   /usr/local/graft/bin/gpurun --timeout 2400 -- 'bash profiles/gpu_session.sh r2'
+#
+# Writes under gpurun_out/<tag>_*: the GPU test log, both bench arms, the ncu launch list of bench.py with its
+# per-kernel shares, and `ncu --set full` captures (raw report + markdown summary) of the three kernels that bound the
+# three measured workloads: spmv_ell_persistent (C2 SpMV), the CG pair spmv_ell_persistent<.,true> + cg_update_fused
+# (C4) and spmv_csr_items (C3, with the L2 hit rate on x that SURVEY 8(d) asks for).  Copy what is to be judged into
+# profiles/ afterwards (gpurun_out/ is scratch) and update profiles/roofline_traffic.json from <tag>_spmv_persistent_ncu.md.
+# Every step has its own timeout so that a hang costs one step, not the session; numbers printed by a run under ncu
+# are never bench values.
+TAG=${1:-session}
+OUT=gpurun_out
+mkdir -p $OUT
+PY=python
+NCU="ncu --clock-control none"
+step() { echo "== $1 ($(date +%T))"; }
+
+step "gpu tests"
+timeout 1800 $PY -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest_gpu.log 2>&1
+echo "pytest exit $?" | tee -a $OUT/${TAG}_pytest_gpu.log
+tail -5 $OUT/${TAG}_pytest_gpu.log
+
+step "smoke"
+timeout 300 $PY -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; tail -2 $OUT/${TAG}_smoke.log
+
+step "bench (reference arm, then ours)"
+timeout 600 $PY bench.py --impl reference > $OUT/${TAG}_bench_reference.json 2> $OUT/${TAG}_bench_reference.err
+timeout 900 $PY bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
+tail -c 1500 $OUT/${TAG}_bench.json
+
+step "ncu launch list of bench.py (C2 SpMV + C4 CG)"
+timeout 1200 $NCU --metrics gpu__time_duration.sum -c 900 --csv --log-file $OUT/${TAG}_launches.csv \
+  $PY bench.py --steps 20 --warmup 3 --no-extra --no-cpu --cg-maxiters 100 > $OUT/${TAG}_launches.log 2>&1
+$PY profiles/summarize_launches.py $OUT/${TAG}_launches.csv > $OUT/${TAG}_launches_summary.md 2>> $OUT/${TAG}_launches.log
+head -12 $OUT/${TAG}_launches_summary.md
+
+step "ncu --set full: persistent SpMV on C2"
+timeout 900 $NCU --set full --import-source on -k regex:spmv_ell_persistent -s 5 -c 1 -f -o $OUT/${TAG}_spmv_persistent \
+  $PY bench.py --steps 10 --warmup 3 --no-cg --no-extra --no-cpu > $OUT/${TAG}_ncu_spmv.log 2>&1
+ncu -i $OUT/${TAG}_spmv_persistent.ncu-rep --page raw --csv 2>/dev/null | $PY profiles/summarize_ncu.py > $OUT/${TAG}_spmv_persistent_ncu.md
+cat $OUT/${TAG}_spmv_persistent_ncu.md
+
+step "ncu --set full: one CG iteration on C4 (SpMV + dot, fused update)"
+timeout 1200 $NCU --set full --import-source on -k regex:"spmv_ell_persistent|cg_update_fused" -s 60 -c 2 -f -o $OUT/${TAG}_cg_iteration \
+  $PY bench.py --steps 3 --warmup 3 --no-extra --no-cpu --cg-maxiters 60 > $OUT/${TAG}_ncu_cg.log 2>&1
+ncu -i $OUT/${TAG}_cg_iteration.ncu-rep --page raw --csv 2>/dev/null | $PY profiles/summarize_ncu.py > $OUT/${TAG}_cg_iteration_ncu.md
+cat $OUT/${TAG}_cg_iteration_ncu.md
+
+step "ncu --set full: gather-CSR SpMV on C3 (R-MAT)"
+timeout 1500 $NCU --set full --import-source on -k regex:spmv_csr_items -s 3 -c 1 -f -o $OUT/${TAG}_spmv_csr_rmat \
+  $PY bench.py --steps 3 --warmup 3 --no-cg --only-rmat --no-cpu > $OUT/${TAG}_ncu_rmat.log 2>&1
+ncu -i $OUT/${TAG}_spmv_csr_rmat.ncu-rep --page raw --csv 2>/dev/null | $PY profiles/summarize_ncu.py > $OUT/${TAG}_spmv_csr_rmat_ncu.md
+cat $OUT/${TAG}_spmv_csr_rmat_ncu.md
+
+step "done"
+ls -la $OUT | tail -30
