@@ -166,6 +166,7 @@ def ref():
         L.ref_solvers_last_error.restype = C.c_char_p
         L.ref_pcg_timed.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_double)]
         L.ref_ilu_apply.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 5
+        L.ref_symv_timed.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.POINTER(C.c_double)]
         assert L.ref_solvers_real_mkl() == 1
         _ref = L
     return _ref
@@ -187,6 +188,18 @@ def pcg(n, row_ptr, col_ind, values, rhs, x0=None, precon=0, iterations=0):
     if rc < 0:
         raise RuntimeError(ref().ref_solvers_last_error().decode())
     return bool(rc), it.value, x, sec.value
+
+
+def symv(n, row_ptr, col_ind, values, x, reps=1):
+    """y = A x the way the reference's pcg<> computes it: mkl_dcsrsymv('l') on one-based copies of the CSR handed over
+    (A symmetric, stored lower triangle read), through the compiled adapter.  Returns (y, seconds of `reps` calls)."""
+    rp, ci, va = _csr3(row_ptr, col_ind, values)
+    x = np.ascontiguousarray(x, np.float64)
+    y = np.zeros(n, np.float64)
+    sec = C.c_double(0.0)
+    if ref().ref_symv_timed(n, len(va), _p(rp), _p(ci), _p(va), _p(x), _p(y), reps, C.byref(sec)) < 0:
+        raise RuntimeError(ref().ref_solvers_last_error().decode())
+    return y, sec.value
 
 
 def ilu_apply(n, row_ptr, col_ind, values, x):

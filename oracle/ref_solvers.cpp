@@ -52,6 +52,26 @@ int ref_pcg(int n, int nnz, const int* rp, const int* ci, const double* va, cons
   return ref_pcg_timed(n, nnz, rp, ci, va, rhs, x, iterations, precon, nullptr);
 }
 
+// y = A x exactly as the reference's pcg<> computes it (SparseLinearSolvers.hpp:175-190, 206): one-based copies of the
+// CSR handed over, then mkl_dcsrsymv('l', ...) - A symmetric, only its stored lower triangle read.  `reps` timed calls
+// after one warm-up; *seconds receives the total of the timed calls.
+int ref_symv_timed(int n, int nnz, const int* rp, const int* ci, const double* va, const double* x, double* y, int reps,
+                   double* seconds) {
+  try {
+    CsrMatrix a = make(n, n, nnz, rp, ci, va);
+    char tr = 'l';
+    auto values = a.values;
+    auto row_ptr = a.getRowPtrWithOneBasedIndex();
+    auto col_ind = a.getColIndWithOneBasedIndex();
+    mkl_dcsrsymv(&tr, &n, values.data(), row_ptr.data(), col_ind.data(), x, y);
+    cask::utils::Timer t;
+    t.tic("symv");
+    for (int r = 0; r < reps; r++) mkl_dcsrsymv(&tr, &n, values.data(), row_ptr.data(), col_ind.data(), x, y);
+    if (seconds) *seconds = t.toc("symv").count();
+    return 0;
+  } catch (std::exception& e) { g_serr = e.what(); return -1; }
+}
+
 // 1 when this build runs on Intel MKL's arithmetic (ref_shim_mkl/mkl.h), 0 with the sequential stand-in (ref_shim/mkl.h)
 int ref_solvers_real_mkl() {
 #ifdef CASK_REF_REAL_MKL
