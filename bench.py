@@ -48,12 +48,17 @@ def parse():
     ap.add_argument("--no-extra", action="store_true", help="skip the C3 (R-MAT SpMV) and C5 (BiCGStab) side measurements")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cache", type=int, default=8192)
+    ap.add_argument("--soak", type=int, default=1500,
+                    help="untimed launches between the warm-up and the timed region (clock sampling under load)")
     ap.add_argument("--only-rmat", action="store_true", help="profiling: run only the C3 R-MAT SpMV side measurement")
     ap.add_argument("--cg-maxiters", type=int, default=2000, help="cap on CG iterations (profiling runs)")
     ap.add_argument("--cg-emulate-shard", type=int, default=0,
                     help="profiling: on ONE GPU, run CG on the stripe that rank W/2 of a W-way sharded C4 system owns "
                          "(principal submatrix, halo columns read zeros): the per-rank work of the W-GPU job under ncu")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if any(k in os.environ for k in ("CUDA_INJECTION64_PATH", "NV_COMPUTE_PROFILER_PERFWORKS_DIR")):
+        args.soak = 0  # under ncu every launch is replayed and serialised: no soak, and the numbers are not bench values
+    return args
 
 
 def algorithmic_bytes(nnz, rows, cols):
@@ -72,15 +77,19 @@ def workload_name(G, world, nnz_rank0=None):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  Every sample carries
+    nvidia-smi's own timestamp; stop(t0, t1) keeps the samples that fall inside the timed region [t0, t1] and, when the
+    region is too short to hold three of them (K steps of a 0.2 ms kernel), the samples of the soak window that
+    precedes it, where the GPU runs the very same launches back to back - the window used is named in the result."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
 
-    def start(self):
+    def start(self, wait_first_s=3.0):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "20"],
@@ -88,31 +97,56 @@ class ClockSampler:
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None
+            return
+        t_end = time.time() + wait_first_s  # nvidia-smi needs a few hundred ms before its first sample
+        while not self.lines and time.time() < t_end and self.proc.poll() is None:
+            time.sleep(0.01)
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    @staticmethod
+    def parse(received, line):
+        """(time, sm MHz, max MHz, [reasons]) of one csv line, or None."""
+        f = [t.strip() for t in line.split(",")]
+        if len(f) < 10:
+            return None
+        try:
+            sm, mx = float(f[2]), float(f[3])
+        except ValueError:
+            return None
+        try:
+            import datetime
+            ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            if abs(ts - received) > 5.0:  # clock / time-zone disagreement: trust the arrival time
+                ts = received
+        except ValueError:
+            ts = received
+        return ts, sm, mx, [n for n, v in zip(ClockSampler.NAMES, f[6:10]) if v.lower().startswith("active")]
+
+    @staticmethod
+    def summarize(samples, t0=None, t1=None, t_soak=None):
+        window, sel = "all samples", samples
+        if t0 is not None and t1 is not None:
+            timed = [s for s in samples if t0 <= s[0] <= t1]
+            soak = [s for s in samples if (t_soak if t_soak is not None else t0) <= s[0] <= t1]
+            if len(timed) >= 3:
+                window, sel = "timed region", timed
+            elif soak:
+                window, sel = "soak + timed region (same launches back to back; the timed region alone held %d samples)" % len(timed), soak
+        reasons = sorted({r for s in sel for r in s[3]})
+        return {"sm_mhz": statistics.median([s[1] for s in sel]) if sel else None,
+                "sm_max_mhz": max(s[2] for s in sel) if sel else None, "samples": len(sel), "window": window,
+                "reasons": reasons}
+
+    def stop(self, t0=None, t1=None, t_soak=None):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "window": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for ln in self.lines:
-            f = [t.strip() for t in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        samples = [p for p in (self.parse(r, ln) for r, ln in list(self.lines)) if p]
+        return self.summarize(samples, t0, t1, t_soak)
 
 
 def measured_peak():
@@ -392,20 +426,29 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        ctx.spmv_device(x_full.data_ptr(), y.data_ptr())
+    barrier()
+    # soak: the same launch back to back for a few hundred ms (a fixed count, identical on every rank), untimed, so that
+    # the clock sampler sees the GPU under exactly this load even when K steps last only a few milliseconds
+    t_soak = time.time()
+    for _ in range(args.soak):
         ctx.spmv_device(x_full.data_ptr(), y.data_ptr())
     barrier()
     l0 = ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_begin = time.time()
     e0.record()
     for _ in range(args.steps):
         ctx.spmv_device(x_full.data_ptr(), y.data_ptr())
     e1.record()
     barrier()
+    t_end = time.time()
     ms = e0.elapsed_time(e1)
     launches = ctx.launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, t_end, t_soak) if rank == 0 else None
     # correctness of the timed result: interior rows vanish for this x, boundary rows are known
     xg = x_full.view(G * world, G)
     lo, hi = rank * G, (rank + 1) * G
@@ -485,25 +528,34 @@ def main():
     cg = bicg = rmat = None
     del x_full, y, cols, vals, rp
     torch.cuda.empty_cache()
+    # The side measurements never take the headline line down with them: a failure is recorded in place of the numbers.
+    def side(fn, *a):
+        try:
+            return fn(*a)
+        except Exception as e:  # noqa: BLE001 - reported, not swallowed
+            return {"error": "%s: %s" % (type(e).__name__, e)}
+        finally:
+            try:
+                torch.cuda.empty_cache()
+            except Exception:
+                pass
     if not args.no_cg:
-        cg = bench_cg(ctx, cb, torch, dist, dev, rank, world, barrier, args.cg_maxiters, args.cg_emulate_shard)
-        torch.cuda.empty_cache()
+        cg = side(bench_cg, ctx, cb, torch, dist, dev, rank, world, barrier, args.cg_maxiters, args.cg_emulate_shard)
     if not args.no_extra:
         if not args.only_rmat:
-            bicg = bench_bicgstab(ctx, cb, torch, dist, dev, rank, world, barrier)
-            torch.cuda.empty_cache()
-        rmat = bench_rmat(ctx, cb, torch, dist, dev, rank, world, barrier)
-        torch.cuda.empty_cache()
+            bicg = side(bench_bicgstab, ctx, cb, torch, dist, dev, rank, world, barrier)
+        rmat = side(bench_rmat, ctx, cb, torch, dist, dev, rank, world, barrier)
 
     if rank == 0:
         line = {
             "metric": "fp64 SpMV GFLOP/s", "value": value, "unit": "GFLOP/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": kernel_ms,
+            "steps": args.steps, "warmup": warm, "ms_per_step": kernel_ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": workload_name(G, world, nnz_local)[0],
                        "global_rows": n_global, "sharding": "row stripes over ranks (Spmv.cpp:334-364), NCCL x halo",
                        "l2": "inputs (%.2f GB per launch) larger than L2 (126 MB); no flush needed" % (bytes_per_launch / 1e9),
+                       "soak_steps": args.soak,
                        "design": {"num_pipes": 1, "cache_size": args.cache, "input_width": 16},
                        "preprocess_s": preprocess_s, "plan": stats},
             "hbm_gbs": achieved, "frac_of_nominal_8tbs": achieved / 8000.0,
@@ -523,7 +575,7 @@ def main():
                 line["cpu_baseline"] = cpu_port_baseline(G)
             except Exception as e:
                 line["cpu_baseline"] = {"value": None, "unit": "GFLOP/s", "cores": 0, "kind": "port", "sample": "failed: %s" % e}
-            if cg:
+            if cg and "error" not in cg:
                 try:
                     cg["cpu_baseline"] = cpu_reference_cg()
                 except Exception as e:

@@ -32,25 +32,25 @@ tail -c 1500 $OUT/${TAG}_bench.json
 
 step "ncu launch list of bench.py (C2 SpMV + C4 CG)"
 timeout 1200 $NCU --metrics gpu__time_duration.sum -c 900 --csv --log-file $OUT/${TAG}_launches.csv \
-  $PY bench.py --steps 20 --warmup 3 --no-extra --no-cpu --cg-maxiters 100 > $OUT/${TAG}_launches.log 2>&1
+  $PY bench.py --steps 20 --warmup 3 --no-extra --no-cpu --soak 0 --cg-maxiters 100 > $OUT/${TAG}_launches.log 2>&1
 $PY profiles/summarize_launches.py $OUT/${TAG}_launches.csv > $OUT/${TAG}_launches_summary.md 2>> $OUT/${TAG}_launches.log
 head -12 $OUT/${TAG}_launches_summary.md
 
 step "ncu --set full: persistent SpMV on C2"
 timeout 900 $NCU --set full --import-source on -k regex:spmv_ell_persistent -s 5 -c 1 -f -o $OUT/${TAG}_spmv_persistent \
-  $PY bench.py --steps 10 --warmup 3 --no-cg --no-extra --no-cpu > $OUT/${TAG}_ncu_spmv.log 2>&1
+  $PY bench.py --steps 10 --warmup 3 --soak 0 --no-cg --no-extra --no-cpu > $OUT/${TAG}_ncu_spmv.log 2>&1
 ncu -i $OUT/${TAG}_spmv_persistent.ncu-rep --page raw --csv 2>/dev/null | $PY profiles/summarize_ncu.py > $OUT/${TAG}_spmv_persistent_ncu.md
 cat $OUT/${TAG}_spmv_persistent_ncu.md
 
 step "ncu --set full: one CG iteration on C4 (SpMV + dot, fused update)"
 timeout 1200 $NCU --set full --import-source on -k regex:"spmv_ell_persistent|cg_update_fused" -s 60 -c 2 -f -o $OUT/${TAG}_cg_iteration \
-  $PY bench.py --steps 3 --warmup 3 --no-extra --no-cpu --cg-maxiters 60 > $OUT/${TAG}_ncu_cg.log 2>&1
+  $PY bench.py --steps 3 --warmup 3 --soak 0 --no-extra --no-cpu --cg-maxiters 60 > $OUT/${TAG}_ncu_cg.log 2>&1
 ncu -i $OUT/${TAG}_cg_iteration.ncu-rep --page raw --csv 2>/dev/null | $PY profiles/summarize_ncu.py > $OUT/${TAG}_cg_iteration_ncu.md
 cat $OUT/${TAG}_cg_iteration_ncu.md
 
 step "ncu --set full: gather-CSR SpMV on C3 (R-MAT)"
 timeout 1500 $NCU --set full --import-source on -k regex:spmv_csr_items -s 3 -c 1 -f -o $OUT/${TAG}_spmv_csr_rmat \
-  $PY bench.py --steps 3 --warmup 3 --no-cg --only-rmat --no-cpu > $OUT/${TAG}_ncu_rmat.log 2>&1
+  $PY bench.py --steps 3 --warmup 3 --soak 0 --no-cg --only-rmat --no-cpu > $OUT/${TAG}_ncu_rmat.log 2>&1
 ncu -i $OUT/${TAG}_spmv_csr_rmat.ncu-rep --page raw --csv 2>/dev/null | $PY profiles/summarize_ncu.py > $OUT/${TAG}_spmv_csr_rmat_ncu.md
 cat $OUT/${TAG}_spmv_csr_rmat_ncu.md
 

@@ -66,3 +66,34 @@ def test_reference_arm_runs_on_cpu():
     assert set(other) >= {"port", "mkl"} and other["port"]["gflops"] > 0
     assert line["config"]["workload"].startswith("C2: 2D 5-pt Poisson 4096x4096")
     assert line["cg"].get("value", 0) > 0 and line["cg"]["kind"] in ("reference", "port")
+
+
+def test_clock_sampler_windows():
+    """The sampler keeps the samples of the timed region, widens to the soak window when the region is too short to
+    hold three samples, and reports throttle reasons only from the window it used."""
+    import datetime
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    S = bench.ClockSampler
+    base = 1.7e9
+
+    def line(t, sm, power_cap="Not Active", thermal="Not Active"):
+        ts = datetime.datetime.fromtimestamp(t).strftime("%Y/%m/%d %H:%M:%S.%f")[:-3]
+        return "%s, 0, %d, 1965, 700.0, 0x0000000000000004, Not Active, %s, Not Active, %s" % (ts, sm, thermal, power_cap)
+
+    idle = [S.parse(base + 0.02 * i, line(base + 0.02 * i, 1200, thermal="Active")) for i in range(10)]
+    soak = [S.parse(base + 0.3 + 0.02 * i, line(base + 0.3 + 0.02 * i, 1950)) for i in range(20)]
+    timed = [S.parse(base + 0.8 + 0.02 * i, line(base + 0.8 + 0.02 * i, 1935, power_cap="Active")) for i in range(5)]
+    assert all(p is not None for p in idle + soak + timed)
+    assert abs(soak[0][0] - (base + 0.3)) < 2e-3 and soak[0][1:3] == (1950.0, 1965.0)
+    r = S.summarize(idle + soak + timed, base + 0.8, base + 0.9, base + 0.3)
+    assert r["window"] == "timed region" and r["samples"] == 5 and r["sm_mhz"] == 1935 and r["reasons"] == ["sw_power_cap"]
+    r = S.summarize(idle + soak + timed, base + 0.8, base + 0.83, base + 0.3)   # 2 samples only: widen to the soak
+    assert r["window"].startswith("soak + timed") and r["samples"] == 22 and r["sm_mhz"] == 1950
+    assert "hw_thermal_slowdown" not in r["reasons"]                            # the idle samples are outside the window
+    assert S.parse(base, "garbage") is None and S.parse(base, line(base, 1).replace(" 1,", " [N/A],")) is None
+    # a clock that disagrees with the host by hours (time zone): the arrival time is used
+    assert S.parse(base + 7200.0, line(base, 1800))[0] == base + 7200.0
+    assert S.summarize([], 0.0, 1.0, 0.0)["sm_mhz"] is None
