@@ -48,6 +48,9 @@ def parse():
     ap.add_argument("--no-extra", action="store_true", help="skip the C3 (R-MAT SpMV) and C5 (BiCGStab) side measurements")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cache", type=int, default=8192)
+    ap.add_argument("--value-dict", action="store_true",
+                    help="coded staged ELL: values as 8-bit codes into per-slice tables (3 B per stored nonzero instead of "
+                         "10, bit-identical y); off by default until measured on the GPU")
     ap.add_argument("--soak", type=int, default=1500,
                     help="untimed launches between the warm-up and the timed region (clock sampling under load)")
     ap.add_argument("--only-rmat", action="store_true", help="profiling: run only the C3 R-MAT SpMV side measurement")
@@ -377,6 +380,8 @@ def main():
     ctx = cb.Context(local)
     stream = torch.cuda.current_stream().cuda_stream
     ctx.set_stream(stream)
+    if args.value_dict:
+        ctx.set_option("value_dict", 1)
     if world > 1:
         idt = torch.zeros(128, dtype=torch.uint8, device=dev)
         if rank == 0:
@@ -418,6 +423,7 @@ def main():
     ctx.synchronize()
     preprocess_s = time.perf_counter() - t0
     stats = ctx.plan_stats()
+    vd_active, vd_entries, vd_matrix_bytes = ctx.value_dict()
 
     x_full = ((torch.arange(n_global, device=dev) % 1024).double() * 0.25).contiguous()
     y = torch.empty(n_local, dtype=torch.float64, device=dev)
@@ -557,10 +563,14 @@ def main():
                        "l2": "inputs (%.2f GB per launch) larger than L2 (126 MB); no flush needed" % (bytes_per_launch / 1e9),
                        "soak_steps": args.soak,
                        "design": {"num_pipes": 1, "cache_size": args.cache, "input_width": 16},
-                       "preprocess_s": preprocess_s, "plan": stats},
+                       "preprocess_s": preprocess_s, "plan": stats,
+                       "format": {"value_dict": vd_active, "table_doubles_per_slice": vd_entries,
+                                  "stored_bytes_per_launch": vd_matrix_bytes + 8 * (n_local + n_local),
+                                  "note": "bytes one SpMV moves in the stored format: staged-ELL entries (10 B each, or 3 B "
+                                          "coded) + x read once + y written once"}},
             "hbm_gbs": achieved, "frac_of_nominal_8tbs": achieved / 8000.0,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "spmv_ell_persistent_kernel<2,false>",
+                         "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "spmv_ell_persistent_kernel<%d,false,%s>" % (2 if not vd_active else 4, "true" if vd_active else "false"),
                          "algorithmic_bytes_per_launch": bytes_per_launch},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }

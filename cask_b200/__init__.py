@@ -32,7 +32,7 @@ EXPORTED_SYMBOLS = (
     "cask_b200_mm_read_info", "cask_b200_mm_read_coo", "cask_b200_mm_read_vector", "cask_b200_ingest_coo",
     "cask_b200_ingest_coo_device", "cask_b200_read_matrix", "cask_b200_csr_get_info", "cask_b200_csr_export",
     "cask_b200_csr_device_arrays", "cask_b200_csr_free", "cask_b200_preprocess_csr",
-    "cask_b200_pcg", "cask_b200_pcg_device", "cask_b200_precond_set_matrix", "cask_b200_ilu_factor", "cask_b200_ilu_apply",
+    "cask_b200_plan_value_dict", "cask_b200_pcg", "cask_b200_pcg_device", "cask_b200_precond_set_matrix", "cask_b200_ilu_factor", "cask_b200_ilu_apply",
 )
 PRECON_IDENTITY, PRECON_ILU, PRECON_JACOBI, PRECON_ILU_UNIT = range(4)
 INGEST_ONE_BASED, INGEST_SYMMETRIC, INGEST_DROP_UPPER = 1, 2, 4
@@ -104,6 +104,7 @@ def lib():
         L.cask_b200_preprocess_device.argtypes = [vp, C.POINTER(Design), i64, i64, i64, vp, vp, vp]
         L.cask_b200_preprocess_shard_device.argtypes = [vp, C.POINTER(Design), i64, i64, i64, i64, i64, vp, vp, vp]
         L.cask_b200_plan_get_stats.argtypes = [vp, C.POINTER(PlanStats)]
+        L.cask_b200_plan_value_dict.argtypes = [vp, vp, vp, vp]
         L.cask_b200_partition_get_info.argtypes = [vp, i32, C.POINTER(PartitionInfo)]
         L.cask_b200_partition_export.argtypes = [vp, i32, vp, vp]
         L.cask_b200_spmv.argtypes = [vp, vp, vp]
@@ -327,6 +328,12 @@ class Context:
         st = PlanStats()
         check(lib().cask_b200_plan_get_stats(self.h, C.byref(st)))
         return st.as_dict()
+
+    def value_dict(self):
+        """(active, doubles staged per slice table, matrix bytes one SpMV streams) of the current plan."""
+        a, e, b = C.c_int32(), C.c_int32(), C.c_int64()
+        check(lib().cask_b200_plan_value_dict(self.h, C.byref(a), C.byref(e), C.byref(b)))
+        return bool(a.value), e.value, b.value
 
     def partition(self, pipe, arrays=True):
         """(info dict, colptr, pairs) of reference partition `pipe`, produced by the GPU partitioner."""

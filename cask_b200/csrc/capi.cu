@@ -104,6 +104,8 @@ int cask_b200_create(cask_b200_ctx** out, int device) {
   if (const char* e = getenv("CASK_B200_L2_KEEP")) ctx->l2_keep = atoi(e);
   if (const char* e = getenv("CASK_B200_CSR_STREAM")) ctx->csr_stream = atoi(e);
   if (const char* e = getenv("CASK_B200_CSR_ITEM_NNZ")) ctx->csr_item_nnz = atoi(e);
+  if (const char* e = getenv("CASK_B200_VALUE_DICT")) ctx->value_dict = atoi(e);
+  if (const char* e = getenv("CASK_B200_PERSIST_CTAS")) ctx->persist_ctas = atoi(e);
   *out = ctx;
   return CASK_B200_OK;
 }
@@ -162,6 +164,8 @@ int cask_b200_set_option(cask_b200_ctx* ctx, const char* name, double value) {
   else if (k == "l2_keep") ctx->l2_keep = (int32_t)value;
   else if (k == "csr_stream") ctx->csr_stream = (int32_t)value;
   else if (k == "csr_item_nnz") ctx->csr_item_nnz = (int32_t)value;
+  else if (k == "value_dict") ctx->value_dict = (int32_t)value;
+  else if (k == "persist_ctas") ctx->persist_ctas = (int32_t)value;
   else return fail(CASK_B200_ERR_INVALID_ARGUMENT, "set_option: unknown option " + k);
   return CASK_B200_OK;
 }
@@ -233,6 +237,22 @@ int cask_b200_preprocess(cask_b200_ctx* ctx, const cask_b200_design* design, int
 int cask_b200_plan_get_stats(cask_b200_ctx* ctx, cask_b200_plan_stats* out) {
   if (!ctx || !out || !ctx->have_design) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "plan_get_stats: preprocess first");
   *out = ctx->plan.stats;
+  return CASK_B200_OK;
+}
+
+int cask_b200_plan_value_dict(cask_b200_ctx* ctx, int32_t* active, int32_t* max_entries, int64_t* matrix_bytes_per_spmv) {
+  if (!ctx || !ctx->have_design) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "plan_value_dict: preprocess first");
+  const Plan& p = ctx->plan;
+  const bool on = p.coded && ctx->ell_kernel == 1 && p.persist_ku != 0;  // only the persistent kernel reads the codes
+  if (active) *active = on ? 1 : 0;
+  if (max_entries) *max_entries = on ? p.dict_len : 0;
+  if (matrix_bytes_per_spmv) {
+    const int64_t csr = p.stats.nnz - p.stats.ell_nnz;
+    int64_t csr_rows = 0;
+    for (const SliceDesc& sd : p.h_slices) if (sd.kind != kSliceStagedEll) csr_rows += sd.nrows;
+    *matrix_bytes_per_spmv = p.stats.ell_padded_entries * (on ? 3 : 10) + (on ? (int64_t)p.n_ell * p.dict_len * 8 : 0) +
+                             csr * 12 + csr_rows * 4;
+  }
   return CASK_B200_OK;
 }
 

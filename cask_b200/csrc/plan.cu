@@ -18,6 +18,9 @@
 #include <cstring>
 
 #include "ctx.cuh"
+#include "devlogic.cuh"
+
+#include "valuedict_logic.inl"
 
 namespace caskb200 {
 
@@ -246,6 +249,7 @@ void free_plan(cask_b200_ctx* ctx) {
     cudaFree((void*)p.d_val);
   }
   cudaFree(p.d_slices); cudaFree(p.d_runs); cudaFree(p.d_ell_vals); cudaFree(p.d_ell_idx);
+  cudaFree(p.d_ell_codes); cudaFree(p.d_ell_dict);
   cudaFree(p.d_list_ell); cudaFree(p.d_list_csr);
   cudaFree(p.d_csr_items); cudaFree(p.d_split_rows); cudaFree(p.d_csr_scratch);
   p = Plan();
@@ -317,6 +321,43 @@ int build_csr_items(cask_b200_ctx* ctx) {
     CB_CUDA(cudaMemcpyAsync(p.d_split_rows, splits.data(), sizeof(SplitRow) * splits.size(), cudaMemcpyHostToDevice, s));
   CB_CUDA(cudaMalloc(&p.d_csr_scratch, sizeof(double) * std::max(n_scratch, 1)));
   CB_CUDA(cudaStreamSynchronize(s));
+  return CASK_B200_OK;
+}
+
+// Coded staged ELL (option value_dict): per-slice tables of the distinct values + 8-bit codes (valuedict_logic.inl).
+// All staged slices or none: if any slice holds more than 256 distinct values the plan stays uncoded.
+// val_off_total = entries of the ELL arrays.
+static int build_value_dict(cask_b200_ctx* ctx, int64_t val_off_total) {
+  Plan& p = ctx->plan;
+  p.coded = false;
+  p.dict_len = 0;
+  if (!ctx->value_dict || p.n_ell == 0 || p.nslices == 0) return CASK_B200_OK;
+  dev::Exec ex = dev::exec_of(ctx);
+  std::vector<int64_t> h_off((size_t)p.nslices, 0);
+  std::vector<int32_t> h_width((size_t)p.nslices, 0);  // 0 for gather-CSR slices: empty table, nothing scanned
+  for (int32_t i = 0; i < p.nslices; i++)
+    if (p.h_slices[i].kind == kSliceStagedEll) { h_off[i] = p.h_slices[i].val_off; h_width[i] = p.h_slices[i].width; }
+  struct Tmp {
+    void* q[3] = {nullptr, nullptr, nullptr};
+    ~Tmp() { for (void* x : q) dev::release(x); }
+  } tmp;
+  CB_TRY(dev::alloc(&tmp.q[0], sizeof(int64_t) * (size_t)p.nslices));
+  CB_TRY(dev::alloc(&tmp.q[1], sizeof(int32_t) * (size_t)p.nslices));
+  CB_TRY(dev::alloc(&tmp.q[2], sizeof(int32_t) * (size_t)p.nslices));
+  CB_TRY(dev::upload(ex, tmp.q[0], h_off.data(), sizeof(int64_t) * (size_t)p.nslices));
+  CB_TRY(dev::upload(ex, tmp.q[1], h_width.data(), sizeof(int32_t) * (size_t)p.nslices));
+  CB_CUDA(cudaMalloc(&p.d_ell_codes, (size_t)std::max<int64_t>(val_off_total, 16)));
+  CB_CUDA(cudaMalloc(&p.d_ell_dict, sizeof(double) * (size_t)valuedict::kStride * (size_t)p.nslices));
+  int32_t overflow = 0, max_entries = 0;
+  CB_TRY(valuedict::build(ex, p.nslices, (const int64_t*)tmp.q[0], (const int32_t*)tmp.q[1], p.slice_rows, p.d_ell_vals,
+                          p.d_ell_dict, p.d_ell_codes, (int32_t*)tmp.q[2], &overflow, &max_entries));
+  if (overflow || max_entries == 0) {
+    cudaFree(p.d_ell_codes); cudaFree(p.d_ell_dict);
+    p.d_ell_codes = nullptr; p.d_ell_dict = nullptr;
+    return CASK_B200_OK;
+  }
+  p.coded = true;
+  p.dict_len = (max_entries + 1) & ~1;  // bulk copies move multiples of 16 bytes
   return CASK_B200_OK;
 }
 
@@ -455,6 +496,7 @@ int build_plan(cask_b200_ctx* ctx) {
   CB_CUDA(cudaGetLastError());
   cudaFree(d_row0); cudaFree(d_nrows); cudaFree(d_counts); cudaFree(d_hist); cudaFree(d_maxlen);
 
+  CB_TRY(build_value_dict(ctx, val_off));
   CB_TRY(configure_persistent(ctx));
   CB_TRY(build_csr_items(ctx));
   p.stats.slices_staged_ell = p.n_ell;
@@ -462,7 +504,8 @@ int build_plan(cask_b200_ctx* ctx) {
   p.stats.csr_lanes_per_row = vec;
   p.stats.max_row_length = maxlen;
   for (int i = 0; i < 8; i++) p.stats.row_length_histogram[i] = (int64_t)hist[i];
-  p.stats.device_bytes = val_off * 10 + (int64_t)run_off * sizeof(Run) + (int64_t)p.nslices * sizeof(SliceDesc) +
+  p.stats.device_bytes = val_off * (p.coded ? 11 : 10) + (p.coded ? (int64_t)p.nslices * valuedict::kStride * 8 : 0) +
+                         (int64_t)run_off * sizeof(Run) + (int64_t)p.nslices * sizeof(SliceDesc) +
                          (p.n_csr ? (csr_nnz * 12 + csr_rows * 4) : 0);
   return CASK_B200_OK;
 }

@@ -212,21 +212,40 @@ struct PersistHeader {
 };
 static_assert(sizeof(PersistHeader) <= kPersistHeaderBytes, "header must fit its reservation");
 
-template <int KU, bool kDot>
+// kCoded (option value_dict, plan.cu: build_value_dict): the value stream is replaced by 8-bit codes into a table of the
+// slice's distinct values.  The table (dict_len doubles) travels with the x windows into the tail of the x buffer, a
+// ring stage holds KU*1024 codes + KU*1024 16-bit indices (3 bytes per stored nonzero instead of 10), and a consumer
+// reads its four codes with one 32-bit load and looks the doubles up in shared memory - the multiplied values, the
+// order of the operations and therefore y are those of the uncoded kernel, bit for bit.
+struct CodedArgs {
+  const uint8_t* codes = nullptr;  // same indexing as ell_vals
+  const double* dict = nullptr;    // valuedict::kStride doubles per slice id
+  int32_t dict_len = 0;            // doubles staged per slice (even)
+  int32_t pad_ = 0;
+};
+constexpr int kDictStride = 256;   // == valuedict::kStride (plan.cu)
+
+template <int KU, bool kDot, bool kCoded>
 __global__ void __launch_bounds__(kPersistThreads, 1)
 spmv_ell_persistent_kernel(const SliceDesc* __restrict__ slices, const int32_t* __restrict__ list, int count,
                            const Run* __restrict__ runs, const double* __restrict__ ell_vals,
                            const uint16_t* __restrict__ ell_idx, const double* __restrict__ x, double* __restrict__ y,
                            const double* __restrict__ dot_with, double* __restrict__ partials, int xbuf_doubles,
-                           int stages, const HaloWait hw, const __grid_constant__ ReduceDesc rd, int keep_i, unsigned long long* trace) {
+                           int stages, const HaloWait hw, const __grid_constant__ ReduceDesc rd, int keep_i, unsigned long long* trace,
+                           const CodedArgs ca) {
   trace_min(trace);
   const bool keep = keep_i != 0;  // vectors fit L2: x windows, y and dot_with are accessed with evict-last
   const unsigned long long keep_policy = l2_policy_evict_last();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   PersistHeader* hdr = reinterpret_cast<PersistHeader*>(smem_raw);
   double* xbuf = reinterpret_cast<double*>(smem_raw + kPersistHeaderBytes);
+  // ring: [values | indices] per stage, or [indices | codes] in the coded format (every region a multiple of 2 KB)
   double* cvals = xbuf + 2 * (size_t)xbuf_doubles;
-  uint16_t* cidx = reinterpret_cast<uint16_t*>(cvals + (size_t)stages * KU * kSliceRows);
+  uint16_t* cidx = kCoded ? reinterpret_cast<uint16_t*>(cvals)
+                          : reinterpret_cast<uint16_t*>(cvals + (size_t)stages * KU * kSliceRows);
+  uint8_t* ccode = reinterpret_cast<uint8_t*>(cidx + (size_t)stages * KU * kSliceRows);  // coded format only
+  // the table of a slice sits in the last ((dict_len + 15) & ~15) doubles of its x buffer
+  const int dict_base = kCoded ? xbuf_doubles - ((ca.dict_len + 15) & ~15) : 0;
   __shared__ double red[kPersistThreads / 32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -252,10 +271,17 @@ spmv_ell_persistent_kernel(const SliceDesc* __restrict__ slices, const int32_t* 
     const int s = chunk_no % stages;
     const int cols = min(KU, L - c * KU);
     const uint32_t fc = smem_u32(&hdr->full_c[s]);
-    mbar_expect_tx(fc, (uint32_t)cols * kSliceRows * 10u);
-    const size_t src = (size_t)sdp->val_off + (size_t)c * KU * kSliceRows;
-    bulk_g2s_hint(smem_u32(cvals + (size_t)s * KU * kSliceRows), ell_vals + src, (uint32_t)cols * kSliceRows * 8u, fc, stream_policy);
-    bulk_g2s_hint(smem_u32(cidx + (size_t)s * KU * kSliceRows), ell_idx + src, (uint32_t)cols * kSliceRows * 2u, fc, stream_policy);
+    if constexpr (kCoded) {
+      mbar_expect_tx(fc, (uint32_t)cols * kSliceRows * 3u);
+      const size_t src = (size_t)sdp->val_off + (size_t)c * KU * kSliceRows;
+      bulk_g2s_hint(smem_u32(ccode + (size_t)s * KU * kSliceRows), ca.codes + src, (uint32_t)cols * kSliceRows, fc, stream_policy);
+      bulk_g2s_hint(smem_u32(cidx + (size_t)s * KU * kSliceRows), ell_idx + src, (uint32_t)cols * kSliceRows * 2u, fc, stream_policy);
+    } else {
+      mbar_expect_tx(fc, (uint32_t)cols * kSliceRows * 10u);
+      const size_t src = (size_t)sdp->val_off + (size_t)c * KU * kSliceRows;
+      bulk_g2s_hint(smem_u32(cvals + (size_t)s * KU * kSliceRows), ell_vals + src, (uint32_t)cols * kSliceRows * 8u, fc, stream_policy);
+      bulk_g2s_hint(smem_u32(cidx + (size_t)s * KU * kSliceRows), ell_idx + src, (uint32_t)cols * kSliceRows * 2u, fc, stream_policy);
+    }
   };
   // Programmatic dependent launch: this CTA may be resident while the kernel that produces x is still running.
   // The matrix is static, so the producer warp fills the ring with the first chunks of its first slice BEFORE it
@@ -308,6 +334,11 @@ spmv_ell_persistent_kernel(const SliceDesc* __restrict__ slices, const int32_t* 
         }
         if (r.len & 1) xs[r.local_base + r.len - 1] = x[r.col0 + r.len - 1];  // odd tail at column m-1
       }
+      if constexpr (kCoded) if (lane == 31) {  // the slice's value table rides on the same barrier phase as its x windows
+        const uint32_t b = (uint32_t)ca.dict_len * 8u;
+        bytes += b;
+        bulk_g2s(smem_u32(xs + dict_base), ca.dict + (size_t)list[item] * kDictStride, b, fx);
+      }
 #pragma unroll
       for (int d = 16; d; d >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, d);
       if (lane == 0) {
@@ -342,11 +373,21 @@ spmv_ell_persistent_kernel(const SliceDesc* __restrict__ slices, const int32_t* 
         const int cols = min(KU, L - c * KU);
         const double* vb = cvals + (size_t)s * KU * kSliceRows + (size_t)tid * RPT;
         const uint16_t* ib = cidx + (size_t)s * KU * kSliceRows + (size_t)tid * RPT;
+        const uint8_t* cb = ccode + (size_t)s * KU * kSliceRows + (size_t)tid * RPT;
+        const double* dict = xs + dict_base;
 #pragma unroll
         for (int u = 0; u < KU; u++) {
           if (u < cols) {
-            const double2 v0 = *reinterpret_cast<const double2*>(vb + (size_t)u * kSliceRows);
-            const double2 v1 = *reinterpret_cast<const double2*>(vb + (size_t)u * kSliceRows + 2);
+            double2 v0, v1;
+            if constexpr (kCoded) {
+              // entry (k, row j*256 + t) is byte j of thread t's 32-bit word (little endian), as in the value layout
+              const uint32_t cw = *reinterpret_cast<const uint32_t*>(cb + (size_t)u * kSliceRows);
+              v0 = make_double2(dict[cw & 0xffu], dict[(cw >> 8) & 0xffu]);
+              v1 = make_double2(dict[(cw >> 16) & 0xffu], dict[cw >> 24]);
+            } else {
+              v0 = *reinterpret_cast<const double2*>(vb + (size_t)u * kSliceRows);
+              v1 = *reinterpret_cast<const double2*>(vb + (size_t)u * kSliceRows + 2);
+            }
             const uint2 ix = *reinterpret_cast<const uint2*>(ib + (size_t)u * kSliceRows);
             // ascending column order, separate multiply and add (DokMatrix::dot, SparseMatrix.hpp:255-264)
             acc[0] = __dadd_rn(acc[0], __dmul_rn(v0.x, xs[ix.x & 0xffffu]));
@@ -541,20 +582,32 @@ int configure_persistent(cask_b200_ctx* ctx) {
   if (p.n_ell == 0) return CASK_B200_OK;
   int dev_smem = 0;
   CB_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
-  const size_t xbuf = ((size_t)p.max_xcache + 15) & ~(size_t)15;  // doubles, keeps every buffer 128-B aligned
+  // doubles per x buffer (keeps every buffer 128-B aligned); the coded format appends the slice's value table
+  const size_t xbuf = (((size_t)p.max_xcache + 15) & ~(size_t)15) + (p.coded ? (((size_t)p.dict_len + 15) & ~(size_t)15) : 0);
   const size_t fixed = kPersistHeaderBytes + 2 * xbuf * sizeof(double);
   const size_t per_sm = 228 * 1024, reserve = 1024 + 64;  // 1 KB per CTA is the driver's + static reduction scratch
-  auto stage_bytes = [](int ku) { return (size_t)ku * kSliceRows * 10; };
+  const size_t entry_bytes = p.coded ? 3 : 10;
+  auto stage_bytes = [&](int ku) { return (size_t)ku * kSliceRows * entry_bytes; };
   int ku = 0, stages = 0, ctas = 0;
   auto fits = [&](int k, int st, int c) { return c * (fixed + st * stage_bytes(k) + reserve) <= per_sm &&
                                                   fixed + st * stage_bytes(k) <= (size_t)dev_smem; };
-  if ((ctx->persist_ku == 0 || ctx->persist_ku == 2) && fits(2, 3, 2)) { ku = 2; stages = 3; ctas = 2; while (stages < 4 && fits(2, stages + 1, 2)) stages++; }
-  if (!ku || ctx->persist_ku == 4) {
-    ku = 0;
-    for (int st = 4; st >= 2 && !ku; st--)
-      if (fits(4, st, 1)) { ku = 4; stages = st; ctas = 1; }
+  if (p.coded) {
+    // a stage is 3 KB per ELL column: deep rings of 4-column stages fit beside the x buffers; more CTAs per SM keep
+    // more slices (x windows) in flight, which is what the shorter per-slice time needs
+    const int k = ctx->persist_ku == 2 ? 2 : 4;
+    const int c_hi = ctx->persist_ctas >= 1 && ctx->persist_ctas <= 3 ? ctx->persist_ctas : 2;
+    for (int c = c_hi; c >= 1 && !ku; c--)
+      for (int st = 6; st >= 2 && !ku; st--)
+        if (fits(k, st, c)) { ku = k; stages = st; ctas = c; }
+  } else {
+    if ((ctx->persist_ku == 0 || ctx->persist_ku == 2) && fits(2, 3, 2)) { ku = 2; stages = 3; ctas = 2; while (stages < 4 && fits(2, stages + 1, 2)) stages++; }
+    if (!ku || ctx->persist_ku == 4) {
+      ku = 0;
+      for (int st = 4; st >= 2 && !ku; st--)
+        if (fits(4, st, 1)) { ku = 4; stages = st; ctas = 1; }
+    }
+    if (!ku && fits(2, 2, 1)) { ku = 2; stages = 2; ctas = 1; while (stages < kMaxStages && fits(2, stages + 1, 1)) stages++; }
   }
-  if (!ku && fits(2, 2, 1)) { ku = 2; stages = 2; ctas = 1; while (stages < kMaxStages && fits(2, stages + 1, 1)) stages++; }
   if (!ku) return CASK_B200_OK;  // x cache too large for the ring: the one-CTA-per-slice kernel is used
   p.persist_ku = ku;
   p.persist_stages = stages;
@@ -589,16 +642,16 @@ int launch_spmv_range(cask_b200_ctx* ctx, const double* d_x, double* d_y, int el
   const double* w = dot ? fusion->d_dot_with : nullptr;
   if (ell_hi > ell_lo && ctx->ell_kernel == 1 && p.persist_ku) {
     const int grid = ell_grid(ctx, ell_hi - ell_lo);
-#define CB_PERSIST(KU, DOT)                                                                                          \
+#define CB_PERSIST(KU, DOT, CODED)                                                                                   \
   do {                                                                                                               \
-    CB_CUDA(cudaFuncSetAttribute(spmv_ell_persistent_kernel<KU, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                 (int)p.persist_smem));                                                              \
-    CB_CUDA(cudaLaunchKernelEx(&cfg, spmv_ell_persistent_kernel<KU, DOT>, (const SliceDesc*)p.d_slices,              \
+    CB_CUDA(cudaFuncSetAttribute(spmv_ell_persistent_kernel<KU, DOT, CODED>,                                         \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.persist_smem));                 \
+    CB_CUDA(cudaLaunchKernelEx(&cfg, spmv_ell_persistent_kernel<KU, DOT, CODED>, (const SliceDesc*)p.d_slices,       \
                                (const int32_t*)(p.d_list_ell + ell_lo), ell_hi - ell_lo, (const Run*)p.d_runs,       \
                                (const double*)p.d_ell_vals, (const uint16_t*)p.d_ell_idx, d_x, d_y, w, partials,     \
                                (int)p.persist_xbuf, (int)p.persist_stages, hw, rd,                                   \
                                fusion ? fusion->keep_vectors : 0,                                                    \
-                               fusion ? fusion->trace : (unsigned long long*)nullptr));                              \
+                               fusion ? fusion->trace : (unsigned long long*)nullptr, ca));                          \
   } while (0)
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -612,8 +665,15 @@ int launch_spmv_range(cask_b200_ctx* ctx, const double* d_x, double* d_y, int el
     cfg.numAttrs = fusion && fusion->pdl ? 1 : 0;
     const ReduceDesc rd = dot && fusion->reduce.partials && ell_lo == 0 && ell_hi == p.n_ell && csr_hi == csr_lo
                               ? fusion->reduce : ReduceDesc();
-    if (p.persist_ku == 2) { if (dot) CB_PERSIST(2, true); else CB_PERSIST(2, false); }
-    else { if (dot) CB_PERSIST(4, true); else CB_PERSIST(4, false); }
+    CodedArgs ca;
+    if (p.coded) { ca.codes = p.d_ell_codes; ca.dict = p.d_ell_dict; ca.dict_len = p.dict_len; }
+    if (p.coded) {
+      if (p.persist_ku == 2) { if (dot) CB_PERSIST(2, true, true); else CB_PERSIST(2, false, true); }
+      else { if (dot) CB_PERSIST(4, true, true); else CB_PERSIST(4, false, true); }
+    } else {
+      if (p.persist_ku == 2) { if (dot) CB_PERSIST(2, true, false); else CB_PERSIST(2, false, false); }
+      else { if (dot) CB_PERSIST(4, true, false); else CB_PERSIST(4, false, false); }
+    }
 #undef CB_PERSIST
     ctx->launches++;
     if (partials) partials += grid;

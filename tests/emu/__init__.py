@@ -35,6 +35,7 @@ def lib():
         L.emu_coo_to_csr.argtypes = [i64, i64, i64, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, i64, vp]
         L.emu_ilu.argtypes = [i64, i64, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp]
         L.emu_inv_diag.argtypes = [i64, vp, vp, vp, vp]
+        L.emu_valuedict.argtypes = [i64, vp, vp, C.c_int32, vp, C.c_int, vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -86,3 +87,18 @@ def inv_diag(n, row_ptr, col_ind, values):
     out = np.zeros(max(n, 1), np.float64)
     lib().emu_inv_diag(n, _p(rp), _p(ci), _p(va), _p(out))
     return out[:n]
+
+
+def valuedict(val_off, width, vals, slice_rows=1024, order=1):
+    """Per-slice value dictionaries of the coded staged-ELL format.  Returns dict(rc, overflow, max_entries, table
+    [nlisted, 256], codes, ndict)."""
+    vo = np.ascontiguousarray(val_off, np.int64)
+    w = np.ascontiguousarray(width, np.int32)
+    va = np.ascontiguousarray(vals, np.float64)
+    table = np.full((max(len(vo), 1), 256), np.nan)
+    codes = np.full(max(len(va), 1), 255, np.uint8)
+    ndict = np.full(max(len(vo), 1), -1, np.int32)
+    info = np.zeros(3, np.int64)
+    rc = lib().emu_valuedict(len(vo), _p(vo), _p(w), slice_rows, _p(va), order, _p(table), _p(codes), _p(ndict), _p(info))
+    return {"rc": rc, "overflow": bool(info[0]), "max_entries": int(info[1]), "table": table[:len(vo)],
+            "codes": codes[:len(va)], "ndict": ndict[:len(vo)], "message": lib().emu_error().decode()}

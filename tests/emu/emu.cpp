@@ -67,3 +67,24 @@ int emu_inv_diag(int64_t n, const int32_t* rp, const int32_t* ci, const double* 
 }
 
 }  // extern "C"
+
+// ---- value dictionaries of the coded staged-ELL format ---------------------------------------------------------
+#include "../../cask_b200/csrc/valuedict_logic.inl"
+
+extern "C" {
+
+// table: nlisted * 256 doubles; codes: as long as vals; ndict: nlisted.  info[0] = overflow, info[1] = max entries,
+// info[2] = launches
+int emu_valuedict(int64_t nlisted, const int64_t* val_off, const int32_t* width, int32_t slice_rows, const double* vals,
+                  int order, double* table, uint8_t* codes, int32_t* ndict, int64_t* info) {
+  dev::Exec ex;
+  int64_t launches = 0;
+  ex.launches = &launches;
+  ex.order = order;
+  int32_t overflow = 0, max_entries = 0;
+  const int rc = valuedict::build(ex, nlisted, val_off, width, slice_rows, vals, table, codes, ndict, &overflow, &max_entries);
+  info[0] = overflow; info[1] = max_entries; info[2] = launches;
+  return rc;
+}
+
+}  // extern "C"
