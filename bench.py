@@ -51,6 +51,9 @@ def parse():
     ap.add_argument("--value-dict", action="store_true",
                     help="coded staged ELL: values as 8-bit codes into per-slice tables (3 B per stored nonzero instead of "
                          "10, bit-identical y); off by default until measured on the GPU")
+    ap.add_argument("--no-probe", action="store_true",
+                    help="skip the coded-staged-ELL probe (a child bench.py --value-dict run, bounded by a timeout)")
+    ap.add_argument("--probe-timeout", type=float, default=240.0, help="seconds the probe's child process may take")
     ap.add_argument("--soak", type=int, default=1500,
                     help="untimed launches between the warm-up and the timed region (clock sampling under load)")
     ap.add_argument("--only-rmat", action="store_true", help="profiling: run only the C3 R-MAT SpMV side measurement")
@@ -61,6 +64,7 @@ def parse():
     args = ap.parse_args()
     if any(k in os.environ for k in ("CUDA_INJECTION64_PATH", "NV_COMPUTE_PROFILER_PERFWORKS_DIR")):
         args.soak = 0  # under ncu every launch is replayed and serialised: no soak, and the numbers are not bench values
+        args.no_probe = True  # and no child process for the profiler to follow
     return args
 
 
@@ -352,6 +356,43 @@ def cpu_reference_cg(N=96):
             "sample": "3D 27-pt Poisson %d^3 (%d rows, %d nnz; C4 is 256^3), %s" % (N, n, len(va), what)}
 
 
+def value_dict_probe(args):
+    """The coded staged-ELL format (option value_dict, off by default) measured on the same workload in a CHILD process:
+    `bench.py --value-dict` with the side measurements off, bounded by a timeout.  The child checks y against the
+    closed-form stencil result like the main arm does (a wrong y is a non-zero exit), so the record says whether the
+    format is correct on this machine and what it would buy; a child that hangs or dies costs this record only, never
+    the headline line (its CUDA context is its own).  Informational: `value` stays the default format's number."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--value-dict", "--no-probe", "--no-cg", "--no-extra", "--no-cpu",
+           "--steps", str(args.steps), "--warmup", str(args.warmup), "--soak", str(min(args.soak, 500)),
+           "--grid", str(args.grid), "--cache", str(args.cache)]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
+    t0 = time.time()
+    child = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, cwd=ROOT)
+    try:
+        out, err = child.communicate(timeout=args.probe_timeout)
+    except subprocess.TimeoutExpired:
+        child.kill()
+        try:
+            child.communicate(timeout=30)
+        except subprocess.TimeoutExpired:  # stuck in the driver: leave it behind rather than wait for it
+            pass
+        return {"error": "child exceeded %.0f s and was killed" % args.probe_timeout}
+    if child.returncode != 0:
+        return {"error": "child exit %d: %s" % (child.returncode, (err or out).strip()[-400:])}
+    try:
+        d = json.loads(out.strip().splitlines()[-1])
+    except (ValueError, IndexError):
+        return {"error": "child printed no JSON line: %s" % out.strip()[-200:]}
+    fmt = d.get("config", {}).get("format", {})
+    return {"what": "child process: bench.py --value-dict on the same workload; y checked against the closed-form stencil result",
+            "active": bool(fmt.get("value_dict")), "value": d.get("value"), "unit": d.get("unit"), "ms_per_step": d.get("ms_per_step"),
+            "algorithmic_gbs": d.get("hbm_gbs"), "stored_bytes_per_launch": fmt.get("stored_bytes_per_launch"),
+            "stored_gbs": (fmt["stored_bytes_per_launch"] / (d["ms_per_step"] * 1e-3) / 1e9
+                           if fmt.get("stored_bytes_per_launch") and d.get("ms_per_step") else None),
+            "table_doubles_per_slice": fmt.get("table_doubles_per_slice"), "kernel": d.get("roofline", {}).get("kernel"),
+            "gpu_launches": d.get("gpu_launches"), "clocks": d.get("clocks"), "seconds": time.time() - t0}
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -580,6 +621,11 @@ def main():
             line["bicgstab"] = bicg
         if rmat:
             line["rmat_spmv"] = rmat
+        if world == 1 and not args.value_dict and not args.no_probe:
+            try:
+                line["value_dict_probe"] = value_dict_probe(args)
+            except Exception as e:  # noqa: BLE001 - informational
+                line["value_dict_probe"] = {"error": "%s: %s" % (type(e).__name__, e)}
         if world == 1 and not args.no_cpu:
             try:
                 line["cpu_baseline"] = cpu_port_baseline(G)

@@ -97,3 +97,26 @@ def test_clock_sampler_windows():
     # a clock that disagrees with the host by hours (time zone): the arrival time is used
     assert S.parse(base + 7200.0, line(base, 1800))[0] == base + 7200.0
     assert S.summarize([], 0.0, 1.0, 0.0)["sm_mhz"] is None
+
+
+def test_value_dict_probe_is_contained():
+    """The coded-format probe is a child process: without a GPU the child fails ("no CPU fallback") and the parent
+    records the failure instead of raising; a child that outlives its timeout is killed and recorded the same way."""
+    import argparse
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod2", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    a = argparse.Namespace(steps=5, warmup=3, soak=10, grid=64, cache=8192, probe_timeout=300.0)
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    r = bench.value_dict_probe(a)
+    if has_gpu:
+        assert "error" in r or r["value"] > 0
+    else:
+        assert "no CPU fallback" in r["error"]
+    a.probe_timeout = 0.2
+    assert "killed" in bench.value_dict_probe(a)["error"]
