@@ -38,6 +38,13 @@ CASK_B200_PERSIST_CTAS=1 timeout 600 $PY bench.py --value-dict --no-cpu --no-cg 
 CASK_B200_PERSIST_KU=2 timeout 600 $PY bench.py --value-dict --no-cpu --no-cg --no-extra > $OUT/${TAG}_bench_value_dict_ku2.json 2>> $OUT/${TAG}_bench_value_dict.err
 for f in 3ctas 1cta ku2; do $PY -c "import json,sys; d=json.loads(open('$OUT/${TAG}_bench_value_dict_$f.json').read().strip().splitlines()[-1]); print('$f', d['value'], d['ms_per_step'], d['config']['format'])" 2>/dev/null; done
 
+step "C3 (R-MAT) sweep: gather-CSR default vs CSR-stream at three item sizes"
+for v in "CASK_B200_CSR_STREAM=0" "CASK_B200_CSR_STREAM=1 CASK_B200_CSR_ITEM_NNZ=2048" "CASK_B200_CSR_STREAM=1 CASK_B200_CSR_ITEM_NNZ=4096" "CASK_B200_CSR_STREAM=1 CASK_B200_CSR_ITEM_NNZ=8192"; do
+  f=$OUT/${TAG}_rmat_$(echo $v | tr ' =' '__').json
+  env $v timeout 600 $PY bench.py --only-rmat --no-cg --no-cpu --no-probe --steps 20 --warmup 3 --soak 0 > $f 2>> $OUT/${TAG}_rmat.err
+  $PY -c "import json; d=json.loads(open('$f').read().strip().splitlines()[-1])['rmat_spmv']; print('$v', d.get('ms_per_spmv'), d.get('algorithmic_gbs'), d.get('error'))" 2>/dev/null
+done
+
 step "ncu launch list of bench.py (C2 SpMV + C4 CG)"
 timeout 1200 $NCU --metrics gpu__time_duration.sum -c 900 --csv --log-file $OUT/${TAG}_launches.csv \
   $PY bench.py --steps 20 --warmup 3 --no-extra --no-cpu --soak 0 --cg-maxiters 100 > $OUT/${TAG}_launches.log 2>&1
