@@ -356,17 +356,14 @@ def cpu_reference_cg(N=96):
             "sample": "3D 27-pt Poisson %d^3 (%d rows, %d nnz; C4 is 256^3), %s" % (N, n, len(va), what)}
 
 
-def value_dict_probe(args):
-    """The coded staged-ELL format (option value_dict, off by default) measured on the same workload in a CHILD process:
-    `bench.py --value-dict` with the side measurements off, bounded by a timeout.  The child checks y against the
-    closed-form stencil result like the main arm does (a wrong y is a non-zero exit), so the record says whether the
-    format is correct on this machine and what it would buy; a child that hangs or dies costs this record only, never
-    the headline line (its CUDA context is its own).  Informational: `value` stays the default format's number."""
-    cmd = [sys.executable, os.path.abspath(__file__), "--value-dict", "--no-probe", "--no-cg", "--no-extra", "--no-cpu",
-           "--steps", str(args.steps), "--warmup", str(args.warmup), "--soak", str(min(args.soak, 500)),
-           "--grid", str(args.grid), "--cache", str(args.cache)]
+def child_bench(args, extra, env_extra=None):
+    """One bounded child run of this script (its own process, its own CUDA context): returns the child's JSON line as a
+    dict, or {"error": ...} when it exits non-zero, prints nothing parseable, or outlives --probe-timeout (killed).  A
+    child that crashes or hangs costs its own record only, never the headline line of the parent."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--no-probe", "--no-cpu", "--steps", str(args.steps), "--warmup",
+           str(args.warmup), "--soak", str(min(args.soak, 500)), "--grid", str(args.grid), "--cache", str(args.cache)] + list(extra)
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
-    t0 = time.time()
+    env.update(env_extra or {})
     child = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, cwd=ROOT)
     try:
         out, err = child.communicate(timeout=args.probe_timeout)
@@ -380,17 +377,47 @@ def value_dict_probe(args):
     if child.returncode != 0:
         return {"error": "child exit %d: %s" % (child.returncode, (err or out).strip()[-400:])}
     try:
-        d = json.loads(out.strip().splitlines()[-1])
+        return json.loads(out.strip().splitlines()[-1])
     except (ValueError, IndexError):
         return {"error": "child printed no JSON line: %s" % out.strip()[-200:]}
+
+
+def value_dict_probe(args):
+    """The coded staged-ELL format (option value_dict, off by default) measured on the same workload in a CHILD process:
+    `bench.py --value-dict` (C2 SpMV, then C4 CG with the same option).  The child checks y against the closed-form
+    stencil result like the main arm does (a wrong y is a non-zero exit), so the record says whether the format is
+    correct on this machine and what it would buy.  Informational: `value` stays the default format's number."""
+    t0 = time.time()
+    d = child_bench(args, ["--value-dict", "--no-extra"] + (["--no-cg"] if args.no_cg else []))
+    if "error" in d and "value" not in d:
+        return d
     fmt = d.get("config", {}).get("format", {})
+    cg = d.get("cg") or {}
     return {"what": "child process: bench.py --value-dict on the same workload; y checked against the closed-form stencil result",
             "active": bool(fmt.get("value_dict")), "value": d.get("value"), "unit": d.get("unit"), "ms_per_step": d.get("ms_per_step"),
             "algorithmic_gbs": d.get("hbm_gbs"), "stored_bytes_per_launch": fmt.get("stored_bytes_per_launch"),
             "stored_gbs": (fmt["stored_bytes_per_launch"] / (d["ms_per_step"] * 1e-3) / 1e9
                            if fmt.get("stored_bytes_per_launch") and d.get("ms_per_step") else None),
             "table_doubles_per_slice": fmt.get("table_doubles_per_slice"), "kernel": d.get("roofline", {}).get("kernel"),
-            "gpu_launches": d.get("gpu_launches"), "clocks": d.get("clocks"), "seconds": time.time() - t0}
+            "gpu_launches": d.get("gpu_launches"), "clocks": d.get("clocks"),
+            "cg": {k: cg.get(k) for k in ("iters_per_s", "loop_trips", "converged", "max_abs_err_vs_x_true",
+                                          "us_per_iteration_marginal", "error") if k in cg} or None,
+            "seconds": time.time() - t0}
+
+
+def rmat_stream_probe(args):
+    """C3 with the CSR-stream variant of the gather kernel (option csr_stream, off by default), same child mechanism:
+    the A/B beside `rmat_spmv`, which runs the default variant.  The child's spot check against torch's own product
+    on sampled rows travels with it."""
+    t0 = time.time()
+    d = child_bench(args, ["--only-rmat", "--no-cg"], {"CASK_B200_CSR_STREAM": "1"})
+    if "error" in d and "value" not in d:
+        return d
+    r = dict(d.get("rmat_spmv") or {"error": "child line carries no rmat_spmv"})
+    r.pop("plan", None)
+    r["what"] = "child process: bench.py --only-rmat with CASK_B200_CSR_STREAM=1 (products staged in shared memory)"
+    r["seconds"] = time.time() - t0
+    return r
 
 
 def main():
@@ -622,10 +649,14 @@ def main():
         if rmat:
             line["rmat_spmv"] = rmat
         if world == 1 and not args.value_dict and not args.no_probe:
-            try:
-                line["value_dict_probe"] = value_dict_probe(args)
-            except Exception as e:  # noqa: BLE001 - informational
-                line["value_dict_probe"] = {"error": "%s: %s" % (type(e).__name__, e)}
+            probes = [("value_dict_probe", value_dict_probe)]
+            if rmat and "error" not in rmat and not os.environ.get("CASK_B200_CSR_STREAM"):
+                probes.append(("rmat_stream_probe", rmat_stream_probe))
+            for key, fn in probes:
+                try:
+                    line[key] = fn(args)
+                except Exception as e:  # noqa: BLE001 - informational
+                    line[key] = {"error": "%s: %s" % (type(e).__name__, e)}
         if world == 1 and not args.no_cpu:
             try:
                 line["cpu_baseline"] = cpu_port_baseline(G)

@@ -107,7 +107,7 @@ def test_value_dict_probe_is_contained():
     spec = importlib.util.spec_from_file_location("bench_mod2", os.path.join(ROOT, "bench.py"))
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
-    a = argparse.Namespace(steps=5, warmup=3, soak=10, grid=64, cache=8192, probe_timeout=300.0)
+    a = argparse.Namespace(steps=5, warmup=3, soak=10, grid=64, cache=8192, probe_timeout=300.0, no_cg=True)
     try:
         import torch
         has_gpu = torch.cuda.is_available()
@@ -120,3 +120,4 @@ def test_value_dict_probe_is_contained():
         assert "no CPU fallback" in r["error"]
     a.probe_timeout = 0.2
     assert "killed" in bench.value_dict_probe(a)["error"]
+    assert "killed" in bench.rmat_stream_probe(a)["error"]
