@@ -585,12 +585,26 @@ int configure_persistent(cask_b200_ctx* ctx) {
   // doubles per x buffer (keeps every buffer 128-B aligned); the coded format appends the slice's value table
   const size_t xbuf = (((size_t)p.max_xcache + 15) & ~(size_t)15) + (p.coded ? (((size_t)p.dict_len + 15) & ~(size_t)15) : 0);
   const size_t fixed = kPersistHeaderBytes + 2 * xbuf * sizeof(double);
-  const size_t per_sm = 228 * 1024, reserve = 1024 + 64;  // 1 KB per CTA is the driver's + static reduction scratch
+  const size_t per_sm = 228 * 1024, sys_reserve = 1024;  // 1 KB per resident CTA belongs to the driver
   const size_t entry_bytes = p.coded ? 3 : 10;
   auto stage_bytes = [&](int ku) { return (size_t)ku * kSliceRows * entry_bytes; };
+  // Static shared memory of the instantiations this plan can launch (reduction scratch of the fused-dot variants):
+  // it counts against the per-CTA limit together with the dynamic part, so it is asked of the runtime, not guessed.
+  size_t static_smem[5] = {0, 0, 0, 0, 0};  // indexed by KU
+  {
+    cudaFuncAttributes fa;
+#define CB_STATIC(KU_, DOT, CODED)                                                              \
+    CB_CUDA(cudaFuncGetAttributes(&fa, spmv_ell_persistent_kernel<KU_, DOT, CODED>));            \
+    static_smem[KU_] = std::max(static_smem[KU_], (size_t)fa.sharedSizeBytes)
+    if (p.coded) { CB_STATIC(2, false, true); CB_STATIC(2, true, true); CB_STATIC(4, false, true); CB_STATIC(4, true, true); }
+    else { CB_STATIC(2, false, false); CB_STATIC(2, true, false); CB_STATIC(4, false, false); CB_STATIC(4, true, false); }
+#undef CB_STATIC
+  }
   int ku = 0, stages = 0, ctas = 0;
-  auto fits = [&](int k, int st, int c) { return c * (fixed + st * stage_bytes(k) + reserve) <= per_sm &&
-                                                  fixed + st * stage_bytes(k) <= (size_t)dev_smem; };
+  auto fits = [&](int k, int st, int c) {
+    const size_t cta = fixed + st * stage_bytes(k) + static_smem[k];
+    return c * (cta + sys_reserve) <= per_sm && cta <= (size_t)dev_smem;
+  };
   if (p.coded) {
     // a stage is 3 KB per ELL column: deep rings of 4-column stages fit beside the x buffers; more CTAs per SM keep
     // more slices (x windows) in flight, which is what the shorter per-slice time needs
