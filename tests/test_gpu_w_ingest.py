@@ -122,31 +122,3 @@ def test_large_ingest_is_sorted_and_complete(gpu_lib, ctx, oracle):
     k_sorted = (((rows.astype(np.int64) - 1) << 32) | (cols - 1))[order]
     last = np.r_[k_sorted[1:] != k_sorted[:-1], True]
     assert np.array_equal(va, vals[order][last])
-
-
-def test_architecture_selector_tool(tmp_path, golden, oracle):
-    """bin/cask_dse (src/main.cpp + Dse.cpp of the reference, B200 edition): candidates preprocessed on the GPU, the
-    reference's table on stdout, dse_out.json with the reference's keys; the stencil is scored all-staged-ELL."""
-    import json
-    import os
-    import subprocess
-    from conftest import ROOT
-    exe = os.path.join(ROOT, "cask_b200", "host", "bin", "cask_dse")
-    assert os.path.exists(exe), "run `make -C cask_b200/host` (__graft_entry__.build())"
-    n, rp, ci, va = oracle.gen_poisson2d(128)
-    p1, p2, out = str(tmp_path / "poisson.mtx"), str(tmp_path / "cage.mtx"), str(tmp_path / "dse_out.json")
-    write_mtx(p1, n, n, *coo_of(n, rp, ci, va))
-    n2, m2, rp2, ci2, va2 = golden.csr("test_cage6")
-    write_mtx(p2, n2, m2, *coo_of(n2, rp2, ci2, va2))
-    r = subprocess.run([exe, "--out", out, p1, p2], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-3000:]
-    assert "File Architecture CacheSize InputWidth NumPipes" in r.stdout and " Best " in r.stdout
-    assert r.stdout.count("/poisson.mtx SkipEmpty ") >= 4  # one line per cache size + the best line
-    d = json.load(open(out))
-    best = d["best_architectures"]
-    assert 1 <= len(best) <= 2 and sum(len(b["matrices"]) for b in best) == 2
-    for b in best:
-        assert b["name"] == "SkipEmpty" and float(b["estimated_gflops"]) > 0
-        assert set(b["architecture_params"]) == {"num_pipes", "cache_size", "input_width", "max_rows", "num_controllers"}
-    pb = [b for b in best if p1 in b["matrices"]][0]
-    assert int(pb["estimated_impl_params"]["slices_gather_csr"]) == 0 and float(pb["estimated_impl_params"]["ell_fill"]) > 0.95

@@ -90,26 +90,3 @@ def test_unsorted_rows_are_refused(gpu_lib, ctx):
     with pytest.raises(gpu_lib.CaskError) as e:
         ctx.ilu_factor(3)
     assert e.value.code == gpu_lib.ERR_UNSUPPORTED
-
-
-def test_host_mirror_reference_ilu_suites(tmp_path, golden):
-    """test/LinearSolvers.cpp:54-146 (CGSymWithILUPC, ILUCompute2, ILUCompute, ILUComputeAndApply) on the host mirror's
-    ILUPreconditioner / pcg<double, ILUPreconditioner>, plus the Jacobi / unit-ILU extensions and io::gpu readers."""
-    import os
-    import subprocess
-    from conftest import ROOT
-    exe = os.path.join(ROOT, "cask_b200", "host", "bin", "test_client")
-    assert os.path.exists(exe)
-    for name, s in golden.systems.items():
-        n = s["n"]
-        rp, ci, va = np.array(s["row_ptr"]), np.array(s["col_ind"]), np.array(s["values"])
-        rows = np.repeat(np.arange(n), np.diff(rp))
-        with open(tmp_path / (name + ".mtx"), "w") as f:
-            f.write("%%%%MatrixMarket matrix coordinate real symmetric\n%%\n%d %d %d\n" % (n, n, len(va)))
-            f.write("".join("%d %d %s\n" % (r + 1, c + 1, repr(float(v))) for r, c, v in zip(rows, ci, va)))
-        for suffix, vec in (("_b", s["rhs"]), ("_sol", s["sol_file"])):
-            with open(tmp_path / (name + suffix + ".mtx"), "w") as f:
-                f.write("%%%%MatrixMarket matrix array real general\n%%\n%d 1\n" % n)
-                f.write("".join("%s\n" % repr(float(v)) for v in vec))
-    p = subprocess.run([exe, str(tmp_path), "extra"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
-    assert p.returncode == 0 and "PASSED (0 failures)" in p.stdout, p.stdout[-4000:]
