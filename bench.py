@@ -48,9 +48,10 @@ def parse():
     ap.add_argument("--no-extra", action="store_true", help="skip the C3 (R-MAT SpMV) and C5 (BiCGStab) side measurements")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cache", type=int, default=8192)
-    ap.add_argument("--value-dict", action="store_true",
-                    help="coded staged ELL: values as 8-bit codes into per-slice tables (3 B per stored nonzero instead of "
-                         "10, bit-identical y); off by default until measured on the GPU")
+    ap.add_argument("--value-dict", type=int, nargs="?", const=1, default=0,
+                    help="coded staged ELL, bit-identical y; 1: values as 8-bit codes into per-slice tables (3 B per stored "
+                         "nonzero instead of 10); 2: (value, displacement) pair codes (1 B); off by default until measured "
+                         "on the GPU")
     ap.add_argument("--no-probe", action="store_true",
                     help="skip the coded-staged-ELL probe (a child bench.py --value-dict run, bounded by a timeout)")
     ap.add_argument("--probe-timeout", type=float, default=240.0, help="seconds the probe's child process may take")
@@ -382,23 +383,23 @@ def child_bench(args, extra, env_extra=None):
         return {"error": "child printed no JSON line: %s" % out.strip()[-200:]}
 
 
-def value_dict_probe(args):
-    """The coded staged-ELL format (option value_dict, off by default) measured on the same workload in a CHILD process:
-    `bench.py --value-dict` (C2 SpMV, then C4 CG with the same option).  The child checks y against the closed-form
-    stencil result like the main arm does (a wrong y is a non-zero exit), so the record says whether the format is
-    correct on this machine and what it would buy.  Informational: `value` stays the default format's number."""
+def value_dict_probe(args, mode=1):
+    """A coded staged-ELL format (option value_dict = mode, off by default) measured on the same workload in a CHILD
+    process: `bench.py --value-dict <mode>` (C2 SpMV, then C4 CG with the same option).  The child checks y against the
+    closed-form stencil result like the main arm does (a wrong y is a non-zero exit), so the record says whether the
+    format is correct on this machine and what it would buy.  Informational: `value` stays the default format's number."""
     t0 = time.time()
-    d = child_bench(args, ["--value-dict", "--no-extra"] + (["--no-cg"] if args.no_cg else []))
+    d = child_bench(args, ["--value-dict", str(mode), "--no-extra"] + (["--no-cg"] if args.no_cg else []))
     if "error" in d and "value" not in d:
         return d
     fmt = d.get("config", {}).get("format", {})
     cg = d.get("cg") or {}
-    return {"what": "child process: bench.py --value-dict on the same workload; y checked against the closed-form stencil result",
-            "active": bool(fmt.get("value_dict")), "value": d.get("value"), "unit": d.get("unit"), "ms_per_step": d.get("ms_per_step"),
+    return {"what": "child process: bench.py --value-dict %d on the same workload; y checked against the closed-form stencil result" % mode,
+            "format_in_use": fmt.get("value_dict"), "value": d.get("value"), "unit": d.get("unit"), "ms_per_step": d.get("ms_per_step"),
             "algorithmic_gbs": d.get("hbm_gbs"), "stored_bytes_per_launch": fmt.get("stored_bytes_per_launch"),
             "stored_gbs": (fmt["stored_bytes_per_launch"] / (d["ms_per_step"] * 1e-3) / 1e9
                            if fmt.get("stored_bytes_per_launch") and d.get("ms_per_step") else None),
-            "table_doubles_per_slice": fmt.get("table_doubles_per_slice"), "kernel": d.get("roofline", {}).get("kernel"),
+            "table_entries_per_slice": fmt.get("table_entries_per_slice"), "kernel": d.get("roofline", {}).get("kernel"),
             "gpu_launches": d.get("gpu_launches"), "clocks": d.get("clocks"),
             "cg": {k: cg.get(k) for k in ("iters_per_s", "loop_trips", "converged", "max_abs_err_vs_x_true",
                                           "us_per_iteration_marginal", "error") if k in cg} or None,
@@ -449,7 +450,7 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
     ctx.set_stream(stream)
     if args.value_dict:
-        ctx.set_option("value_dict", 1)
+        ctx.set_option("value_dict", args.value_dict)
     if world > 1:
         idt = torch.zeros(128, dtype=torch.uint8, device=dev)
         if rank == 0:
@@ -492,6 +493,7 @@ def main():
     preprocess_s = time.perf_counter() - t0
     stats = ctx.plan_stats()
     vd_active, vd_entries, vd_matrix_bytes = ctx.value_dict()
+    vd_mode = ctx.value_dict_mode()
 
     x_full = ((torch.arange(n_global, device=dev) % 1024).double() * 0.25).contiguous()
     y = torch.empty(n_local, dtype=torch.float64, device=dev)
@@ -632,13 +634,13 @@ def main():
                        "soak_steps": args.soak,
                        "design": {"num_pipes": 1, "cache_size": args.cache, "input_width": 16},
                        "preprocess_s": preprocess_s, "plan": stats,
-                       "format": {"value_dict": vd_active, "table_doubles_per_slice": vd_entries,
+                       "format": {"value_dict": vd_mode, "table_entries_per_slice": vd_entries,
                                   "stored_bytes_per_launch": vd_matrix_bytes + 8 * (n_local + n_local),
-                                  "note": "bytes one SpMV moves in the stored format: staged-ELL entries (10 B each, or 3 B "
-                                          "coded) + x read once + y written once"}},
+                                  "note": "bytes one SpMV moves in the stored format: staged-ELL entries (10 B each; 3 B "
+                                          "with value codes, 1 B with pair codes) + x read once + y written once"}},
             "hbm_gbs": achieved, "frac_of_nominal_8tbs": achieved / 8000.0,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "spmv_ell_persistent_kernel<%d,false,%s>" % (2 if not vd_active else 4, "true" if vd_active else "false"),
+                         "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "spmv_ell_persistent_kernel<%d,false,%d>" % (2 if not vd_active else 4, vd_mode),
                          "algorithmic_bytes_per_launch": bytes_per_launch},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
@@ -649,7 +651,7 @@ def main():
         if rmat:
             line["rmat_spmv"] = rmat
         if world == 1 and not args.value_dict and not args.no_probe:
-            probes = [("value_dict_probe", value_dict_probe)]
+            probes = [("value_dict_probe", value_dict_probe), ("pair_dict_probe", lambda a: value_dict_probe(a, 2))]
             if rmat and "error" not in rmat and not os.environ.get("CASK_B200_CSR_STREAM"):
                 probes.append(("rmat_stream_probe", rmat_stream_probe))
             for key, fn in probes:

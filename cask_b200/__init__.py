@@ -330,10 +330,16 @@ class Context:
         return st.as_dict()
 
     def value_dict(self):
-        """(active, doubles staged per slice table, matrix bytes one SpMV streams) of the current plan."""
+        """(active, table entries staged per slice, matrix bytes one SpMV streams) of the current plan."""
         a, e, b = C.c_int32(), C.c_int32(), C.c_int64()
         check(lib().cask_b200_plan_value_dict(self.h, C.byref(a), C.byref(e), C.byref(b)))
         return bool(a.value), e.value, b.value
+
+    def value_dict_mode(self):
+        """0 uncoded, 1 value codes (3 B per stored nonzero), 2 (value, displacement) pair codes (1 B)."""
+        a = C.c_int32()
+        check(lib().cask_b200_plan_value_dict(self.h, C.byref(a), None, None))
+        return a.value
 
     def partition(self, pipe, arrays=True):
         """(info dict, colptr, pairs) of reference partition `pipe`, produced by the GPU partitioner."""

@@ -243,15 +243,15 @@ int cask_b200_plan_get_stats(cask_b200_ctx* ctx, cask_b200_plan_stats* out) {
 int cask_b200_plan_value_dict(cask_b200_ctx* ctx, int32_t* active, int32_t* max_entries, int64_t* matrix_bytes_per_spmv) {
   if (!ctx || !ctx->have_design) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "plan_value_dict: preprocess first");
   const Plan& p = ctx->plan;
-  const bool on = p.coded && ctx->ell_kernel == 1 && p.persist_ku != 0;  // only the persistent kernel reads the codes
-  if (active) *active = on ? 1 : 0;
+  const int on = p.coded && ctx->ell_kernel == 1 && p.persist_ku != 0 ? p.coded : 0;  // only the persistent kernel reads the codes
+  if (active) *active = on;  // 0 uncoded, 1 value codes, 2 pair codes
   if (max_entries) *max_entries = on ? p.dict_len : 0;
   if (matrix_bytes_per_spmv) {
     const int64_t csr = p.stats.nnz - p.stats.ell_nnz;
     int64_t csr_rows = 0;
     for (const SliceDesc& sd : p.h_slices) if (sd.kind != kSliceStagedEll) csr_rows += sd.nrows;
-    *matrix_bytes_per_spmv = p.stats.ell_padded_entries * (on ? 3 : 10) + (on ? (int64_t)p.n_ell * p.dict_len * 8 : 0) +
-                             csr * 12 + csr_rows * 4;
+    const int64_t entry = on == 2 ? 1 : on == 1 ? 3 : 10, table = on == 2 ? 10 : on == 1 ? 8 : 0;
+    *matrix_bytes_per_spmv = p.stats.ell_padded_entries * entry + (int64_t)p.n_ell * p.dict_len * table + csr * 12 + csr_rows * 4;
   }
   return CASK_B200_OK;
 }

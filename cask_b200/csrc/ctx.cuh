@@ -104,10 +104,14 @@ struct Plan {
   uint16_t* d_ell_idx = nullptr;
   // coded staged ELL (option value_dict; plan.cu: build_value_dict, valuedict_logic.inl): 8-bit codes into a per-slice
   // table of the slice's distinct values - 3 bytes per stored nonzero instead of 10, same doubles multiplied
-  bool coded = false;
+  // pair-coded staged ELL (value_dict = 2; valuedict_logic.inl: BuildPairs): the code names a (value, x-cache
+  // displacement) pair, position = displacement + row inside the slice - 1 byte per stored nonzero, no index stream
+  int32_t coded = 0;                  // 0 uncoded, 1 value codes (+ 16-bit indices), 2 pair codes
   uint8_t* d_ell_codes = nullptr;     // same indexing as d_ell_vals
   double* d_ell_dict = nullptr;       // valuedict::kStride doubles per slice id
-  int32_t dict_len = 0;               // doubles staged per slice: the largest table, rounded up to an even count
+  uint16_t* d_ell_delta = nullptr;    // pair codes: valuedict::kDeltaStride displacements per slice id
+  int32_t dict_len = 0;               // table entries staged per slice: the largest table, rounded up to a multiple of
+                                      // 2 (value codes) or 8 (pair codes) so that every bulk copy moves whole 16 bytes
   int32_t* d_list_ell = nullptr;      // slice ids, staged ELL, interior first then halo-dependent
   int32_t* d_list_csr = nullptr;
   int32_t n_ell = 0, n_ell_interior = 0;
@@ -244,7 +248,8 @@ struct cask_b200_ctx {
   int32_t ell_kernel = 1;    // 1 persistent warp-specialised kernel, 0 one CTA per slice
   int32_t persist_ku = 0;    // 0 auto, else 2 or 4
   int32_t persist_ctas = 0;  // coded format only: 0 auto, else CTAs per SM of the persistent kernel (1..3)
-  int32_t value_dict = 0;    // 1: staged-ELL values as 8-bit codes into per-slice tables when every slice has <= 256 distinct values
+  int32_t value_dict = 0;    // 1: staged-ELL values as 8-bit codes into per-slice tables when every slice has <= 256 distinct values;
+                             // 2: (value, displacement) pair codes where every slice has <= 255 pairs, else as 1
   int64_t l2_persist_bytes = -1;  // persisting L2 set-aside claimed for evict-last vector accesses (-1: not asked yet)
   int32_t csr_stream = 0;    // 1: CSR-stream variant of the gather-CSR kernel (products staged in shared memory)
   int32_t csr_item_nnz = 4096;  // nonzeros per work item of the CSR-stream variant (its shared-memory footprint)

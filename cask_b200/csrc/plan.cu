@@ -249,7 +249,7 @@ void free_plan(cask_b200_ctx* ctx) {
     cudaFree((void*)p.d_val);
   }
   cudaFree(p.d_slices); cudaFree(p.d_runs); cudaFree(p.d_ell_vals); cudaFree(p.d_ell_idx);
-  cudaFree(p.d_ell_codes); cudaFree(p.d_ell_dict);
+  cudaFree(p.d_ell_codes); cudaFree(p.d_ell_dict); cudaFree(p.d_ell_delta);
   cudaFree(p.d_list_ell); cudaFree(p.d_list_csr);
   cudaFree(p.d_csr_items); cudaFree(p.d_split_rows); cudaFree(p.d_csr_scratch);
   p = Plan();
@@ -324,12 +324,14 @@ int build_csr_items(cask_b200_ctx* ctx) {
   return CASK_B200_OK;
 }
 
-// Coded staged ELL (option value_dict): per-slice tables of the distinct values + 8-bit codes (valuedict_logic.inl).
-// All staged slices or none: if any slice holds more than 256 distinct values the plan stays uncoded.
-// val_off_total = entries of the ELL arrays.
+// Coded staged ELL (option value_dict): per-slice tables + 8-bit codes (valuedict_logic.inl).
+//   value_dict = 2  (value, x-cache displacement) PAIR codes: 1 byte per stored nonzero, no index stream;
+//   value_dict = 1  value codes beside the 16-bit indices: 3 bytes per stored nonzero.
+// All staged slices or none: if any slice needs more than 255 pairs the plan falls back to value codes, and if any
+// slice holds more than 256 distinct values it stays uncoded.  val_off_total = entries of the ELL arrays.
 static int build_value_dict(cask_b200_ctx* ctx, int64_t val_off_total) {
   Plan& p = ctx->plan;
-  p.coded = false;
+  p.coded = 0;
   p.dict_len = 0;
   if (!ctx->value_dict || p.n_ell == 0 || p.nslices == 0) return CASK_B200_OK;
   dev::Exec ex = dev::exec_of(ctx);
@@ -349,6 +351,19 @@ static int build_value_dict(cask_b200_ctx* ctx, int64_t val_off_total) {
   CB_CUDA(cudaMalloc(&p.d_ell_codes, (size_t)std::max<int64_t>(val_off_total, 16)));
   CB_CUDA(cudaMalloc(&p.d_ell_dict, sizeof(double) * (size_t)valuedict::kStride * (size_t)p.nslices));
   int32_t overflow = 0, max_entries = 0;
+  if (ctx->value_dict >= 2) {
+    CB_CUDA(cudaMalloc(&p.d_ell_delta, sizeof(uint16_t) * (size_t)valuedict::kDeltaStride * (size_t)p.nslices));
+    CB_TRY(valuedict::build_pairs(ex, p.nslices, (const int64_t*)tmp.q[0], (const int32_t*)tmp.q[1], p.slice_rows, p.d_ell_vals,
+                                  p.d_ell_idx, p.d_ell_dict, p.d_ell_delta, p.d_ell_codes, (int32_t*)tmp.q[2], &overflow,
+                                  &max_entries));
+    if (!overflow && max_entries > 0) {
+      p.coded = 2;
+      p.dict_len = (max_entries + 7) & ~7;  // 8 displacements = 16 bytes: the unit of a bulk copy
+      return CASK_B200_OK;
+    }
+    cudaFree(p.d_ell_delta);
+    p.d_ell_delta = nullptr;
+  }
   CB_TRY(valuedict::build(ex, p.nslices, (const int64_t*)tmp.q[0], (const int32_t*)tmp.q[1], p.slice_rows, p.d_ell_vals,
                           p.d_ell_dict, p.d_ell_codes, (int32_t*)tmp.q[2], &overflow, &max_entries));
   if (overflow || max_entries == 0) {
@@ -356,7 +371,7 @@ static int build_value_dict(cask_b200_ctx* ctx, int64_t val_off_total) {
     p.d_ell_codes = nullptr; p.d_ell_dict = nullptr;
     return CASK_B200_OK;
   }
-  p.coded = true;
+  p.coded = 1;
   p.dict_len = (max_entries + 1) & ~1;  // bulk copies move multiples of 16 bytes
   return CASK_B200_OK;
 }
@@ -505,6 +520,7 @@ int build_plan(cask_b200_ctx* ctx) {
   p.stats.max_row_length = maxlen;
   for (int i = 0; i < 8; i++) p.stats.row_length_histogram[i] = (int64_t)hist[i];
   p.stats.device_bytes = val_off * (p.coded ? 11 : 10) + (p.coded ? (int64_t)p.nslices * valuedict::kStride * 8 : 0) +
+                         (p.coded == 2 ? (int64_t)p.nslices * valuedict::kDeltaStride * 2 : 0) +
                          (int64_t)run_off * sizeof(Run) + (int64_t)p.nslices * sizeof(SliceDesc) +
                          (p.n_csr ? (csr_nnz * 12 + csr_rows * 4) : 0);
   return CASK_B200_OK;

@@ -212,20 +212,31 @@ struct PersistHeader {
 };
 static_assert(sizeof(PersistHeader) <= kPersistHeaderBytes, "header must fit its reservation");
 
-// kCoded (option value_dict, plan.cu: build_value_dict): the value stream is replaced by 8-bit codes into a table of the
-// slice's distinct values.  The table (dict_len doubles) travels with the x windows into the tail of the x buffer, a
-// ring stage holds KU*1024 codes + KU*1024 16-bit indices (3 bytes per stored nonzero instead of 10), and a consumer
-// reads its four codes with one 32-bit load and looks the doubles up in shared memory - the multiplied values, the
-// order of the operations and therefore y are those of the uncoded kernel, bit for bit.
+// kCoded (option value_dict, plan.cu: build_value_dict):
+//   1  the value stream is replaced by 8-bit codes into a table of the slice's distinct values.  The table (dict_len
+//      doubles) travels with the x windows into the tail of the x buffer, a ring stage holds KU*1024 codes + KU*1024
+//      16-bit indices (3 bytes per stored nonzero instead of 10), and a consumer reads its four codes with one 32-bit
+//      load and looks the doubles up in shared memory;
+//   2  the code names a (value, x-cache displacement) pair: position = (displacement + row inside the slice) mod 2^16,
+//      code 0 = padding (+0.0 at the zero slot).  The index stream is gone too: a ring stage holds KU*1024 codes, one
+//      byte per stored nonzero; the two tables (dict_len doubles, dict_len 16-bit displacements) ride with the x windows.
+// In both the multiplied doubles, the x entries, the order of the operations and therefore y are those of the uncoded
+// kernel, bit for bit.
 struct CodedArgs {
-  const uint8_t* codes = nullptr;  // same indexing as ell_vals
-  const double* dict = nullptr;    // valuedict::kStride doubles per slice id
-  int32_t dict_len = 0;            // doubles staged per slice (even)
+  const uint8_t* codes = nullptr;   // same indexing as ell_vals
+  const double* dict = nullptr;     // valuedict::kStride doubles per slice id
+  const uint16_t* delta = nullptr;  // pair codes: valuedict::kDeltaStride displacements per slice id
+  int32_t dict_len = 0;             // table entries staged per slice (multiple of 2; of 8 with pair codes)
   int32_t pad_ = 0;
 };
-constexpr int kDictStride = 256;   // == valuedict::kStride (plan.cu)
+constexpr int kDictStride = 256;    // == valuedict::kStride (plan.cu)
+constexpr int kDeltaStride = 256;   // == valuedict::kDeltaStride
 
-template <int KU, bool kDot, bool kCoded>
+// doubles appended to an x buffer for the slice's table(s)
+__host__ __device__ constexpr int dict_value_doubles(int dict_len) { return (dict_len + 15) & ~15; }
+__host__ __device__ constexpr int dict_delta_doubles(int dict_len) { return (((dict_len + 3) >> 2) + 15) & ~15; }
+
+template <int KU, bool kDot, int kCoded>
 __global__ void __launch_bounds__(kPersistThreads, 1)
 spmv_ell_persistent_kernel(const SliceDesc* __restrict__ slices, const int32_t* __restrict__ list, int count,
                            const Run* __restrict__ runs, const double* __restrict__ ell_vals,
@@ -239,13 +250,17 @@ spmv_ell_persistent_kernel(const SliceDesc* __restrict__ slices, const int32_t* 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   PersistHeader* hdr = reinterpret_cast<PersistHeader*>(smem_raw);
   double* xbuf = reinterpret_cast<double*>(smem_raw + kPersistHeaderBytes);
-  // ring: [values | indices] per stage, or [indices | codes] in the coded format (every region a multiple of 2 KB)
+  // ring: [values | indices] per stage; value codes: [indices | codes]; pair codes: [codes] (every region a multiple
+  // of 2 KB)
   double* cvals = xbuf + 2 * (size_t)xbuf_doubles;
   uint16_t* cidx = kCoded ? reinterpret_cast<uint16_t*>(cvals)
                           : reinterpret_cast<uint16_t*>(cvals + (size_t)stages * KU * kSliceRows);
-  uint8_t* ccode = reinterpret_cast<uint8_t*>(cidx + (size_t)stages * KU * kSliceRows);  // coded format only
-  // the table of a slice sits in the last ((dict_len + 15) & ~15) doubles of its x buffer
-  const int dict_base = kCoded ? xbuf_doubles - ((ca.dict_len + 15) & ~15) : 0;
+  uint8_t* ccode = kCoded == 2 ? reinterpret_cast<uint8_t*>(cvals)
+                               : reinterpret_cast<uint8_t*>(cidx + (size_t)stages * KU * kSliceRows);  // coded formats only
+  // the table(s) of a slice sit at the tail of its x buffer: values, then (pair codes) the displacements
+  const int dict_base = kCoded == 2 ? xbuf_doubles - dict_value_doubles(ca.dict_len) - dict_delta_doubles(ca.dict_len)
+                        : kCoded == 1 ? xbuf_doubles - dict_value_doubles(ca.dict_len) : 0;
+  const int delta_base = dict_base + dict_value_doubles(ca.dict_len);  // pair codes only
   __shared__ double red[kPersistThreads / 32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -271,7 +286,11 @@ spmv_ell_persistent_kernel(const SliceDesc* __restrict__ slices, const int32_t* 
     const int s = chunk_no % stages;
     const int cols = min(KU, L - c * KU);
     const uint32_t fc = smem_u32(&hdr->full_c[s]);
-    if constexpr (kCoded) {
+    if constexpr (kCoded == 2) {
+      mbar_expect_tx(fc, (uint32_t)cols * kSliceRows);
+      const size_t src = (size_t)sdp->val_off + (size_t)c * KU * kSliceRows;
+      bulk_g2s_hint(smem_u32(ccode + (size_t)s * KU * kSliceRows), ca.codes + src, (uint32_t)cols * kSliceRows, fc, stream_policy);
+    } else if constexpr (kCoded == 1) {
       mbar_expect_tx(fc, (uint32_t)cols * kSliceRows * 3u);
       const size_t src = (size_t)sdp->val_off + (size_t)c * KU * kSliceRows;
       bulk_g2s_hint(smem_u32(ccode + (size_t)s * KU * kSliceRows), ca.codes + src, (uint32_t)cols * kSliceRows, fc, stream_policy);
@@ -334,10 +353,15 @@ spmv_ell_persistent_kernel(const SliceDesc* __restrict__ slices, const int32_t* 
         }
         if (r.len & 1) xs[r.local_base + r.len - 1] = x[r.col0 + r.len - 1];  // odd tail at column m-1
       }
-      if constexpr (kCoded) if (lane == 31) {  // the slice's value table rides on the same barrier phase as its x windows
+      if constexpr (kCoded != 0) if (lane == 31) {  // the slice's value table rides on the same barrier phase as its x windows
         const uint32_t b = (uint32_t)ca.dict_len * 8u;
         bytes += b;
         bulk_g2s(smem_u32(xs + dict_base), ca.dict + (size_t)list[item] * kDictStride, b, fx);
+      }
+      if constexpr (kCoded == 2) if (lane == 30) {  // ... and so does its displacement table
+        const uint32_t b = (uint32_t)ca.dict_len * 2u;
+        bytes += b;
+        bulk_g2s(smem_u32(xs + delta_base), ca.delta + (size_t)list[item] * kDeltaStride, b, fx);
       }
 #pragma unroll
       for (int d = 16; d; d >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, d);
@@ -375,25 +399,41 @@ spmv_ell_persistent_kernel(const SliceDesc* __restrict__ slices, const int32_t* 
         const uint16_t* ib = cidx + (size_t)s * KU * kSliceRows + (size_t)tid * RPT;
         const uint8_t* cb = ccode + (size_t)s * KU * kSliceRows + (size_t)tid * RPT;
         const double* dict = xs + dict_base;
+        const uint16_t* ddel = reinterpret_cast<const uint16_t*>(xs + delta_base);
 #pragma unroll
         for (int u = 0; u < KU; u++) {
           if (u < cols) {
-            double2 v0, v1;
-            if constexpr (kCoded) {
-              // entry (k, row j*256 + t) is byte j of thread t's 32-bit word (little endian), as in the value layout
+            if constexpr (kCoded == 2) {
+              // byte j of thread t's word = code of entry (k, row j*256 + t); code 0 = padding -> the zero slot
               const uint32_t cw = *reinterpret_cast<const uint32_t*>(cb + (size_t)u * kSliceRows);
-              v0 = make_double2(dict[cw & 0xffu], dict[(cw >> 8) & 0xffu]);
-              v1 = make_double2(dict[(cw >> 16) & 0xffu], dict[cw >> 24]);
+              const uint32_t c0 = cw & 0xffu, c1 = (cw >> 8) & 0xffu, c2 = (cw >> 16) & 0xffu, c3 = cw >> 24;
+              const uint32_t p0 = c0 ? ((uint32_t)ddel[c0] + (uint32_t)tid) & 0xffffu : 0u;
+              const uint32_t p1 = c1 ? ((uint32_t)ddel[c1] + (uint32_t)(kConsumerThreads + tid)) & 0xffffu : 0u;
+              const uint32_t p2 = c2 ? ((uint32_t)ddel[c2] + (uint32_t)(2 * kConsumerThreads + tid)) & 0xffffu : 0u;
+              const uint32_t p3 = c3 ? ((uint32_t)ddel[c3] + (uint32_t)(3 * kConsumerThreads + tid)) & 0xffffu : 0u;
+              // ascending column order, separate multiply and add (DokMatrix::dot, SparseMatrix.hpp:255-264)
+              acc[0] = __dadd_rn(acc[0], __dmul_rn(dict[c0], xs[p0]));
+              acc[1] = __dadd_rn(acc[1], __dmul_rn(dict[c1], xs[p1]));
+              acc[2] = __dadd_rn(acc[2], __dmul_rn(dict[c2], xs[p2]));
+              acc[3] = __dadd_rn(acc[3], __dmul_rn(dict[c3], xs[p3]));
             } else {
-              v0 = *reinterpret_cast<const double2*>(vb + (size_t)u * kSliceRows);
-              v1 = *reinterpret_cast<const double2*>(vb + (size_t)u * kSliceRows + 2);
+              double2 v0, v1;
+              if constexpr (kCoded == 1) {
+                // entry (k, row j*256 + t) is byte j of thread t's 32-bit word (little endian), as in the value layout
+                const uint32_t cw = *reinterpret_cast<const uint32_t*>(cb + (size_t)u * kSliceRows);
+                v0 = make_double2(dict[cw & 0xffu], dict[(cw >> 8) & 0xffu]);
+                v1 = make_double2(dict[(cw >> 16) & 0xffu], dict[cw >> 24]);
+              } else {
+                v0 = *reinterpret_cast<const double2*>(vb + (size_t)u * kSliceRows);
+                v1 = *reinterpret_cast<const double2*>(vb + (size_t)u * kSliceRows + 2);
+              }
+              const uint2 ix = *reinterpret_cast<const uint2*>(ib + (size_t)u * kSliceRows);
+              // ascending column order, separate multiply and add (DokMatrix::dot, SparseMatrix.hpp:255-264)
+              acc[0] = __dadd_rn(acc[0], __dmul_rn(v0.x, xs[ix.x & 0xffffu]));
+              acc[1] = __dadd_rn(acc[1], __dmul_rn(v0.y, xs[ix.x >> 16]));
+              acc[2] = __dadd_rn(acc[2], __dmul_rn(v1.x, xs[ix.y & 0xffffu]));
+              acc[3] = __dadd_rn(acc[3], __dmul_rn(v1.y, xs[ix.y >> 16]));
             }
-            const uint2 ix = *reinterpret_cast<const uint2*>(ib + (size_t)u * kSliceRows);
-            // ascending column order, separate multiply and add (DokMatrix::dot, SparseMatrix.hpp:255-264)
-            acc[0] = __dadd_rn(acc[0], __dmul_rn(v0.x, xs[ix.x & 0xffffu]));
-            acc[1] = __dadd_rn(acc[1], __dmul_rn(v0.y, xs[ix.x >> 16]));
-            acc[2] = __dadd_rn(acc[2], __dmul_rn(v1.x, xs[ix.y & 0xffffu]));
-            acc[3] = __dadd_rn(acc[3], __dmul_rn(v1.y, xs[ix.y >> 16]));
           }
         }
         __syncwarp();
@@ -583,10 +623,11 @@ int configure_persistent(cask_b200_ctx* ctx) {
   int dev_smem = 0;
   CB_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
   // doubles per x buffer (keeps every buffer 128-B aligned); the coded format appends the slice's value table
-  const size_t xbuf = (((size_t)p.max_xcache + 15) & ~(size_t)15) + (p.coded ? (((size_t)p.dict_len + 15) & ~(size_t)15) : 0);
+  const size_t xbuf = (((size_t)p.max_xcache + 15) & ~(size_t)15) + (p.coded ? (size_t)dict_value_doubles(p.dict_len) : 0) +
+                      (p.coded == 2 ? (size_t)dict_delta_doubles(p.dict_len) : 0);
   const size_t fixed = kPersistHeaderBytes + 2 * xbuf * sizeof(double);
   const size_t per_sm = 228 * 1024, sys_reserve = 1024;  // 1 KB per resident CTA belongs to the driver
-  const size_t entry_bytes = p.coded ? 3 : 10;
+  const size_t entry_bytes = p.coded == 2 ? 1 : p.coded == 1 ? 3 : 10;
   auto stage_bytes = [&](int ku) { return (size_t)ku * kSliceRows * entry_bytes; };
   // Static shared memory of the instantiations this plan can launch (reduction scratch of the fused-dot variants):
   // it counts against the per-CTA limit together with the dynamic part, so it is asked of the runtime, not guessed.
@@ -596,8 +637,9 @@ int configure_persistent(cask_b200_ctx* ctx) {
 #define CB_STATIC(KU_, DOT, CODED)                                                              \
     CB_CUDA(cudaFuncGetAttributes(&fa, spmv_ell_persistent_kernel<KU_, DOT, CODED>));            \
     static_smem[KU_] = std::max(static_smem[KU_], (size_t)fa.sharedSizeBytes)
-    if (p.coded) { CB_STATIC(2, false, true); CB_STATIC(2, true, true); CB_STATIC(4, false, true); CB_STATIC(4, true, true); }
-    else { CB_STATIC(2, false, false); CB_STATIC(2, true, false); CB_STATIC(4, false, false); CB_STATIC(4, true, false); }
+    if (p.coded == 2) { CB_STATIC(2, false, 2); CB_STATIC(2, true, 2); CB_STATIC(4, false, 2); CB_STATIC(4, true, 2); }
+    else if (p.coded == 1) { CB_STATIC(2, false, 1); CB_STATIC(2, true, 1); CB_STATIC(4, false, 1); CB_STATIC(4, true, 1); }
+    else { CB_STATIC(2, false, 0); CB_STATIC(2, true, 0); CB_STATIC(4, false, 0); CB_STATIC(4, true, 0); }
 #undef CB_STATIC
   }
   int ku = 0, stages = 0, ctas = 0;
@@ -606,12 +648,12 @@ int configure_persistent(cask_b200_ctx* ctx) {
     return c * (cta + sys_reserve) <= per_sm && cta <= (size_t)dev_smem;
   };
   if (p.coded) {
-    // a stage is 3 KB per ELL column: deep rings of 4-column stages fit beside the x buffers; more CTAs per SM keep
-    // more slices (x windows) in flight, which is what the shorter per-slice time needs
+    // a stage is 3 KB (pair codes: 1 KB) per ELL column: deep rings of 4-column stages fit beside the x buffers; more
+    // CTAs per SM keep more slices (x windows) in flight, which is what the shorter per-slice time needs
     const int k = ctx->persist_ku == 2 ? 2 : 4;
     const int c_hi = ctx->persist_ctas >= 1 && ctx->persist_ctas <= 3 ? ctx->persist_ctas : 2;
     for (int c = c_hi; c >= 1 && !ku; c--)
-      for (int st = 6; st >= 2 && !ku; st--)
+      for (int st = p.coded == 2 ? kMaxStages : 6; st >= 2 && !ku; st--)
         if (fits(k, st, c)) { ku = k; stages = st; ctas = c; }
   } else {
     if ((ctx->persist_ku == 0 || ctx->persist_ku == 2) && fits(2, 3, 2)) { ku = 2; stages = 3; ctas = 2; while (stages < 4 && fits(2, stages + 1, 2)) stages++; }
@@ -680,13 +722,16 @@ int launch_spmv_range(cask_b200_ctx* ctx, const double* d_x, double* d_y, int el
     const ReduceDesc rd = dot && fusion->reduce.partials && ell_lo == 0 && ell_hi == p.n_ell && csr_hi == csr_lo
                               ? fusion->reduce : ReduceDesc();
     CodedArgs ca;
-    if (p.coded) { ca.codes = p.d_ell_codes; ca.dict = p.d_ell_dict; ca.dict_len = p.dict_len; }
-    if (p.coded) {
-      if (p.persist_ku == 2) { if (dot) CB_PERSIST(2, true, true); else CB_PERSIST(2, false, true); }
-      else { if (dot) CB_PERSIST(4, true, true); else CB_PERSIST(4, false, true); }
+    if (p.coded) { ca.codes = p.d_ell_codes; ca.dict = p.d_ell_dict; ca.delta = p.d_ell_delta; ca.dict_len = p.dict_len; }
+    if (p.coded == 2) {
+      if (p.persist_ku == 2) { if (dot) CB_PERSIST(2, true, 2); else CB_PERSIST(2, false, 2); }
+      else { if (dot) CB_PERSIST(4, true, 2); else CB_PERSIST(4, false, 2); }
+    } else if (p.coded == 1) {
+      if (p.persist_ku == 2) { if (dot) CB_PERSIST(2, true, 1); else CB_PERSIST(2, false, 1); }
+      else { if (dot) CB_PERSIST(4, true, 1); else CB_PERSIST(4, false, 1); }
     } else {
-      if (p.persist_ku == 2) { if (dot) CB_PERSIST(2, true, false); else CB_PERSIST(2, false, false); }
-      else { if (dot) CB_PERSIST(4, true, false); else CB_PERSIST(4, false, false); }
+      if (p.persist_ku == 2) { if (dot) CB_PERSIST(2, true, 0); else CB_PERSIST(2, false, 0); }
+      else { if (dot) CB_PERSIST(4, true, 0); else CB_PERSIST(4, false, 0); }
     }
 #undef CB_PERSIST
     ctx->launches++;

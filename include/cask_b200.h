@@ -97,7 +97,7 @@ int cask_b200_synchronize(cask_b200_ctx* ctx);
  * "force_kind" (-1 auto, 0 staged ELL wherever the x windows fit, 1 gather CSR everywhere),
  * "force_csr_vec" (0 auto, else 2/4/8/16/32 lanes per row), "peer_mode" (row-sharded solvers: 1 = halo pushes
  * and scalar all-reduces by the library's own kernels over IPC-mapped peer memory, 0 = NCCL send/recv and
- * all-reduce; every rank must use the same value), "value_dict" (0 default, 1 = coded staged ELL, see
+ * all-reduce; every rank must use the same value), "value_dict" (0 default, 1 / 2 = coded staged ELL, see
  * cask_b200_plan_value_dict), "persist_ctas" (coded format: CTAs per SM of the persistent kernel, 0 auto).
  * Takes effect at the next preprocess. */
 int cask_b200_set_option(cask_b200_ctx* ctx, const char* name, double value);
@@ -112,12 +112,18 @@ int cask_b200_preprocess_device(cask_b200_ctx* ctx, const cask_b200_design* desi
                                 int64_t m, int64_t nnz, const int32_t* d_row_ptr,
                                 const int32_t* d_col_ind, const double* d_values);
 int cask_b200_plan_get_stats(cask_b200_ctx* ctx, cask_b200_plan_stats* out);
-/* Coded staged ELL (option "value_dict" = 1, off by default; set before preprocess).  When every staged slice
- * holds at most 256 distinct fp64 bit patterns - constant-coefficient stencils hold 2-3 - the values are stored as
- * 8-bit codes into a per-slice table that travels with the slice's x windows: 3 bytes per stored nonzero instead of
- * 10, the same doubles multiplied in the same order, y bit-identical to the uncoded kernel.  *active = 1 if the
- * current plan runs coded, *max_entries = doubles staged per slice table, *matrix_bytes_per_spmv = bytes of the
- * matrix stream one SpMV reads from HBM in the format in use (x and y not included).  Pointers may be NULL. */
+/* Coded staged ELL (option "value_dict", off by default; set before preprocess).
+ *   1  When every staged slice holds at most 256 distinct fp64 bit patterns - constant-coefficient stencils hold 2-6 -
+ *      the values are stored as 8-bit codes into a per-slice table that travels with the slice's x windows: 3 bytes
+ *      per stored nonzero instead of 10.
+ *   2  When every staged slice holds at most 255 distinct (value, displacement) pairs - displacement = position of the
+ *      entry in the slice's x cache minus its row inside the slice, constant along a diagonal, so a stencil needs one
+ *      pair per stencil point - the 8-bit code names the pair and the 16-bit index stream disappears: 1 byte per
+ *      stored nonzero.  Falls back to 1, then to the uncoded format, when a slice does not qualify.
+ * Either way the same doubles are multiplied by the same x entries in the same order: y is bit-identical to the uncoded
+ * kernel.  *active = the format the current plan runs (0 uncoded, 1, 2), *max_entries = table entries staged per slice,
+ * *matrix_bytes_per_spmv = bytes of the matrix stream one SpMV reads from HBM in the format in use (x and y not
+ * included).  Pointers may be NULL. */
 int cask_b200_plan_value_dict(cask_b200_ctx* ctx, int32_t* active, int32_t* max_entries,
                               int64_t* matrix_bytes_per_spmv);
 
