@@ -31,11 +31,15 @@ timeout 900 $PY bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
 tail -c 1500 $OUT/${TAG}_bench.json
 
 step "bench, coded staged ELL (A/B against the line above; CTAs per SM 2 and 3)"
-timeout 900 $PY bench.py --value-dict --no-cpu > $OUT/${TAG}_bench_value_dict.json 2> $OUT/${TAG}_bench_value_dict.err
+timeout 900 $PY bench.py --value-dict --no-cpu --no-probe > $OUT/${TAG}_bench_value_dict.json 2> $OUT/${TAG}_bench_value_dict.err
 tail -c 600 $OUT/${TAG}_bench_value_dict.json
-CASK_B200_PERSIST_CTAS=3 timeout 600 $PY bench.py --value-dict --no-cpu --no-cg --no-extra > $OUT/${TAG}_bench_value_dict_3ctas.json 2>> $OUT/${TAG}_bench_value_dict.err
-CASK_B200_PERSIST_CTAS=1 timeout 600 $PY bench.py --value-dict --no-cpu --no-cg --no-extra > $OUT/${TAG}_bench_value_dict_1cta.json 2>> $OUT/${TAG}_bench_value_dict.err
-CASK_B200_PERSIST_KU=2 timeout 600 $PY bench.py --value-dict --no-cpu --no-cg --no-extra > $OUT/${TAG}_bench_value_dict_ku2.json 2>> $OUT/${TAG}_bench_value_dict.err
+CASK_B200_PERSIST_CTAS=3 timeout 600 $PY bench.py --value-dict --no-cpu --no-cg --no-extra --no-probe > $OUT/${TAG}_bench_value_dict_3ctas.json 2>> $OUT/${TAG}_bench_value_dict.err
+CASK_B200_PERSIST_CTAS=1 timeout 600 $PY bench.py --value-dict --no-cpu --no-cg --no-extra --no-probe > $OUT/${TAG}_bench_value_dict_1cta.json 2>> $OUT/${TAG}_bench_value_dict.err
+CASK_B200_PERSIST_KU=2 timeout 600 $PY bench.py --value-dict --no-cpu --no-cg --no-extra --no-probe > $OUT/${TAG}_bench_value_dict_ku2.json 2>> $OUT/${TAG}_bench_value_dict.err
+timeout 900 $PY bench.py --value-dict 2 --no-cpu --no-probe > $OUT/${TAG}_bench_pair_dict.json 2> $OUT/${TAG}_bench_pair_dict.err
+tail -c 600 $OUT/${TAG}_bench_pair_dict.json
+CASK_B200_PERSIST_CTAS=3 timeout 600 $PY bench.py --value-dict 2 --no-cpu --no-cg --no-extra --no-probe > $OUT/${TAG}_bench_pair_dict_3ctas.json 2>> $OUT/${TAG}_bench_pair_dict.err
+for f in pair_dict pair_dict_3ctas; do $PY -c "import json,sys; d=json.loads(open('$OUT/${TAG}_bench_$f.json').read().strip().splitlines()[-1]); print('$f', d['value'], d['ms_per_step'], d['config']['format'])" 2>/dev/null; done
 for f in 3ctas 1cta ku2; do $PY -c "import json,sys; d=json.loads(open('$OUT/${TAG}_bench_value_dict_$f.json').read().strip().splitlines()[-1]); print('$f', d['value'], d['ms_per_step'], d['config']['format'])" 2>/dev/null; done
 
 step "C3 (R-MAT) sweep: gather-CSR default vs CSR-stream at three item sizes"
@@ -62,6 +66,12 @@ timeout 900 $NCU --set full --import-source on -k regex:spmv_ell_persistent -s 5
   $PY bench.py --value-dict --steps 10 --warmup 3 --soak 0 --no-cg --no-extra --no-cpu > $OUT/${TAG}_ncu_spmv_coded.log 2>&1
 ncu -i $OUT/${TAG}_spmv_persistent_coded.ncu-rep --page raw --csv 2>/dev/null | $PY profiles/summarize_ncu.py > $OUT/${TAG}_spmv_persistent_coded_ncu.md
 cat $OUT/${TAG}_spmv_persistent_coded_ncu.md
+
+step "ncu --set full: pair-coded persistent SpMV on C2"
+timeout 900 $NCU --set full --import-source on -k regex:spmv_ell_persistent -s 5 -c 1 -f -o $OUT/${TAG}_spmv_persistent_pair \
+  $PY bench.py --value-dict 2 --steps 10 --warmup 3 --soak 0 --no-cg --no-extra --no-cpu > $OUT/${TAG}_ncu_spmv_pair.log 2>&1
+ncu -i $OUT/${TAG}_spmv_persistent_pair.ncu-rep --page raw --csv 2>/dev/null | $PY profiles/summarize_ncu.py > $OUT/${TAG}_spmv_persistent_pair_ncu.md
+cat $OUT/${TAG}_spmv_persistent_pair_ncu.md
 
 step "ncu --set full: one CG iteration on C4 (SpMV + dot, fused update)"
 timeout 1200 $NCU --set full --import-source on -k regex:"spmv_ell_persistent|cg_update_fused" -s 60 -c 2 -f -o $OUT/${TAG}_cg_iteration \
