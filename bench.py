@@ -54,7 +54,7 @@ def parse():
                          "on the GPU")
     ap.add_argument("--no-probe", action="store_true",
                     help="skip the coded-staged-ELL probe (a child bench.py --value-dict run, bounded by a timeout)")
-    ap.add_argument("--probe-timeout", type=float, default=240.0, help="seconds the probe's child process may take")
+    ap.add_argument("--probe-timeout", type=float, default=150.0, help="seconds a probe's child process may take")
     ap.add_argument("--soak", type=int, default=1500,
                     help="untimed launches between the warm-up and the timed region (clock sampling under load)")
     ap.add_argument("--only-rmat", action="store_true", help="profiling: run only the C3 R-MAT SpMV side measurement")
@@ -654,11 +654,16 @@ def main():
             probes = [("value_dict_probe", value_dict_probe), ("pair_dict_probe", lambda a: value_dict_probe(a, 2))]
             if rmat and "error" not in rmat and not os.environ.get("CASK_B200_CSR_STREAM"):
                 probes.append(("rmat_stream_probe", rmat_stream_probe))
+            timed_out = False
             for key, fn in probes:
+                if timed_out:  # one child already cost its full time limit: the run stays within minutes
+                    line[key] = {"error": "skipped: an earlier probe exceeded its time limit"}
+                    continue
                 try:
                     line[key] = fn(args)
                 except Exception as e:  # noqa: BLE001 - informational
                     line[key] = {"error": "%s: %s" % (type(e).__name__, e)}
+                timed_out = "was killed" in str(line[key].get("error", ""))
         if world == 1 and not args.no_cpu:
             try:
                 line["cpu_baseline"] = cpu_port_baseline(G)
