@@ -125,3 +125,44 @@ def test_255_pairs_fit_and_256_overflow():
     assert r["overflow"] and r["npairs"].tolist() == [4, 0, 3]   # the caller drops the whole plan to the next format
     assert emu.pairdict([], [], np.zeros(0), np.zeros(0, np.uint16))["rc"] == 0
     assert emu.lib().emu_live_allocations() == 0
+
+
+def plan_model(n, rp, ci, va, pipes, sr=1024):
+    """numpy model of plan.cu for matrices whose slices are all staged: row stripes (Spmv.cpp:334-364) cut into slices of
+    sr rows, x-cache position = 2 + 16 * (rank of the column's granule among the slice's referenced granules) + col % 16,
+    ELL storage order of plan_fill_kernel."""
+    T = sr // 4
+    slices, start = [], 0
+    for q in range(pipes):
+        rows = (n - start) if q == pipes - 1 else n // pipes
+        slices += [(start + r, min(sr, rows - r)) for r in range(0, rows, sr)]
+        start += rows
+    widths, vals, idxs = [], [], []
+    for r0, nr in slices:
+        gran = np.unique(ci[rp[r0]:rp[r0 + nr]] >> 4)
+        rank = {g: i for i, g in enumerate(gran.tolist())}
+        lens = np.diff(rp[r0:r0 + nr + 1])
+        w = int(lens.max()) if nr else 0
+        v, ix = np.zeros(w * sr), np.zeros(w * sr, np.uint16)
+        for row in range(nr):
+            t, j = row % T, row // T
+            for k in range(lens[row]):
+                c = int(ci[rp[r0 + row] + k])
+                e = (k * T + t) * 4 + j
+                v[e], ix[e] = va[rp[r0 + row] + k], 2 + rank[c >> 4] * 16 + (c & 15)
+        widths.append(w); vals.append(v); idxs.append(ix)
+    off = np.concatenate([[0], np.cumsum(np.array(widths, np.int64) * sr)])
+    return off[:-1], widths, np.concatenate(vals), np.concatenate(idxs)
+
+
+def test_one_pair_per_stencil_point_on_the_plan_layout(oracle):
+    """BASELINE's stencils, down-scaled, laid out as the GPU partitioner lays them out (granule-ranked x windows, two
+    stripes): every slice needs exactly one pair per stencil point - what tests/test_gpu_x_value_dict.py asserts of the
+    GPU plan - and decoding reproduces every stored (value, position)."""
+    for gen, N, points in (("gen_poisson2d", 96, 5), ("gen_poisson3d27", 14, 27), ("gen_convdiff3d7", 16, 7)):
+        n, rp, ci, va = getattr(oracle, gen)(N)
+        for pipes in (1, 2):
+            off, widths, vals, idx = plan_model(n, rp, ci, va, pipes)
+            r = emu.pairdict(off, widths, vals, idx, 1024)
+            assert r["rc"] == 0 and not r["overflow"] and r["max_pairs"] == points + 1, (gen, pipes, r["max_pairs"])
+            decode_and_check(off, widths, vals, idx, 1024, r)
