@@ -878,9 +878,14 @@ extern "C" int cask_b200_bicgstab_device(cask_b200_ctx* ctx, const double* d_b, 
   double *y_full = peer ? peer_vector(ctx, 0) : w.d_vec[4], *z_full = peer ? peer_vector(ctx, 1) : w.d_vec[5];
   double *s = w.d_vec[6], *t = w.d_vec[7];
   double *y = y_full + off, *z = z_full + off;
-  // invdiag shares the tail of the partials allocation? keep it simple: own buffer
-  double* invd = nullptr;
-  CB_CUDA(cudaMalloc(&invd, sizeof(double) * std::max<int64_t>(n, 1)));
+  // inverse diagonal of the Jacobi preconditioner: own buffer, released on every exit path (cudaFree waits for the
+  // kernels that still read it)
+  struct DeviceBuffer {
+    double* p = nullptr;
+    ~DeviceBuffer() { cudaFree(p); }
+  } invd_owner;
+  CB_CUDA(cudaMalloc(&invd_owner.p, sizeof(double) * std::max<int64_t>(n, 1)));
+  double* const invd = invd_owner.p;
   double* scal = w.d_scalars;
   int32_t* flags = reinterpret_cast<int32_t*>(w.d_counters);
   const int vg = vec_grid(ctx, n);
@@ -913,7 +918,6 @@ extern "C" int cask_b200_bicgstab_device(cask_b200_ctx* ctx, const double* d_b, 
   CB_CUDA(cudaStreamSynchronize(st));
   const double rhs_sq = w.h_scalars[B_RHSSQ];
   if (rhs_sq == 0.0) {  // Eigen: x = 0, return
-    cudaFree(invd);
     *iters = 0; *tol_error = 0.0;
     return CASK_B200_OK;
   }
@@ -982,7 +986,6 @@ extern "C" int cask_b200_bicgstab_device(cask_b200_ctx* ctx, const double* d_b, 
   CB_CUDA(cudaMemcpyAsync(w.h_scalars, scal, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, st));
   CB_CUDA(cudaStreamSynchronize(st));
   CB_CUDA(cudaGetLastError());
-  cudaFree(invd);
   *iters = hf[F_I];
   *tol_error = std::sqrt(w.h_scalars[B_RR] / rhs_sq);
   return peer_check_error(ctx);
