@@ -250,7 +250,7 @@ int cask_b200_plan_value_dict(cask_b200_ctx* ctx, int32_t* active, int32_t* max_
     const int64_t csr = p.stats.nnz - p.stats.ell_nnz;
     int64_t csr_rows = 0;
     for (const SliceDesc& sd : p.h_slices) if (sd.kind != kSliceStagedEll) csr_rows += sd.nrows;
-    const int64_t entry = on == 2 ? 1 : on == 1 ? 3 : 10, table = on == 2 ? 10 : on == 1 ? 8 : 0;
+    const int64_t entry = on == 2 ? 1 : on == 1 ? 3 : 10, table = on == 2 ? 16 : on == 1 ? 8 : 0;
     *matrix_bytes_per_spmv = p.stats.ell_padded_entries * entry + (int64_t)p.n_ell * p.dict_len * table + csr * 12 + csr_rows * 4;
   }
   return CASK_B200_OK;

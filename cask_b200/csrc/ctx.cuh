@@ -109,7 +109,7 @@ struct Plan {
   int32_t coded = 0;                  // 0 uncoded, 1 value codes (+ 16-bit indices), 2 pair codes
   uint8_t* d_ell_codes = nullptr;     // same indexing as d_ell_vals
   double* d_ell_dict = nullptr;       // valuedict::kStride doubles per slice id
-  uint16_t* d_ell_delta = nullptr;    // pair codes: valuedict::kDeltaStride displacements per slice id
+  void* d_ell_pairs = nullptr;        // pair codes: valuedict::kPairStride 16-byte {value, displacement} records per slice id
   int32_t dict_len = 0;               // table entries staged per slice: the largest table, rounded up to a multiple of
                                       // 2 (value codes) or 8 (pair codes) so that every bulk copy moves whole 16 bytes
   int32_t* d_list_ell = nullptr;      // slice ids, staged ELL, interior first then halo-dependent

@@ -249,7 +249,7 @@ void free_plan(cask_b200_ctx* ctx) {
     cudaFree((void*)p.d_val);
   }
   cudaFree(p.d_slices); cudaFree(p.d_runs); cudaFree(p.d_ell_vals); cudaFree(p.d_ell_idx);
-  cudaFree(p.d_ell_codes); cudaFree(p.d_ell_dict); cudaFree(p.d_ell_delta);
+  cudaFree(p.d_ell_codes); cudaFree(p.d_ell_dict); cudaFree(p.d_ell_pairs);
   cudaFree(p.d_list_ell); cudaFree(p.d_list_csr);
   cudaFree(p.d_csr_items); cudaFree(p.d_split_rows); cudaFree(p.d_csr_scratch);
   p = Plan();
@@ -349,21 +349,21 @@ static int build_value_dict(cask_b200_ctx* ctx, int64_t val_off_total) {
   CB_TRY(dev::upload(ex, tmp.q[0], h_off.data(), sizeof(int64_t) * (size_t)p.nslices));
   CB_TRY(dev::upload(ex, tmp.q[1], h_width.data(), sizeof(int32_t) * (size_t)p.nslices));
   CB_CUDA(cudaMalloc(&p.d_ell_codes, (size_t)std::max<int64_t>(val_off_total, 16)));
-  CB_CUDA(cudaMalloc(&p.d_ell_dict, sizeof(double) * (size_t)valuedict::kStride * (size_t)p.nslices));
   int32_t overflow = 0, max_entries = 0;
   if (ctx->value_dict >= 2) {
-    CB_CUDA(cudaMalloc(&p.d_ell_delta, sizeof(uint16_t) * (size_t)valuedict::kDeltaStride * (size_t)p.nslices));
+    CB_CUDA(cudaMalloc(&p.d_ell_pairs, sizeof(valuedict::PairEntry) * (size_t)valuedict::kPairStride * (size_t)p.nslices));
     CB_TRY(valuedict::build_pairs(ex, p.nslices, (const int64_t*)tmp.q[0], (const int32_t*)tmp.q[1], p.slice_rows, p.d_ell_vals,
-                                  p.d_ell_idx, p.d_ell_dict, p.d_ell_delta, p.d_ell_codes, (int32_t*)tmp.q[2], &overflow,
-                                  &max_entries));
+                                  p.d_ell_idx, (valuedict::PairEntry*)p.d_ell_pairs, p.d_ell_codes, (int32_t*)tmp.q[2],
+                                  &overflow, &max_entries));
     if (!overflow && max_entries > 0) {
       p.coded = 2;
-      p.dict_len = (max_entries + 7) & ~7;  // 8 displacements = 16 bytes: the unit of a bulk copy
+      p.dict_len = (max_entries + 7) & ~7;  // records staged per slice (16 bytes each)
       return CASK_B200_OK;
     }
-    cudaFree(p.d_ell_delta);
-    p.d_ell_delta = nullptr;
+    cudaFree(p.d_ell_pairs);
+    p.d_ell_pairs = nullptr;
   }
+  CB_CUDA(cudaMalloc(&p.d_ell_dict, sizeof(double) * (size_t)valuedict::kStride * (size_t)p.nslices));
   CB_TRY(valuedict::build(ex, p.nslices, (const int64_t*)tmp.q[0], (const int32_t*)tmp.q[1], p.slice_rows, p.d_ell_vals,
                           p.d_ell_dict, p.d_ell_codes, (int32_t*)tmp.q[2], &overflow, &max_entries));
   if (overflow || max_entries == 0) {
@@ -519,8 +519,8 @@ int build_plan(cask_b200_ctx* ctx) {
   p.stats.csr_lanes_per_row = vec;
   p.stats.max_row_length = maxlen;
   for (int i = 0; i < 8; i++) p.stats.row_length_histogram[i] = (int64_t)hist[i];
-  p.stats.device_bytes = val_off * (p.coded ? 11 : 10) + (p.coded ? (int64_t)p.nslices * valuedict::kStride * 8 : 0) +
-                         (p.coded == 2 ? (int64_t)p.nslices * valuedict::kDeltaStride * 2 : 0) +
+  p.stats.device_bytes = val_off * (p.coded ? 11 : 10) + (p.coded == 1 ? (int64_t)p.nslices * valuedict::kStride * 8 : 0) +
+                         (p.coded == 2 ? (int64_t)p.nslices * valuedict::kPairStride * 16 : 0) +
                          (int64_t)run_off * sizeof(Run) + (int64_t)p.nslices * sizeof(SliceDesc) +
                          (p.n_csr ? (csr_nnz * 12 + csr_rows * 4) : 0);
   return CASK_B200_OK;

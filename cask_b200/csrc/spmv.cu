@@ -217,24 +217,27 @@ static_assert(sizeof(PersistHeader) <= kPersistHeaderBytes, "header must fit its
 //      doubles) travels with the x windows into the tail of the x buffer, a ring stage holds KU*1024 codes + KU*1024
 //      16-bit indices (3 bytes per stored nonzero instead of 10), and a consumer reads its four codes with one 32-bit
 //      load and looks the doubles up in shared memory;
-//   2  the code names a (value, x-cache displacement) pair: position = (displacement + row inside the slice) mod 2^16,
-//      code 0 = padding (+0.0 at the zero slot).  The index stream is gone too: a ring stage holds KU*1024 codes, one
-//      byte per stored nonzero; the two tables (dict_len doubles, dict_len 16-bit displacements) ride with the x windows.
+//   2  the code names a (value, x-cache displacement) pair: position = displacement + row inside the slice.  The index
+//      stream is gone too: a ring stage holds KU*1024 codes, one byte per stored nonzero; the slice's table of dict_len
+//      16-byte records {value, displacement in bytes} rides with the x windows.  Code 0 = padding = (+0.0, -1024 rows):
+//      every x cache is preceded by 1024 zeros, so a padding entry reads a zero like any other entry reads its x - the
+//      inner loop has no special case (value lookup, displacement lookup, one add, x load, multiply, add).
 // In both the multiplied doubles, the x entries, the order of the operations and therefore y are those of the uncoded
 // kernel, bit for bit.
 struct CodedArgs {
   const uint8_t* codes = nullptr;   // same indexing as ell_vals
-  const double* dict = nullptr;     // valuedict::kStride doubles per slice id
-  const uint16_t* delta = nullptr;  // pair codes: valuedict::kDeltaStride displacements per slice id
+  const double* dict = nullptr;     // value codes: valuedict::kStride doubles per slice id
+  const void* pairs = nullptr;      // pair codes: valuedict::kPairStride 16-byte records per slice id
   int32_t dict_len = 0;             // table entries staged per slice (multiple of 2; of 8 with pair codes)
   int32_t pad_ = 0;
 };
 constexpr int kDictStride = 256;    // == valuedict::kStride (plan.cu)
-constexpr int kDeltaStride = 256;   // == valuedict::kDeltaStride
+constexpr int kPairStride = 256;    // == valuedict::kPairStride
 
-// doubles appended to an x buffer for the slice's table(s)
+// doubles appended to an x buffer for the slice's table: values (8 B per entry) or pair records (16 B per entry);
+// pair codes also put kSliceRows zeros in FRONT of the x cache (what a padding entry reads)
 __host__ __device__ constexpr int dict_value_doubles(int dict_len) { return (dict_len + 15) & ~15; }
-__host__ __device__ constexpr int dict_delta_doubles(int dict_len) { return (((dict_len + 3) >> 2) + 15) & ~15; }
+__host__ __device__ constexpr int dict_pair_doubles(int dict_len) { return (2 * dict_len + 15) & ~15; }
 
 template <int KU, bool kDot, int kCoded>
 __global__ void __launch_bounds__(kPersistThreads, 1)
@@ -258,9 +261,11 @@ spmv_ell_persistent_kernel(const SliceDesc* __restrict__ slices, const int32_t* 
   uint8_t* ccode = kCoded == 2 ? reinterpret_cast<uint8_t*>(cvals)
                                : reinterpret_cast<uint8_t*>(cidx + (size_t)stages * KU * kSliceRows);  // coded formats only
   // the table(s) of a slice sit at the tail of its x buffer: values, then (pair codes) the displacements
-  const int dict_base = kCoded == 2 ? xbuf_doubles - dict_value_doubles(ca.dict_len) - dict_delta_doubles(ca.dict_len)
+  // an x buffer: [pair codes: kSliceRows zeros] [x cache: zero slots, staged windows] [table]; positions, and the
+  // table offset dict_base, count from the x cache
+  constexpr int zpre = kCoded == 2 ? kSliceRows : 0;
+  const int dict_base = kCoded == 2 ? xbuf_doubles - zpre - dict_pair_doubles(ca.dict_len)
                         : kCoded == 1 ? xbuf_doubles - dict_value_doubles(ca.dict_len) : 0;
-  const int delta_base = dict_base + dict_value_doubles(ca.dict_len);  // pair codes only
   __shared__ double red[kPersistThreads / 32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -268,8 +273,8 @@ spmv_ell_persistent_kernel(const SliceDesc* __restrict__ slices, const int32_t* 
     for (int b = 0; b < 2; b++) {
       mbar_init(smem_u32(&hdr->full_x[b]), 1);
       mbar_init(smem_u32(&hdr->empty_x[b]), kConsumerThreads / 32);
-      xbuf[(size_t)b * xbuf_doubles] = 0.0;      // zero slots: target of every padding entry,
-      xbuf[(size_t)b * xbuf_doubles + 1] = 0.0;  // never overwritten (runs start at local index 2)
+      xbuf[(size_t)b * xbuf_doubles + zpre] = 0.0;      // zero slots: target of every padding entry,
+      xbuf[(size_t)b * xbuf_doubles + zpre + 1] = 0.0;  // never overwritten (runs start at local index 2)
     }
     for (int s = 0; s < stages; s++) {
       mbar_init(smem_u32(&hdr->full_c[s]), 1);
@@ -277,6 +282,9 @@ spmv_ell_persistent_kernel(const SliceDesc* __restrict__ slices, const int32_t* 
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if constexpr (kCoded == 2)  // the zeros a padding entry reads: position = row - kSliceRows, never written again
+    for (int i = tid; i < 2 * kSliceRows; i += kPersistThreads)
+      xbuf[(size_t)(i / kSliceRows) * xbuf_doubles + (i % kSliceRows)] = 0.0;
   __syncthreads();
 
   const bool is_producer = warp == kConsumerThreads / 32;
@@ -339,7 +347,7 @@ spmv_ell_persistent_kernel(const SliceDesc* __restrict__ slices, const int32_t* 
       const int L = sdp->width, nruns = sdp->nruns;
       const int xb = it & 1;
       mbar_wait(smem_u32(&hdr->empty_x[xb]), ((it >> 1) & 1) ^ 1);
-      double* xs = xbuf + (size_t)xb * xbuf_doubles;
+      double* xs = xbuf + (size_t)xb * xbuf_doubles + zpre;
       const uint32_t fx = smem_u32(&hdr->full_x[xb]);
       const Run* rr = nruns <= kInlineRuns ? sdp->inl : runs + sdp->run_off;
       uint32_t bytes = 0;
@@ -353,15 +361,15 @@ spmv_ell_persistent_kernel(const SliceDesc* __restrict__ slices, const int32_t* 
         }
         if (r.len & 1) xs[r.local_base + r.len - 1] = x[r.col0 + r.len - 1];  // odd tail at column m-1
       }
-      if constexpr (kCoded != 0) if (lane == 31) {  // the slice's value table rides on the same barrier phase as its x windows
+      if constexpr (kCoded == 1) if (lane == 31) {  // the slice's value table rides on the same barrier phase as its x windows
         const uint32_t b = (uint32_t)ca.dict_len * 8u;
         bytes += b;
         bulk_g2s(smem_u32(xs + dict_base), ca.dict + (size_t)list[item] * kDictStride, b, fx);
       }
-      if constexpr (kCoded == 2) if (lane == 30) {  // ... and so does its displacement table
-        const uint32_t b = (uint32_t)ca.dict_len * 2u;
+      if constexpr (kCoded == 2) if (lane == 31) {  // ... or its table of {value, displacement} records
+        const uint32_t b = (uint32_t)ca.dict_len * 16u;
         bytes += b;
-        bulk_g2s(smem_u32(xs + delta_base), ca.delta + (size_t)list[item] * kDeltaStride, b, fx);
+        bulk_g2s(smem_u32(xs + dict_base), static_cast<const char*>(ca.pairs) + (size_t)list[item] * kPairStride * 16u, b, fx);
       }
 #pragma unroll
       for (int d = 16; d; d >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, d);
@@ -388,7 +396,7 @@ spmv_ell_persistent_kernel(const SliceDesc* __restrict__ slices, const int32_t* 
       const int xb = it & 1;
       mbar_wait(smem_u32(&hdr->full_x[xb]), (it >> 1) & 1);
       const int row0 = hdr->meta[xb][0], nrows = hdr->meta[xb][1], L = hdr->meta[xb][2];
-      const double* xs = xbuf + (size_t)xb * xbuf_doubles;
+      const double* xs = xbuf + (size_t)xb * xbuf_doubles + zpre;
       double acc[RPT] = {0.0, 0.0, 0.0, 0.0};
       const int nchunks = (L + KU - 1) / KU;
       for (int c = 0; c < nchunks; c++, chunk_no++) {
@@ -399,23 +407,29 @@ spmv_ell_persistent_kernel(const SliceDesc* __restrict__ slices, const int32_t* 
         const uint16_t* ib = cidx + (size_t)s * KU * kSliceRows + (size_t)tid * RPT;
         const uint8_t* cb = ccode + (size_t)s * KU * kSliceRows + (size_t)tid * RPT;
         const double* dict = xs + dict_base;
-        const uint16_t* ddel = reinterpret_cast<const uint16_t*>(xs + delta_base);
+        const char* tab = reinterpret_cast<const char*>(xs + dict_base);  // pair codes: 16-byte records
+        const char* xrow = reinterpret_cast<const char*>(xs + tid);       // pair codes: x cache at this thread's row 0
 #pragma unroll
         for (int u = 0; u < KU; u++) {
           if (u < cols) {
             if constexpr (kCoded == 2) {
-              // byte j of thread t's word = code of entry (k, row j*256 + t); code 0 = padding -> the zero slot
+              // byte j of thread t's word = code of entry (k, row j*256 + t); record = {value, (position - row) * 8};
+              // a padding entry (code 0) reads one of the zeros in front of the x cache
               const uint32_t cw = *reinterpret_cast<const uint32_t*>(cb + (size_t)u * kSliceRows);
-              const uint32_t c0 = cw & 0xffu, c1 = (cw >> 8) & 0xffu, c2 = (cw >> 16) & 0xffu, c3 = cw >> 24;
-              const uint32_t p0 = c0 ? ((uint32_t)ddel[c0] + (uint32_t)tid) & 0xffffu : 0u;
-              const uint32_t p1 = c1 ? ((uint32_t)ddel[c1] + (uint32_t)(kConsumerThreads + tid)) & 0xffffu : 0u;
-              const uint32_t p2 = c2 ? ((uint32_t)ddel[c2] + (uint32_t)(2 * kConsumerThreads + tid)) & 0xffffu : 0u;
-              const uint32_t p3 = c3 ? ((uint32_t)ddel[c3] + (uint32_t)(3 * kConsumerThreads + tid)) & 0xffffu : 0u;
+              const char* e0 = tab + ((cw & 0xffu) << 4);
+              const char* e1 = tab + ((cw >> 4) & 0xff0u);
+              const char* e2 = tab + ((cw >> 12) & 0xff0u);
+              const char* e3 = tab + ((cw >> 20) & 0xff0u);
+              constexpr int kRowStep = kConsumerThreads * (int)sizeof(double);  // rows j and j+1 of a thread
+              const double x0 = *reinterpret_cast<const double*>(xrow + *reinterpret_cast<const int*>(e0 + 8));
+              const double x1 = *reinterpret_cast<const double*>(xrow + kRowStep + *reinterpret_cast<const int*>(e1 + 8));
+              const double x2 = *reinterpret_cast<const double*>(xrow + 2 * kRowStep + *reinterpret_cast<const int*>(e2 + 8));
+              const double x3 = *reinterpret_cast<const double*>(xrow + 3 * kRowStep + *reinterpret_cast<const int*>(e3 + 8));
               // ascending column order, separate multiply and add (DokMatrix::dot, SparseMatrix.hpp:255-264)
-              acc[0] = __dadd_rn(acc[0], __dmul_rn(dict[c0], xs[p0]));
-              acc[1] = __dadd_rn(acc[1], __dmul_rn(dict[c1], xs[p1]));
-              acc[2] = __dadd_rn(acc[2], __dmul_rn(dict[c2], xs[p2]));
-              acc[3] = __dadd_rn(acc[3], __dmul_rn(dict[c3], xs[p3]));
+              acc[0] = __dadd_rn(acc[0], __dmul_rn(*reinterpret_cast<const double*>(e0), x0));
+              acc[1] = __dadd_rn(acc[1], __dmul_rn(*reinterpret_cast<const double*>(e1), x1));
+              acc[2] = __dadd_rn(acc[2], __dmul_rn(*reinterpret_cast<const double*>(e2), x2));
+              acc[3] = __dadd_rn(acc[3], __dmul_rn(*reinterpret_cast<const double*>(e3), x3));
             } else {
               double2 v0, v1;
               if constexpr (kCoded == 1) {
@@ -623,8 +637,8 @@ int configure_persistent(cask_b200_ctx* ctx) {
   int dev_smem = 0;
   CB_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
   // doubles per x buffer (keeps every buffer 128-B aligned); the coded format appends the slice's value table
-  const size_t xbuf = (((size_t)p.max_xcache + 15) & ~(size_t)15) + (p.coded ? (size_t)dict_value_doubles(p.dict_len) : 0) +
-                      (p.coded == 2 ? (size_t)dict_delta_doubles(p.dict_len) : 0);
+  const size_t xbuf = (((size_t)p.max_xcache + 15) & ~(size_t)15) + (p.coded == 1 ? (size_t)dict_value_doubles(p.dict_len) : 0) +
+                      (p.coded == 2 ? (size_t)kSliceRows + (size_t)dict_pair_doubles(p.dict_len) : 0);
   const size_t fixed = kPersistHeaderBytes + 2 * xbuf * sizeof(double);
   const size_t per_sm = 228 * 1024, sys_reserve = 1024;  // 1 KB per resident CTA belongs to the driver
   const size_t entry_bytes = p.coded == 2 ? 1 : p.coded == 1 ? 3 : 10;
@@ -722,7 +736,7 @@ int launch_spmv_range(cask_b200_ctx* ctx, const double* d_x, double* d_y, int el
     const ReduceDesc rd = dot && fusion->reduce.partials && ell_lo == 0 && ell_hi == p.n_ell && csr_hi == csr_lo
                               ? fusion->reduce : ReduceDesc();
     CodedArgs ca;
-    if (p.coded) { ca.codes = p.d_ell_codes; ca.dict = p.d_ell_dict; ca.delta = p.d_ell_delta; ca.dict_len = p.dict_len; }
+    if (p.coded) { ca.codes = p.d_ell_codes; ca.dict = p.d_ell_dict; ca.pairs = p.d_ell_pairs; ca.dict_len = p.dict_len; }
     if (p.coded == 2) {
       if (p.persist_ku == 2) { if (dot) CB_PERSIST(2, true, 2); else CB_PERSIST(2, false, 2); }
       else { if (dot) CB_PERSIST(4, true, 2); else CB_PERSIST(4, false, 2); }

@@ -87,17 +87,27 @@ inline int build(dev::Exec& ex, int64_t nlisted, const int64_t* d_val_off, const
 
 // ---- pair dictionaries ("pair-coded ELL", option value_dict = 2) ----------------------------------------------
 // One step further: the 8-bit code names a (value, x-cache displacement) PAIR, where the displacement of a stored entry
-// is its 16-bit x-cache position minus its row number inside the slice (mod 2^16).  Along a diagonal of a banded
-// matrix the displacement is constant - a row's neighbour in the x window moves with the row - so a constant-coefficient
-// stencil needs one pair per stencil point (2D 5-point: 5, 3D 27-point: 27) whatever the slice, the 16-bit index stream
-// disappears and a stored nonzero costs ONE byte.  The kernel rebuilds position = (displacement + row) mod 2^16 and
-// multiplies the very same double by the very same x entry in the same order: y stays bit-identical.
-// Code 0 is reserved for padding entries (value +0.0 at the zero slot, written by plan_fill_kernel as index 0 - a real
-// entry never has index 0 or 1); real pairs take codes 1..255 in order of first appearance.  A slice with more than 255
-// distinct pairs raises *overflow and the caller falls back to the value dictionaries above.
+// is its x-cache position minus its row number inside the slice.  Along a diagonal of a banded matrix the position moves
+// with the row, so the displacement is constant: a constant-coefficient stencil needs one pair per stencil point (2D
+// 5-point: 5, 3D 27-point: 27) whatever the slice, the 16-bit index stream disappears and a stored nonzero costs ONE
+// byte.  The kernel rebuilds position = displacement + row and multiplies the very same double by the very same x entry
+// in the same order: y stays bit-identical.
+// Code 0 is reserved for padding entries (written by plan_fill_kernel as value +0.0 at index 0; a real entry never has
+// index 0 or 1): its pair is (+0.0, -slice_rows), i.e. position = row - slice_rows - the kernel keeps slice_rows zeros in
+// front of every x cache, so padding needs no special case in the inner loop.  Real pairs take codes 1..255 in order of
+// first appearance.  A slice with more than 255 distinct pairs raises *overflow and the caller falls back to the value
+// dictionaries above.  Table entries are 16-byte records {value bits, displacement in BYTES (x 8), 0}: one shared-memory
+// address per code serves both lookups.
 // Storage order inside a slice (plan.cu): entry e = (k * T + t) * 4 + j, row = j * T + t, T = slice_rows / 4.
 constexpr int kMaxPairs = 255;
-constexpr int kDeltaStride = 256;   // uint16 displacements reserved per slice (slot c of slice q: q * kDeltaStride + c)
+constexpr int kPairStride = 256;    // records reserved per slice (slot c of slice q: q * kPairStride + c)
+
+struct PairEntry {
+  unsigned long long value_bits;
+  int32_t disp8;   // (x-cache position - row) * 8
+  int32_t zero_;
+};
+static_assert(sizeof(PairEntry) == 16, "pair records are 16 bytes");
 
 struct BuildPairs {
   const int64_t* val_off;
@@ -105,8 +115,7 @@ struct BuildPairs {
   int32_t slice_rows;
   const double* vals;
   const uint16_t* idx;       // ELL x-cache positions, same indexing as vals
-  double* table_v;           // kStride doubles per listed slice; slot 0 = +0.0 (padding), unused slots 0.0
-  uint16_t* table_d;         // kDeltaStride displacements per listed slice; slot 0 and unused slots 0
+  PairEntry* table;          // kPairStride records per listed slice; unused slots are zero
   uint8_t* codes;
   int32_t* npairs;           // per listed slice: table length including slot 0 (0 if the slice is empty or overflowed)
   int32_t* overflow;
@@ -117,24 +126,24 @@ struct BuildPairs {
     const int64_t total = (int64_t)width[q] * slice_rows;
     const int32_t T = slice_rows / 4;
     unsigned long long dv[kMaxPairs + 1];
-    uint16_t dd[kMaxPairs + 1];
+    int32_t dd[kMaxPairs + 1];
     dv[0] = 0ull;
-    dd[0] = 0;
+    dd[0] = -slice_rows;
     int32_t n = total > 0 ? 1 : 0;
     unsigned long long last_v = 0;
-    uint16_t last_d = 0;
+    int32_t last_d = 0;
     int32_t last_code = -1;
     bool over = false;
-    for (int64_t e = 0; e < total; e++) {
-      const int32_t rem = (int32_t)(e % slice_rows);
+    int32_t rem = 0;  // e % slice_rows
+    for (int64_t e = 0; e < total; e++, rem = rem + 1 == slice_rows ? 0 : rem + 1) {
       const int32_t row = (rem & 3) * T + (rem >> 2);
-      const uint16_t pos = si[e];
+      const int32_t pos = si[e];
       if (pos == 0) {  // padding
         dst[e] = 0;
         continue;
       }
       const unsigned long long b = sv[e];
-      const uint16_t d = (uint16_t)(pos - (uint16_t)row);
+      const int32_t d = pos - row;
       if (last_code < 0 || b != last_v || d != last_d) {
         int32_t c = 1;
         while (c < n && !(dv[c] == b && dd[c] == d)) c++;
@@ -155,15 +164,19 @@ struct BuildPairs {
       n = 0;
     }
     npairs[q] = n;
-    unsigned long long* ov = reinterpret_cast<unsigned long long*>(table_v) + q * kStride;
-    uint16_t* od = table_d + q * kDeltaStride;
-    for (int32_t c = 0; c < kStride; c++) ov[c] = c < n ? dv[c] : 0ull;
-    for (int32_t c = 0; c < kDeltaStride; c++) od[c] = c < n ? dd[c] : (uint16_t)0;
+    PairEntry* out = table + q * kPairStride;
+    for (int32_t c = 0; c < kPairStride; c++) {
+      PairEntry r;
+      r.value_bits = c < n ? dv[c] : 0ull;
+      r.disp8 = c < n ? dd[c] * 8 : 0;
+      r.zero_ = 0;
+      out[c] = r;
+    }
   }
 };
 
 inline int build_pairs(dev::Exec& ex, int64_t nlisted, const int64_t* d_val_off, const int32_t* d_width, int32_t slice_rows,
-                       const double* d_vals, const uint16_t* d_idx, double* d_table_v, uint16_t* d_table_d, uint8_t* d_codes,
+                       const double* d_vals, const uint16_t* d_idx, PairEntry* d_table, uint8_t* d_codes,
                        int32_t* d_npairs, int32_t* overflow, int32_t* max_pairs) {
   *overflow = 0;
   *max_pairs = 0;
@@ -172,7 +185,7 @@ inline int build_pairs(dev::Exec& ex, int64_t nlisted, const int64_t* d_val_off,
   int32_t* d_over = nullptr;
   CB_TRY(dev::alloc((void**)&d_over, 16));
   int rc = dev::zero(ex, d_over, 16);
-  BuildPairs f{d_val_off, d_width, slice_rows, d_vals, d_idx, d_table_v, d_table_d, d_codes, d_npairs, d_over};
+  BuildPairs f{d_val_off, d_width, slice_rows, d_vals, d_idx, d_table, d_codes, d_npairs, d_over};
   if (rc == CASK_B200_OK) rc = dev::for_each(ex, nlisted, f);
   if (rc == CASK_B200_OK) rc = dev::download(ex, overflow, d_over, sizeof(int32_t));
   dev::release(d_over);

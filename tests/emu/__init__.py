@@ -36,7 +36,7 @@ def lib():
         L.emu_ilu.argtypes = [i64, i64, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp]
         L.emu_inv_diag.argtypes = [i64, vp, vp, vp, vp]
         L.emu_valuedict.argtypes = [i64, vp, vp, C.c_int32, vp, C.c_int, vp, vp, vp, vp]
-        L.emu_pairdict.argtypes = [i64, vp, vp, C.c_int32, vp, vp, C.c_int, vp, vp, vp, vp, vp]
+        L.emu_pairdict.argtypes = [i64, vp, vp, C.c_int32, vp, vp, C.c_int, vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -105,20 +105,22 @@ def valuedict(val_off, width, vals, slice_rows=1024, order=1):
             "codes": codes[:len(va)], "ndict": ndict[:len(vo)], "message": lib().emu_error().decode()}
 
 
+PAIR_DTYPE = np.dtype([("value_bits", "<u8"), ("disp8", "<i4"), ("zero", "<i4")])
+
+
 def pairdict(val_off, width, vals, idx, slice_rows=1024, order=1):
     """Per-slice (value, displacement) pair dictionaries of the pair-coded staged-ELL format.  Returns dict(rc, overflow,
-    max_pairs, table_v [nlisted, 256], table_d [nlisted, 256], codes, npairs)."""
+    max_pairs, table [nlisted, 256] of PAIR_DTYPE records, codes, npairs)."""
     vo = np.ascontiguousarray(val_off, np.int64)
     w = np.ascontiguousarray(width, np.int32)
     va = np.ascontiguousarray(vals, np.float64)
     ix = np.ascontiguousarray(idx, np.uint16)
-    table_v = np.full((max(len(vo), 1), 256), np.nan)
-    table_d = np.full((max(len(vo), 1), 256), 0xffff, np.uint16)
+    table = np.zeros((max(len(vo), 1), 256), PAIR_DTYPE)
+    table["zero"] = -1
     codes = np.full(max(len(va), 1), 255, np.uint8)
     npairs = np.full(max(len(vo), 1), -1, np.int32)
     info = np.zeros(3, np.int64)
-    rc = lib().emu_pairdict(len(vo), _p(vo), _p(w), slice_rows, _p(va), _p(ix), order, _p(table_v), _p(table_d), _p(codes),
-                            _p(npairs), _p(info))
-    return {"rc": rc, "overflow": bool(info[0]), "max_pairs": int(info[1]), "table_v": table_v[:len(vo)],
-            "table_d": table_d[:len(vo)], "codes": codes[:len(va)], "npairs": npairs[:len(vo)],
-            "message": lib().emu_error().decode()}
+    rc = lib().emu_pairdict(len(vo), _p(vo), _p(w), slice_rows, _p(va), _p(ix), order, _p(table), _p(codes), _p(npairs),
+                            _p(info))
+    return {"rc": rc, "overflow": bool(info[0]), "max_pairs": int(info[1]), "table": table[:len(vo)],
+            "codes": codes[:len(va)], "npairs": npairs[:len(vo)], "message": lib().emu_error().decode()}

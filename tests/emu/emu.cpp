@@ -87,18 +87,17 @@ int emu_valuedict(int64_t nlisted, const int64_t* val_off, const int32_t* width,
   return rc;
 }
 
-// pair dictionaries: table_v nlisted * 256 doubles, table_d nlisted * 256 uint16, npairs nlisted.
+// pair dictionaries: table nlisted * 256 records of 16 bytes {value bits, displacement * 8, 0}, npairs nlisted.
 // info[0] = overflow, info[1] = longest table (slot 0 included), info[2] = launches
 int emu_pairdict(int64_t nlisted, const int64_t* val_off, const int32_t* width, int32_t slice_rows, const double* vals,
-                 const uint16_t* idx, int order, double* table_v, uint16_t* table_d, uint8_t* codes, int32_t* npairs,
-                 int64_t* info) {
+                 const uint16_t* idx, int order, void* table, uint8_t* codes, int32_t* npairs, int64_t* info) {
   dev::Exec ex;
   int64_t launches = 0;
   ex.launches = &launches;
   ex.order = order;
   int32_t overflow = 0, max_pairs = 0;
-  const int rc = valuedict::build_pairs(ex, nlisted, val_off, width, slice_rows, vals, idx, table_v, table_d, codes, npairs,
-                                        &overflow, &max_pairs);
+  const int rc = valuedict::build_pairs(ex, nlisted, val_off, width, slice_rows, vals, idx,
+                                        static_cast<valuedict::PairEntry*>(table), codes, npairs, &overflow, &max_pairs);
   info[0] = overflow; info[1] = max_pairs; info[2] = launches;
   return rc;
 }

@@ -177,7 +177,7 @@ def test_pair_codes_stencils_bit_identical(gpu_lib, ctx, oracle, gen, N, points,
     st = ctx.plan_stats()
     assert active and entries % 8 == 0 and points + 1 <= entries <= ((2 * points + 1 + 7) & ~7)
     assert st["slices_gather_csr"] == 0
-    assert mbytes == st["ell_padded_entries"] + 10 * entries * st["slices_staged_ell"]
+    assert mbytes == st["ell_padded_entries"] + 16 * entries * st["slices_staged_ell"]
     assert np.array_equal(plain, coded)
     assert np.array_equal(coded, oracle.csr_dot(n, rp, ci, va, x))
     ctx.set_option("persist_ku", 0)

@@ -30,20 +30,26 @@ def decode_and_check(val_off, widths, vals, idx, slice_rows, r):
     bits = vals.view(np.uint64)
     for q, (o, w) in enumerate(zip(val_off, widths)):
         n = r["npairs"][q]
-        tv, td = r["table_v"][q].view(np.uint64), r["table_d"][q]
-        assert tv[0] == 0 and td[0] == 0                       # slot 0: padding (+0.0 at the zero slot)
-        assert np.all(tv[n:] == 0) and np.all(td[n:] == 0)
+        tab = r["table"][q]
+        tv, td8 = tab["value_bits"], tab["disp8"].astype(np.int64)
+        assert np.all(tab["zero"] == 0)
+        if n:                                                  # slot 0: padding = +0.0 read slice_rows entries before the row
+            assert tv[0] == 0 and td8[0] == -8 * slice_rows
+        assert np.all(tv[n:] == 0) and np.all(td8[n:] == 0)
+        assert np.all(td8 % 8 == 0)
         e = np.arange(w * slice_rows)
         rem = e % slice_rows
         row = (rem & 3) * T + (rem >> 2)
         codes = r["codes"][o:o + w * slice_rows].astype(np.int64)
         assert codes.max(initial=0) < max(n, 1)
-        pos = np.where(codes == 0, 0, (td[codes].astype(np.int64) + row) & 0xffff)
-        assert np.array_equal(pos, idx[o:o + w * slice_rows].astype(np.int64))
-        assert np.array_equal(tv[codes], bits[o:o + w * slice_rows])
-        assert np.array_equal(codes == 0, idx[o:o + w * slice_rows] == 0)
+        pos = td8[codes] // 8 + row                            # what the kernel computes, no special case for padding
+        pad = idx[o:o + w * slice_rows] == 0
+        assert np.array_equal(codes == 0, pad)
+        assert np.array_equal(pos[~pad], idx[o:o + w * slice_rows].astype(np.int64)[~pad])
+        assert np.all((pos[pad] >= -slice_rows) & (pos[pad] < 0))          # inside the zero region in front of the x cache
+        assert np.array_equal(tv[codes], bits[o:o + w * slice_rows])      # padding value is +0.0 in both
         # pairs are distinct and listed in order of first appearance
-        pairs = list(zip(tv[1:n].tolist(), td[1:n].tolist()))
+        pairs = list(zip(tv[1:n].tolist(), td8[1:n].tolist()))
         assert len(set(pairs)) == len(pairs)
         first = {}
         for c in codes[codes > 0].tolist():
