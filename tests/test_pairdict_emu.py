@@ -172,3 +172,43 @@ def test_one_pair_per_stencil_point_on_the_plan_layout(oracle):
             r = emu.pairdict(off, widths, vals, idx, 1024)
             assert r["rc"] == 0 and not r["overflow"] and r["max_pairs"] == points + 1, (gen, pipes, r["max_pairs"])
             decode_and_check(off, widths, vals, idx, 1024, r)
+
+
+def test_decoded_product_is_bit_identical_to_the_reference_dot(oracle):
+    """The consumer loop of the pair-coded kernel, restated in numpy on the modelled plan: x cache = 1024 zeros, two zero
+    slots, then the referenced 16-double granules of x; per row, ELL columns in ascending order, product then add, the x
+    entry found at displacement + row with NO special case for padding.  y equals CsrMatrix::dot bit for bit - also when x
+    holds Inf and NaN, which a padding entry multiplied by a real x entry would spread to rows that never reference them."""
+    sr = 1024
+    T = sr // 4
+    n, rp, ci, va = oracle.gen_poisson2d(40)
+    x = np.random.default_rng(4).standard_normal(n)
+    x[[5, 900, 1599]] = [np.inf, np.nan, -np.inf]
+    exp = oracle.csr_dot(n, rp, ci, va, x)
+    off, widths, vals, idx = plan_model(n, rp, ci, va, 1, sr)
+    r = emu.pairdict(off, widths, vals, idx, sr)
+    assert r["rc"] == 0 and not r["overflow"]
+    y = np.zeros(n)
+    with np.errstate(invalid="ignore"):
+        for q, (o, w) in enumerate(zip(off, widths)):
+            r0 = q * sr
+            nr = min(sr, n - r0)
+            gran = np.unique(ci[rp[r0]:rp[r0 + nr]] >> 4)
+            xs = np.zeros(sr + 2 + 16 * len(gran))                 # [zero region | zero slots | granules]
+            for i, g in enumerate(gran.tolist()):
+                seg = x[g * 16:min(n, g * 16 + 16)]
+                xs[sr + 2 + 16 * i: sr + 2 + 16 * i + len(seg)] = seg
+            tab = r["table"][q]
+            tv = tab["value_bits"].view(np.float64)
+            td = tab["disp8"].astype(np.int64) // 8
+            codes = r["codes"][o:o + w * sr].astype(np.int64)
+            for row in range(nr):
+                t, j = row % T, row // T
+                acc = 0.0
+                for k in range(w):
+                    c = codes[(k * T + t) * 4 + j]
+                    acc = acc + tv[c] * xs[sr + td[c] + row]
+                y[r0 + row] = acc
+    assert np.array_equal(np.isnan(y), np.isnan(exp))
+    ok = ~np.isnan(exp)
+    assert np.array_equal(y[ok].view(np.uint64), exp[ok].view(np.uint64))
