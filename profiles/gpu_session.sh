@@ -18,7 +18,7 @@ NCU="ncu --clock-control none"
 step() { echo "== $1 ($(date +%T))"; }
 
 step "gpu tests"
-timeout 1800 $PY -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest_gpu.log 2>&1
+timeout 1800 $PY -m pytest tests -m gpu -q -rs --durations=15 > $OUT/${TAG}_pytest_gpu.log 2>&1
 echo "pytest exit $?" | tee -a $OUT/${TAG}_pytest_gpu.log
 tail -5 $OUT/${TAG}_pytest_gpu.log
 
@@ -30,20 +30,8 @@ timeout 600 $PY bench.py --impl reference > $OUT/${TAG}_bench_reference.json 2> 
 timeout 900 $PY bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
 tail -c 1500 $OUT/${TAG}_bench.json
 
-step "bench, coded staged ELL (A/B against the line above; CTAs per SM 2 and 3)"
-timeout 900 $PY bench.py --value-dict --no-cpu --no-probe > $OUT/${TAG}_bench_value_dict.json 2> $OUT/${TAG}_bench_value_dict.err
-tail -c 600 $OUT/${TAG}_bench_value_dict.json
-CASK_B200_PERSIST_CTAS=3 timeout 600 $PY bench.py --value-dict --no-cpu --no-cg --no-extra --no-probe > $OUT/${TAG}_bench_value_dict_3ctas.json 2>> $OUT/${TAG}_bench_value_dict.err
-CASK_B200_PERSIST_CTAS=1 timeout 600 $PY bench.py --value-dict --no-cpu --no-cg --no-extra --no-probe > $OUT/${TAG}_bench_value_dict_1cta.json 2>> $OUT/${TAG}_bench_value_dict.err
-CASK_B200_PERSIST_KU=2 timeout 600 $PY bench.py --value-dict --no-cpu --no-cg --no-extra --no-probe > $OUT/${TAG}_bench_value_dict_ku2.json 2>> $OUT/${TAG}_bench_value_dict.err
-timeout 900 $PY bench.py --value-dict 2 --no-cpu --no-probe > $OUT/${TAG}_bench_pair_dict.json 2> $OUT/${TAG}_bench_pair_dict.err
-tail -c 600 $OUT/${TAG}_bench_pair_dict.json
-CASK_B200_PERSIST_CTAS=3 timeout 600 $PY bench.py --value-dict 2 --no-cpu --no-cg --no-extra --no-probe > $OUT/${TAG}_bench_pair_dict_3ctas.json 2>> $OUT/${TAG}_bench_pair_dict.err
-for f in pair_dict pair_dict_3ctas; do $PY -c "import json,sys; d=json.loads(open('$OUT/${TAG}_bench_$f.json').read().strip().splitlines()[-1]); print('$f', d['value'], d['ms_per_step'], d['config']['format'])" 2>/dev/null; done
-for f in 3ctas 1cta ku2; do $PY -c "import json,sys; d=json.loads(open('$OUT/${TAG}_bench_value_dict_$f.json').read().strip().splitlines()[-1]); print('$f', d['value'], d['ms_per_step'], d['config']['format'])" 2>/dev/null; done
-
 step "C3 (R-MAT) sweep: gather-CSR default vs CSR-stream at three item sizes"
-for v in "CASK_B200_CSR_STREAM=0" "CASK_B200_CSR_STREAM=1 CASK_B200_CSR_ITEM_NNZ=2048" "CASK_B200_CSR_STREAM=1 CASK_B200_CSR_ITEM_NNZ=4096" "CASK_B200_CSR_STREAM=1 CASK_B200_CSR_ITEM_NNZ=8192"; do
+for v in "CASK_B200_CSR_STREAM=0" "CASK_B200_CSR_STREAM=1 CASK_B200_CSR_ITEM_NNZ=4096"; do
   f=$OUT/${TAG}_rmat_$(echo $v | tr ' =' '__').json
   env $v timeout 600 $PY bench.py --only-rmat --no-cg --no-cpu --no-probe --steps 20 --warmup 3 --soak 0 > $f 2>> $OUT/${TAG}_rmat.err
   $PY -c "import json; d=json.loads(open('$f').read().strip().splitlines()[-1])['rmat_spmv']; print('$v', d.get('ms_per_spmv'), d.get('algorithmic_gbs'), d.get('error'))" 2>/dev/null
