@@ -40,8 +40,8 @@ CG_GRID = 256  # BASELINE.json configs[3]
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=500)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default 500; 20 for --impl reference)")
+    ap.add_argument("--warmup", type=int, default=None, help="untimed steps (default 10; 3 for --impl reference)")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--grid", type=int, default=GRID)
     ap.add_argument("--no-cg", action="store_true")
@@ -63,6 +63,10 @@ def parse():
                     help="profiling: on ONE GPU, run CG on the stripe that rank W/2 of a W-way sharded C4 system owns "
                          "(principal submatrix, halo columns read zeros): the per-rank work of the W-GPU job under ncu")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 20 if args.impl == "reference" else 500
+    if args.warmup is None:
+        args.warmup = 3 if args.impl == "reference" else 10
     if any(k in os.environ for k in ("CUDA_INJECTION64_PATH", "NV_COMPUTE_PROFILER_PERFWORKS_DIR")):
         args.soak = 0  # under ncu every launch is replayed and serialised: no soak, and the numbers are not bench values
         args.no_probe = True  # and no child process for the profiler to follow
@@ -165,14 +169,32 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the SpMV kernel, from the committed
-    ncu --set full capture (profiles/roofline_traffic.json); None until one exists."""
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` (an instantiation name such as
+    spmv_ell_persistent_kernel<2,false,0>) from the committed `ncu --set full` captures: profiles/roofline_traffic.json
+    is WRITTEN by profiles/summarize_ncu.py from the raw reports, keyed by instantiation.  (bytes, source) or (None, None)
+    when no capture of that instantiation is on record."""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(p):
-        with open(p) as f:
-            return json.load(f).get("spmv_ell_persistent_kernel_bytes_per_launch")
-    return None
+    if not os.path.exists(p):
+        return None, None
+    with open(p) as f:
+        kern = json.load(f).get("kernels", {})
+    for rec in kern.values():
+        if rec.get("kernel") == kernel:
+            return rec.get("dram_bytes_per_launch"), rec.get("source")
+    return None, None
+
+
+def roofline_of(bytes_alg, bytes_stored, seconds, peak):
+    """Achieved GB/s of one unit of work (an SpMV, a solver iteration) on algorithmic and on stored bytes, as fractions
+    of the measured HBM peak."""
+    out = {"algorithmic_bytes": int(bytes_alg), "achieved": bytes_alg / seconds / 1e9, "peak": peak, "unit": "GB/s"}
+    out["frac"] = out["achieved"] / peak
+    if bytes_stored:
+        out["stored_bytes"] = int(bytes_stored)
+        out["stored_gbs"] = bytes_stored / seconds / 1e9
+        out["stored_frac"] = out["stored_gbs"] / peak
+    return out
 
 
 def cpu_allcore_spmv(grid, min_reps=10, max_reps=50, budget_s=5.0):
@@ -232,84 +254,137 @@ def cpu_port_baseline(grid):
             "implementations": out}
 
 
+def use_all_host_cores():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU legs run on rank 0 alone and are meant to use every
+    host core, so the thread count is set explicitly BEFORE the OpenMP / MKL runtimes are loaded."""
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        pass
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[k] = str(cores)
+    os.environ.pop("OMP_PROC_BIND", None)
+    return cores
+
+
 def reference_arm(args):
-    """The reference's own CPU implementations of y = A x, timed on the GPU box's host cores.  Two code paths of the
-    reference compute the product, both compiled in place from /root/reference (oracle/_ref):
+    """The reference's own CPU implementations of y = A x, timed on the GPU box's host cores (rank 0 only; the other
+    ranks of a torchrun launch exit at once).  Two code paths of the reference compute the product, both compiled in
+    place from /root/reference (oracle/_ref):
+      reference_symv  the product inside its CPU solver, pcg<> (SparseLinearSolvers.hpp:175-206): one-based copies, then
+                      mkl_dcsrsymv('l') on the stored lower triangle - Intel MKL, ALL host cores;
       reference_code  cask::CsrMatrix::dot (src/runtime/SparseMatrix.hpp:422-424), what its tests use as the CPU product:
                       single-threaded by construction and it rebuilds a hash map per call, so it runs on a bounded
-                      512 x 512 sample of the operator;
-      reference_symv  the product inside its CPU solver, pcg<> (SparseLinearSolvers.hpp:175-206): one-based copies, then
-                      mkl_dcsrsymv('l') on the stored lower triangle - Intel MKL, all host cores - on the FULL workload.
-    `value` is the faster of the two (cpu_baseline.kind "reference").  For context the line also carries `other_cpu`:
-    all-core CSR products that are NOT reference code (MKL's general mkl_sparse_d_mv and the OpenMP port); the main
-    arm's cpu_baseline is the faster of those."""
+                      512 x 512 sample of the operator, a bounded number of times (reported, never the headline).
+    A step is one pass over the WHOLE job of the GPU arm at this N: the N stripes of the weak-scaling grid, one after the
+    other on the same cores (every stripe is the same 4096 x 4096 operator up to its boundary rows, so the stripe matrix
+    is built once and multiplied N times per step).  Exactly --warmup untimed and --steps timed steps are run; `value` =
+    flops of those steps / their time (cpu_baseline.kind "reference").  For context the line also carries `other_cpu`:
+    all-core CSR products that are NOT reference code (MKL's general mkl_sparse_d_mv and the OpenMP port)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    cores = use_all_host_cores()
     import numpy as np
     from oracle import oraclebind as O
     from oracle import refbind as R
+    stripes = max(1, args.gpus)
     line = {"impl": "reference", "metric": "fp64 SpMV GFLOP/s", "unit": "GFLOP/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.grid, args.gpus)[0]}}
-    steps = max(1, min(args.steps, 20))
-    warm = max(1, min(args.warmup, 2))
+            "config": {"workload": workload_name(args.grid, args.gpus)[0],
+                       "step": "one pass over the %d stripe(s) of the job, %d host threads" % (stripes, cores)}}
+    steps, warm = max(1, args.steps), max(0, args.warmup)
     impls = {}
-    if R.available():
-        sample_grid = 512  # 262 144 rows, 1.3M nnz: same operator, bounded so the calls end within seconds
-        n, rp, ci, va = O.gen_poisson2d(sample_grid)
-        x = (np.arange(n) % 1024) * 0.25
-        m = R.RefMatrix.from_csr(n, n, rp, ci, va)
-        for _ in range(warm):
-            m.dot(x)
-        t = 0.0
-        for _ in range(steps):
-            y, s = m.dot(x, return_seconds=True)
-            t += s
-        assert np.array_equal(y, O.csr_dot(n, rp, ci, va, x))
-        impls["reference_code"] = {
-            "gflops": 2.0 * len(va) * steps / t / 1e9, "ms": 1e3 * t / steps, "cores": 1, "reps": steps, "kind": "reference",
-            "what": "cask::CsrMatrix::dot (reference code, single-threaded by construction) on a %dx%d sample of the operator"
-                    % (sample_grid, sample_grid)}
-    other, best_other, n, nnz = cpu_allcore_spmv(args.grid, min_reps=steps, max_reps=steps)
+    n, rp, ci, va = O.gen_poisson2d(args.grid)
+    nnz = len(va)
+    x = (np.arange(n) % 1024) * 0.25
+    y_port = np.zeros(n)
+    O.csr_spmv_omp(n, rp, ci, va, x, y_port)
+    t_ref = None
     try:
         from oracle import mklbind as M
         if not M.ref_available():
             raise RuntimeError("oracle/_ref/libcaskref_mkl.so or MKL missing")
-        n, rp, ci, va = O.gen_poisson2d(args.grid)
         rows = np.repeat(np.arange(n, dtype=np.int32), np.diff(rp))
         keep = ci <= rows
         rpl = np.zeros(n + 1, np.int32)
         rpl[1:] = np.cumsum(np.bincount(rows[keep], minlength=n))
-        x = (np.arange(n) % 1024) * 0.25
-        reps = max(1, min(steps, 10))
-        y, sec = M.symv(n, rpl, ci[keep], va[keep], x, reps=reps)
-        yy = np.zeros(n)
-        O.csr_spmv_omp(n, rp, ci, va, x, yy)
-        if not np.allclose(y, yy, rtol=1e-12, atol=1e-9):
+        cil, val = ci[keep].copy(), va[keep].copy()
+        del rows
+        if warm:
+            M.symv(n, rpl, cil, val, x, reps=warm * stripes)
+        y, sec = M.symv(n, rpl, cil, val, x, reps=steps * stripes)
+        if not np.allclose(y, y_port, rtol=1e-12, atol=1e-9):
             raise RuntimeError("mkl_dcsrsymv result differs from the port")
+        t_ref = sec
         impls["reference_symv"] = {
-            "gflops": 2.0 * len(va) * reps / sec / 1e9, "ms": 1e3 * sec / reps, "cores": M.max_threads(), "reps": reps,
-            "kind": "reference",
-            "what": "the product of the reference's pcg<>: mkl_dcsrsymv('l') on the stored lower triangle (%d of %d nnz), "
-                    "%dx%d grid (full workload), flops counted for the full operator; %s"
-                    % (int(keep.sum()), len(va), args.grid, args.grid, M.version())}
-        del rows, keep, rpl, y, yy
+            "gflops": 2.0 * nnz * steps * stripes / sec / 1e9, "ms_per_step": 1e3 * sec / steps, "cores": M.max_threads(),
+            "steps": steps, "warmup": warm, "kind": "reference",
+            "what": "the product of the reference's pcg<>: mkl_dcsrsymv('l') on the stored lower triangle (%d of %d nnz per "
+                    "stripe), %dx%d grid per stripe, flops counted for the full operator; %s"
+                    % (int(keep.sum()), nnz, args.grid, args.grid, M.version())}
+        del keep, rpl, cil, val, y
     except Exception as e:
         impls["reference_symv"] = {"error": str(e)}
-    timed = [k for k in impls if "gflops" in impls[k]]
-    if timed:
-        best = max(timed, key=lambda k: impls[k]["gflops"])
-        b, kind = impls[best], "reference"
-    else:  # no compiled reference on this machine: the port stands in, and says so
-        best, b, kind = best_other, other[best_other], "port"
-    v = b["gflops"]
-    line.update({"value": v, "ms_per_step": b["ms"], "steps": b["reps"], "warmup": warm,
+    if R.available():
+        sample_grid, reps = 512, max(1, min(steps, 5))  # 262 144 rows, 1.3M nnz: same operator, bounded
+        sn, srp, sci, sva = O.gen_poisson2d(sample_grid)
+        sx = (np.arange(sn) % 1024) * 0.25
+        m = R.RefMatrix.from_csr(sn, sn, srp, sci, sva)
+        m.dot(sx)
+        t = 0.0
+        for _ in range(reps):
+            sy, sec1 = m.dot(sx, return_seconds=True)
+            t += sec1
+        assert np.array_equal(sy, O.csr_dot(sn, srp, sci, sva, sx))
+        impls["reference_code"] = {
+            "gflops": 2.0 * len(sva) * reps / t / 1e9, "ms_per_call": 1e3 * t / reps, "cores": 1, "calls": reps, "kind": "reference",
+            "what": "cask::CsrMatrix::dot (reference code, single-threaded by construction) on a %dx%d sample of the operator"
+                    % (sample_grid, sample_grid)}
+    # all-core products that are not reference code, same step definition (bounded to ~20 s each)
+    other = {}
+    y = np.zeros(n)
+
+    def timed(fn, label, what, cores_fn):
+        fn()
+        t0 = time.perf_counter()
+        fn()
+        once = time.perf_counter() - t0
+        k = max(1, min(steps * stripes, int(20.0 / max(once, 1e-6))))
+        t0 = time.perf_counter()
+        for _ in range(k):
+            fn()
+        dt = time.perf_counter() - t0
+        other[label] = {"gflops": 2.0 * nnz * k / dt / 1e9, "gbs": algorithmic_bytes(nnz, n, n) * k / dt / 1e9,
+                        "ms_per_stripe": 1e3 * dt / k, "cores": cores_fn(), "calls": k, "what": what}
+    thr = [1]
+
+    def port():
+        thr[0] = O.csr_spmv_omp(n, rp, ci, va, x, y)[1]
+    timed(port, "port", "OpenMP CSR row loop (oracle/cask_oracle.c)", lambda: int(thr[0]))
+    try:
+        from oracle import mklbind as M
+        h = M.CsrHandle(n, n, rp, ci, va)
+        timed(lambda: h.spmv(x, y), "mkl", "mkl_sparse_d_mv, " + M.version(), M.max_threads)
+        if not np.allclose(y, y_port, rtol=1e-12, atol=1e-9):
+            raise RuntimeError("MKL result differs from the port")
+    except Exception as e:
+        other["mkl"] = {"error": str(e)}
+    best_other = max((k for k in other if "gflops" in other[k]), key=lambda k: other[k]["gflops"])
+    if "gflops" in impls.get("reference_symv", {}):
+        b, kind, best = impls["reference_symv"], "reference", "reference_symv"
+        v, ms_step = b["gflops"], b["ms_per_step"]
+    else:  # no compiled reference / MKL on this machine: the port stands in, and says so
+        b, kind, best = other[best_other], "port", best_other
+        v, ms_step = b["gflops"], b["ms_per_stripe"] * stripes
+    line.update({"value": v, "ms_per_step": ms_step,
                  "cpu_baseline": {"value": v, "unit": "GFLOP/s", "cores": b["cores"], "kind": kind,
-                                  "sample": "%s: %s, %d timed calls" % (best, b["what"], b["reps"]),
+                                  "sample": "%s: %s; %d warm-up + %d timed steps of %d stripe pass(es)"
+                                            % (best, b["what"], warm, steps, stripes),
                                   "implementations": impls},
-                 "other_cpu": {"note": "all-core CSR products that are not reference code, full workload",
+                 "other_cpu": {"note": "all-core CSR products that are not reference code, same stripe matrix",
                                "implementations": other, "fastest": best_other, "gflops": other[best_other]["gflops"]},
                  "e2e": {"value": v, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
     if not args.no_cg:
@@ -597,8 +672,23 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
     e2e = {"value": flops / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": 8 * n_local * world,
-           "d2h_bytes_per_step": 8 * n_local * world, "ms_per_step": 1e3 * e2e_s, "steps": e2e_steps,
-           "api": "cask_b200_spmv(ctx, x_host, y_host)" if world == 1 else "H2D + cask_b200_spmv_device + D2H per rank"}
+           "d2h_bytes_per_step": 8 * n_local * world, "ms_per_step": 1e3 * e2e_s, "steps": e2e_steps, "host_buffers": "pinned",
+           "api": "cask_b200_spmv(ctx, x_host, y_host)" if world == 1 else "cask_b200_spmv_shard(ctx, x_host_slice, y_host_slice) per rank"}
+    if world == 1:
+        # the same call with PAGEABLE buffers - what a caller holding a cask::Vector (std::vector<double>) sees through
+        # host/include/Spmv.hpp: the copies then stage through the driver's bounce buffers
+        px, py = hx.numpy().copy(), np.empty(n_local, dtype=np.float64)
+        for _ in range(2):
+            ctx.spmv_into(px, py)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            ctx.spmv_into(px, py)
+        barrier()
+        pg_s = (time.perf_counter() - t0) / e2e_steps
+        assert np.array_equal(py, hy.numpy())
+        e2e["pageable"] = {"value": flops / pg_s / 1e9, "ms_per_step": 1e3 * pg_s}
+        del px, py
 
     # ---- CG iterations / s on the 3D 27-point system (strong scaling: fixed 256^3 grid) -----------
     cg = bicg = rmat = None
@@ -623,62 +713,103 @@ def main():
         rmat = side(bench_rmat, ctx, cb, torch, dist, dev, rank, world, barrier)
 
     if rank == 0:
+        stored_per_launch = vd_matrix_bytes + 8 * (n_local + n_local) + 12 * stats.get("csr_nnz", 0)
+        kernel = "spmv_ell_persistent_kernel<%d,false,%d>" % (stats.get("persist_ku", 2) or 2, vd_mode)
+        traffic, traffic_src = ncu_traffic(kernel)
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": kernel,
+                "algorithmic_bytes_per_launch": bytes_per_launch,
+                "stored_bytes_per_launch": stored_per_launch,
+                "stored_gbs": stored_per_launch / (kernel_ms * 1e-3) / 1e9,
+                "stored_frac": stored_per_launch / (kernel_ms * 1e-3) / 1e9 / peak,
+                "frac_of_nominal_8tbs": achieved / 8000.0,
+                "note": "achieved/frac: algorithmic bytes 12 nnz + 8 (rows + cols) (SURVEY 8d) / kernel time; stored_*: the bytes "
+                        "the format really streams (10 B per stored nonzero: 16-bit x-cache positions) - frac > 1 is the "
+                        "format moving fewer bytes than the algorithmic count, stored_frac is the kernel's distance from the copy peak"}
         line = {
             "metric": "fp64 SpMV GFLOP/s", "value": value, "unit": "GFLOP/s", "n_gpus": world,
             "steps": args.steps, "warmup": warm, "ms_per_step": kernel_ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": workload_name(G, world, nnz_local)[0],
-                       "global_rows": n_global, "sharding": "row stripes over ranks (Spmv.cpp:334-364), NCCL x halo",
+                       "sharding": "row stripes over ranks (Spmv.cpp:334-364)" + ("; x halo over mapped peer memory, one launch per step"
+                                   if world > 1 and ctx.peer_active() else "; x halo over NCCL" if world > 1 else ""),
                        "l2": "inputs (%.2f GB per launch) larger than L2 (126 MB); no flush needed" % (bytes_per_launch / 1e9),
-                       "soak_steps": args.soak,
-                       "design": {"num_pipes": 1, "cache_size": args.cache, "input_width": 16},
-                       "preprocess_s": preprocess_s, "plan": stats,
-                       "format": {"value_dict": vd_mode, "table_entries_per_slice": vd_entries,
-                                  "stored_bytes_per_launch": vd_matrix_bytes + 8 * (n_local + n_local),
-                                  "note": "bytes one SpMV moves in the stored format: staged-ELL entries (10 B each; 3 B "
-                                          "with value codes, 1 B with pair codes) + x read once + y written once"}},
-            "hbm_gbs": achieved, "frac_of_nominal_8tbs": achieved / 8000.0,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "spmv_ell_persistent_kernel<%d,false,%d>" % (2 if not vd_active else 4, vd_mode),
-                         "algorithmic_bytes_per_launch": bytes_per_launch},
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                       "soak_steps": args.soak, "value_dict": vd_mode},
+            "roofline": roof, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
+        details = {"config": {"global_rows": n_global, "design": {"num_pipes": 1, "cache_size": args.cache, "input_width": 16},
+                              "preprocess_s": preprocess_s, "plan": stats,
+                              "format": {"value_dict": vd_mode, "table_entries_per_slice": vd_entries,
+                                         "stored_bytes_per_launch": stored_per_launch}}}
+        # solver / R-MAT side measurements: fixed compact keys in the line, everything else in the details file
+        def compact(src, keys):
+            return {k: src[k] for k in keys if k in src} if src else None
         if cg:
-            line["cg"] = cg
+            details["cg"] = cg
+            line["cg"] = compact(cg, ("iters_per_s", "us_per_iteration_marginal", "loop_trips", "iterations_reported", "converged",
+                                      "max_abs_err_vs_x_true", "gpu_launches", "peer_memory_path", "roofline", "error"))
         if bicg:
-            line["bicgstab"] = bicg
+            details["bicgstab"] = bicg
+            line["bicgstab"] = compact(bicg, ("iters_per_s", "iterations", "converged", "rel_residual", "max_abs_err_vs_ones",
+                                              "gpu_launches", "timed", "roofline", "error"))
         if rmat:
-            line["rmat_spmv"] = rmat
+            details["rmat"] = rmat
+            line["rmat"] = compact(rmat, ("ms_per_spmv", "gflops", "nnz", "kernel", "l2_hit_rate_on_x_pct", "max_rel_diff_256_sampled_rows",
+                                          "preprocess_s", "nnz_share_max_rank", "roofline", "error"))
         if world == 1 and not args.value_dict and not args.no_probe:
-            probes = [("value_dict_probe", value_dict_probe), ("pair_dict_probe", lambda a: value_dict_probe(a, 2))]
-            if rmat and "error" not in rmat and not os.environ.get("CASK_B200_CSR_STREAM"):
-                probes.append(("rmat_stream_probe", rmat_stream_probe))
+            probes = [("pair_dict_probe", lambda a: value_dict_probe(a, 2))]
             timed_out = False
             for key, fn in probes:
                 if timed_out:  # one child already cost its full time limit: the run stays within minutes
-                    line[key] = {"error": "skipped: an earlier probe exceeded its time limit"}
+                    details[key] = {"error": "skipped: an earlier probe exceeded its time limit"}
                     continue
                 try:
-                    line[key] = fn(args)
+                    details[key] = fn(args)
                 except Exception as e:  # noqa: BLE001 - informational
-                    line[key] = {"error": "%s: %s" % (type(e).__name__, e)}
-                timed_out = "was killed" in str(line[key].get("error", ""))
+                    details[key] = {"error": "%s: %s" % (type(e).__name__, e)}
+                timed_out = "was killed" in str(details[key].get("error", ""))
+            pr = details.get("pair_dict_probe") or {}
+            line["pair_dict_probe"] = {k: pr.get(k) for k in ("value", "ms_per_step", "stored_gbs", "error") if k in pr}
+            if pr.get("cg"):
+                line["pair_dict_probe"]["cg_iters_per_s"] = pr["cg"].get("iters_per_s")
         if world == 1 and not args.no_cpu:
             try:
-                line["cpu_baseline"] = cpu_port_baseline(G)
+                cpu = cpu_port_baseline(G)
             except Exception as e:
-                line["cpu_baseline"] = {"value": None, "unit": "GFLOP/s", "cores": 0, "kind": "port", "sample": "failed: %s" % e}
+                cpu = {"value": None, "unit": "GFLOP/s", "cores": 0, "kind": "port", "sample": "failed: %s" % e}
+            details["cpu_baseline"] = cpu
+            line["cpu_baseline"] = {k: cpu.get(k) for k in ("value", "unit", "cores", "kind", "sample")}
             if cg and "error" not in cg:
                 try:
-                    cg["cpu_baseline"] = cpu_reference_cg()
+                    ccpu = cpu_reference_cg()
                 except Exception as e:
-                    cg["cpu_baseline"] = {"value": None, "unit": "CG iterations/s", "cores": 0, "kind": "port",
-                                          "sample": "failed: %s" % e}
+                    ccpu = {"value": None, "unit": "CG iterations/s", "cores": 0, "kind": "port", "sample": "failed: %s" % e}
+                details["cg"]["cpu_baseline"] = ccpu
+                line["cg"]["cpu_baseline"] = {k: ccpu.get(k) for k in ("value", "unit", "cores", "kind", "row_iterations_per_s")}
+        dpath = os.environ.get("CASK_B200_BENCH_DETAILS") or os.path.join(
+            ROOT, "gpurun_out" if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else "", "bench_details_n%d.json" % world)
+        try:
+            with open(dpath, "w") as f:
+                json.dump(dict(line, details=details), f, indent=1)
+            line["details_file"] = os.path.relpath(dpath, ROOT)
+        except OSError:
+            pass
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def stored_spmv_bytes(ctx, torch, dist, dev, world, n_local):
+    """Bytes one SpMV streams in the stored format, whole job: staged-ELL entries (10 / 3 / 1 B each) + gather-CSR
+    entries (12 B + 4 B per row) + the rank's x slice read once + y written once, summed over the ranks."""
+    st = ctx.plan_stats()
+    b = ctx.value_dict()[2] + 12 * st["csr_nnz"] + 4 * st["csr_rows"] + 16 * n_local
+    t = torch.tensor([float(b)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t)
+    return float(t.item())
 
 
 def bench_cg(ctx, cb, torch, dist, dev, rank, world, barrier, maxiters=2000, emulate=0):
@@ -734,7 +865,12 @@ def bench_cg(ctx, cb, torch, dist, dev, rank, world, barrier, maxiters=2000, emu
     if world > 1:
         dist.all_reduce(et, op=dist.ReduceOp.MAX)
     nnz_total = cb.synth_nnz(kind, N, 0, n)
+    stored = stored_spmv_bytes(ctx, torch, dist, dev, world, nr)
+    sec_per_it = (marginal_us * 1e-6) if marginal_us else dt / max(trips, 1)
+    roof = roofline_of(algorithmic_bytes(nnz_total, n, n) + 72 * n, stored + 72 * n, sec_per_it, measured_peak()[0] * world)
+    roof["per"] = "CG iteration (marginal cost), whole job; peak = %d x measured HBM copy peak; bytes = SpMV + 72 n (SURVEY 8d)" % world
     return {"workload": "C4: CG on 3D 27-pt Poisson %d^3 (%d rows, %d nnz), row-sharded over %d GPU(s)" % (N, n, nnz_total, world),
+            "roofline": roof,
             "scaling": "strong", "iters_per_s": trips / dt, "loop_trips": trips, "iterations_reported": iters,
             "converged": conv, "rs_final": rs, "seconds": dt, "max_abs_err_vs_x_true": float(et.item()),
             "gpu_launches": int(launches), "us_per_iteration_marginal": marginal_us,

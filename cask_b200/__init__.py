@@ -56,7 +56,10 @@ class PlanStats(C.Structure):
                 ("num_slices", C.c_int32), ("slices_staged_ell", C.c_int32), ("slices_gather_csr", C.c_int32),
                 ("csr_lanes_per_row", C.c_int32), ("max_row_length", C.c_int32),
                 ("ell_padded_entries", C.c_int64), ("ell_nnz", C.c_int64), ("xcache_doubles_total", C.c_int64),
-                ("device_bytes", C.c_int64), ("row_length_histogram", C.c_int64 * 8)]
+                ("device_bytes", C.c_int64), ("row_length_histogram", C.c_int64 * 8),
+                ("csr_nnz", C.c_int64), ("csr_rows", C.c_int64), ("csr_items", C.c_int32), ("csr_kernel", C.c_int32),
+                ("persist_ku", C.c_int32), ("persist_stages", C.c_int32), ("persist_ctas_per_sm", C.c_int32),
+                ("value_dict", C.c_int32)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k != "row_length_histogram"}

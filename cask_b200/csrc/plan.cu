@@ -518,6 +518,14 @@ int build_plan(cask_b200_ctx* ctx) {
   p.stats.slices_gather_csr = p.n_csr;
   p.stats.csr_lanes_per_row = vec;
   p.stats.max_row_length = maxlen;
+  p.stats.csr_nnz = csr_nnz;
+  p.stats.csr_rows = csr_rows;
+  p.stats.csr_items = p.h_item_begin.empty() ? 0 : p.h_item_begin.back();
+  p.stats.csr_kernel = 0;
+  p.stats.persist_ku = ctx->ell_kernel == 1 ? p.persist_ku : 0;
+  p.stats.persist_stages = p.persist_stages;
+  p.stats.persist_ctas_per_sm = p.persist_ctas_per_sm;
+  p.stats.value_dict = p.coded;
   for (int i = 0; i < 8; i++) p.stats.row_length_histogram[i] = (int64_t)hist[i];
   p.stats.device_bytes = val_off * (p.coded ? 11 : 10) + (p.coded == 1 ? (int64_t)p.nslices * valuedict::kStride * 8 : 0) +
                          (p.coded == 2 ? (int64_t)p.nslices * valuedict::kPairStride * 16 : 0) +

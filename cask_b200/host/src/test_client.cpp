@@ -103,17 +103,29 @@ void ILUComputeAndApply() {  // test/LinearSolvers.cpp:125-146
   for (size_t i = 0; i < res.size(); i++) CHECK(double_eq(res[i], expPcApply[i]));
 }
 
-void PreconditionersBeyondTheReference() {  // Jacobi and the unit-lower ILU: converge to the reference's solution
+void PreconditionersBeyondTheReference() {  // Jacobi converges to the reference's solution; the unit-lower ILU follows the oracle
   Vector rhs = io::readVector(g_dir + "/tinysym_b.mtx");
   SymCsrMatrix a = io::readSymMatrix(g_dir + "/tinysym.mtx");
   Vector exp_sol{-2, 2, 3, 3};
-  for (int which = 0; which < 2; which++) {
+  {
     int iterations = 0;
     Vector sol(a.n);
-    const bool ok = which == 0 ? pcg<double, JacobiPreconditioner>(a.matrix, &rhs[0], &sol[0], iterations)
-                               : pcg<double, IluUnitPreconditioner>(a.matrix, &rhs[0], &sol[0], iterations);
+    const bool ok = pcg<double, JacobiPreconditioner>(a.matrix, &rhs[0], &sol[0], iterations);
     CHECK(ok);
     for (int i = 0; i < sol.size(); i++) CHECK(std::fabs(sol[i] - exp_sol[i]) < 1e-6);
+  }
+  {
+    // pcg<> builds its preconditioner from the arrays it is HANDED, the stored lower triangle (:171), so the factors are
+    // those of a triangular matrix and M is not symmetric whichever way the lower solve is applied: like the reference's
+    // own CGSymWithILUPC the loop runs out of iterations (oracle_pcg_precond, PRECON_ILU_UNIT: not converged, 1999,
+    // x = {-2.0982, 1.9875, 2.9812, 3.0366})
+    int iterations = 0;
+    Vector sol(a.n);
+    const bool ok = pcg<double, IluUnitPreconditioner>(a.matrix, &rhs[0], &sol[0], iterations);
+    CHECK(!ok);
+    CHECK(iterations == 1999);
+    const double oracle_x[4] = {-2.09821451, 1.9874614, 2.9811921, 3.03656865};
+    for (int i = 0; i < sol.size(); i++) CHECK(std::fabs(sol[i] - oracle_x[i]) < 1e-3);
   }
 }
 

@@ -79,6 +79,12 @@ typedef struct {
   int64_t xcache_doubles_total; /* sum over staged slices of staged x doubles */
   int64_t device_bytes;         /* bytes of the compute format resident in HBM */
   int64_t row_length_histogram[8]; /* rows with length 0, 1-2, 3-4, 5-8, 9-16, 17-32, 33-64, >64 */
+  int64_t csr_nnz, csr_rows;    /* nonzeros / rows of the gather slices */
+  int32_t csr_items;            /* work items of the gather kernel (merge-path tiles or row groups) */
+  int32_t csr_kernel;           /* 0 row-group items (spmv_csr_items_kernel), 1 merge-path tiles (spmv_csr_merge_kernel) */
+  int32_t persist_ku;           /* persistent staged-ELL kernel: ELL columns per ring stage (0: kernel not in use) */
+  int32_t persist_stages, persist_ctas_per_sm;
+  int32_t value_dict;           /* format in use: 0 uncoded, 1 value codes, 2 pair codes */
 } cask_b200_plan_stats;
 
 /* ---- context ---------------------------------------------------------------------------- */
