@@ -993,13 +993,37 @@ def bench_rmat(ctx, cb, torch, dist, dev, rank, world, barrier, scale=25, edge_f
     ref = torch.stack([(va[a:b] * x[ci[a:b].long()]).sum() for a, b in zip(lo.tolist()[:256], hi.tolist()[:256])])
     got = y[sample[:256]]
     rel = float(((got - ref).abs() / (ref.abs() + 1e-30)).max().item())
+    # ... and against a full fp64 product by torch's CSR kernel (library code, checker only): every row, hubs included
+    a_t = torch.sparse_csr_tensor(rp.long(), ci.long(), va, size=(nr, n))
+    y_ref = torch.mv(a_t, x)
+    a_abs = torch.sparse_csr_tensor(rp.long(), ci.long(), va.abs(), size=(nr, n))
+    scale_rows = torch.mv(a_abs, x.abs()).clamp_min(1e-300)
+    rel_all = float(((y - y_ref).abs() / scale_rows).max().item())
+    del a_t, a_abs, y_ref, scale_rows
+    share = torch.tensor([float(nnz)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(share, op=dist.ReduceOp.MAX)
+    stored = 12.0 * nnz_total + 4.0 * n + 16.0 * n
+    roof = roofline_of(algorithmic_bytes(nnz_total, n, n), stored, ms * 1e-3, measured_peak()[0] * world)
+    kernel = "spmv_csr_merge_kernel<false>" if stats.get("csr_kernel") == 1 else "spmv_csr_items_kernel<0,0>"
+    roof["traffic"], roof["traffic_source"] = ncu_traffic(kernel)
+    roof["per"] = "SpMV, whole job; peak = %d x measured HBM copy peak; the kernel is bound by the x gather, not by these bytes" % world
+    l2 = None
+    tj = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tj):
+        with open(tj) as f:
+            for rec in json.load(f).get("kernels", {}).values():
+                if rec.get("kernel") == kernel and rec.get("l2_hit_rate_on_x_pct") is not None:
+                    l2 = rec["l2_hit_rate_on_x_pct"]
     return {"workload": "C3: R-MAT scale %d, %d rows, %d nnz (after merging duplicates), y = A x, row-sharded over %d GPU(s)"
                         % (scale, n, nnz_total, world),
-            "scaling": "strong", "ms_per_spmv": ms, "gflops": 2.0 * nnz_total / (ms * 1e-3) / 1e9,
+            "scaling": "strong", "ms_per_spmv": ms, "gflops": 2.0 * nnz_total / (ms * 1e-3) / 1e9, "nnz": nnz_total,
             "algorithmic_gbs": algorithmic_bytes(nnz_total, n, n) / (ms * 1e-3) / 1e9, "preprocess_s": prep,
-            "max_rel_diff_256_sampled_rows": rel,
+            "kernel": kernel, "l2_hit_rate_on_x_pct": l2, "roofline": roof,
+            "nnz_share_max_rank": float(share.item()) / nnz_total,
+            "max_rel_diff_256_sampled_rows": rel, "max_err_all_rows_rel_to_sum_abs": rel_all,
             "plan": {k: stats[k] for k in ("slices_staged_ell", "slices_gather_csr", "csr_lanes_per_row", "max_row_length",
-                                           "row_length_histogram")}}
+                                           "row_length_histogram", "csr_items", "csr_kernel")}}
 
 
 if __name__ == "__main__":

@@ -104,6 +104,7 @@ int cask_b200_create(cask_b200_ctx** out, int device) {
   if (const char* e = getenv("CASK_B200_L2_KEEP")) ctx->l2_keep = atoi(e);
   if (const char* e = getenv("CASK_B200_CSR_STREAM")) ctx->csr_stream = atoi(e);
   if (const char* e = getenv("CASK_B200_CSR_ITEM_NNZ")) ctx->csr_item_nnz = atoi(e);
+  if (const char* e = getenv("CASK_B200_CSR_KERNEL")) ctx->csr_kernel = atoi(e);
   if (const char* e = getenv("CASK_B200_VALUE_DICT")) ctx->value_dict = atoi(e);
   if (const char* e = getenv("CASK_B200_PERSIST_CTAS")) ctx->persist_ctas = atoi(e);
   *out = ctx;
@@ -164,6 +165,7 @@ int cask_b200_set_option(cask_b200_ctx* ctx, const char* name, double value) {
   else if (k == "l2_keep") ctx->l2_keep = (int32_t)value;
   else if (k == "csr_stream") ctx->csr_stream = (int32_t)value;
   else if (k == "csr_item_nnz") ctx->csr_item_nnz = (int32_t)value;
+  else if (k == "csr_kernel") ctx->csr_kernel = (int32_t)value;
   else if (k == "value_dict") ctx->value_dict = (int32_t)value;
   else if (k == "persist_ctas") ctx->persist_ctas = (int32_t)value;
   else return fail(CASK_B200_ERR_INVALID_ARGUMENT, "set_option: unknown option " + k);
@@ -376,7 +378,8 @@ int cask_b200_spmv(cask_b200_ctx* ctx, const double* x, double* y) {
   if (dist_active(ctx)) return fail(CASK_B200_ERR_UNSUPPORTED, "spmv (host buffers) is single-rank; use spmv_device when sharded");
   const Plan& p = ctx->plan;
   if ((!x && p.m) || (!y && p.n)) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "spmv: null vector");
-  if (ctx->host_pipeline_chunks > 1 && p.nslices >= 128) return spmv_host_pipelined(ctx, x, y);
+  // merge-path tiles cross slice boundaries, so the chunked pipeline (which launches slice ranges) is for plans without them
+  if (ctx->host_pipeline_chunks > 1 && p.nslices >= 128 && !p.csr_merge) return spmv_host_pipelined(ctx, x, y);
   CB_TRY(stage_in(ctx, x, p.m, p.n));
   CB_TRY(launch_spmv(ctx, ctx->d_x, ctx->d_y, 0, ctx->stream, nullptr));
   if (p.n) CB_CUDA(cudaMemcpyAsync(y, ctx->d_y, sizeof(double) * p.n, cudaMemcpyDeviceToHost, ctx->stream));

@@ -80,6 +80,15 @@ constexpr int kCsrItemNnz = 8192;    // target nonzeros per multi-row item
 constexpr int kCsrLongRow = 2048;    // rows at least this long get a CTA (or several) of their own
 constexpr int kCsrSegment = 16384;   // nonzeros per segment of a split row
 
+// Merge-path tiles of the gather path (spmv.cu: spmv_csr_merge_kernel; plan.cu: build_merge_tiles): the rows of a run
+// of consecutive gather slices and their nonzeros are ONE merged sequence (a row end after the row's last nonzero),
+// cut every kMergeTile items, so a tile is bounded in rows AND nonzeros whatever the row-length distribution.
+struct MergeTile { int32_t r0, k0, r1, k1; };  // merge coordinates (local row, nonzero) of the tile's start and end
+constexpr int kMergeThreads = 256;
+constexpr int kMergeItems = 17;       // merge items per thread: odd, so that neighbouring threads start in different banks
+constexpr int kMergeTile = kMergeThreads * kMergeItems;
+constexpr int64_t kMergeAutoNnz = 1 << 20;  // gather slices holding at least this many nonzeros run the merge kernel
+
 struct RefPartition {  // reference-format partition resident on the device
   cask_b200_partition_info info{};
   int32_t* d_colptr = nullptr;
@@ -123,6 +132,11 @@ struct Plan {
   SplitRow* d_split_rows = nullptr;
   double* d_csr_scratch = nullptr;
   std::vector<int32_t> h_item_begin, h_split_begin;  // per position of the CSR slice list (+1 sentinel)
+  // merge-path variant: h_item_begin[pos] = first tile of the run that starts at list position pos, -1 inside a run
+  bool csr_merge = false;
+  MergeTile* d_merge_tiles = nullptr;
+  double* d_merge_carry = nullptr;    // per tile: partial sum of the row the tile ends in (0 if it ends on a row boundary)
+  int32_t n_merge_tiles = 0;
   int32_t max_xcache = 0;
   // persistent staged-ELL kernel configuration (spmv.cu: configure_persistent)
   int32_t persist_ku = 0;       // ELL columns per ring stage (0: persistent kernel not usable)
@@ -253,6 +267,7 @@ struct cask_b200_ctx {
   int64_t l2_persist_bytes = -1;  // persisting L2 set-aside claimed for evict-last vector accesses (-1: not asked yet)
   int32_t csr_stream = 0;    // 1: CSR-stream variant of the gather-CSR kernel (products staged in shared memory)
   int32_t csr_item_nnz = 4096;  // nonzeros per work item of the CSR-stream variant (its shared-memory footprint)
+  int32_t csr_kernel = -1;   // gather slices: -1 auto (merge-path tiles from kMergeAutoNnz nonzeros), 0 row-group items, 1 merge-path tiles
   int32_t l2_keep = -1;      // -1 auto (vectors of a solver iteration fit L2), 0 never, 1 always: evict-last on vector accesses
   int32_t peer_mode = 1;     // 1: halo pushes and scalar all-reduces by own kernels over mapped peer memory; 0: NCCL
 

@@ -239,6 +239,40 @@ __global__ void row_length_histogram_kernel(const int32_t* __restrict__ row_ptr,
   if (threadIdx.x < 8) atomicAdd(&hist[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
 }
 
+// Merge-path partition of the gather runs, one thread per tile boundary: tile g of run q starts on diagonal
+// g * kMergeTile of the run's merge grid (rows of the run x its nonzeros).  The number of row ends consumed before
+// diagonal d is #{ i : row_ptr[ra + i + 1] - ka <= d - i - 1 }, a prefix of the rows, found by binary search.
+struct MergeRun { int32_t ra, rb, ka, kb, tile0, ntiles; };
+
+__global__ void merge_tiles_kernel(const MergeRun* __restrict__ runs, int nruns, int total_tiles,
+                                   const int32_t* __restrict__ row_ptr, MergeTile* __restrict__ tiles) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total_tiles) return;
+  int q = 0;
+  {
+    int lo = 0, hi = nruns - 1;  // last run whose tile0 <= g
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (runs[mid].tile0 <= g) lo = mid; else hi = mid - 1; }
+    q = lo;
+  }
+  const MergeRun run = runs[q];
+  const int64_t nrows = run.rb - run.ra, nnz = run.kb - run.ka, total = nrows + nnz;
+  auto split = [&](int64_t diag, int32_t* r_out, int32_t* k_out) {
+    diag = diag < total ? diag : total;
+    int64_t lo = diag > nnz ? diag - nnz : 0, hi = diag < nrows ? diag : nrows;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if ((int64_t)row_ptr[run.ra + mid + 1] - run.ka <= diag - mid - 1) lo = mid + 1; else hi = mid;
+    }
+    *r_out = (int32_t)(run.ra + lo);
+    *k_out = (int32_t)(run.ka + (diag - lo));
+  };
+  const int64_t i = g - run.tile0;
+  MergeTile t;
+  split(i * kMergeTile, &t.r0, &t.k0);
+  split((i + 1) * kMergeTile, &t.r1, &t.k1);
+  tiles[g] = t;
+}
+
 }  // namespace
 
 void free_plan(cask_b200_ctx* ctx) {
@@ -252,19 +286,80 @@ void free_plan(cask_b200_ctx* ctx) {
   cudaFree(p.d_ell_codes); cudaFree(p.d_ell_dict); cudaFree(p.d_ell_pairs);
   cudaFree(p.d_list_ell); cudaFree(p.d_list_csr);
   cudaFree(p.d_csr_items); cudaFree(p.d_split_rows); cudaFree(p.d_csr_scratch);
+  cudaFree(p.d_merge_tiles); cudaFree(p.d_merge_carry);
   p = Plan();
 }
 
 // Cuts the rows of the gather-CSR slices (in list order) into work items of bounded nonzero count.
 // Rows of >= kCsrLongRow nonzeros get CTAs of their own; beyond kCsrSegment they are split into segments
 // whose partial sums meet again, in order, in a fix-up kernel (deterministic, no atomics).
+// Merge-path tiles for the gather slices, built ON THE DEVICE (the replacement of Spmv::preprocess's host loops,
+// src/runtime/Spmv.cpp:329-365, for irregular matrices): the host only walks the slice list (32 K entries for R-MAT
+// scale 25, nonzero counts per slice are already known from plan_count_kernel) to find the runs of consecutive gather
+// slices; every tile boundary is then one binary search over row_ptr by one GPU thread.  Runs never cross the
+// interior / halo-dependent split of the list, so either part can be launched on its own.
+static int build_merge_tiles(cask_b200_ctx* ctx) {
+  Plan& p = ctx->plan;
+  cudaStream_t s = ctx->stream;
+  std::vector<int64_t> k_at(p.nslices + 1, 0);  // row_ptr at every slice boundary = prefix sum of the slices' nonzeros
+  for (int32_t i = 0; i < p.nslices; i++) k_at[i + 1] = k_at[i] + p.h_slices[i].nnz;
+  std::vector<MergeRun> runs;
+  p.h_item_begin.assign((size_t)p.n_csr + 1, -1);
+  p.h_split_begin.assign((size_t)p.n_csr + 1, 0);
+  int32_t tiles = 0;
+  for (int32_t pos = 0; pos < p.n_csr;) {
+    int32_t end = pos + 1;
+    while (end < p.n_csr && end != p.n_csr_interior && p.h_list_csr[end] == p.h_list_csr[end - 1] + 1) end++;
+    const SliceDesc& a = p.h_slices[p.h_list_csr[pos]];
+    const SliceDesc& b = p.h_slices[p.h_list_csr[end - 1]];
+    MergeRun r;
+    r.ra = a.row0; r.rb = b.row0 + b.nrows;
+    r.ka = (int32_t)k_at[p.h_list_csr[pos]]; r.kb = (int32_t)k_at[p.h_list_csr[end - 1] + 1];
+    const int64_t total = (int64_t)(r.rb - r.ra) + (r.kb - r.ka);
+    r.tile0 = tiles;
+    r.ntiles = (int32_t)((total + kMergeTile - 1) / kMergeTile);
+    p.h_item_begin[pos] = tiles;
+    tiles += r.ntiles;
+    runs.push_back(r);
+    pos = end;
+  }
+  p.h_item_begin[p.n_csr] = tiles;
+  p.n_merge_tiles = tiles;
+  CB_CUDA(cudaMalloc(&p.d_merge_tiles, sizeof(MergeTile) * std::max(tiles, 1)));
+  CB_CUDA(cudaMalloc(&p.d_merge_carry, sizeof(double) * std::max(tiles, 1)));
+  if (tiles) {
+    MergeRun* d_runs = nullptr;
+    CB_CUDA(cudaMalloc(&d_runs, sizeof(MergeRun) * runs.size()));
+    CB_CUDA(cudaMemcpyAsync(d_runs, runs.data(), sizeof(MergeRun) * runs.size(), cudaMemcpyHostToDevice, s));
+    merge_tiles_kernel<<<(tiles + 255) / 256, 256, 0, s>>>(d_runs, (int)runs.size(), tiles, p.d_row_ptr, p.d_merge_tiles);
+    ctx->launches++;
+    CB_CUDA(cudaStreamSynchronize(s));
+    cudaFree(d_runs);
+    CB_CUDA(cudaGetLastError());
+  }
+  return CASK_B200_OK;
+}
+
 int build_csr_items(cask_b200_ctx* ctx) {
   Plan& p = ctx->plan;
   cudaFree(p.d_csr_items); cudaFree(p.d_split_rows); cudaFree(p.d_csr_scratch);
+  cudaFree(p.d_merge_tiles); cudaFree(p.d_merge_carry);
   p.d_csr_items = nullptr; p.d_split_rows = nullptr; p.d_csr_scratch = nullptr;
+  p.d_merge_tiles = nullptr; p.d_merge_carry = nullptr;
+  p.n_merge_tiles = 0;
+  p.csr_merge = false;
   p.h_item_begin.assign(1, 0);
   p.h_split_begin.assign(1, 0);
   if (p.n_csr == 0) return CASK_B200_OK;
+  int64_t gather_nnz = 0;
+  for (int32_t pos = 0; pos < p.n_csr; pos++) gather_nnz += p.h_slices[p.h_list_csr[pos]].nnz;
+  p.csr_merge = ctx->csr_kernel == 1 || (ctx->csr_kernel < 0 && !ctx->csr_stream && gather_nnz >= kMergeAutoNnz);
+  p.stats.csr_kernel = p.csr_merge ? 1 : 0;
+  if (p.csr_merge) {
+    CB_TRY(build_merge_tiles(ctx));
+    p.stats.csr_items = p.n_merge_tiles;
+    return CASK_B200_OK;
+  }
   cudaStream_t s = ctx->stream;
   std::vector<int32_t> rp((size_t)p.n + 1);
   CB_CUDA(cudaMemcpyAsync(rp.data(), p.d_row_ptr, sizeof(int32_t) * (p.n + 1), cudaMemcpyDeviceToHost, s));
@@ -321,6 +416,7 @@ int build_csr_items(cask_b200_ctx* ctx) {
     CB_CUDA(cudaMemcpyAsync(p.d_split_rows, splits.data(), sizeof(SplitRow) * splits.size(), cudaMemcpyHostToDevice, s));
   CB_CUDA(cudaMalloc(&p.d_csr_scratch, sizeof(double) * std::max(n_scratch, 1)));
   CB_CUDA(cudaStreamSynchronize(s));
+  p.stats.csr_items = (int32_t)items.size();
   return CASK_B200_OK;
 }
 
@@ -520,8 +616,6 @@ int build_plan(cask_b200_ctx* ctx) {
   p.stats.max_row_length = maxlen;
   p.stats.csr_nnz = csr_nnz;
   p.stats.csr_rows = csr_rows;
-  p.stats.csr_items = p.h_item_begin.empty() ? 0 : p.h_item_begin.back();
-  p.stats.csr_kernel = 0;
   p.stats.persist_ku = ctx->ell_kernel == 1 ? p.persist_ku : 0;
   p.stats.persist_stages = p.persist_stages;
   p.stats.persist_ctas_per_sm = p.persist_ctas_per_sm;

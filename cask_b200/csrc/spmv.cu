@@ -599,6 +599,171 @@ spmv_csr_fixup_kernel(const SplitRow* __restrict__ rows, int count, const double
   }
 }
 
+// ---- gather path, merge-path tiles (default for large irregular matrices: R-MAT, BASELINE configs[2]) -----------
+// What bounded the row-group kernel above on R-MAT scale 25 (ncu, profiles/r2a_spmv_csr_rmat_ncu.md): 65 long-scoreboard
+// stall cycles per issued instruction at 16 % issue utilisation, DRAM at 45 % - a latency chain row_ptr -> col -> x ->
+// shuffle per row with one or two gathers in flight per lane - and the matrix stream fetched 1.4x (8.7 GB of DRAM reads for
+// 6.0 GB of values + indices) because vec lanes per row touch every sector of a row twice.  Here a CTA owns one TILE of
+// the merge path of (row ends, nonzeros) (plan.cu: build_merge_tiles), i.e. at most kMergeTile nonzeros AND at most
+// kMergeTile rows whatever the degree distribution, and works in three decoupled phases:
+//   A  the tile's nonzeros are read perfectly coalesced (thread t takes nonzeros t, t+256, ...: every sector of the matrix
+//      stream is requested exactly once, evict-first), eight column indices and values per thread in flight, THEN the
+//      eight x gathers (all independent), then the products go to shared memory;
+//   B  every thread walks its kMergeItems steps of the merge path over shared memory only (products and row ends),
+//      emitting finished rows and keeping the partial sum of the row it stops in;
+//   C  a segmented scan over the threads' partial sums (keys = row, monotonic) hands each thread the part of its first
+//      row that earlier threads summed; rows that finish inside the tile are stored, the tile's last partial row goes to
+//      carry[tile], and spmv_csr_merge_fixup_kernel adds the carries of the tiles a long row spans, in tile order.
+// Everything is deterministic (fixed tile -> CTA and item -> thread maps, ordered carries); the summation order inside a
+// row differs from CsrMatrix::dot, as for every gather kernel (parity bar: 1e-12 relative to sum |a_ij x_j|).
+template <bool kDot>
+__global__ void __launch_bounds__(kMergeThreads, 4)
+spmv_csr_merge_kernel(const MergeTile* __restrict__ tiles, int32_t n_rows, const int32_t* __restrict__ row_ptr,
+                      const int32_t* __restrict__ col, const double* __restrict__ val, const double* __restrict__ x,
+                      double* __restrict__ y, const double* __restrict__ dot_with, double* __restrict__ partials,
+                      double* __restrict__ carry) {
+  extern __shared__ __align__(16) unsigned char merge_smem[];
+  double* prod = reinterpret_cast<double*>(merge_smem);                 // [kMergeTile] products of the tile's nonzeros
+  int32_t* rend = reinterpret_cast<int32_t*>(prod + kMergeTile);        // [kMergeTile + 1] row ends relative to k0
+  __shared__ double red[kMergeThreads / 32];
+  __shared__ double tail_val[kMergeThreads / 32], pre_val[kMergeThreads / 32];
+  __shared__ int32_t tail_key[kMergeThreads / 32], head_key[kMergeThreads / 32], pre_key[kMergeThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const MergeTile t = tiles[blockIdx.x];
+  const int nnzT = t.k1 - t.k0, nrowsT = t.r1 - t.r0;
+
+  // ---- A: row ends, then products ----
+  for (int r = tid; r <= nrowsT; r += kMergeThreads)
+    rend[r] = t.r0 + r < n_rows ? row_ptr[t.r0 + r + 1] - t.k0 : 0x7fffffff;  // entry nrowsT: the row the tile stops in
+  const int32_t* cp = col + t.k0;
+  const double* vp = val + t.k0;
+  for (int j0 = 0; j0 < nnzT; j0 += kMergeThreads * 8) {
+    int32_t c[8];
+    double v[8], xv[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int j = j0 + u * kMergeThreads + tid;
+      c[u] = j < nnzT ? __ldcs(cp + j) : 0;
+      v[u] = j < nnzT ? __ldcs(vp + j) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) xv[u] = __ldg(x + c[u]);
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int j = j0 + u * kMergeThreads + tid;
+      if (j < nnzT) prod[j] = v[u] * xv[u];
+    }
+  }
+  __syncthreads();
+
+  // ---- B: this thread's stretch of the merge path ----
+  const int total = nnzT + nrowsT;
+  const int diag = min(tid * kMergeItems, total), diag_end = min(diag + kMergeItems, total);
+  int lo = max(0, diag - nnzT), hi = min(diag, nrowsT);
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (rend[mid] <= diag - mid - 1) lo = mid + 1; else hi = mid;
+  }
+  int r = lo, k = diag - lo;
+  const int r_start = r;
+  double acc = 0.0, first_val = 0.0, dot = 0.0;
+  bool has_first = false;
+  // the tile's row 0 continues a row begun in an earlier tile iff the tile does not start on that row's first nonzero
+  const bool row0_continues = t.k0 > row_ptr[t.r0];
+  for (int step = diag; step < diag_end; step++) {
+    if (k < rend[r]) {
+      acc += prod[k];
+      k++;
+    } else {
+      if (!has_first) {
+        has_first = true;
+        first_val = acc;
+      } else {
+        y[t.r0 + r] = acc;
+        if (kDot) dot += acc * dot_with[t.r0 + r];
+      }
+      acc = 0.0;
+      r++;
+    }
+  }
+
+  // ---- C: segmented inclusive scan of (row r, partial acc) over the threads; rows are non-decreasing in tid ----
+  int key = r;
+  double sv = acc;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int ok = __shfl_up_sync(0xffffffffu, key, d);
+    const double ov = __shfl_up_sync(0xffffffffu, sv, d);
+    if (lane >= d && ok == key) sv += ov;
+  }
+  if (lane == 31) { tail_key[warp] = key; tail_val[warp] = sv; }
+  if (lane == 0) head_key[warp] = key;
+  __syncthreads();
+  if (tid == 0) {
+    // pre_*[w]: the partial sum (and its row) that the threads of warps < w hand to warp w
+    pre_key[0] = -1; pre_val[0] = 0.0;
+    for (int w = 1; w < kMergeThreads / 32; w++) {
+      double pv = tail_val[w - 1];
+      if (head_key[w - 1] == tail_key[w - 1] && pre_key[w - 1] == tail_key[w - 1]) pv += pre_val[w - 1];  // a row spanning whole warps
+      pre_key[w] = tail_key[w - 1];
+      pre_val[w] = pv;
+    }
+  }
+  __syncthreads();
+  if (key == pre_key[warp]) sv += pre_val[warp];
+  // what the previous thread hands over: its inclusive sum if it stopped in the row this thread started in
+  int prev_key = __shfl_up_sync(0xffffffffu, key, 1);
+  double prev_val = __shfl_up_sync(0xffffffffu, sv, 1);
+  if (lane == 0) { prev_key = pre_key[warp]; prev_val = pre_val[warp]; }
+  if (has_first) {
+    const double total_first = prev_key == r_start ? prev_val + first_val : first_val;
+    y[t.r0 + r_start] = total_first;
+    // a row continued from an earlier tile is finished (and enters the dot product) in the fix-up kernel
+    if (kDot && !(r_start == 0 && row0_continues)) dot += total_first * dot_with[t.r0 + r_start];
+  }
+  if (tid == kMergeThreads - 1) carry[blockIdx.x] = key == nrowsT ? sv : 0.0;
+  if (kDot) {
+    const double s = cta_sum_d(dot, red);
+    if (tid == 0) partials[blockIdx.x] = s;
+  }
+}
+
+// Rows that span tiles: tile i ends inside row R = r1 iff k1 > row_ptr[R]; the chain of such tiles with the same R is
+// summed in tile order by the thread of its first tile and added in front of what the finishing tile stored.
+template <bool kDot>
+__global__ void __launch_bounds__(256)
+spmv_csr_merge_fixup_kernel(const MergeTile* __restrict__ tiles, int count, const int32_t* __restrict__ row_ptr,
+                            const double* __restrict__ carry, double* __restrict__ y, const double* __restrict__ dot_with,
+                            double* __restrict__ partials) {
+  __shared__ double red[8];
+  double dot = 0.0;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) {
+    const MergeTile t = tiles[i];
+    const bool open = t.k1 > row_ptr[t.r1];
+    bool head = open;
+    if (open && i > 0) {
+      const MergeTile q = tiles[i - 1];
+      head = !(q.r1 == t.r1 && q.k1 > row_ptr[q.r1] && q.k1 == t.k0);
+    }
+    if (head) {
+      double sum = carry[i];
+      for (int j = i + 1; j < count; j++) {
+        const MergeTile u = tiles[j];
+        if (u.r1 != t.r1 || u.k0 != tiles[j - 1].k1) break;  // tile j finished the row (or belongs to another run)
+        sum += carry[j];
+      }
+      const double v = sum + y[t.r1];
+      y[t.r1] = v;
+      if (kDot) dot = v * dot_with[t.r1];
+    }
+  }
+  if (kDot) {
+    const double s = cta_sum_d(dot, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = s;
+  }
+}
+
 }  // namespace
 
 bool spmv_single_launch(const cask_b200_ctx* ctx) {
@@ -616,6 +781,10 @@ static int ell_grid(const cask_b200_ctx* ctx, int n_slices) {
 // for the fix-up kernel when split rows are involved
 static int csr_partials(const Plan& p, int lo, int hi) {
   if (hi <= lo || p.h_item_begin.size() <= (size_t)hi) return 0;
+  if (p.csr_merge) {  // one partial per tile + one per CTA of the fix-up kernel
+    const int tiles = p.h_item_begin[hi] - p.h_item_begin[lo];
+    return tiles + (tiles + 255) / 256;
+  }
   return (p.h_item_begin[hi] - p.h_item_begin[lo]) + (p.h_split_begin[hi] > p.h_split_begin[lo] ? 1 : 0);
 }
 
@@ -767,7 +936,29 @@ int launch_spmv_range(cask_b200_ctx* ctx, const double* d_x, double* d_y, int el
     ctx->launches++;
     if (partials) partials += ell_hi - ell_lo;
   }
-  if (csr_hi > csr_lo) {
+  if (csr_hi > csr_lo && p.csr_merge) {
+    const int i_lo = p.h_item_begin[csr_lo], i_hi = p.h_item_begin[csr_hi];
+    if (i_lo < 0 || i_hi < 0) return fail(CASK_B200_ERR_RUNTIME, "gather range splits a merge-path run");
+    const int tiles = i_hi - i_lo;
+    if (tiles > 0) {
+      const size_t smem = sizeof(double) * kMergeTile + sizeof(int32_t) * (kMergeTile + 4);
+      const int fix = (tiles + 255) / 256;
+      if (dot) {
+        CB_CUDA(cudaFuncSetAttribute(spmv_csr_merge_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        spmv_csr_merge_kernel<true><<<tiles, kMergeThreads, smem, s>>>(p.d_merge_tiles + i_lo, (int32_t)p.n, p.d_row_ptr, p.d_col, p.d_val,
+                                                                       d_x, d_y, w, partials, p.d_merge_carry + i_lo);
+        spmv_csr_merge_fixup_kernel<true><<<fix, 256, 0, s>>>(p.d_merge_tiles + i_lo, tiles, p.d_row_ptr, p.d_merge_carry + i_lo, d_y, w,
+                                                              partials + tiles);
+      } else {
+        CB_CUDA(cudaFuncSetAttribute(spmv_csr_merge_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        spmv_csr_merge_kernel<false><<<tiles, kMergeThreads, smem, s>>>(p.d_merge_tiles + i_lo, (int32_t)p.n, p.d_row_ptr, p.d_col, p.d_val,
+                                                                        d_x, d_y, nullptr, nullptr, p.d_merge_carry + i_lo);
+        spmv_csr_merge_fixup_kernel<false><<<fix, 256, 0, s>>>(p.d_merge_tiles + i_lo, tiles, p.d_row_ptr, p.d_merge_carry + i_lo, d_y,
+                                                               nullptr, nullptr);
+      }
+      ctx->launches += 2;
+    }
+  } else if (csr_hi > csr_lo) {
     const int i_lo = p.h_item_begin[csr_lo], i_hi = p.h_item_begin[csr_hi];
     const int s_lo = p.h_split_begin[csr_lo], s_hi = p.h_split_begin[csr_hi];
     if (i_hi > i_lo) {

@@ -97,8 +97,12 @@ def main():
             du = num(row[col["gpu__time_duration.sum"]])
             du_u = units[col["gpu__time_duration.sum"]]
             du_us = du * {"ns": 1e-3, "us": 1, "ms": 1e3, "s": 1e6}.get(du_u, 1)
-            t = traffic.setdefault(name, {"launches": 0, "read": 0.0, "write": 0.0, "us": 0.0})
+            t = traffic.setdefault(name, {"launches": 0, "read": 0.0, "write": 0.0, "us": 0.0, "nh": 0.0, "nm": 0.0})
             t["launches"] += 1; t["read"] += rd; t["write"] += wr; t["us"] += du_us
+            kh, km = "lts__t_sectors_srcunit_tex_evict_normal_lookup_hit.sum", "lts__t_sectors_srcunit_tex_evict_normal_lookup_miss.sum"
+            if kh in col and km in col:
+                t["nh"] += num(row[col[kh]]) or 0.0
+                t["nm"] += num(row[col[km]]) or 0.0
         except (KeyError, TypeError):
             pass
     for row in r[2:]:
@@ -131,7 +135,9 @@ def main():
                 "kernel": name, "workload": args.workload,
                 "dram_bytes_per_launch": int(round((t["read"] + t["write"]) / n)),
                 "dram_read_bytes": int(round(t["read"] / n)), "dram_write_bytes": int(round(t["write"] / n)),
-                "duration_us_under_ncu": round(t["us"] / n, 2), "launches_averaged": n, "source": args.source}
+                "duration_us_under_ncu": round(t["us"] / n, 2), "launches_averaged": n, "source": args.source,
+                # evict-normal class = x gathers / x windows, y, row pointers (the matrix stream is evict-first)
+                "l2_hit_rate_on_x_pct": round(100.0 * t["nh"] / (t["nh"] + t["nm"]), 2) if t["nh"] + t["nm"] > 0 else None}
         cur.pop("spmv_ell_persistent_kernel_bytes_per_launch", None)
         cur.pop("source", None)
         with open(args.traffic_json, "w") as f:

@@ -120,3 +120,85 @@ def test_argument_checks_mirror_reference(golden, gpu_lib, ctx):
     assert e.value.message.startswith("Matrix is too small! Minimum supported rows with DRAM reduction: 35000")
     with pytest.raises(gpu_lib.CaskError):
         gpu_lib.Context(0).spmv(x)
+
+
+# ---- merge-path tiles (csr_kernel = 1; automatic from 2^20 gather nonzeros) -----------------------------------------
+def test_merge_path_all_fixtures(golden, gpu_lib, ctx):
+    """Every fixture through spmv_csr_merge_kernel + fix-up: forced gather everywhere, and mixed with staged slices."""
+    ctx.set_option("csr_kernel", 1)
+    ctx.set_option("force_kind", 1)
+    _check_all(golden, gpu_lib, ctx, gpu_lib.design(3, 2048, 16), exact=False)
+    st = ctx.plan_stats()
+    assert st["slices_staged_ell"] == 0 and st["csr_kernel"] == 1 and st["csr_items"] > 0
+    ctx.set_option("force_kind", -1)
+    for dsg in (gpu_lib.design(1, 2048, 16), gpu_lib.design(4, 512, 8, arch=1), gpu_lib.design(48, 64, 2)):
+        _check_all(golden, gpu_lib, ctx, dsg, exact=False)
+
+
+def test_merge_path_edge_cases(gpu_lib, ctx, oracle):
+    """Empty matrices, rows of zero length in long stretches, one row far longer than a tile (4352 merge items), rectangular."""
+    ctx.set_option("csr_kernel", 1)
+    ctx.set_option("force_kind", 1)
+    d = gpu_lib.design(2, 64, 4)
+    rng = np.random.default_rng(11)
+    cases = [(5, 7, np.zeros(6, np.int32), np.zeros(0, np.int32), np.zeros(0)),
+             (1, 9, np.array([0, 9], np.int32), np.arange(9, dtype=np.int32), np.arange(1.0, 10.0))]
+    import scipy.sparse as sp
+    for n, m, hub_rows, hub_len, p_empty in ((3000, 50000, (7, 1500, 2999), 30000, 0.7), (20000, 20000, (0,), 19000, 0.95),
+                                             (9000, 300, (), 0, 0.0), (4353, 4353, (4352,), 4353, 0.5)):
+        lens = np.where(rng.random(n) < p_empty, 0, rng.integers(1, 12, n))
+        lens = np.minimum(lens, m)
+        rows = np.repeat(np.arange(n), lens)
+        cols = rng.integers(0, m, len(rows))
+        a = sp.csr_matrix((np.ones(len(rows)), (rows, cols)), shape=(n, m)).tolil()
+        for r in hub_rows:
+            a[r, rng.choice(m, hub_len, replace=False)] = 1.0
+        a = a.tocsr()
+        a.sort_indices()
+        a.data = rng.standard_normal(len(a.data))
+        cases.append((n, m, a.indptr.astype(np.int32), a.indices.astype(np.int32), a.data.astype(np.float64)))
+    for n, m, rp, ci, va in cases:
+        x = rng.standard_normal(m)
+        ctx.preprocess(d, n, m, rp, ci, va)
+        assert ctx.plan_stats()["csr_kernel"] == 1
+        exp = oracle.csr_dot(n, rp, ci, va, x)
+        got = ctx.spmv(x)
+        assert_y_close(got, exp, row_scale(n, rp, ci, va, x))
+        assert np.array_equal(got[np.diff(rp) == 0], np.zeros(int((np.diff(rp) == 0).sum())))   # empty rows are written, as zeros
+        assert np.array_equal(got, ctx.spmv(x))                                                 # deterministic
+
+
+def test_merge_path_rmat_matches_row_group_kernel(gpu_lib, ctx, oracle):
+    """R-MAT twin (scale 16, 1.4M nonzeros: hubs of 8 000 nonzeros, a third of the rows empty): automatic selection picks the merge kernel from 2^20 gather nonzeros; its
+    result agrees with the row-group kernel and the oracle."""
+    n, rp, ci, va = oracle.gen_rmat(16, 24, 3)
+    x = np.random.default_rng(2).standard_normal(n)
+    d = gpu_lib.design(1, 8192, 16)
+    ctx.preprocess(d, n, n, rp, ci, va)
+    st = ctx.plan_stats()
+    assert st["csr_nnz"] >= 1 << 20 and st["csr_kernel"] == 1, st
+    y_merge = ctx.spmv(x)
+    ctx.set_option("csr_kernel", 0)
+    ctx.preprocess(d, n, n, rp, ci, va)
+    assert ctx.plan_stats()["csr_kernel"] == 0
+    y_rows = ctx.spmv(x)
+    scale = row_scale(n, rp, ci, va, x)
+    assert_y_close(y_merge, oracle.csr_dot(n, rp, ci, va, x), scale)
+    assert_y_close(y_merge, y_rows, scale)
+
+
+def test_merge_path_fused_dot_in_cg(gpu_lib, ctx, oracle):
+    """kDot instantiation: CG on an SPD system forced through the merge kernel stops where the row-group kernel and the
+    restated pcg stop (+-1) and reaches the same solution."""
+    n, rp, ci, va = oracle.gen_poisson3d27(14)
+    b = oracle.csr_dot(n, rp, ci, va, 1.0 + 0.25 * (np.arange(n) % 4))
+    ctx.set_option("force_kind", 1)
+    res = {}
+    for k in (0, 1):
+        ctx.set_option("csr_kernel", k)
+        ctx.preprocess(gpu_lib.design(1, 8192, 16), n, n, rp, ci, va)
+        assert ctx.plan_stats()["csr_kernel"] == k and ctx.plan_stats()["slices_staged_ell"] == 0
+        res[k] = ctx.cg(b)
+    oc, oi, ox, _ = oracle.pcg(n, rp, ci, va, b, lower=False)
+    assert res[1][0] and abs(res[1][1] - oi) <= 1 and abs(res[1][1] - res[0][1]) <= 1
+    assert np.allclose(res[1][2], ox, rtol=0, atol=1e-6)
