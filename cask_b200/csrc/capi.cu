@@ -105,6 +105,7 @@ int cask_b200_create(cask_b200_ctx** out, int device) {
   if (const char* e = getenv("CASK_B200_CSR_STREAM")) ctx->csr_stream = atoi(e);
   if (const char* e = getenv("CASK_B200_CSR_ITEM_NNZ")) ctx->csr_item_nnz = atoi(e);
   if (const char* e = getenv("CASK_B200_CSR_KERNEL")) ctx->csr_kernel = atoi(e);
+  if (const char* e = getenv("CASK_B200_MERGE_ITEMS")) ctx->merge_items = atoi(e);
   if (const char* e = getenv("CASK_B200_VALUE_DICT")) ctx->value_dict = atoi(e);
   if (const char* e = getenv("CASK_B200_PERSIST_CTAS")) ctx->persist_ctas = atoi(e);
   *out = ctx;
@@ -166,6 +167,7 @@ int cask_b200_set_option(cask_b200_ctx* ctx, const char* name, double value) {
   else if (k == "csr_stream") ctx->csr_stream = (int32_t)value;
   else if (k == "csr_item_nnz") ctx->csr_item_nnz = (int32_t)value;
   else if (k == "csr_kernel") ctx->csr_kernel = (int32_t)value;
+  else if (k == "merge_items") ctx->merge_items = (int32_t)value;
   else if (k == "value_dict") ctx->value_dict = (int32_t)value;
   else if (k == "persist_ctas") ctx->persist_ctas = (int32_t)value;
   else return fail(CASK_B200_ERR_INVALID_ARGUMENT, "set_option: unknown option " + k);

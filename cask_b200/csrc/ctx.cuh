@@ -85,8 +85,10 @@ constexpr int kCsrSegment = 16384;   // nonzeros per segment of a split row
 // cut every kMergeTile items, so a tile is bounded in rows AND nonzeros whatever the row-length distribution.
 struct MergeTile { int32_t r0, k0, r1, k1; };  // merge coordinates (local row, nonzero) of the tile's start and end
 constexpr int kMergeThreads = 256;
-constexpr int kMergeItems = 17;       // merge items per thread: odd, so that neighbouring threads start in different banks
-constexpr int kMergeTile = kMergeThreads * kMergeItems;
+constexpr int kMergeItemsDefault = 7;  // merge items per thread (5, 7, 11 or 17: odd, so that neighbouring threads start
+                                       // in different banks); the tile's products and row ends live in shared memory
+                                       // (12 bytes per item), and what shared memory takes L1 loses - the x gathers in
+                                       // flight are bounded by the L1 that is left (profiles/r2b_spmv_merge_rmat_ncu.md)
 constexpr int64_t kMergeAutoNnz = 1 << 20;  // gather slices holding at least this many nonzeros run the merge kernel
 
 struct RefPartition {  // reference-format partition resident on the device
@@ -137,6 +139,7 @@ struct Plan {
   MergeTile* d_merge_tiles = nullptr;
   double* d_merge_carry = nullptr;    // per tile: partial sum of the row the tile ends in (0 if it ends on a row boundary)
   int32_t n_merge_tiles = 0;
+  int32_t merge_items = kMergeItemsDefault;   // merge items per thread the tiles were cut for
   int32_t max_xcache = 0;
   // persistent staged-ELL kernel configuration (spmv.cu: configure_persistent)
   int32_t persist_ku = 0;       // ELL columns per ring stage (0: persistent kernel not usable)
@@ -267,6 +270,7 @@ struct cask_b200_ctx {
   int64_t l2_persist_bytes = -1;  // persisting L2 set-aside claimed for evict-last vector accesses (-1: not asked yet)
   int32_t csr_stream = 0;    // 1: CSR-stream variant of the gather-CSR kernel (products staged in shared memory)
   int32_t csr_item_nnz = 4096;  // nonzeros per work item of the CSR-stream variant (its shared-memory footprint)
+  int32_t merge_items = 0;   // merge-path tiles: merge items per thread (0: default; 5, 7, 11, 17)
   int32_t csr_kernel = -1;   // gather slices: -1 auto (merge-path tiles from kMergeAutoNnz nonzeros), 0 row-group items, 1 merge-path tiles
   int32_t l2_keep = -1;      // -1 auto (vectors of a solver iteration fit L2), 0 never, 1 always: evict-last on vector accesses
   int32_t peer_mode = 1;     // 1: halo pushes and scalar all-reduces by own kernels over mapped peer memory; 0: NCCL

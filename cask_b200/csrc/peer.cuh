@@ -114,7 +114,9 @@ __device__ __forceinline__ void pdl_enter() {
 // sums into slot [seq & 3][me] of every rank's control block (low-latency 8-byte {data, sequence} stores), polls
 // the W slots of its own block and adds the W contributions in rank order - the same order on every rank, so all
 // ranks hold bit-identical scalars and take identical convergence decisions.
-__device__ __forceinline__ void grid_finish_reduce(const ReduceDesc& rd, double t0, double t1, int cta, int ncta,
+// Returns true in every thread of the CTA that wrote out[] (after a CTA barrier, so out[] may be read at once by any of
+// its threads - the solver loops hang their scalar recurrences on it), false elsewhere.
+__device__ __forceinline__ bool grid_finish_reduce(const ReduceDesc& rd, double t0, double t1, int cta, int ncta,
                                                    unsigned int gen0 = 0u) {
   __shared__ int s_last;
   __shared__ double s_red[2][32];
@@ -131,12 +133,18 @@ __device__ __forceinline__ void grid_finish_reduce(const ReduceDesc& rd, double 
   __syncthreads();
   if (!s_last) {
     if (rd.gen) {  // grid barrier: wait until the last CTA has published the result (gen0 was read at kernel entry)
-      if (tid == 0)
-        while (*reinterpret_cast<volatile unsigned int*>(rd.gen) == gen0) {}
+      if (tid == 0) {
+        // co-residency of the grid is checked on the host (occupancy query); should the SMs nevertheless be taken away
+        // (another stream of the process, MPS), the launch fails loudly after the timeout instead of spinning forever
+        const unsigned long long t_begin = globaltimer_ns();
+        unsigned int spins = 0;
+        while (*reinterpret_cast<volatile unsigned int*>(rd.gen) == gen0)
+          if ((++spins & 0x3ffu) == 0 && globaltimer_ns() - t_begin > kPeerTimeoutNs) asm volatile("trap;");
+      }
       __syncthreads();
       __threadfence();
     }
-    return;
+    return false;
   }
   __threadfence();
   for (int q = 0; q < rd.nq; q++) {
@@ -166,7 +174,8 @@ __device__ __forceinline__ void grid_finish_reduce(const ReduceDesc& rd, double 
       __syncthreads();
       if (tid == 0) { __threadfence(); atomicExch(rd.gen, gen0 + 1u); }
     }
-    return;
+    __syncthreads();
+    return true;
   }
   const unsigned long long seq = s_seq;
   const int slot = (int)(seq & 3ull);
@@ -175,7 +184,7 @@ __device__ __forceinline__ void grid_finish_reduce(const ReduceDesc& rd, double 
     PeerCtrl* pc = rd.peers[tid];
     for (int q = 0; q < rd.nq; q++) ll_send(&pc->ar_ll[slot][rd.me][q][0], s_tot[q], seq32);
   }
-  if (rd.publish_only) return;
+  if (rd.publish_only) return false;
   if (tid < rd.world)
     for (int q = 0; q < rd.nq; q++) s_contrib[tid][q] = ll_recv(&rd.ctrl->ar_ll[slot][tid][q][0], seq32, &rd.ctrl->error);
   __syncthreads();
@@ -188,6 +197,8 @@ __device__ __forceinline__ void grid_finish_reduce(const ReduceDesc& rd, double 
     __syncthreads();
     if (tid == 0) { __threadfence(); atomicExch(rd.gen, gen0 + 1u); }
   }
+  __syncthreads();
+  return true;
 }
 
 // In-situ timeline (profiling runs: CASK_B200_TRACE=<file>): per kernel, the earliest CTA entry, the earliest CTA

@@ -244,7 +244,7 @@ __global__ void row_length_histogram_kernel(const int32_t* __restrict__ row_ptr,
 // diagonal d is #{ i : row_ptr[ra + i + 1] - ka <= d - i - 1 }, a prefix of the rows, found by binary search.
 struct MergeRun { int32_t ra, rb, ka, kb, tile0, ntiles; };
 
-__global__ void merge_tiles_kernel(const MergeRun* __restrict__ runs, int nruns, int total_tiles,
+__global__ void merge_tiles_kernel(const MergeRun* __restrict__ runs, int nruns, int total_tiles, int tile_items,
                                    const int32_t* __restrict__ row_ptr, MergeTile* __restrict__ tiles) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= total_tiles) return;
@@ -268,8 +268,8 @@ __global__ void merge_tiles_kernel(const MergeRun* __restrict__ runs, int nruns,
   };
   const int64_t i = g - run.tile0;
   MergeTile t;
-  split(i * kMergeTile, &t.r0, &t.k0);
-  split((i + 1) * kMergeTile, &t.r1, &t.k1);
+  split(i * tile_items, &t.r0, &t.k0);
+  split((i + 1) * tile_items, &t.r1, &t.k1);
   tiles[g] = t;
 }
 
@@ -304,6 +304,9 @@ static int build_merge_tiles(cask_b200_ctx* ctx) {
   std::vector<int64_t> k_at(p.nslices + 1, 0);  // row_ptr at every slice boundary = prefix sum of the slices' nonzeros
   for (int32_t i = 0; i < p.nslices; i++) k_at[i + 1] = k_at[i] + p.h_slices[i].nnz;
   std::vector<MergeRun> runs;
+  p.merge_items = ctx->merge_items == 5 || ctx->merge_items == 7 || ctx->merge_items == 11 || ctx->merge_items == 17
+                      ? ctx->merge_items : kMergeItemsDefault;
+  const int64_t tile_items = (int64_t)kMergeThreads * p.merge_items;
   p.h_item_begin.assign((size_t)p.n_csr + 1, -1);
   p.h_split_begin.assign((size_t)p.n_csr + 1, 0);
   int32_t tiles = 0;
@@ -317,7 +320,7 @@ static int build_merge_tiles(cask_b200_ctx* ctx) {
     r.ka = (int32_t)k_at[p.h_list_csr[pos]]; r.kb = (int32_t)k_at[p.h_list_csr[end - 1] + 1];
     const int64_t total = (int64_t)(r.rb - r.ra) + (r.kb - r.ka);
     r.tile0 = tiles;
-    r.ntiles = (int32_t)((total + kMergeTile - 1) / kMergeTile);
+    r.ntiles = (int32_t)((total + tile_items - 1) / tile_items);
     p.h_item_begin[pos] = tiles;
     tiles += r.ntiles;
     runs.push_back(r);
@@ -331,7 +334,7 @@ static int build_merge_tiles(cask_b200_ctx* ctx) {
     MergeRun* d_runs = nullptr;
     CB_CUDA(cudaMalloc(&d_runs, sizeof(MergeRun) * runs.size()));
     CB_CUDA(cudaMemcpyAsync(d_runs, runs.data(), sizeof(MergeRun) * runs.size(), cudaMemcpyHostToDevice, s));
-    merge_tiles_kernel<<<(tiles + 255) / 256, 256, 0, s>>>(d_runs, (int)runs.size(), tiles, p.d_row_ptr, p.d_merge_tiles);
+    merge_tiles_kernel<<<(tiles + 255) / 256, 256, 0, s>>>(d_runs, (int)runs.size(), tiles, (int)tile_items, p.d_row_ptr, p.d_merge_tiles);
     ctx->launches++;
     CB_CUDA(cudaStreamSynchronize(s));
     cudaFree(d_runs);

@@ -68,16 +68,24 @@ __device__ __forceinline__ double cta_sum(double v, double* red) {
   return t;
 }
 
-// Every vector kernel walks tiles of kVecTile elements grid-stride; a thread owns kVecItems elements of a tile,
-// kVecThreads apart (coalesced), loads all its operands into registers first and only then computes and stores,
-// so kVecItems x (number of operand arrays) loads are in flight per thread whatever the compiler can prove about
-// aliasing.
-// CTA c owns the contiguous chunk [lo_, hi_) of the vector (chunks are multiples of kVecThreads elements, so every
-// access is 2 KB aligned and the CTAs of the single wave are balanced to within 256 elements).
+// Every vector kernel walks tiles of kVecTile elements; a thread owns kVecItems elements of a tile, kVecThreads apart
+// (coalesced), loads all its operands into registers first and only then computes and stores, so kVecItems x (number
+// of operand arrays) loads are in flight per thread whatever the compiler can prove about aliasing.
+// Tile -> CTA map (c_vec_rr, CASK_B200_VEC_RR):
+//   1 (default)  round robin: CTA c takes tiles c, c + grid, c + 2 grid ... - at any moment the resident wave reads ONE
+//                window of grid x 16 KB per array, so consecutive requests reaching a DRAM channel fall into the same
+//                few open rows (the order in which a plain copy, and the persistent SpMV kernel, sweep memory);
+//   0            contiguous chunk per CTA (round 1): 2 x SMs x 6 arrays = 1 776 widely separated streams at once, which
+//                measured 3.0 TB/s on the 72 n bytes of the fused CG update (ncu launch list, profiles/r2a_launches_summary.md).
+// Either map is fixed for a given (n, grid), so the per-CTA partial sums - and the reductions - stay deterministic, and
+// both phases of the fused kernels use the same map (a thread re-reads only what it wrote itself).
+__constant__ int c_vec_rr = 1;
 #define CB_TILE_LOOP(n)                                                                                             \
   const int64_t chunk_ = (((n) + gridDim.x - 1) / gridDim.x + kVecThreads - 1) / kVecThreads * kVecThreads;         \
-  const int64_t lo_ = (int64_t)blockIdx.x * chunk_, hi_ = lo_ + chunk_ < (n) ? lo_ + chunk_ : (n);                  \
-  for (int64_t tile = lo_; tile < hi_; tile += kVecTile)
+  const int64_t lo_ = c_vec_rr ? (int64_t)blockIdx.x * kVecTile : (int64_t)blockIdx.x * chunk_;                     \
+  const int64_t hi_ = c_vec_rr ? (int64_t)(n) : (lo_ + chunk_ < (n) ? lo_ + chunk_ : (n));                          \
+  const int64_t step_ = c_vec_rr ? (int64_t)gridDim.x * kVecTile : (int64_t)kVecTile;                               \
+  for (int64_t tile = lo_; tile < hi_; tile += step_)
 #define CB_ITEMS for (int i = 0; i < kVecItems; i++)
 #define CB_IDX(tile) ((tile) + threadIdx.x + (int64_t)i * kVecThreads)
 
@@ -516,7 +524,8 @@ __global__ void __launch_bounds__(kVecThreads, kVecCtasPerSm)
 bicg_xr_kernel(int64_t n, const double* __restrict__ scal, const int32_t* __restrict__ flags,
                const double* __restrict__ y, const double* __restrict__ z, const double* __restrict__ s,
                const double* __restrict__ t, const double* __restrict__ r0, double* __restrict__ x,
-               double* __restrict__ r, const __grid_constant__ ReduceDesc rd) {
+               double* __restrict__ r, const __grid_constant__ ReduceDesc rd, double* __restrict__ scal_rw,
+               int32_t* __restrict__ flags_rw, int fused_scalars) {
   pdl_enter();
   if (flags[F_DONE] || flags[F_RESTART]) return;
   __shared__ double red[kVecThreads / 32];
@@ -547,7 +556,26 @@ bicg_xr_kernel(int64_t n, const double* __restrict__ scal, const int32_t* __rest
   }
   const double t0 = cta_sum(a0, red);
   const double t1 = cta_sum(a1, red);
-  grid_finish_reduce(rd, t0, t1, blockIdx.x, gridDim.x);
+  const bool finished = grid_finish_reduce(rd, t0, t1, blockIdx.x, gridDim.x);
+  // Single rank / peer path: the CTA that finished the reduction (every other CTA of the grid has read the scalars and
+  // the flags by then) also runs the scalar end of this trip (bicg_tail_kernel) and the scalar head of the next one
+  // (bicg_head_kernel: while-test, rho, restart test) - two single-thread launches less per iteration.  On the peer
+  // path every rank holds bit-identical sums and takes the same decisions.
+  if (fused_scalars && finished && threadIdx.x == 0) {
+    scal_rw[B_W] = w;
+    flags_rw[F_I] += 1;
+    flags_rw[F_TRIPS] += 1;
+    const bool go = scal_rw[B_RR] > scal_rw[B_TOL2] && flags_rw[F_I] < flags_rw[F_MAXIT];
+    if (!go) {
+      flags_rw[F_DONE] = 1;
+    } else {
+      scal_rw[B_RHO_OLD] = scal_rw[B_RHO];
+      scal_rw[B_RHO] = scal_rw[B_R0R];
+      const double eps2 = DBL_EPSILON * DBL_EPSILON;
+      if (fabs(scal_rw[B_RHO]) < eps2 * scal_rw[B_R0SQ]) flags_rw[F_RESTART] = 1;
+    }
+    __threadfence();
+  }
 }
 
 __global__ void bicg_tail_kernel(double* scal, int32_t* flags) {
@@ -590,6 +618,11 @@ int prefer_max_shared() {
   CB_CARVE(bicg_s_kernel); CB_CARVE(bicg_xr_kernel); CB_CARVE(bicg_tail_kernel); CB_CARVE(bicg_restart_scalars_kernel);
   CB_CARVE(reduce_partials_kernel); CB_CARVE(jacobi_diag_kernel);
 #undef CB_CARVE
+  {
+    const char* e = getenv("CASK_B200_VEC_RR");
+    const int rr = e ? atoi(e) : 1;
+    CB_CUDA(cudaMemcpyToSymbol(c_vec_rr, &rr, sizeof(rr)));
+  }
   done_for_device = dev;
   return CASK_B200_OK;
 }
@@ -670,7 +703,8 @@ int reduce_dots(cask_b200_ctx* ctx, int count, int stride, int nq, int slot0, co
 //    halo-dependent slices after the event, then a reduction kernel + ncclAllReduce.
 // flags != nullptr: the launches do nothing once the solver's DONE / RESTART flag is up.
 int spmv_full(cask_b200_ctx* ctx, double* d_full, double* d_y, const double* d_dot_with, int dot_slot, int channel,
-              const int32_t* flags, unsigned long long* trace = nullptr, bool publish_only = false, int keep = 0) {
+              const int32_t* flags, unsigned long long* trace = nullptr, bool publish_only = false, int keep = 0,
+              int nq = 1, int stride = 0) {
   cudaStream_t s = ctx->stream;
   SolverWork& w = ctx->work;
   const bool peer = channel >= 0 && peer_ready(ctx);
@@ -685,7 +719,9 @@ int spmv_full(cask_b200_ctx* ctx, double* d_full, double* d_y, const double* d_d
   if (flags) { hw.skip0 = flags + F_DONE; hw.skip1 = flags + F_RESTART; }
   if (!dist_active(ctx) || peer) {
     const bool in_kernel = d_dot_with && spmv_single_launch(ctx);
-    if (in_kernel) f.reduce = make_reduce(ctx, T_SPMV, 0, 1, dot_slot);
+    if (nq == 2 && !in_kernel) return fail(CASK_B200_ERR_RUNTIME, "fused y.w + y.y needs the single-launch persistent SpMV");
+    if (in_kernel) f.reduce = make_reduce(ctx, T_SPMV, nq == 2 ? stride : 0, nq, dot_slot);  // nq == 2: scal[dot_slot + 1] = y.y
+    f.fuse_self_dot = nq == 2 ? 1 : 0;
     if (publish_only) {
       if (!(in_kernel && peer)) return fail(CASK_B200_ERR_RUNTIME, "publish-only reduction needs the in-kernel peer path");
       f.reduce.publish_only = 1;
@@ -737,7 +773,20 @@ extern "C" int cask_b200_cg_device(cask_b200_ctx* ctx, const double* d_rhs, doub
   const PushDesc pd = peer_push_desc(ctx, 0);
   // fused update kernel (single rank / peer path): r lives in the arena too (vector 1) - its boundary rows are what
   // travels every iteration, and each rank recomputes the halo rows of p from them
-  const bool fused = !dist_active(ctx) || peer;
+  bool fused = !dist_active(ctx) || peer;
+  if (fused) {
+    // cg_update_fused_kernel holds a whole-grid barrier: every CTA of the grid must be resident at once.  The grid is
+    // sized as ONE wave of kVecCtasPerSm CTAs per SM; that the device really co-schedules that many is asked of the
+    // runtime (registers, carve-out, MPS partitions all count) instead of assumed; the barrier's spin itself carries
+    // a timeout (peer.cuh: grid_finish_reduce traps after kPeerTimeoutNs), so SMs taken by another stream of the
+    // process surface as a CUDA error on the host instead of a hung GPU.
+    int resident = 0;
+    CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, cg_update_fused_kernel, kVecThreads, 0));
+    if ((int64_t)resident * ctx->sm_count < vec_grid(ctx, n)) {
+      if (peer) return fail(CASK_B200_ERR_RUNTIME, "cg: the fused update kernel's grid cannot be co-resident on this device");
+      fused = false;  // two kernels (update_xr, update_p) with the reduction between them: no barrier needed
+    }
+  }
   // x, r, p, Ap of this rank fit L2 (with room for the matrix stream): keep them there (peer.cuh: L2 residency control)
   // evict-last lines live in the persisting set-aside of L2, which is 0 by default: claim the device maximum once
   if (ctx->l2_persist_bytes < 0) {
@@ -928,16 +977,28 @@ extern "C" int cask_b200_bicgstab_device(cask_b200_ctx* ctx, const double* d_b, 
   h_scal[B_R0R] = w.h_scalars[B_R0SQ];  // r0.r with r0 == r
   CB_CUDA(cudaMemcpyAsync(scal, h_scal, sizeof(h_scal), cudaMemcpyHostToDevice, st));
 
+  // Single rank or peer path with every slice in one persistent launch: t.s and t.t are finished inside the second SpMV
+  // (no dot2 pass over t and s) and the scalar tail / head run in bicg_xr's finishing CTA - 5 launches per iteration
+  // (p, SpMV + r0.v, s, SpMV + t.s + t.t, xr) instead of 8.  The NCCL path keeps the separate kernels: its all-reduces
+  // sit between them.
+  const bool fused = spmv_single_launch(ctx) && (!dist_active(ctx) || peer) && !getenv("CASK_B200_BICG_UNFUSED");
   // body of one iteration after the loop head; every kernel no-ops while F_DONE or F_RESTART is up
   auto enqueue_body = [&]() -> int {
     CB_CUDA(launch_pdl(bicg_p_kernel, vg, kVecThreads, st, n, scal, flags, r, v, invd, p, y, pd_y));
     CB_TRY(spmv_full(ctx, y_full, v, r0, B_R0V, ch_y, flags));               // v = A y, r0.v finished in-kernel
     CB_CUDA(launch_pdl(bicg_s_kernel, vg, kVecThreads, st, n, scal, flags, r, v, invd, s, z, pd_z));   // alpha, s, z
+    if (fused) {
+      CB_TRY(spmv_full(ctx, z_full, t, s, B_TS, ch_z, flags, nullptr, false, 0, 2, stride));   // t = A z, t.s and t.t in-kernel
+      CB_CUDA(launch_pdl(bicg_xr_kernel, vg, kVecThreads, st, n, scal, flags, y, z, s, t, r0, d_x, r,
+                         make_reduce(ctx, T_VEC, stride, 2, B_RR), scal, flags, 1));
+      ctx->launches += 3;
+      return CASK_B200_OK;
+    }
     CB_TRY(spmv_full(ctx, z_full, t, nullptr, 0, ch_z, flags));              // t = A z
     CB_CUDA(launch_pdl(dot2_kernel, vg, kVecThreads, st, n, flags, t, s, t, t, make_reduce(ctx, T_VEC, stride, 2, B_TS)));
     CB_TRY(finish_reduce(ctx, 2, B_TS));
     CB_CUDA(launch_pdl(bicg_xr_kernel, vg, kVecThreads, st, n, scal, flags, y, z, s, t, r0, d_x, r,
-                       make_reduce(ctx, T_VEC, stride, 2, B_RR)));
+                       make_reduce(ctx, T_VEC, stride, 2, B_RR), scal, flags, 0));
     CB_TRY(finish_reduce(ctx, 2, B_RR));
     CB_CUDA(launch_pdl(bicg_tail_kernel, 1, 1, st, scal, flags));
     ctx->launches += 5;
@@ -949,10 +1010,16 @@ extern "C" int cask_b200_bicgstab_device(cask_b200_ctx* ctx, const double* d_b, 
   int64_t enq = 0;
   const int64_t enq_cap = (int64_t)maxit * 2 + 2;  // the first restart rewinds i once (BiCGSTAB.h)
   bool skip_check = true;
+  if (fused) {  // the head of the first trip; every later head runs inside bicg_xr
+    CB_CUDA(launch_pdl(bicg_head_kernel, 1, 1, st, scal, flags));
+    ctx->launches++;
+  }
   for (int batch = 0;; batch++) {
     for (int b = 0; b < kBatch && enq < enq_cap; b++, enq++) {
-      CB_CUDA(launch_pdl(bicg_head_kernel, 1, 1, st, scal, flags));
-      ctx->launches++;
+      if (!fused) {
+        CB_CUDA(launch_pdl(bicg_head_kernel, 1, 1, st, scal, flags));
+        ctx->launches++;
+      }
       CB_TRY(enqueue_body());
     }
     CB_CUDA(cudaMemcpyAsync(hf + (batch & 1) * (F_COUNT + 1), flags, sizeof(int32_t) * (F_COUNT + 1),
@@ -981,7 +1048,7 @@ extern "C" int cask_b200_bicgstab_device(cask_b200_ctx* ctx, const double* d_b, 
     skip_check = false;
     if (enq >= enq_cap) break;
   }
-  bicg_head_kernel<<<1, 1, 0, st>>>(scal, flags);  // evaluates the while-test one last time (sets DONE)
+  if (!fused) bicg_head_kernel<<<1, 1, 0, st>>>(scal, flags);  // evaluates the while-test one last time (sets DONE)
   CB_CUDA(cudaMemcpyAsync(hf, flags, sizeof(int32_t) * (F_COUNT + 1), cudaMemcpyDeviceToHost, st));
   CB_CUDA(cudaMemcpyAsync(w.h_scalars, scal, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, st));
   CB_CUDA(cudaStreamSynchronize(st));

@@ -16,6 +16,7 @@
 //
 // Both can fuse the per-CTA partial of dot(y, w) (CG's p.Ap) into their epilogue.
 #include <algorithm>
+#include <cstdlib>
 
 #include "ctx.cuh"
 #include "peer.cuh"
@@ -246,7 +247,7 @@ spmv_ell_persistent_kernel(const SliceDesc* __restrict__ slices, const int32_t* 
                            const uint16_t* __restrict__ ell_idx, const double* __restrict__ x, double* __restrict__ y,
                            const double* __restrict__ dot_with, double* __restrict__ partials, int xbuf_doubles,
                            int stages, const HaloWait hw, const __grid_constant__ ReduceDesc rd, int keep_i, unsigned long long* trace,
-                           const CodedArgs ca) {
+                           const CodedArgs ca, int self_dot) {
   trace_min(trace);
   const bool keep = keep_i != 0;  // vectors fit L2: x windows, y and dot_with are accessed with evict-last
   const unsigned long long keep_policy = l2_policy_evict_last();
@@ -330,7 +331,7 @@ spmv_ell_persistent_kernel(const SliceDesc* __restrict__ slices, const int32_t* 
     return;
   }
 
-  double dot = 0.0;
+  double dot = 0.0, dot2 = 0.0;  // y . dot_with and (self_dot: BiCGStab's t.t beside t.s) y . y
   if (is_producer) {
     // ===== producer warp =====
     int chunk_no = 0;
@@ -460,14 +461,22 @@ spmv_ell_persistent_kernel(const SliceDesc* __restrict__ slices, const int32_t* 
         const int row = j * kConsumerThreads + tid;
         if (row < nrows) {
           st_keep(y + row0 + row, acc[j], keep_policy, keep);
-          if (kDot) dot += acc[j] * ld_keep(dot_with + row0 + row, keep_policy, keep);
+          if (kDot) {
+            dot += acc[j] * ld_keep(dot_with + row0 + row, keep_policy, keep);
+            if (self_dot) dot2 += acc[j] * acc[j];
+          }
         }
       }
     }
   }
   if (kDot) {
     const double t = cta_sum_d(dot, red);  // deterministic: fixed slice->CTA map, fixed order inside the CTA
-    if (rd.partials) grid_finish_reduce(rd, t, 0.0, blockIdx.x, gridDim.x);  // last CTA: sum (+ all-reduce) in place
+    double t2 = 0.0;
+    if (self_dot) {
+      __syncthreads();  // red[] is reused
+      t2 = cta_sum_d(dot2, red);
+    }
+    if (rd.partials) grid_finish_reduce(rd, t, t2, blockIdx.x, gridDim.x);  // last CTA: sum (+ all-reduce) in place
     else if (tid == 0) partials[blockIdx.x] = t;
   }
   trace_max(trace ? trace + 2 : nullptr);
@@ -604,27 +613,29 @@ spmv_csr_fixup_kernel(const SplitRow* __restrict__ rows, int count, const double
 // stall cycles per issued instruction at 16 % issue utilisation, DRAM at 45 % - a latency chain row_ptr -> col -> x ->
 // shuffle per row with one or two gathers in flight per lane - and the matrix stream fetched 1.4x (8.7 GB of DRAM reads for
 // 6.0 GB of values + indices) because vec lanes per row touch every sector of a row twice.  Here a CTA owns one TILE of
-// the merge path of (row ends, nonzeros) (plan.cu: build_merge_tiles), i.e. at most kMergeTile nonzeros AND at most
-// kMergeTile rows whatever the degree distribution, and works in three decoupled phases:
+// the merge path of (row ends, nonzeros) (plan.cu: build_merge_tiles), i.e. at most 256 x merge_items nonzeros AND as many
+// rows whatever the degree distribution, and works in three decoupled phases:
 //   A  the tile's nonzeros are read perfectly coalesced (thread t takes nonzeros t, t+256, ...: every sector of the matrix
 //      stream is requested exactly once, evict-first), eight column indices and values per thread in flight, THEN the
 //      eight x gathers (all independent), then the products go to shared memory;
-//   B  every thread walks its kMergeItems steps of the merge path over shared memory only (products and row ends),
+//   B  every thread walks its merge_items steps of the merge path over shared memory only (products and row ends),
 //      emitting finished rows and keeping the partial sum of the row it stops in;
 //   C  a segmented scan over the threads' partial sums (keys = row, monotonic) hands each thread the part of its first
 //      row that earlier threads summed; rows that finish inside the tile are stored, the tile's last partial row goes to
 //      carry[tile], and spmv_csr_merge_fixup_kernel adds the carries of the tiles a long row spans, in tile order.
 // Everything is deterministic (fixed tile -> CTA and item -> thread maps, ordered carries); the summation order inside a
 // row differs from CsrMatrix::dot, as for every gather kernel (parity bar: 1e-12 relative to sum |a_ij x_j|).
-template <bool kDot>
-__global__ void __launch_bounds__(kMergeThreads, 4)
+template <bool kDot, int ITEMS>
+__global__ void __launch_bounds__(kMergeThreads, ITEMS > 11 ? 4 : 5)
 spmv_csr_merge_kernel(const MergeTile* __restrict__ tiles, int32_t n_rows, const int32_t* __restrict__ row_ptr,
                       const int32_t* __restrict__ col, const double* __restrict__ val, const double* __restrict__ x,
                       double* __restrict__ y, const double* __restrict__ dot_with, double* __restrict__ partials,
-                      double* __restrict__ carry) {
+                      double* __restrict__ carry, int x_past_l1) {
+  constexpr int TILE = kMergeThreads * ITEMS;       // merge items (row ends + nonzeros) per tile
+  constexpr int BATCH = ITEMS < 8 ? ITEMS : 8;      // nonzeros per thread in flight in phase A
   extern __shared__ __align__(16) unsigned char merge_smem[];
-  double* prod = reinterpret_cast<double*>(merge_smem);                 // [kMergeTile] products of the tile's nonzeros
-  int32_t* rend = reinterpret_cast<int32_t*>(prod + kMergeTile);        // [kMergeTile + 1] row ends relative to k0
+  double* prod = reinterpret_cast<double*>(merge_smem);           // [TILE] products of the tile's nonzeros
+  int32_t* rend = reinterpret_cast<int32_t*>(prod + TILE);        // [TILE + 1] row ends relative to k0
   __shared__ double red[kMergeThreads / 32];
   __shared__ double tail_val[kMergeThreads / 32], pre_val[kMergeThreads / 32];
   __shared__ int32_t tail_key[kMergeThreads / 32], head_key[kMergeThreads / 32], pre_key[kMergeThreads / 32];
@@ -635,30 +646,34 @@ spmv_csr_merge_kernel(const MergeTile* __restrict__ tiles, int32_t n_rows, const
   // ---- A: row ends, then products ----
   for (int r = tid; r <= nrowsT; r += kMergeThreads)
     rend[r] = t.r0 + r < n_rows ? row_ptr[t.r0 + r + 1] - t.k0 : 0x7fffffff;  // entry nrowsT: the row the tile stops in
-  const int32_t* cp = col + t.k0;
-  const double* vp = val + t.k0;
-  for (int j0 = 0; j0 < nnzT; j0 += kMergeThreads * 8) {
-    int32_t c[8];
-    double v[8], xv[8];
+  // the sweep starts on the 32-element boundary below k0: every warp-wide load then covers whole 128-byte lines of the
+  // index stream (256 bytes of the value stream) and no sector of the matrix is requested by two warps
+  const int lead = t.k0 & 31;
+  const int32_t* cp = col + (t.k0 - lead);
+  const double* vp = val + (t.k0 - lead);
+  for (int j0 = 0; j0 < nnzT + lead; j0 += kMergeThreads * BATCH) {
+    int32_t c[BATCH];
+    double v[BATCH], xv[BATCH];
 #pragma unroll
-    for (int u = 0; u < 8; u++) {
+    for (int u = 0; u < BATCH; u++) {
       const int j = j0 + u * kMergeThreads + tid;
-      c[u] = j < nnzT ? __ldcs(cp + j) : 0;
-      v[u] = j < nnzT ? __ldcs(vp + j) : 0.0;
+      const bool ok = j >= lead && j < nnzT + lead;
+      c[u] = ok ? __ldcs(cp + j) : 0;
+      v[u] = ok ? __ldcs(vp + j) : 0.0;
     }
 #pragma unroll
-    for (int u = 0; u < 8; u++) xv[u] = __ldg(x + c[u]);
+    for (int u = 0; u < BATCH; u++) xv[u] = x_past_l1 ? __ldcg(x + c[u]) : __ldg(x + c[u]);  // A/B: gathers cached in L2 only
 #pragma unroll
-    for (int u = 0; u < 8; u++) {
+    for (int u = 0; u < BATCH; u++) {
       const int j = j0 + u * kMergeThreads + tid;
-      if (j < nnzT) prod[j] = v[u] * xv[u];
+      if (j >= lead && j < nnzT + lead) prod[j - lead] = v[u] * xv[u];
     }
   }
   __syncthreads();
 
   // ---- B: this thread's stretch of the merge path ----
   const int total = nnzT + nrowsT;
-  const int diag = min(tid * kMergeItems, total), diag_end = min(diag + kMergeItems, total);
+  const int diag = min(tid * ITEMS, total), diag_end = min(diag + ITEMS, total);
   int lo = max(0, diag - nnzT), hi = min(diag, nrowsT);
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
@@ -670,8 +685,9 @@ spmv_csr_merge_kernel(const MergeTile* __restrict__ tiles, int32_t n_rows, const
   bool has_first = false;
   // the tile's row 0 continues a row begun in an earlier tile iff the tile does not start on that row's first nonzero
   const bool row0_continues = t.k0 > row_ptr[t.r0];
+  int re = rend[r];
   for (int step = diag; step < diag_end; step++) {
-    if (k < rend[r]) {
+    if (k < re) {
       acc += prod[k];
       k++;
     } else {
@@ -684,6 +700,7 @@ spmv_csr_merge_kernel(const MergeTile* __restrict__ tiles, int32_t n_rows, const
       }
       acc = 0.0;
       r++;
+      re = rend[r];
     }
   }
 
@@ -890,7 +907,7 @@ int launch_spmv_range(cask_b200_ctx* ctx, const double* d_x, double* d_y, int el
                                (const double*)p.d_ell_vals, (const uint16_t*)p.d_ell_idx, d_x, d_y, w, partials,     \
                                (int)p.persist_xbuf, (int)p.persist_stages, hw, rd,                                   \
                                fusion ? fusion->keep_vectors : 0,                                                    \
-                               fusion ? fusion->trace : (unsigned long long*)nullptr, ca));                          \
+                               fusion ? fusion->trace : (unsigned long long*)nullptr, ca, self_dot));                \
   } while (0)
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -904,6 +921,9 @@ int launch_spmv_range(cask_b200_ctx* ctx, const double* d_x, double* d_y, int el
     cfg.numAttrs = fusion && fusion->pdl ? 1 : 0;
     const ReduceDesc rd = dot && fusion->reduce.partials && ell_lo == 0 && ell_hi == p.n_ell && csr_hi == csr_lo
                               ? fusion->reduce : ReduceDesc();
+    const int self_dot = dot && fusion->fuse_self_dot && rd.partials && rd.nq == 2 ? 1 : 0;
+    if (dot && fusion->fuse_self_dot && !self_dot)
+      return fail(CASK_B200_ERR_RUNTIME, "fused y.y needs the in-kernel reduction of a single persistent launch");
     CodedArgs ca;
     if (p.coded) { ca.codes = p.d_ell_codes; ca.dict = p.d_ell_dict; ca.pairs = p.d_ell_pairs; ca.dict_len = p.dict_len; }
     if (p.coded == 2) {
@@ -941,21 +961,36 @@ int launch_spmv_range(cask_b200_ctx* ctx, const double* d_x, double* d_y, int el
     if (i_lo < 0 || i_hi < 0) return fail(CASK_B200_ERR_RUNTIME, "gather range splits a merge-path run");
     const int tiles = i_hi - i_lo;
     if (tiles > 0) {
-      const size_t smem = sizeof(double) * kMergeTile + sizeof(int32_t) * (kMergeTile + 4);
+      const int tile_items = kMergeThreads * p.merge_items;
+      const size_t smem = sizeof(double) * tile_items + sizeof(int32_t) * (tile_items + 4);
       const int fix = (tiles + 255) / 256;
+      static const int x_past_l1 = getenv("CASK_B200_MERGE_XCG") ? atoi(getenv("CASK_B200_MERGE_XCG")) : 0;
+#define CB_MERGE(DOT, ITEMS)                                                                                              \
+  do {                                                                                                                    \
+    CB_CUDA(cudaFuncSetAttribute(spmv_csr_merge_kernel<DOT, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    spmv_csr_merge_kernel<DOT, ITEMS><<<tiles, kMergeThreads, smem, s>>>(p.d_merge_tiles + i_lo, (int32_t)p.n, p.d_row_ptr, p.d_col, \
+                                                                         p.d_val, d_x, d_y, w, partials, p.d_merge_carry + i_lo,     \
+                                                                         x_past_l1);                                                 \
+  } while (0)
+#define CB_MERGE_ITEMS(DOT)                                                      \
+  switch (p.merge_items) {                                                       \
+    case 5: CB_MERGE(DOT, 5); break;                                             \
+    case 7: CB_MERGE(DOT, 7); break;                                             \
+    case 11: CB_MERGE(DOT, 11); break;                                           \
+    case 17: CB_MERGE(DOT, 17); break;                                           \
+    default: return fail(CASK_B200_ERR_RUNTIME, "merge_items must be 5, 7, 11 or 17"); \
+  }
       if (dot) {
-        CB_CUDA(cudaFuncSetAttribute(spmv_csr_merge_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        spmv_csr_merge_kernel<true><<<tiles, kMergeThreads, smem, s>>>(p.d_merge_tiles + i_lo, (int32_t)p.n, p.d_row_ptr, p.d_col, p.d_val,
-                                                                       d_x, d_y, w, partials, p.d_merge_carry + i_lo);
+        CB_MERGE_ITEMS(true);
         spmv_csr_merge_fixup_kernel<true><<<fix, 256, 0, s>>>(p.d_merge_tiles + i_lo, tiles, p.d_row_ptr, p.d_merge_carry + i_lo, d_y, w,
                                                               partials + tiles);
       } else {
-        CB_CUDA(cudaFuncSetAttribute(spmv_csr_merge_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        spmv_csr_merge_kernel<false><<<tiles, kMergeThreads, smem, s>>>(p.d_merge_tiles + i_lo, (int32_t)p.n, p.d_row_ptr, p.d_col, p.d_val,
-                                                                        d_x, d_y, nullptr, nullptr, p.d_merge_carry + i_lo);
+        CB_MERGE_ITEMS(false);
         spmv_csr_merge_fixup_kernel<false><<<fix, 256, 0, s>>>(p.d_merge_tiles + i_lo, tiles, p.d_row_ptr, p.d_merge_carry + i_lo, d_y,
                                                                nullptr, nullptr);
       }
+#undef CB_MERGE_ITEMS
+#undef CB_MERGE
       ctx->launches += 2;
     }
   } else if (csr_hi > csr_lo) {
