@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = (
     "cask_b200_partition_export", "cask_b200_spmv", "cask_b200_spmv_device", "cask_b200_spmv_refformat",
     "cask_b200_cg", "cask_b200_cg_device", "cask_b200_bicgstab", "cask_b200_bicgstab_device",
     "cask_b200_nccl_unique_id", "cask_b200_dist_init", "cask_b200_shard_rows",
-    "cask_b200_preprocess_shard_device", "cask_b200_dist_halo_counts", "cask_b200_dist_peer_active", "cask_b200_halo_plan_host", "cask_b200_synth_rows",
+    "cask_b200_preprocess_shard_device", "cask_b200_dist_halo_counts", "cask_b200_dist_peer_active", "cask_b200_dist_vector", "cask_b200_spmv_shard", "cask_b200_halo_plan_host", "cask_b200_synth_rows",
     "cask_b200_synth_nnz", "cask_b200_synth_device", "cask_b200_launch_count", "cask_b200_legacy_write",
     "cask_b200_legacy_read", "cask_b200_legacy_run", "cask_b200_legacy_reset", "cask_b200_legacy_launch_count",
     "cask_b200_mm_read_info", "cask_b200_mm_read_coo", "cask_b200_mm_read_vector", "cask_b200_ingest_coo",
@@ -122,6 +122,8 @@ def lib():
         L.cask_b200_shard_rows.argtypes = [i64, i32, i32, vp, vp]
         L.cask_b200_dist_halo_counts.argtypes = [vp, vp]
         L.cask_b200_dist_peer_active.argtypes = [vp, vp]
+        L.cask_b200_dist_vector.argtypes = [vp, i32, C.POINTER(vp)]
+        L.cask_b200_spmv_shard.argtypes = [vp, vp, vp]
         L.cask_b200_halo_plan_host.argtypes = [i64, i32, i32, i64, vp, vp, i64, vp, vp, vp, vp]
         L.cask_b200_synth_rows.argtypes = [i32, i32, vp]
         L.cask_b200_synth_nnz.argtypes = [i32, i32, i64, i64, vp]
@@ -443,6 +445,20 @@ class Context:
         out = np.zeros(world, np.int64)
         check(lib().cask_b200_dist_halo_counts(self.h, _p(out)))
         return out
+
+    def dist_vector(self, channel=0):
+        """Collective.  Device pointer (int) of full-layout vector `channel` of the symmetric arena, or None when the
+        peer-memory path is not available for the current plan (use an own buffer then)."""
+        ptr = C.c_void_p()
+        check(lib().cask_b200_dist_vector(self.h, channel, C.byref(ptr)))
+        return ptr.value
+
+    def spmv_shard(self, x_slice, y_slice=None):
+        """Collective.  Host buffers: this rank's slice of x in, its rows of y out."""
+        x_slice = np.ascontiguousarray(x_slice, np.float64)
+        y_slice = np.empty(len(x_slice), np.float64) if y_slice is None else y_slice
+        check(lib().cask_b200_spmv_shard(self.h, _p(x_slice), _p(y_slice)))
+        return y_slice
 
     def peer_active(self):
         a = C.c_int32()

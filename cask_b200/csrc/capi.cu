@@ -309,6 +309,17 @@ int cask_b200_spmv_device(cask_b200_ctx* ctx, const double* d_x, double* d_y) {
   if (!d_x || (!d_y && ctx->plan.n)) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "spmv: null vector");
   if (dist_active(ctx)) {
     // d_x is the full-layout vector (global length); halo entries are refreshed in place
+    const int ch = peer_channel_of(ctx, d_x);
+    if (ch >= 0 && peer_ready(ctx) && spmv_single_launch(ctx)) {
+      // x lives in the symmetric arena (cask_b200_dist_vector): boundary rows go straight into the neighbours' copies,
+      // then ONE persistent launch over all slices, interior first; its producer warp acquires the neighbours' epoch
+      // flags only when it reaches the first halo-dependent slice
+      CB_TRY(peer_push_acked(ctx, ch, ctx->stream));
+      const HaloWait hw = peer_halo_wait(ctx, ch);
+      SpmvFusion f;
+      f.pdl = true;
+      return launch_spmv(ctx, d_x, d_y, 0, ctx->stream, &f, &hw);
+    }
     CB_TRY(dist_exchange_begin(ctx, const_cast<double*>(d_x), ctx->stream));
     CB_TRY(launch_spmv(ctx, d_x, d_y, 1, ctx->stream, nullptr));
     CB_TRY(dist_exchange_wait(ctx, ctx->stream));
@@ -377,7 +388,7 @@ static int spmv_host_pipelined(cask_b200_ctx* ctx, const double* x, double* y) {
 
 int cask_b200_spmv(cask_b200_ctx* ctx, const double* x, double* y) {
   CB_TRY(check_spmv(ctx));
-  if (dist_active(ctx)) return fail(CASK_B200_ERR_UNSUPPORTED, "spmv (host buffers) is single-rank; use spmv_device when sharded");
+  if (dist_active(ctx)) return fail(CASK_B200_ERR_UNSUPPORTED, "spmv (host buffers, whole vectors) is single-rank; sharded: cask_b200_spmv_shard");
   const Plan& p = ctx->plan;
   if ((!x && p.m) || (!y && p.n)) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "spmv: null vector");
   // merge-path tiles cross slice boundaries, so the chunked pipeline (which launches slice ranges) is for plans without them
@@ -387,6 +398,37 @@ int cask_b200_spmv(cask_b200_ctx* ctx, const double* x, double* y) {
   if (p.n) CB_CUDA(cudaMemcpyAsync(y, ctx->d_y, sizeof(double) * p.n, cudaMemcpyDeviceToHost, ctx->stream));
   CB_CUDA(cudaStreamSynchronize(ctx->stream));
   return CASK_B200_OK;
+}
+
+int cask_b200_dist_vector(cask_b200_ctx* ctx, int32_t channel, double** d_vector) {
+  if (!ctx || !d_vector || !ctx->have_design) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "dist_vector: preprocess_shard first");
+  if (channel < 0 || channel >= kHaloChannels) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "dist_vector: channel is 0 or 1");
+  *d_vector = nullptr;
+  if (!dist_active(ctx)) return CASK_B200_OK;
+  CB_TRY(ensure_device(ctx));
+  CB_TRY(peer_ensure_arena(ctx, ctx->plan.m));  // collective
+  if (peer_ready(ctx) && spmv_single_launch(ctx)) *d_vector = peer_vector(ctx, channel);
+  return CASK_B200_OK;
+}
+
+int cask_b200_spmv_shard(cask_b200_ctx* ctx, const double* x_slice, double* y_slice) {
+  CB_TRY(check_spmv(ctx));
+  const Plan& p = ctx->plan;
+  if (!dist_active(ctx)) return cask_b200_spmv(ctx, x_slice, y_slice);
+  if (p.n_global != p.m) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "spmv_shard: x is sharded like the rows, the system must be square");
+  if ((!x_slice || !y_slice) && p.n) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "spmv: null vector");
+  double* full = nullptr;
+  CB_TRY(cask_b200_dist_vector(ctx, 0, &full));
+  if (!full) {  // NCCL path: an own full-layout buffer
+    CB_TRY(grow(&ctx->d_x, &ctx->d_x_len, p.m));
+    full = ctx->d_x;
+  }
+  CB_TRY(grow(&ctx->d_y, &ctx->d_y_len, p.n));
+  if (p.n) CB_CUDA(cudaMemcpyAsync(full + p.row0_global, x_slice, sizeof(double) * p.n, cudaMemcpyHostToDevice, ctx->stream));
+  CB_TRY(cask_b200_spmv_device(ctx, full, ctx->d_y));
+  if (p.n) CB_CUDA(cudaMemcpyAsync(y_slice, ctx->d_y, sizeof(double) * p.n, cudaMemcpyDeviceToHost, ctx->stream));
+  CB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return peer_check_error(ctx);
 }
 
 int cask_b200_spmv_refformat(cask_b200_ctx* ctx, const double* x, double* y) {

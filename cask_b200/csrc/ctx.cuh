@@ -171,6 +171,9 @@ struct PeerCtrl {
   // low-latency slots of the in-kernel all-reduce: [slot][source rank][quantity][half] = {32 data bits, 32-bit
   // sequence number} in ONE 8-byte store - data and flag arrive together, no fence, one NVLink traversal
   unsigned long long ar_ll[4][kMaxPeers][2][2];
+  // flow control of the plain sharded SpMV (dist.cu: halo_push_acked_kernel): [channel][rank q] = number of SpMVs on
+  // that channel rank q has FINISHED, i.e. the halo rows this rank pushed for them may be overwritten
+  unsigned long long halo_ack[kHaloChannels][kMaxPeers];
   // local
   unsigned long long ar_seq;                    // all-reduces performed
   unsigned long long push_seq[kHaloChannels];   // halo epochs pushed per channel (== the epoch the next SpMV expects)
@@ -187,6 +190,14 @@ struct PushDesc {       // by-value kernel argument of every kernel that produce
   double* dst[kMaxPush];               // peer's copy of the vector, rebased: dst[i] is its entry for local row i
   PeerCtrl* peer_ctrl[kMaxPush];       // that peer's control block
   PeerCtrl* ctrl = nullptr;            // this rank's control block
+};
+
+struct AckDesc {        // by-value kernel argument of the acknowledged halo push (plain sharded SpMV)
+  PeerCtrl* peers[kMaxPeers] = {nullptr};  // control blocks of all ranks
+  uint32_t send_mask = 0;          // ranks that stage rows of this rank's slice
+  int32_t me = 0, world = 1;
+  int32_t pad_ = 0;
+  unsigned long long want = 0;     // SpMVs this rank has finished on the channel (== the acknowledgement it waits for)
 };
 
 struct ReduceDesc {     // by-value kernel argument: the grid's last CTA finishes a dot product (and its all-reduce)
@@ -338,6 +349,8 @@ void peer_fill_reduce(cask_b200_ctx* ctx, ReduceDesc* rd);           // adds the
 HaloWait peer_halo_wait(cask_b200_ctx* ctx, int channel);
 HaloUpdate peer_halo_update(cask_b200_ctx* ctx, int channel);
 int peer_push(cask_b200_ctx* ctx, int channel, cudaStream_t stream); // standalone push of the channel's own slice
+int peer_push_acked(cask_b200_ctx* ctx, int channel, cudaStream_t stream);  // same, flow-controlled (plain sharded SpMV)
+int peer_channel_of(const cask_b200_ctx* ctx, const double* d_full); // arena vector index of a pointer, or -1
 int peer_allreduce_partials(cask_b200_ctx* ctx, const double* d_partials, int count, int stride, int nq, double* d_scal,
                             int slot0, const int32_t* d_skip0, const int32_t* d_skip1, cudaStream_t stream);
 int peer_check_error(cask_b200_ctx* ctx);

@@ -96,6 +96,7 @@ struct DistState {
   int64_t arena_len = 0;         // doubles per full-layout vector
   unsigned char* peer_base[kMaxPeers] = {nullptr};
   uint32_t recv_mask = 0;
+  unsigned long long acked_pushes[kHaloChannels] = {0};  // flow-controlled pushes launched per channel (same on every rank)
 };
 
 constexpr size_t kCtrlBytes = 4096;
@@ -111,6 +112,7 @@ static void peer_unmap(DistState* d) {
   d->arena_bytes = 0;
   d->arena_len = 0;
   d->peer_mapped = false;
+  for (auto& a : d->acked_pushes) a = 0;  // the control block (and its acknowledgement counters) went with the arena
 }
 
 bool dist_active(const cask_b200_ctx* ctx) { return ctx->dist && ctx->dist->world > 1; }
@@ -436,6 +438,30 @@ __global__ void __launch_bounds__(256) halo_push_kernel(const double* __restrict
   push_signal(pd);
 }
 
+// The plain sharded SpMV calls this before every launch.  Its halo rows live at fixed positions of the receiver's vector,
+// so epoch j may only be written once the receiver has finished the SpMV that read epoch j - 1: every rank first tells
+// ALL ranks how many SpMVs it has finished on the channel (stream order: the previous SpMV is complete when this kernel
+// runs), then waits for that acknowledgement from the ranks that stage its rows, then copies and signals.  Acks are sent
+// before any wait, so the ranks cannot deadlock; the waits carry the peer timeout.
+__global__ void __launch_bounds__(256) halo_push_acked_kernel(const double* __restrict__ own, const PushDesc pd, const AckDesc ad) {
+  if (threadIdx.x == 0) {
+    if (blockIdx.x == 0 && blockIdx.y == 0)
+      for (int q = 0; q < ad.world; q++)
+        if (q != ad.me) st_release_sys_u64(&ad.peers[q]->halo_ack[pd.channel][ad.me], ad.want);
+    if (ad.want)
+      for (int q = 0; q < ad.world; q++)
+        if (ad.send_mask & (1u << q)) peer_wait_ge(&pd.ctrl->halo_ack[pd.channel][q], ad.want, &pd.ctrl->error);
+  }
+  __syncthreads();
+  const int s = blockIdx.y;
+  if (s < pd.nsend) {
+    double* dst = pd.dst[s];
+    for (int64_t i = pd.lo[s] + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pd.hi[s]; i += (int64_t)gridDim.x * blockDim.x)
+      dst[i] = own[i];
+  }
+  push_signal(pd);
+}
+
 struct PeerCtrlPtrs { PeerCtrl* p[kMaxPeers]; };
 
 // Deterministic sum of per-CTA partials (index order) followed by a one-shot all-reduce over peer memory: every
@@ -501,6 +527,34 @@ int peer_push(cask_b200_ctx* ctx, int channel, cudaStream_t stream) {
   ctx->launches++;
   CB_CUDA(cudaGetLastError());
   return CASK_B200_OK;
+}
+
+int peer_push_acked(cask_b200_ctx* ctx, int channel, cudaStream_t stream) {
+  const PushDesc pd = peer_push_desc(ctx, channel);
+  if (pd.ctrl == nullptr) return fail(CASK_B200_ERR_RUNTIME, "acknowledged push needs the peer-memory path");
+  DistState* d = ctx->dist;
+  AckDesc ad;
+  for (int q = 0; q < kMaxPeers; q++) ad.peers[q] = q < d->world ? reinterpret_cast<PeerCtrl*>(d->peer_base[q]) : nullptr;
+  for (int q = 0; q < d->world; q++)
+    if (!d->send_to[q].empty()) ad.send_mask |= 1u << q;
+  ad.me = d->rank;
+  ad.world = d->world;
+  ad.want = d->acked_pushes[channel]++;
+  int64_t longest = 1;
+  for (int i = 0; i < pd.nsend; i++) longest = std::max(longest, pd.hi[i] - pd.lo[i]);
+  const dim3 grid((unsigned)std::min<int64_t>((longest + 255) / 256, 64), (unsigned)std::max(pd.nsend, 1));
+  halo_push_acked_kernel<<<grid, 256, 0, stream>>>(peer_vector(ctx, channel) + ctx->plan.row0_global, pd, ad);
+  ctx->launches++;
+  CB_CUDA(cudaGetLastError());
+  return CASK_B200_OK;
+}
+
+int peer_channel_of(const cask_b200_ctx* ctx, const double* d_full) {
+  if (!ctx->dist || !ctx->dist->peer_mapped || !d_full) return -1;
+  const DistState* d = ctx->dist;
+  for (int ch = 0; ch < kHaloChannels; ch++)
+    if (d_full == reinterpret_cast<const double*>(d->arena + kCtrlBytes + (size_t)ch * d->vec_stride)) return ch;
+  return -1;
 }
 
 int peer_allreduce_partials(cask_b200_ctx* ctx, const double* d_partials, int count, int stride, int nq, double* d_scal,

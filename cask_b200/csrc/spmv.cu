@@ -399,6 +399,17 @@ spmv_ell_persistent_kernel(const SliceDesc* __restrict__ slices, const int32_t* 
       const int row0 = hdr->meta[xb][0], nrows = hdr->meta[xb][1], L = hdr->meta[xb][2];
       const double* xs = xbuf + (size_t)xb * xbuf_doubles + zpre;
       double acc[RPT] = {0.0, 0.0, 0.0, 0.0};
+      // fused dot: this thread's four entries of dot_with are requested NOW and used after the slice's last column, so
+      // the HBM latency hides behind the column loop instead of stalling the consumers (and, through the full ring, the
+      // producer) at the end of every slice - on a 7-point stencil a slice is only ~3 us of streaming
+      double wv[RPT] = {0.0, 0.0, 0.0, 0.0};
+      if (kDot) {
+#pragma unroll
+        for (int j = 0; j < RPT; j++) {
+          const int row = j * kConsumerThreads + tid;
+          if (row < nrows) wv[j] = ld_keep(dot_with + row0 + row, keep_policy, keep);
+        }
+      }
       const int nchunks = (L + KU - 1) / KU;
       for (int c = 0; c < nchunks; c++, chunk_no++) {
         const int s = chunk_no % stages;
@@ -462,7 +473,7 @@ spmv_ell_persistent_kernel(const SliceDesc* __restrict__ slices, const int32_t* 
         if (row < nrows) {
           st_keep(y + row0 + row, acc[j], keep_policy, keep);
           if (kDot) {
-            dot += acc[j] * ld_keep(dot_with + row0 + row, keep_policy, keep);
+            dot += acc[j] * wv[j];
             if (self_dot) dot2 += acc[j] * acc[j];
           }
         }
@@ -964,7 +975,9 @@ int launch_spmv_range(cask_b200_ctx* ctx, const double* d_x, double* d_y, int el
       const int tile_items = kMergeThreads * p.merge_items;
       const size_t smem = sizeof(double) * tile_items + sizeof(int32_t) * (tile_items + 4);
       const int fix = (tiles + 255) / 256;
-      static const int x_past_l1 = getenv("CASK_B200_MERGE_XCG") ? atoi(getenv("CASK_B200_MERGE_XCG")) : 0;
+      // x gathers cached in L2 only: an L1 line per scattered 8-byte gather buys nothing (4 % sector hit rate) and costs
+      // the miss tracking the next gathers need; measured 3.25 vs 3.33 ms on R-MAT scale 25 (profiles/r2c_rmat_sweep.md)
+      static const int x_past_l1 = getenv("CASK_B200_MERGE_XCG") ? atoi(getenv("CASK_B200_MERGE_XCG")) : 1;
 #define CB_MERGE(DOT, ITEMS)                                                                                              \
   do {                                                                                                                    \
     CB_CUDA(cudaFuncSetAttribute(spmv_csr_merge_kernel<DOT, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \

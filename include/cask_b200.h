@@ -196,6 +196,19 @@ int cask_b200_dist_halo_counts(cask_b200_ctx* ctx, int64_t* recv_counts);
  * 0 if they use NCCL send/recv + all-reduce (option peer_mode = 0, irregular halo, or no IPC on this machine).
  * Meaningful after the first solver call that followed a preprocess_shard. */
 int cask_b200_dist_peer_active(cask_b200_ctx* ctx, int32_t* active);
+/* COLLECTIVE (every rank, after preprocess_shard).  Full-layout vector `channel` (0 or 1; m doubles, this rank's slice at
+ * [row0, row0 + nrows)) of the library's symmetric arena, the allocation every peer has mapped over NVLink.  A sharded
+ * caller that keeps x THERE gets the one-launch SpMV: cask_b200_spmv_device(ctx, that pointer, y) has the producer side
+ * store this rank's boundary rows straight into the neighbours' copies (flow-controlled by acknowledgements) and the
+ * persistent kernel acquire the neighbours' epoch flags when it reaches its first halo-dependent slice - no NCCL call, no
+ * second launch.  *d_vector = NULL (status OK) when the peer-memory path is not available for this plan (gather slices,
+ * irregular halo, no IPC, peer_mode 0): use an own buffer then, spmv_device exchanges it over NCCL.  The solvers use the
+ * same two vectors as scratch: the contents do not survive a cg / bicgstab call. */
+int cask_b200_dist_vector(cask_b200_ctx* ctx, int32_t channel, double** d_vector);
+/* Sharded counterpart of cask_b200_spmv (Spmv::spmv(const Vector&), Spmv.cpp:185-328, where the reference writes x to
+ * every pipe itself, :165-170,234-258): host buffers, x_slice = the nrows entries of x this rank owns (needs a square
+ * system), y_slice = its nrows results; the x exchange with the neighbours happens inside.  Collective. */
+int cask_b200_spmv_shard(cask_b200_ctx* ctx, const double* x_slice, double* y_slice);
 
 /* ---- Matrix Market ingest: file -> CSR on the device ------------------------- */
 /* Replaces io::readHeader / readDokMatrix / readMatrix / readSymMatrix / readVector (src/runtime/IO.hpp:60-176) and

@@ -55,6 +55,29 @@ for name, gen, N in (("poisson2d", O.gen_poisson2d, 96), ("poisson3d27", O.gen_p
     got = y.cpu().numpy()
     scale = np.maximum(np.abs(exp), 1e-300)
     out[name] = {"spmv_max_rel": float((np.abs(got - exp) / np.maximum(scale, 1.0)).max()), "bitexact": bool(np.array_equal(got, exp)), "halo": halo}
+    # sharded host-buffer call (Spmv::spmv(const Vector&) per rank): own slice of x in, own rows of y out
+    ys = ctx.spmv_shard(x[r0:r0 + nr])
+    out[name]["shard_host_bitexact"] = bool(np.array_equal(ys, got))
+    # x kept in the library's symmetric arena: one launch per SpMV (+ the boundary-row push), no NCCL call; x changes
+    # on every call, so epoch k + 1 of a neighbour's rows must not land before this rank's SpMV k has read epoch k
+    ptr = ctx.dist_vector(0)
+    out[name]["arena"] = ptr is not None
+    if ptr is not None:
+        class Holder:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+        xa = torch.as_tensor(Holder(), device=dev)
+        ys_dev, l0 = [], ctx.launch_count()
+        for rep in range(5):
+            xr = np.random.default_rng(100 + rep).random(n)
+            xa.zero_()
+            xa[r0:r0 + nr] = torch.tensor(xr[r0:r0 + nr], device=dev)
+            yy = torch.empty(nr, dtype=torch.float64, device=dev)
+            ctx.spmv_device(ptr, yy.data_ptr())
+            ys_dev.append((xr, yy))
+        ctx.synchronize()
+        out[name]["arena_launches_per_spmv"] = (ctx.launch_count() - l0) / 5.0
+        out[name]["arena_ok"] = all(bool(np.array_equal(yy.cpu().numpy(), O.csr_dot(n, rp, ci, va, xr)[r0:r0 + nr])) for xr, yy in ys_dev) \
+            if name != "rmat" else None
     if name != "rmat":
         xt = 1.0 + 0.25 * (np.arange(n) %% 4)
         b = O.csr_dot(n, rp, ci, va, xt)
@@ -111,6 +134,10 @@ def test_sharded_spmv_and_solvers(world, peer, tmp_path):
         assert sum(r["halo"]) > 0 and r["halo"][0] == 0   # rank 0 receives only from its neighbour(s)
         assert r["cg_conv"] and abs(r["cg_it"] - r["oracle_it"]) <= 1 and r["cg_err"] < 1e-6, r
         assert r["peer"] == bool(peer) and r["cg_repeat_same"], r
+        assert r["shard_host_bitexact"], r
+        assert r["arena"] == bool(peer), r           # the arena vector is offered exactly when the peer path can run
+        if peer:
+            assert r["arena_ok"] and r["arena_launches_per_spmv"] == 2.0, r
     assert res["bicgstab"]["peer"] == bool(peer), res["bicgstab"]
     assert res["rmat"]["spmv_max_rel"] < 1e-12, res["rmat"]
     bi = res["bicgstab"]
