@@ -763,7 +763,7 @@ def main():
         if bicg:
             details["bicgstab"] = bicg
             line["bicgstab"] = compact(bicg, ("iters_per_s", "iterations", "converged", "rel_residual", "max_abs_err_vs_ones",
-                                              "gpu_launches", "timed", "roofline", "error"))
+                                              "gpu_launches", "timed", "roofline", "clocks", "error"))
         if rmat:
             details["rmat"] = rmat
             line["rmat"] = compact(rmat, ("ms_per_spmv", "gflops", "nnz", "kernel", "l2_hit_rate_on_x_pct", "max_err_all_rows_rel_to_sum_abs",
@@ -918,10 +918,15 @@ def bench_bicgstab(ctx, cb, torch, dist, dev, rank, world, barrier, cap=4000):
     # DBL_EPSILON is unreachable in practice), iteration cap 4000
     tol = 1e-10
     l0 = ctx.launch_count()
+    sampler = ClockSampler(torch.cuda.current_device())
+    if rank == 0:
+        sampler.start()
+    t_wall0 = time.time()
     t0 = time.perf_counter()
     its, err = ctx.bicgstab_device(b.data_ptr(), x.data_ptr(), tol=tol, maxit=cap)
     barrier()
     dt = time.perf_counter() - t0
+    clocks = sampler.stop(t_wall0, time.time()) if rank == 0 else None
     tt = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -946,7 +951,7 @@ def bench_bicgstab(ctx, cb, torch, dist, dev, rank, world, barrier, cap=4000):
             "scaling": "strong", "iters_per_s": its / dt, "iterations": its, "converged": bool(err <= tol), "tol": tol,
             "rel_residual": err, "seconds": dt, "timed": "whole solve to ||r|| <= 1e-10 ||b|| (cap %d)" % cap,
             "max_abs_err_vs_ones": float(e.item()), "spmv_per_iteration": 2, "vector_streams_per_iteration": streams,
-            "gpu_launches": launches, "roofline": roof}
+            "gpu_launches": launches, "roofline": roof, "clocks": clocks}
 
 
 def bench_rmat(ctx, cb, torch, dist, dev, rank, world, barrier, scale=25, edge_factor=15):
@@ -954,7 +959,6 @@ def bench_rmat(ctx, cb, torch, dist, dev, rank, world, barrier, scale=25, edge_f
     duplicates merged, rows sorted by column; generated on the device with torch (bench-side synthetic data),
     row-sharded; y = A x with x gathered through L2 (irregular rows -> vector-per-row kernels)."""
     n = 1 << scale
-    r0, nr = cb.shard_rows(n, world, rank)
     g = torch.Generator(device=dev)
     g.manual_seed(1)
     E = edge_factor << scale
@@ -970,11 +974,28 @@ def bench_rmat(ctx, cb, torch, dist, dev, rank, world, barrier, scale=25, edge_f
             cbit = (((u >= 0.57) & (u < 0.76)) | (u >= 0.95)).to(torch.int64)  # quadrants b, d
             row = row * 2 + rb
             col = col * 2 + cbit
-        keep = (row >= r0) & (row < r0 + nr)
-        keys.append(((row[keep] - r0) << scale) | col[keep])
-        del row, col, u, rb, cbit, keep
+        keys.append((row << scale) | col)                          # every rank draws the same edge list (same seed)
+        del row, col, u, rb, cbit
     key = torch.cat(keys)
     del keys
+    # Row stripes.  One GPU: everything.  Sharded: stripes of (nearly) equal NONZERO count, cut at multiples of 1024 rows
+    # from the edge histogram - under the reference's equal-row rule (Spmv.cpp:334) rank 0 of 8 would own 0.76^3 = 44 % of
+    # this matrix and bound the whole job; the library takes any contiguous partition (cask_b200_preprocess_shard_device)
+    if world > 1:
+        hist = torch.bincount(key >> (scale + 10), minlength=n >> 10).double()
+        cum = torch.cumsum(hist, 0)
+        targets = cum[-1] * torch.arange(1, world, device=dev, dtype=torch.float64) / world
+        cuts = (torch.searchsorted(cum, targets) + 1).clamp(max=n >> 10) << 10
+        bounds = [0] + [int(c) for c in cuts.tolist()] + [n]
+        for i in range(1, len(bounds)):
+            bounds[i] = max(bounds[i], bounds[i - 1])
+        r0, nr = bounds[rank], bounds[rank + 1] - bounds[rank]
+        del hist, cum
+    else:
+        r0, nr = 0, n
+    keep = ((key >> scale) >= r0) & ((key >> scale) < r0 + nr)
+    key = key[keep] - (r0 << scale)
+    del keep
     key = torch.unique(key, sorted=True)
     nnz = int(key.numel())
     rows_l = (key >> scale)
@@ -1047,6 +1068,7 @@ def bench_rmat(ctx, cb, torch, dist, dev, rank, world, barrier, scale=25, edge_f
             "algorithmic_gbs": algorithmic_bytes(nnz_total, n, n) / (ms * 1e-3) / 1e9, "preprocess_s": prep,
             "kernel": kernel, "l2_hit_rate_on_x_pct": l2, "roofline": roof,
             "nnz_share_max_rank": float(share.item()) / nnz_total,
+            "stripes": "one" if world == 1 else "equal nonzero count, cut at multiples of 1024 rows (rows of this rank: %d)" % nr,
             "max_rel_diff_256_sampled_rows": rel, "max_err_all_rows_rel_to_sum_abs": rel_all,
             "plan": {k: stats[k] for k in ("slices_staged_ell", "slices_gather_csr", "csr_lanes_per_row", "max_row_length",
                                            "row_length_histogram", "csr_items", "csr_kernel")}}

@@ -97,6 +97,9 @@ struct DistState {
   unsigned char* peer_base[kMaxPeers] = {nullptr};
   uint32_t recv_mask = 0;
   unsigned long long acked_pushes[kHaloChannels] = {0};  // flow-controlled pushes launched per channel (same on every rank)
+  // first row of every rank's stripe (+ n_global): the reference rule rows_per = n / world (Spmv.cpp:334-364) unless the
+  // caller handed preprocess_shard another contiguous partition (e.g. stripes of equal nonzero count for a power-law matrix)
+  std::vector<int64_t> bounds;
 };
 
 constexpr size_t kCtrlBytes = 4096;
@@ -138,10 +141,15 @@ static void stripe_of(int64_t n, int world, int r, int64_t* row0, int64_t* nrows
 // Pure host arithmetic (no CUDA, no NCCL; exported as cask_b200_halo_plan_host and exercised by the world-size-2
 // gloo tests on CPU): the x windows (runs) this rank stages, clipped to the columns it does NOT own, merged, and
 // split by owner according to the reference's row striping.  Returns the number of (peer, range) pairs.
+static void owner_range(const int64_t* bounds, int64_t n_global, int world, int q, int64_t* q0, int64_t* qn) {
+  if (bounds) { *q0 = bounds[q]; *qn = bounds[q + 1] - bounds[q]; }
+  else stripe_of(n_global, world, q, q0, qn);
+}
+
 static int64_t halo_ranges_from_runs(int64_t n_global, int world, int me, const int64_t* run_col0, const int64_t* run_len,
-                                     int64_t nruns, std::vector<std::vector<Range>>* recv_from) {
+                                     int64_t nruns, std::vector<std::vector<Range>>* recv_from, const int64_t* bounds = nullptr) {
   int64_t own_lo, own_n;
-  stripe_of(n_global, world, me, &own_lo, &own_n);
+  owner_range(bounds, n_global, world, me, &own_lo, &own_n);
   const int64_t own_hi = own_lo + own_n;
   std::vector<Range> remote;
   for (int64_t i = 0; i < nruns; i++) {
@@ -163,7 +171,7 @@ static int64_t halo_ranges_from_runs(int64_t n_global, int world, int me, const 
     int64_t lo = r.col0, hi = r.col0 + r.len;
     for (int q = 0; q < world && lo < hi; q++) {
       int64_t q0, qn;
-      stripe_of(n_global, world, q, &q0, &qn);
+      owner_range(bounds, n_global, world, q, &q0, &qn);
       const int64_t a = std::max(lo, q0), b = std::min(hi, q0 + qn);
       if (a < b && q != me) { (*recv_from)[q].push_back({a, b - a}); nranges++; }
     }
@@ -183,6 +191,21 @@ int dist_plan_halo(cask_b200_ctx* ctx) {
   d->recv_from.assign(W, {});
   d->send_to.assign(W, {});
   const int64_t own_lo = p.row0_global, own_hi = p.row0_global + p.n;
+  {
+    // every rank's first row: the partition the callers chose (contiguous, in rank order, covering all rows)
+    int64_t* d_b = nullptr;
+    CB_CUDA(cudaMalloc(&d_b, sizeof(int64_t) * (size_t)(W + 1)));
+    CB_CUDA(cudaMemcpyAsync(d_b + W, &own_lo, sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    CB_NCCL(g_nccl.AllGather(d_b + W, d_b, 1, kNcclInt64, d->comm_halo, s));
+    d->bounds.assign((size_t)W + 1, 0);
+    CB_CUDA(cudaMemcpyAsync(d->bounds.data(), d_b, sizeof(int64_t) * (size_t)W, cudaMemcpyDeviceToHost, s));
+    CB_CUDA(cudaStreamSynchronize(s));
+    cudaFree(d_b);
+    d->bounds[W] = p.n_global;
+    bool ok = d->bounds[0] == 0 && d->bounds[me + 1] == own_hi;
+    for (int q = 0; q < W; q++) ok = ok && d->bounds[q] <= d->bounds[q + 1];
+    if (!ok) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "preprocess_shard: the ranks' row ranges must be contiguous, in rank order, and cover all rows");
+  }
 
   // runs of all staged slices
   int total_runs = 0;
@@ -202,7 +225,7 @@ int dist_plan_halo(cask_b200_ctx* ctx) {
   std::vector<int64_t> run_col0(runs.size()), run_len(runs.size());
   for (size_t i = 0; i < runs.size(); i++) { run_col0[i] = runs[i].col0; run_len[i] = runs[i].len; }
   const int64_t nranges = halo_ranges_from_runs(p.n_global, W, me, run_col0.data(), run_len.data(), (int64_t)runs.size(),
-                                                &d->recv_from);
+                                                &d->recv_from, d->bounds.data());
   bool want_allgather = p.n_csr > 0 || nranges > 512;
   // agree on the mode and exchange the request lists through NCCL itself
   int64_t* d_buf = nullptr;
@@ -590,11 +613,11 @@ int dist_exchange_begin(cask_b200_ctx* ctx, double* d_full, cudaStream_t after) 
   CB_NCCL(g_nccl.GroupStart());
   if (d->allgather) {
     int64_t my0, myn;
-    stripe_of(p.n_global, W, me, &my0, &myn);
+    owner_range(d->bounds.data(), p.n_global, W, me, &my0, &myn);
     for (int q = 0; q < W; q++) {
       if (q == me) continue;
       int64_t q0, qn;
-      stripe_of(p.n_global, W, q, &q0, &qn);
+      owner_range(d->bounds.data(), p.n_global, W, q, &q0, &qn);
       if (myn) CB_NCCL(g_nccl.Send(d_full + my0, (size_t)myn, kNcclFloat64, q, d->comm_halo, cs));
       if (qn) CB_NCCL(g_nccl.Recv(d_full + q0, (size_t)qn, kNcclFloat64, q, d->comm_halo, cs));
     }
@@ -695,7 +718,7 @@ extern "C" int cask_b200_dist_halo_counts(cask_b200_ctx* ctx, int64_t* recv_coun
     int64_t c = 0;
     if (d->allgather) {
       int64_t q0, qn;
-      stripe_of(d->n_global, d->world, q, &q0, &qn);
+      owner_range(d->bounds.empty() ? nullptr : d->bounds.data(), d->n_global, d->world, q, &q0, &qn);
       c = q == d->rank ? 0 : qn;
     } else if (q < (int)d->recv_from.size()) {
       for (auto& r : d->recv_from[q]) c += r.len;

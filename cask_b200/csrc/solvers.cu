@@ -239,16 +239,21 @@ cg_update_p_kernel(int64_t n, int it, double* __restrict__ scal, int32_t* __rest
 // r it received and the old halo rows of p (same arithmetic as the owner, bit-identical).  The NVLink transfer is
 // thereby off the critical path: it overlaps the all-reduce, and the following SpMV needs no halo wait at all.
 // The grid (<= 2 CTAs per SM) is resident as a whole, which the barrier relies on.
+// KEEP is a compile-time switch on purpose: with a run-time flag every load and store of the loops exists twice in the
+// SASS under complementary predicates (with / without the L2 cache hint), and the predicated-off twins still take their
+// turn in the load/store instruction queue - ncu showed "LG throttle" as the top stall and 2.9 TB/s on 72 n bytes
+// (profiles/r2c_cg_iteration_ncu.md) where the same loop without twins streams 6.1 TB/s (profiles/r2d_stream_bench.txt).
+template <bool KEEP>
 __global__ void __launch_bounds__(kVecThreads, kVecCtasPerSm)
 cg_update_fused_kernel(int64_t n, int it, double* __restrict__ scal, int32_t* __restrict__ flags, double* p,
                        const double* __restrict__ Ap, double* __restrict__ x, double* r, const __grid_constant__ ReduceDesc rd,
-                       const PushDesc pd, const HaloUpdate hu, const GatherDesc pap, int keep_i, unsigned long long* trace) {
+                       const PushDesc pd, const HaloUpdate hu, const GatherDesc pap, unsigned long long* trace) {
   trace_min(trace);
   pdl_enter();
   trace_min(trace ? trace + 1 : nullptr);
   if (flags[F_DONE]) return;
   __shared__ double red[kVecThreads / 32];
-  const bool keep = keep_i != 0;  // the vectors fit L2: evict-last on every access (peer.cuh: L2 residency control)
+  constexpr bool keep = KEEP;  // the vectors fit L2: evict-last on every access (peer.cuh: L2 residency control)
   const unsigned long long pol = l2_policy_evict_last();
   const unsigned int gen0 = *reinterpret_cast<volatile unsigned int*>(rd.gen);
   const double rsold = scal[S_RS0 + (it & 1)];
@@ -613,7 +618,7 @@ int prefer_max_shared() {
   CB_CUDA(cudaGetDevice(&dev));
   if (done_for_device == dev) return CASK_B200_OK;
 #define CB_CARVE(k) CB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))
-  CB_CARVE(cg_init_kernel); CB_CARVE(cg_update_xr_kernel); CB_CARVE(cg_update_p_kernel); CB_CARVE(cg_update_fused_kernel);
+  CB_CARVE(cg_init_kernel); CB_CARVE(cg_update_xr_kernel); CB_CARVE(cg_update_p_kernel); CB_CARVE(cg_update_fused_kernel<false>); CB_CARVE(cg_update_fused_kernel<true>);
   CB_CARVE(bicg_residual_kernel); CB_CARVE(dot2_kernel); CB_CARVE(bicg_head_kernel); CB_CARVE(bicg_p_kernel);
   CB_CARVE(bicg_s_kernel); CB_CARVE(bicg_xr_kernel); CB_CARVE(bicg_tail_kernel); CB_CARVE(bicg_restart_scalars_kernel);
   CB_CARVE(reduce_partials_kernel); CB_CARVE(jacobi_diag_kernel);
@@ -781,7 +786,10 @@ extern "C" int cask_b200_cg_device(cask_b200_ctx* ctx, const double* d_rhs, doub
     // a timeout (peer.cuh: grid_finish_reduce traps after kPeerTimeoutNs), so SMs taken by another stream of the
     // process surface as a CUDA error on the host instead of a hung GPU.
     int resident = 0;
-    CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, cg_update_fused_kernel, kVecThreads, 0));
+    CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, cg_update_fused_kernel<false>, kVecThreads, 0));
+    int resident_keep = 0;
+    CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident_keep, cg_update_fused_kernel<true>, kVecThreads, 0));
+    resident = std::min(resident, resident_keep);
     if ((int64_t)resident * ctx->sm_count < vec_grid(ctx, n)) {
       if (peer) return fail(CASK_B200_ERR_RUNTIME, "cg: the fused update kernel's grid cannot be co-resident on this device");
       fused = false;  // two kernels (update_xr, update_p) with the reduction between them: no barrier needed
@@ -860,8 +868,12 @@ extern "C" int cask_b200_cg_device(cask_b200_ctx* ctx, const double* d_rhs, doub
         rd.gen = w.d_tickets + T_GEN;
         GatherDesc gd;
         if (publish) { gd.ctrl = rd.ctrl; gd.world = rd.world; }
-        CB_CUDA(launch_pdl(cg_update_fused_kernel, vg, kVecThreads, s, n, it, scal, flags, p, Ap, d_x, r, rd, pd_r, hu, gd,   // :208-231
-                           keep, tr ? tr + 3 : nullptr));
+        if (keep)
+          CB_CUDA(launch_pdl(cg_update_fused_kernel<true>, vg, kVecThreads, s, n, it, scal, flags, p, Ap, d_x, r, rd, pd_r, hu, gd,   // :208-231
+                             tr ? tr + 3 : nullptr));
+        else
+          CB_CUDA(launch_pdl(cg_update_fused_kernel<false>, vg, kVecThreads, s, n, it, scal, flags, p, Ap, d_x, r, rd, pd_r, hu, gd,
+                             tr ? tr + 3 : nullptr));
         ctx->launches += 1;
       } else {  // NCCL between the two halves
         CB_CUDA(launch_pdl(cg_update_xr_kernel, vg, kVecThreads, s, n, it, scal, flags, p, Ap, d_x, r,   // :208-218

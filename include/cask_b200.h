@@ -183,7 +183,10 @@ int cask_b200_halo_plan_host(int64_t n_global, int32_t world, int32_t rank, int6
                              const int64_t* run_len, int64_t capacity, int32_t* out_peer, int64_t* out_col0,
                              int64_t* out_len, int64_t* out_count);
 /* Local stripe of the global n x m matrix: d_row_ptr has nrows+1 entries rebased to 0 (exactly
- * CsrMatrix::sliceRows, SparseMatrix.hpp:426-443), column indices stay global. */
+ * CsrMatrix::sliceRows, SparseMatrix.hpp:426-443), column indices stay global.  Collective.  The ranks' row ranges must be
+ * contiguous, in rank order and cover all rows; cask_b200_shard_rows gives the reference's partition (equal row counts),
+ * but any other is accepted - a power-law matrix is better cut into stripes of equal NONZERO count (bench.py does that
+ * for R-MAT: under the reference rule rank 0 of 8 owns 44 % of the nonzeros).  Vectors are sharded like the rows. */
 int cask_b200_preprocess_shard_device(cask_b200_ctx* ctx, const cask_b200_design* design,
                                       int64_t n_global, int64_t m, int64_t row0, int64_t nrows,
                                       int64_t nnz_local, const int32_t* d_row_ptr,
