@@ -105,6 +105,7 @@ int cask_b200_create(cask_b200_ctx** out, int device) {
   if (const char* e = getenv("CASK_B200_CSR_STREAM")) ctx->csr_stream = atoi(e);
   if (const char* e = getenv("CASK_B200_CSR_ITEM_NNZ")) ctx->csr_item_nnz = atoi(e);
   if (const char* e = getenv("CASK_B200_CSR_KERNEL")) ctx->csr_kernel = atoi(e);
+  if (const char* e = getenv("CASK_B200_L2_KEEP")) ctx->l2_keep = atoi(e);
   if (const char* e = getenv("CASK_B200_MERGE_ITEMS")) ctx->merge_items = atoi(e);
   if (const char* e = getenv("CASK_B200_VALUE_DICT")) ctx->value_dict = atoi(e);
   if (const char* e = getenv("CASK_B200_PERSIST_CTAS")) ctx->persist_ctas = atoi(e);

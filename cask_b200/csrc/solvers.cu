@@ -795,18 +795,21 @@ extern "C" int cask_b200_cg_device(cask_b200_ctx* ctx, const double* d_rhs, doub
       fused = false;  // two kernels (update_xr, update_p) with the reduction between them: no barrier needed
     }
   }
-  // x, r, p, Ap of this rank fit L2 (with room for the matrix stream): keep them there (peer.cuh: L2 residency control)
-  // evict-last lines live in the persisting set-aside of L2, which is 0 by default: claim the device maximum once
-  if (ctx->l2_persist_bytes < 0) {
-    int max_persist = 0;
-    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
-    if (max_persist > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist) != cudaSuccess) {
-      cudaGetLastError();
-      max_persist = 0;
-    }
-    ctx->l2_persist_bytes = max_persist;
+  // x, r, p, Ap of this rank fit L2 (with room for the matrix stream): keep them there (peer.cuh: L2 residency control).
+  // evict-last lines live in the persisting set-aside of L2, which is 0 by default.  The set-aside is a device-wide carve-out
+  // of the cache that every kernel of the process then runs with, so it is claimed ONLY for a solve that will use it and
+  // given back otherwise: round 1 claimed the maximum once per context, and the BiCGStab solve that followed a CG solve in
+  // the same process lost a third of its rate to the smaller normal L2 (84 vs 127 iterations/s on C5, profiles/r2e_*).
+  int max_persist = 0;
+  cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+  const bool fits = max_persist > 0 && 4 * sizeof(double) * (size_t)n <= (size_t)max_persist;
+  const int keep = ctx->l2_keep < 0 ? (fits ? 1 : 0) : (ctx->l2_keep && max_persist > 0 ? 1 : 0);
+  const int64_t want_persist = keep ? max_persist : 0;
+  if (ctx->l2_persist_bytes != want_persist) {
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)want_persist) != cudaSuccess) cudaGetLastError();
+    if (!want_persist) cudaCtxResetPersistingL2Cache();  // lines kept by an earlier solve become ordinary lines again
+    ctx->l2_persist_bytes = want_persist;
   }
-  const int keep = ctx->l2_keep < 0 ? (4 * sizeof(double) * (size_t)n <= (size_t)ctx->l2_persist_bytes ? 1 : 0) : ctx->l2_keep;
   if (getenv("CASK_B200_TRACE")) fprintf(stderr, "cask_b200: L2 persisting set-aside %lld bytes, keep=%d\n", (long long)ctx->l2_persist_bytes, keep);
   const PushDesc pd_r = peer_push_desc(ctx, 1);
   const HaloUpdate hu = peer_halo_update(ctx, 1);
@@ -917,6 +920,11 @@ extern "C" int cask_b200_cg_device(cask_b200_ctx* ctx, const double* d_rhs, doub
   if (converged) *converged = hf[F_CONVERGED];
   if (loop_trips) *loop_trips = hf[F_TRIPS];
   if (rs_final) *rs_final = w.h_scalars[S_RS_FINAL];
+  if (ctx->l2_persist_bytes > 0) {  // the solve is over (stream synchronised above): the rest of the process gets its L2 back
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0) != cudaSuccess) cudaGetLastError();
+    cudaCtxResetPersistingL2Cache();
+    ctx->l2_persist_bytes = 0;
+  }
   return peer_check_error(ctx);
 }
 

@@ -1,15 +1,18 @@
 #!/bin/bash
 # Multi-GPU evidence session (one box, N GPUs; charged N x the box time - keep it short):
 #
-#   /usr/local/graft/bin/gpurun --gpus 8 --timeout 1500 -- 'bash profiles/gpu_session_multi.sh r2 8'
+#   /usr/local/graft/bin/gpurun --gpus 8 --timeout 1500 -- 'bash profiles/gpu_session_multi.sh r2 8 full'
+#   /usr/local/graft/bin/gpurun --gpus 2 --timeout 900  -- 'bash profiles/gpu_session_multi.sh r2 2 quick'
 #
-# Writes under gpurun_out/<tag>_*: the 2-rank GPU tests (tests/test_gpu_dist.py), bench.py at N = 1, 2, 4 ... <gpus>
-# (C2 SpMV weak scaling + C4 CG / C5 BiCGStab / C3 SpMV strong scaling in the same line), the same CG solve on the NCCL
-# path (peer_mode 0) for an A/B of the peer-memory layer, and the in-situ kernel timeline of the CG loop on every rank
+# Writes under gpurun_out/<tag>_*: the multi-rank GPU tests (tests/test_gpu_dist.py: world 2 on both paths, 4 and 8 as
+# the box allows), bench.py at N = 1, 2, 4 ... <gpus> with the driver's flags (C2 SpMV weak scaling + C4 CG / C5 BiCGStab /
+# C3 SpMV strong scaling in the same line), and in `full` mode the reference arm at every N, the same run on the NCCL path
+# (peer_mode 0) for an A/B of the peer-memory layer, and the in-situ kernel timeline of the CG loop on every rank
 # (CASK_B200_TRACE; ncu cannot follow a multi-rank job) summarised by profiles/trace_summary.py.
 # Every step has its own timeout; nothing here runs under a profiler, so the numbers are bench values.
 TAG=${1:-multi}
 GPUS=${2:-8}
+MODE=${3:-full}
 OUT=gpurun_out
 mkdir -p $OUT
 PY=python
@@ -17,47 +20,55 @@ PORT=29517
 run() {  # run <n> <outfile> <bench args...>
   local n=$1 out=$2; shift 2
   if [ "$n" = 1 ]; then
-    timeout 900 $PY bench.py --gpus 1 "$@" > $out 2> ${out%.json}.err
+    CASK_B200_BENCH_DETAILS=${out%.json}_details.json timeout 900 $PY bench.py --gpus 1 "$@" > $out 2> ${out%.json}.err
   else
-    timeout 900 $PY -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $PORT \
+    CASK_B200_BENCH_DETAILS=${out%.json}_details.json timeout 900 $PY -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $PORT \
       bench.py --gpus $n "$@" > $out 2> ${out%.json}.err
     PORT=$((PORT + 1))
   fi
-  tail -c 400 $out; echo
+  tail -c 300 ${out%.json}.err | grep -v Warning | tail -3
 }
 step() { echo "== $1 ($(date +%T))"; }
 
-step "2-rank GPU tests"
-timeout 900 $PY -m pytest tests/test_gpu_dist.py -x -q > $OUT/${TAG}_pytest_dist.log 2>&1; tail -3 $OUT/${TAG}_pytest_dist.log
+step "multi-rank GPU tests"
+timeout 1200 $PY -m pytest tests/test_gpu_dist.py -q -rs > $OUT/${TAG}_pytest_dist.log 2>&1; tail -6 $OUT/${TAG}_pytest_dist.log
 
-N=1
-while [ $N -le $GPUS ]; do
+if [ "$MODE" = quick ]; then NS="$GPUS"; else NS=""; N=1; while [ $N -le $GPUS ]; do NS="$NS $N"; N=$((N * 2)); done; fi
+for N in $NS; do
   step "bench.py at N=$N"
-  run $N $OUT/${TAG}_bench_n$N.json --no-cpu
-  N=$((N * 2))
+  if [ "$MODE" = full ]; then run $N $OUT/${TAG}_bench_reference_n$N.json --impl reference --steps 20 --warmup 5 --no-cg; fi
+  run $N $OUT/${TAG}_bench_n$N.json --steps 20 --warmup 5 --no-cpu --no-probe
 done
 
-step "C4 CG at N=$GPUS on the NCCL path (peer_mode 0) for the A/B"
-CASK_B200_PEER=0 run $GPUS $OUT/${TAG}_bench_n${GPUS}_nccl.json --no-cpu --no-extra --steps 50 --soak 100
-
-step "CG kernel timeline at N=$GPUS (peer path)"
-CASK_B200_TRACE=$OUT/${TAG}_trace_rank run $GPUS $OUT/${TAG}_bench_n${GPUS}_trace.json --no-cpu --no-extra --steps 20 --soak 0
-$PY profiles/trace_summary.py $OUT/${TAG}_trace_rank > $OUT/${TAG}_trace_summary.txt 2>&1; head -30 $OUT/${TAG}_trace_summary.txt
+if [ "$MODE" = full ]; then
+  step "N=$GPUS on the NCCL path (peer_mode 0) for the A/B"
+  CASK_B200_PEER=0 run $GPUS $OUT/${TAG}_bench_n${GPUS}_nccl.json --no-cpu --no-probe --steps 20 --warmup 5 --bicg-cap 300
+  step "CG kernel timeline at N=$GPUS (peer path)"
+  CASK_B200_TRACE=$OUT/${TAG}_trace_rank run $GPUS $OUT/${TAG}_bench_n${GPUS}_trace.json --no-cpu --no-extra --no-probe --steps 20 --soak 0
+  $PY profiles/trace_summary.py $OUT/${TAG}_trace_rank > $OUT/${TAG}_trace_summary.txt 2>&1; head -30 $OUT/${TAG}_trace_summary.txt
+fi
 
 step "scaling table"
-$PY - <<PYEOF
-import json, glob, re
+$PY - <<PYEOF | tee $OUT/${TAG}_scaling_table.md
+import json, glob
 rows = []
 for f in sorted(glob.glob("$OUT/${TAG}_bench_n*.json")):
+    if "reference" in f:
+        continue
     try:
         d = json.loads(open(f).read().strip().splitlines()[-1])
     except Exception as e:
         print(f, "unreadable:", e); continue
-    cg = d.get("cg") or {}
-    print("%-40s N=%d  SpMV %.0f GFLOP/s (%.3f ms)  e2e %.1f GFLOP/s  CG %s it/s (peer %s)  BiCGStab %s it/s  R-MAT %s ms" % (
-        f.split("/")[-1], d["n_gpus"], d["value"], d["ms_per_step"], d["e2e"]["value"],
-        "%.0f" % cg["iters_per_s"] if "iters_per_s" in cg else cg.get("error"), cg.get("peer_memory_path"),
-        "%.1f" % d["bicgstab"]["iters_per_s"] if "iters_per_s" in (d.get("bicgstab") or {}) else (d.get("bicgstab") or {}).get("error"),
-        "%.2f" % d["rmat_spmv"]["ms_per_spmv"] if "ms_per_spmv" in (d.get("rmat_spmv") or {}) else (d.get("rmat_spmv") or {}).get("error")))
+    rows.append((f.split("/")[-1], d))
+print("| run | N | SpMV GFLOP/s | ms/step | launches/step | e2e GFLOP/s | CG it/s (us/it) | BiCGStab it/s (its) | R-MAT ms | R-MAT max nnz share |")
+print("|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|")
+for name, d in rows:
+    cg, bi, rm = d.get("cg") or {}, d.get("bicgstab") or {}, d.get("rmat") or {}
+    print("| %s | %d | %.0f | %.4f | %.1f | %.1f | %s | %s | %s | %s |" % (
+        name, d["n_gpus"], d["value"], d["ms_per_step"], d["gpu_launches"] / max(d["steps"], 1), d["e2e"]["value"],
+        "%.0f (%s)" % (cg["iters_per_s"], "%.0f" % cg["us_per_iteration_marginal"] if cg.get("us_per_iteration_marginal") else "-") if "iters_per_s" in cg else cg.get("error"),
+        "%.1f (%s)" % (bi["iters_per_s"], bi.get("iterations")) if "iters_per_s" in bi else bi.get("error"),
+        "%.3f" % rm["ms_per_spmv"] if "ms_per_spmv" in rm else rm.get("error"),
+        "%.3f" % rm["nnz_share_max_rank"] if "nnz_share_max_rank" in rm else "-"))
 PYEOF
 step "done"

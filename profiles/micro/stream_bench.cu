@@ -71,6 +71,88 @@ __global__ void __launch_bounds__(256) k_vec2(int64_t n, double alpha, const dou
   if (acc == 123.456) part[blockIdx.x] = acc;
 }
 
+// (d) the fused CG update as the product runs it: phase 1 (x, r, r.r), grid barrier, phase 2 (p = r + beta p), one wave
+template <int ITEMS, bool FENCE_ALL>
+__global__ void __launch_bounds__(256, 2) k_fused(int64_t n, double alpha, double beta, double* p, const double* __restrict__ Ap,
+                                                  double* __restrict__ x, double* r, double* __restrict__ part,
+                                                  unsigned int* ticket, unsigned int* gen) {
+  constexpr int TILE = 256 * ITEMS;
+  __shared__ double red[8];
+  __shared__ int s_last;
+  const unsigned int gen0 = *reinterpret_cast<volatile unsigned int*>(gen);
+  double acc = 0.0;
+  for (int64_t tile = (int64_t)blockIdx.x * TILE; tile < n; tile += (int64_t)gridDim.x * TILE) {
+    double pv[ITEMS], av[ITEMS], xv[ITEMS], rv[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++) {
+      const int64_t k = tile + threadIdx.x + (int64_t)i * 256;
+      const bool ok = k < n;
+      pv[i] = ok ? p[k] : 0.0; av[i] = ok ? Ap[k] : 0.0; xv[i] = ok ? x[k] : 0.0; rv[i] = ok ? r[k] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++) {
+      const int64_t k = tile + threadIdx.x + (int64_t)i * 256;
+      if (k < n) {
+        x[k] = xv[i] + alpha * pv[i];
+        const double v = rv[i] - alpha * av[i];
+        r[k] = v;
+        acc += v * v;
+      }
+    }
+  }
+  for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; w++) t += red[w];
+    part[blockIdx.x] = t;
+    __threadfence();
+    s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) {
+    if (threadIdx.x == 0) while (*reinterpret_cast<volatile unsigned int*>(gen) == gen0) {}
+    __syncthreads();
+    if (FENCE_ALL) __threadfence();
+  } else {
+    if (threadIdx.x == 0) { *ticket = 0; __threadfence(); atomicExch(gen, gen0 + 1u); }
+    __syncthreads();
+  }
+  for (int64_t tile = (int64_t)blockIdx.x * TILE; tile < n; tile += (int64_t)gridDim.x * TILE) {
+    double rv[ITEMS], pv[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++) {
+      const int64_t k = tile + threadIdx.x + (int64_t)i * 256;
+      rv[i] = k < n ? r[k] : 0.0; pv[i] = k < n ? p[k] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++) {
+      const int64_t k = tile + threadIdx.x + (int64_t)i * 256;
+      if (k < n) p[k] = rv[i] + beta * pv[i];
+    }
+  }
+}
+
+// (e) phase 2 alone
+template <int ITEMS>
+__global__ void __launch_bounds__(256, 2) k_phase2(int64_t n, double beta, double* __restrict__ p, const double* __restrict__ r) {
+  constexpr int TILE = 256 * ITEMS;
+  for (int64_t tile = (int64_t)blockIdx.x * TILE; tile < n; tile += (int64_t)gridDim.x * TILE) {
+    double rv[ITEMS], pv[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++) {
+      const int64_t k = tile + threadIdx.x + (int64_t)i * 256;
+      rv[i] = k < n ? r[k] : 0.0; pv[i] = k < n ? p[k] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++) {
+      const int64_t k = tile + threadIdx.x + (int64_t)i * 256;
+      if (k < n) p[k] = rv[i] + beta * pv[i];
+    }
+  }
+}
+
 // (c) plain copy for reference: y = x with 128-bit accesses
 __global__ void __launch_bounds__(256) k_copy(int64_t n2, const double2* __restrict__ a, double2* __restrict__ b) {
   for (int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x; k < n2; k += (int64_t)gridDim.x * 256) b[k] = a[k];
@@ -119,6 +201,30 @@ int main() {
     run(nm, bytes, [&] { k_vec2<2><<<c * sms, 256>>>(n, 0.5, (const double2*)p, (const double2*)Ap, (double2*)x, (double2*)r, part); });
     snprintf(nm, sizeof nm, "128-bit 1 pair, round robin, %d CTAs/SM", c);
     run(nm, bytes, [&] { k_vec2<1><<<c * sms, 256>>>(n, 0.5, (const double2*)p, (const double2*)Ap, (double2*)x, (double2*)r, part); });
+  }
+  {
+    unsigned int* cnt;
+    CK(cudaMalloc(&cnt, 8)); CK(cudaMemset(cnt, 0, 8));
+    const double b72 = 72.0 * n;
+    run("FUSED update (72 n B), barrier, fence by all, 2 CTAs/SM", b72, [&] { k_fused<8, true><<<2 * sms, 256>>>(n, 0.5, 0.25, p, Ap, x, r, part, cnt, cnt + 1); });
+    run("FUSED update (72 n B), barrier, no fence, 2 CTAs/SM", b72, [&] { k_fused<8, false><<<2 * sms, 256>>>(n, 0.5, 0.25, p, Ap, x, r, part, cnt, cnt + 1); });
+    run("two kernels: phase 1 + phase 2 (72 n B), 2 CTAs/SM", b72, [&] {
+      k_scalar<8, true><<<2 * sms, 256>>>(n, 0.5, p, Ap, x, r, part);
+      k_phase2<8><<<2 * sms, 256>>>(n, 0.25, p, r); });
+    run("phase 2 alone (24 n B), 2 CTAs/SM", 24.0 * n, [&] { k_phase2<8><<<2 * sms, 256>>>(n, 0.25, p, r); });
+    for (size_t lim : {(size_t)0, (size_t)32 << 20, (size_t)96 << 20}) {
+      // the same with a persisting-L2 set-aside claimed (what cask_b200_cg_device did once per context in round 1)
+      int maxp = 0;
+      CK(cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, 0));
+      const size_t want = lim < (size_t)maxp ? lim : (size_t)maxp;
+      CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+      char nm[128];
+      snprintf(nm, sizeof nm, "FUSED update, persisting L2 set-aside %zu MB (max %d MB)", want >> 20, maxp >> 20);
+      run(nm, b72, [&] { k_fused<8, true><<<2 * sms, 256>>>(n, 0.5, 0.25, p, Ap, x, r, part, cnt, cnt + 1); });
+      snprintf(nm, sizeof nm, "scalar 8 items RR 2 CTAs/SM, set-aside %zu MB", want >> 20);
+      run(nm, bytes, [&] { k_scalar<8, true><<<2 * sms, 256>>>(n, 0.5, p, Ap, x, r, part); });
+    }
+    CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0));
   }
   run("128-bit 1 pair, grid = n/512 CTAs", bytes, [&] { k_vec2<1><<<(unsigned)(n / 512), 256>>>(n, 0.5, (const double2*)p, (const double2*)Ap, (double2*)x, (double2*)r, part); });
   run("128-bit 2 pairs, grid = n/1024 CTAs", bytes, [&] { k_vec2<2><<<(unsigned)(n / 1024), 256>>>(n, 0.5, (const double2*)p, (const double2*)Ap, (double2*)x, (double2*)r, part); });
