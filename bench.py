@@ -742,11 +742,11 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": workload_name(G, world, nnz_local)[0],
-                       "sharding": "row stripes over ranks (Spmv.cpp:334-364)" + ("; x in the symmetric arena, boundary rows stored into the "
-                                   "neighbours' copies (flow-controlled push kernel) + ONE SpMV launch per step, no NCCL call"
+                       "sharding": "row stripes over ranks (Spmv.cpp:334-364)" + ("; x in the symmetric arena: ONE launch per step, whose last CTA stores the boundary rows "
+                                   "into the neighbours' copies (flow-controlled by acknowledgements); no NCCL call"
                                    if one_launch else "; x halo over NCCL send/recv, interior and boundary launches" if world > 1 else ""),
                        "l2": "inputs (%.2f GB per launch) larger than L2 (126 MB); no flush needed" % (bytes_per_launch / 1e9),
-                       "soak_steps": args.soak, "value_dict": vd_mode},
+                       "soak_steps": args.soak, "value_dict": vd_mode, "preprocess_s": preprocess_s},
             "roofline": roof, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         details = {"config": {"global_rows": n_global, "design": {"num_pipes": 1, "cache_size": args.cache, "input_width": 16},

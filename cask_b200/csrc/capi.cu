@@ -312,11 +312,12 @@ int cask_b200_spmv_device(cask_b200_ctx* ctx, const double* d_x, double* d_y) {
     // d_x is the full-layout vector (global length); halo entries are refreshed in place
     const int ch = peer_channel_of(ctx, d_x);
     if (ch >= 0 && peer_ready(ctx) && spmv_single_launch(ctx)) {
-      // x lives in the symmetric arena (cask_b200_dist_vector): boundary rows go straight into the neighbours' copies,
-      // then ONE persistent launch over all slices, interior first; its producer warp acquires the neighbours' epoch
-      // flags only when it reaches the first halo-dependent slice
-      CB_TRY(peer_push_acked(ctx, ch, ctx->stream));
-      const HaloWait hw = peer_halo_wait(ctx, ch);
+      // x lives in the symmetric arena (cask_b200_dist_vector): ONE persistent launch over all slices, interior first.
+      // Its last CTA stores the boundary rows straight into the neighbours' copies before it turns to its slices
+      // (flow-controlled by acknowledgements); the producer warps acquire the neighbours' epoch flags only when they
+      // reach the first halo-dependent slice
+      HaloWait hw;
+      CB_TRY(peer_acked_wait(ctx, ch, &hw));
       SpmvFusion f;
       f.pdl = true;
       return launch_spmv(ctx, d_x, d_y, 0, ctx->stream, &f, &hw);

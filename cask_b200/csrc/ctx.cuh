@@ -171,9 +171,12 @@ struct PeerCtrl {
   // low-latency slots of the in-kernel all-reduce: [slot][source rank][quantity][half] = {32 data bits, 32-bit
   // sequence number} in ONE 8-byte store - data and flag arrive together, no fence, one NVLink traversal
   unsigned long long ar_ll[4][kMaxPeers][2][2];
-  // flow control of the plain sharded SpMV (dist.cu: halo_push_acked_kernel): [channel][rank q] = number of SpMVs on
+  // flow control of the plain sharded SpMV (peer.cuh: acked_push): [channel][rank q] = number of SpMVs on
   // that channel rank q has FINISHED, i.e. the halo rows this rank pushed for them may be overwritten
   unsigned long long halo_ack[kHaloChannels][kMaxPeers];
+  // [channel][source rank] = number of plain sharded SpMVs whose boundary rows have landed here (host-counted epochs:
+  // the solvers' device-counted halo_flag / push_seq epochs are a separate space and stay untouched)
+  unsigned long long halo_flag_acked[kHaloChannels][kMaxPeers];
   // local
   unsigned long long ar_seq;                    // all-reduces performed
   unsigned long long push_seq[kHaloChannels];   // halo epochs pushed per channel (== the epoch the next SpMV expects)
@@ -192,12 +195,12 @@ struct PushDesc {       // by-value kernel argument of every kernel that produce
   PeerCtrl* ctrl = nullptr;            // this rank's control block
 };
 
-struct AckDesc {        // by-value kernel argument of the acknowledged halo push (plain sharded SpMV)
+struct AckDesc {        // device-resident (one per channel): the plain sharded SpMV's in-kernel boundary-row push
   PeerCtrl* peers[kMaxPeers] = {nullptr};  // control blocks of all ranks
   uint32_t send_mask = 0;          // ranks that stage rows of this rank's slice
   int32_t me = 0, world = 1;
   int32_t pad_ = 0;
-  unsigned long long want = 0;     // SpMVs this rank has finished on the channel (== the acknowledgement it waits for)
+  PushDesc push;                   // what goes where
 };
 
 struct ReduceDesc {     // by-value kernel argument: the grid's last CTA finishes a dot product (and its all-reduce)
@@ -237,6 +240,12 @@ struct HaloWait {       // by-value kernel argument of the persistent SpMV kerne
   int32_t pad_ = 0;
   const int32_t* skip0 = nullptr;  // the kernel returns at once if *skip0 or *skip1 is set (solver flags:
   const int32_t* skip1 = nullptr;  // converged / restart pending) - the producer of x skipped its push as well
+  // plain sharded SpMV (x in the symmetric arena): the grid's LAST CTA first sends this rank's acknowledgement, waits for
+  // the receivers' acknowledgements, stores the boundary rows of x into the neighbours' copies and publishes epoch
+  // acked_want + 1; the halo wait then uses the host-counted acked epochs instead of the solvers' device counters
+  const AckDesc* ack = nullptr;    // nullptr: solver path (the producer of x pushed)
+  unsigned long long acked_want = 0;  // plain sharded SpMVs this rank has finished on the channel
+  int64_t own_row0 = 0;            // first global row of this rank (its slice inside the full-layout x)
 };
 
 struct SolverWork {  // device scratch of the CG / BiCGStab loops
@@ -349,7 +358,7 @@ void peer_fill_reduce(cask_b200_ctx* ctx, ReduceDesc* rd);           // adds the
 HaloWait peer_halo_wait(cask_b200_ctx* ctx, int channel);
 HaloUpdate peer_halo_update(cask_b200_ctx* ctx, int channel);
 int peer_push(cask_b200_ctx* ctx, int channel, cudaStream_t stream); // standalone push of the channel's own slice
-int peer_push_acked(cask_b200_ctx* ctx, int channel, cudaStream_t stream);  // same, flow-controlled (plain sharded SpMV)
+int peer_acked_wait(cask_b200_ctx* ctx, int channel, HaloWait* hw);  // fills the in-kernel push part of a plain sharded SpMV
 int peer_channel_of(const cask_b200_ctx* ctx, const double* d_full); // arena vector index of a pointer, or -1
 int peer_allreduce_partials(cask_b200_ctx* ctx, const double* d_partials, int count, int stride, int nq, double* d_scal,
                             int slot0, const int32_t* d_skip0, const int32_t* d_skip1, cudaStream_t stream);

@@ -100,6 +100,10 @@ struct DistState {
   // first row of every rank's stripe (+ n_global): the reference rule rows_per = n / world (Spmv.cpp:334-364) unless the
   // caller handed preprocess_shard another contiguous partition (e.g. stripes of equal nonzero count for a power-law matrix)
   std::vector<int64_t> bounds;
+  // in-kernel push of the plain sharded SpMV: device copy of its descriptor per channel, rebuilt when stale
+  AckDesc* d_ack[kHaloChannels] = {nullptr};
+  unsigned long long plan_stamp = 0, ack_plan_stamp[kHaloChannels] = {0};
+  unsigned char* ack_arena[kHaloChannels] = {nullptr};
 };
 
 constexpr size_t kCtrlBytes = 4096;
@@ -124,6 +128,7 @@ void dist_free(cask_b200_ctx* ctx) {
   if (!ctx->dist) return;
   DistState* d = ctx->dist;
   peer_unmap(d);
+  for (auto& a : d->d_ack) { cudaFree(a); a = nullptr; }
   if (d->comm_red && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm_red);
   if (d->comm_halo && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm_halo);
   if (d->ev_ready) cudaEventDestroy(d->ev_ready);
@@ -188,6 +193,7 @@ int dist_plan_halo(cask_b200_ctx* ctx) {
   cudaStream_t s = ctx->stream;
   const int W = d->world, me = d->rank;
   d->n_global = p.n_global;
+  d->plan_stamp++;
   d->recv_from.assign(W, {});
   d->send_to.assign(W, {});
   const int64_t own_lo = p.row0_global, own_hi = p.row0_global + p.n;
@@ -461,30 +467,6 @@ __global__ void __launch_bounds__(256) halo_push_kernel(const double* __restrict
   push_signal(pd);
 }
 
-// The plain sharded SpMV calls this before every launch.  Its halo rows live at fixed positions of the receiver's vector,
-// so epoch j may only be written once the receiver has finished the SpMV that read epoch j - 1: every rank first tells
-// ALL ranks how many SpMVs it has finished on the channel (stream order: the previous SpMV is complete when this kernel
-// runs), then waits for that acknowledgement from the ranks that stage its rows, then copies and signals.  Acks are sent
-// before any wait, so the ranks cannot deadlock; the waits carry the peer timeout.
-__global__ void __launch_bounds__(256) halo_push_acked_kernel(const double* __restrict__ own, const PushDesc pd, const AckDesc ad) {
-  if (threadIdx.x == 0) {
-    if (blockIdx.x == 0 && blockIdx.y == 0)
-      for (int q = 0; q < ad.world; q++)
-        if (q != ad.me) st_release_sys_u64(&ad.peers[q]->halo_ack[pd.channel][ad.me], ad.want);
-    if (ad.want)
-      for (int q = 0; q < ad.world; q++)
-        if (ad.send_mask & (1u << q)) peer_wait_ge(&pd.ctrl->halo_ack[pd.channel][q], ad.want, &pd.ctrl->error);
-  }
-  __syncthreads();
-  const int s = blockIdx.y;
-  if (s < pd.nsend) {
-    double* dst = pd.dst[s];
-    for (int64_t i = pd.lo[s] + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pd.hi[s]; i += (int64_t)gridDim.x * blockDim.x)
-      dst[i] = own[i];
-  }
-  push_signal(pd);
-}
-
 struct PeerCtrlPtrs { PeerCtrl* p[kMaxPeers]; };
 
 // Deterministic sum of per-CTA partials (index order) followed by a one-shot all-reduce over peer memory: every
@@ -552,23 +534,34 @@ int peer_push(cask_b200_ctx* ctx, int channel, cudaStream_t stream) {
   return CASK_B200_OK;
 }
 
-int peer_push_acked(cask_b200_ctx* ctx, int channel, cudaStream_t stream) {
-  const PushDesc pd = peer_push_desc(ctx, channel);
-  if (pd.ctrl == nullptr) return fail(CASK_B200_ERR_RUNTIME, "acknowledged push needs the peer-memory path");
+// Plain sharded SpMV with x in the arena: the descriptor of the in-kernel boundary-row push (device-resident, rebuilt
+// when the plan or the arena changes) and this call's host-counted epoch.
+int peer_acked_wait(cask_b200_ctx* ctx, int channel, HaloWait* hw) {
+  if (!peer_ready(ctx)) return fail(CASK_B200_ERR_RUNTIME, "acknowledged push needs the peer-memory path");
   DistState* d = ctx->dist;
-  AckDesc ad;
-  for (int q = 0; q < kMaxPeers; q++) ad.peers[q] = q < d->world ? reinterpret_cast<PeerCtrl*>(d->peer_base[q]) : nullptr;
-  for (int q = 0; q < d->world; q++)
-    if (!d->send_to[q].empty()) ad.send_mask |= 1u << q;
-  ad.me = d->rank;
-  ad.world = d->world;
-  ad.want = d->acked_pushes[channel]++;
-  int64_t longest = 1;
-  for (int i = 0; i < pd.nsend; i++) longest = std::max(longest, pd.hi[i] - pd.lo[i]);
-  const dim3 grid((unsigned)std::min<int64_t>((longest + 255) / 256, 64), (unsigned)std::max(pd.nsend, 1));
-  halo_push_acked_kernel<<<grid, 256, 0, stream>>>(peer_vector(ctx, channel) + ctx->plan.row0_global, pd, ad);
-  ctx->launches++;
-  CB_CUDA(cudaGetLastError());
+  if (!d->d_ack[channel]) CB_CUDA(cudaMalloc(&d->d_ack[channel], sizeof(AckDesc)));
+  if (d->ack_plan_stamp[channel] != d->plan_stamp || d->ack_arena[channel] != d->arena) {
+    AckDesc ad;
+    for (int q = 0; q < kMaxPeers; q++) ad.peers[q] = q < d->world ? reinterpret_cast<PeerCtrl*>(d->peer_base[q]) : nullptr;
+    for (int q = 0; q < d->world; q++)
+      if (!d->send_to[q].empty()) ad.send_mask |= 1u << q;
+    ad.me = d->rank;
+    ad.world = d->world;
+    ad.push = peer_push_desc(ctx, channel);
+    CB_CUDA(cudaMemcpyAsync(d->d_ack[channel], &ad, sizeof(ad), cudaMemcpyHostToDevice, ctx->stream));
+    CB_CUDA(cudaStreamSynchronize(ctx->stream));  // `ad` is a stack object
+    d->ack_plan_stamp[channel] = d->plan_stamp;
+    d->ack_arena[channel] = d->arena;
+  }
+  // every rank with at least one neighbour takes part, receivers and senders alike
+  hw->ctrl = reinterpret_cast<const PeerCtrl*>(d->arena);
+  hw->ctrl_rw = reinterpret_cast<PeerCtrl*>(d->arena);
+  hw->channel = channel;
+  hw->first_item = ctx->plan.n_ell_interior;
+  hw->peer_mask = d->recv_mask;
+  hw->ack = d->d_ack[channel];
+  hw->acked_want = d->acked_pushes[channel]++;
+  hw->own_row0 = ctx->plan.row0_global;
   return CASK_B200_OK;
 }
 
@@ -675,6 +668,18 @@ extern "C" int cask_b200_dist_init(cask_b200_ctx* ctx, int32_t rank, int32_t wor
   CB_NCCL(g_nccl.CommSplit(d->comm_halo, 0, rank, &d->comm_red, nullptr));
   CB_CUDA(cudaEventCreateWithFlags(&d->ev_ready, cudaEventDisableTiming));
   CB_CUDA(cudaEventCreateWithFlags(&d->ev_done, cudaEventDisableTiming));
+  // NCCL builds its channels and connections at the first collective of a communicator (0.8 s at 2 ranks, 2.9 s at 8 on
+  // an NVSwitch box): paid here, once, instead of inside the first preprocess_shard (round 1's "preprocess_s grows with N")
+  {
+    int64_t* d_one = nullptr;
+    CB_CUDA(cudaMalloc(&d_one, sizeof(int64_t) * (size_t)(world + 1)));
+    CB_CUDA(cudaMemsetAsync(d_one, 0, sizeof(int64_t) * (size_t)(world + 1), ctx->stream));
+    CB_NCCL(g_nccl.AllReduce(d_one, d_one, 1, kNcclInt64, kNcclSum, d->comm_halo, ctx->stream));
+    CB_NCCL(g_nccl.AllGather(d_one + world, d_one, 1, kNcclInt64, d->comm_halo, ctx->stream));
+    CB_NCCL(g_nccl.AllReduce(d_one, d_one, 1, kNcclInt64, kNcclSum, d->comm_red, ctx->stream));
+    CB_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_one);
+  }
   return CASK_B200_OK;
 }
 

@@ -274,10 +274,46 @@ __device__ __forceinline__ void push_signal(const PushDesc& d) {
 
 // Consumer side: block until every peer in the mask has published the epoch this rank itself has pushed.
 __device__ __forceinline__ void halo_wait(const HaloWait& w) {
+  if (w.ack) {  // plain sharded SpMV: host-counted epochs
+    for (int q = 0; q < kMaxPeers; q++)
+      if (w.peer_mask & (1u << q)) peer_wait_ge(&w.ctrl->halo_flag_acked[w.channel][q], w.acked_want + 1, &w.ctrl_rw->error);
+    asm volatile("fence.proxy.async;" ::: "memory");
+    return;
+  }
   const unsigned long long want = w.ctrl->push_seq[w.channel];
   for (int q = 0; q < kMaxPeers; q++)
     if (w.peer_mask & (1u << q)) peer_wait_ge(&w.ctrl->halo_flag[w.channel][q], want, &w.ctrl_rw->error);
   asm volatile("fence.proxy.async;" ::: "memory");  // the data is read next by TMA (async proxy)
+}
+
+// Plain sharded SpMV, called by ALL threads of the grid's last CTA before it turns to its slices (it owns one slice less
+// than the first CTAs whenever the slices do not divide evenly): acknowledgement out, acknowledgements in, boundary
+// rows of x into the neighbours' copies, epoch out.  The halo rows sit at fixed positions of the receiver's vector, so
+// epoch k + 1 may only be written once the receiver has finished the SpMV that read epoch k: every rank tells ALL ranks
+// how many SpMVs it has finished on the channel (stream order: the previous one is complete when this kernel runs),
+// then waits for that count from the ranks that stage its rows.  Acknowledgements leave before any wait, so the ranks
+// cannot deadlock; the waits carry the peer timeout.
+__device__ __forceinline__ void acked_push(const HaloWait& w, const double* __restrict__ x_full) {
+  const AckDesc& ad = *w.ack;
+  const PushDesc& pd = ad.push;
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < ad.world; q++)
+      if (q != ad.me) st_release_sys_u64(&ad.peers[q]->halo_ack[pd.channel][ad.me], w.acked_want);
+    if (w.acked_want)
+      for (int q = 0; q < ad.world; q++)
+        if (ad.send_mask & (1u << q)) peer_wait_ge(&pd.ctrl->halo_ack[pd.channel][q], w.acked_want, &pd.ctrl->error);
+  }
+  __syncthreads();
+  for (int s = 0; s < pd.nsend; s++) {
+    double* dst = pd.dst[s];                 // rebased: dst[i] is the peer's entry for LOCAL row i
+    const double* src = x_full + w.own_row0; // this rank's slice inside its full-layout vector
+    for (int64_t i = pd.lo[s] + threadIdx.x; i < pd.hi[s]; i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    for (int s = 0; s < pd.nsend; s++) st_release_sys_u64(&pd.peer_ctrl[s]->halo_flag_acked[pd.channel][pd.me], w.acked_want + 1);
+  }
 }
 
 }  // namespace caskb200

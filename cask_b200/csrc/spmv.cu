@@ -331,6 +331,9 @@ spmv_ell_persistent_kernel(const SliceDesc* __restrict__ slices, const int32_t* 
     return;
   }
 
+  // plain sharded SpMV: the boundary rows of x travel from inside this kernel (peer.cuh: acked_push), by the CTA that
+  // has the least to do; everybody else is already streaming interior slices
+  if (hw.ack && blockIdx.x == gridDim.x - 1) acked_push(hw, x);
   double dot = 0.0, dot2 = 0.0;  // y . dot_with and (self_dot: BiCGStab's t.t beside t.s) y . y
   if (is_producer) {
     // ===== producer warp =====

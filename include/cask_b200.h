@@ -201,10 +201,10 @@ int cask_b200_dist_halo_counts(cask_b200_ctx* ctx, int64_t* recv_counts);
 int cask_b200_dist_peer_active(cask_b200_ctx* ctx, int32_t* active);
 /* COLLECTIVE (every rank, after preprocess_shard).  Full-layout vector `channel` (0 or 1; m doubles, this rank's slice at
  * [row0, row0 + nrows)) of the library's symmetric arena, the allocation every peer has mapped over NVLink.  A sharded
- * caller that keeps x THERE gets the one-launch SpMV: cask_b200_spmv_device(ctx, that pointer, y) has the producer side
- * store this rank's boundary rows straight into the neighbours' copies (flow-controlled by acknowledgements) and the
- * persistent kernel acquire the neighbours' epoch flags when it reaches its first halo-dependent slice - no NCCL call, no
- * second launch.  *d_vector = NULL (status OK) when the peer-memory path is not available for this plan (gather slices,
+ * caller that keeps x THERE gets the one-launch SpMV: in cask_b200_spmv_device(ctx, that pointer, y) the persistent
+ * kernel's last CTA stores this rank's boundary rows straight into the neighbours' copies (flow-controlled by
+ * acknowledgements) while the others stream interior slices, and the producer warps acquire the neighbours' epoch flags
+ * when they reach the first halo-dependent slice - no NCCL call, no second launch.  *d_vector = NULL (status OK) when the peer-memory path is not available for this plan (gather slices,
  * irregular halo, no IPC, peer_mode 0): use an own buffer then, spmv_device exchanges it over NCCL.  The solvers use the
  * same two vectors as scratch: the contents do not survive a cg / bicgstab call. */
 int cask_b200_dist_vector(cask_b200_ctx* ctx, int32_t channel, double** d_vector);
