@@ -36,6 +36,7 @@ struct NcclApi {
   int (*CommDestroy)(NcclComm) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
   int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;
+  int (*Broadcast)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
   int (*Send)(const void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
   int (*Recv)(void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
@@ -59,6 +60,7 @@ int load_nccl() {
   CB_SYM(CommDestroy, "ncclCommDestroy");
   CB_SYM(AllReduce, "ncclAllReduce");
   CB_SYM(AllGather, "ncclAllGather");
+  CB_SYM(Broadcast, "ncclBroadcast");
   CB_SYM(Send, "ncclSend");
   CB_SYM(Recv, "ncclRecv");
   CB_SYM(GroupStart, "ncclGroupStart");
@@ -605,14 +607,14 @@ int dist_exchange_begin(cask_b200_ctx* ctx, double* d_full, cudaStream_t after) 
   const int W = d->world, me = d->rank;
   CB_NCCL(g_nccl.GroupStart());
   if (d->allgather) {
-    int64_t my0, myn;
-    owner_range(d->bounds.data(), p.n_global, W, me, &my0, &myn);
+    // every rank's slice to everybody, in place.  Stripes may differ widely in rows (equal-nonzero stripes of a power-law
+    // matrix: the last rank of 8 owns half of x), so W point-to-point copies per slice would make its owner's NVLink
+    // egress the bottleneck (7 x 134 MB for R-MAT scale 25: 1.2 ms); one broadcast per root moves each slice once
+    // through NCCL's ring / NVSwitch multicast instead.
     for (int q = 0; q < W; q++) {
-      if (q == me) continue;
       int64_t q0, qn;
       owner_range(d->bounds.data(), p.n_global, W, q, &q0, &qn);
-      if (myn) CB_NCCL(g_nccl.Send(d_full + my0, (size_t)myn, kNcclFloat64, q, d->comm_halo, cs));
-      if (qn) CB_NCCL(g_nccl.Recv(d_full + q0, (size_t)qn, kNcclFloat64, q, d->comm_halo, cs));
+      if (qn) CB_NCCL(g_nccl.Broadcast(d_full + q0, d_full + q0, (size_t)qn, kNcclFloat64, q, d->comm_halo, cs));
     }
   } else {
     for (int q = 0; q < W; q++) {

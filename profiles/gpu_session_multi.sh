@@ -30,19 +30,23 @@ run() {  # run <n> <outfile> <bench args...>
 }
 step() { echo "== $1 ($(date +%T))"; }
 
+if [ "$MODE" != bench ]; then
 step "multi-rank GPU tests"
 timeout 1200 $PY -m pytest tests/test_gpu_dist.py -q -rs > $OUT/${TAG}_pytest_dist.log 2>&1; tail -6 $OUT/${TAG}_pytest_dist.log
+fi
 
-if [ "$MODE" = quick ]; then NS="$GPUS"; else NS=""; N=1; while [ $N -le $GPUS ]; do NS="$NS $N"; N=$((N * 2)); done; fi
+if [ "$MODE" = quick ] || [ "$MODE" = bench ]; then NS="$GPUS"; elif [ "$MODE" = scale ]; then NS="4 $GPUS"; else NS=""; N=1; while [ $N -le $GPUS ]; do NS="$NS $N"; N=$((N * 2)); done; fi
 for N in $NS; do
   step "bench.py at N=$N"
   if [ "$MODE" = full ]; then run $N $OUT/${TAG}_bench_reference_n$N.json --impl reference --steps 20 --warmup 5 --no-cg; fi
   run $N $OUT/${TAG}_bench_n$N.json --steps 20 --warmup 5 --no-cpu --no-probe
 done
 
-if [ "$MODE" = full ]; then
+if [ "$MODE" != quick ] && [ "$MODE" != bench ]; then
+  step "N=$GPUS with the solvers' vectors NOT kept in the persisting L2 set-aside (l2_keep 0) for the A/B"
+  CASK_B200_L2_KEEP=0 run $GPUS $OUT/${TAG}_bench_n${GPUS}_l2keep0.json --no-cpu --no-probe --only-bicgstab --steps 20 --warmup 5 --bicg-cap 300
   step "N=$GPUS on the NCCL path (peer_mode 0) for the A/B"
-  CASK_B200_PEER=0 run $GPUS $OUT/${TAG}_bench_n${GPUS}_nccl.json --no-cpu --no-probe --steps 20 --warmup 5 --bicg-cap 300
+  CASK_B200_PEER=0 run $GPUS $OUT/${TAG}_bench_n${GPUS}_nccl.json --no-cpu --no-probe --only-bicgstab --steps 20 --warmup 5 --bicg-cap 300
   step "CG kernel timeline at N=$GPUS (peer path)"
   CASK_B200_TRACE=$OUT/${TAG}_trace_rank run $GPUS $OUT/${TAG}_bench_n${GPUS}_trace.json --no-cpu --no-extra --no-probe --steps 20 --soak 0
   $PY profiles/trace_summary.py $OUT/${TAG}_trace_rank > $OUT/${TAG}_trace_summary.txt 2>&1; head -30 $OUT/${TAG}_trace_summary.txt
@@ -53,7 +57,7 @@ $PY - <<PYEOF | tee $OUT/${TAG}_scaling_table.md
 import json, glob
 rows = []
 for f in sorted(glob.glob("$OUT/${TAG}_bench_n*.json")):
-    if "reference" in f:
+    if "reference" in f or f.endswith("_details.json"):
         continue
     try:
         d = json.loads(open(f).read().strip().splitlines()[-1])
