@@ -1051,6 +1051,10 @@ def bench_rmat(ctx, cb, torch, dist, dev, rank, world, barrier, scale=25, edge_f
     if world > 1:
         dist.all_reduce(share, op=dist.ReduceOp.MAX)
     stored = 12.0 * nnz_total + 4.0 * n + 16.0 * n
+    reordered = torch.tensor([float(stats.get("cols_referenced", 0)) if stats.get("col_reorder") else 0.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(reordered)
+    stored += 20.0 * float(reordered.item())   # hub clustering: perm (4 B) + x read + permuted x written per referenced column
     roof = roofline_of(algorithmic_bytes(nnz_total, n, n), stored, ms * 1e-3, measured_peak()[0] * world)
     kernel = "spmv_csr_merge_kernel<false>" if stats.get("csr_kernel") == 1 else "spmv_csr_items_kernel<0,0>"
     roof["traffic"], roof["traffic_source"] = ncu_traffic(kernel)
@@ -1066,12 +1070,12 @@ def bench_rmat(ctx, cb, torch, dist, dev, rank, world, barrier, scale=25, edge_f
                         % (scale, n, nnz_total, world),
             "scaling": "strong", "ms_per_spmv": ms, "gflops": 2.0 * nnz_total / (ms * 1e-3) / 1e9, "nnz": nnz_total,
             "algorithmic_gbs": algorithmic_bytes(nnz_total, n, n) / (ms * 1e-3) / 1e9, "preprocess_s": prep,
-            "kernel": kernel, "l2_hit_rate_on_x_pct": l2, "roofline": roof,
+            "kernel": kernel, "l2_hit_rate_on_x_pct": l2, "roofline": roof, "col_reorder": int(stats.get("col_reorder", 0)),
             "nnz_share_max_rank": float(share.item()) / nnz_total,
             "stripes": "one" if world == 1 else "equal nonzero count, cut at multiples of 1024 rows (rows of this rank: %d)" % nr,
             "max_rel_diff_256_sampled_rows": rel, "max_err_all_rows_rel_to_sum_abs": rel_all,
             "plan": {k: stats[k] for k in ("slices_staged_ell", "slices_gather_csr", "csr_lanes_per_row", "max_row_length",
-                                           "row_length_histogram", "csr_items", "csr_kernel")}}
+                                           "row_length_histogram", "csr_items", "csr_kernel", "col_reorder", "cols_referenced")}}
 
 
 if __name__ == "__main__":

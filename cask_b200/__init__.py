@@ -59,7 +59,7 @@ class PlanStats(C.Structure):
                 ("device_bytes", C.c_int64), ("row_length_histogram", C.c_int64 * 8),
                 ("csr_nnz", C.c_int64), ("csr_rows", C.c_int64), ("csr_items", C.c_int32), ("csr_kernel", C.c_int32),
                 ("persist_ku", C.c_int32), ("persist_stages", C.c_int32), ("persist_ctas_per_sm", C.c_int32),
-                ("value_dict", C.c_int32)]
+                ("value_dict", C.c_int32), ("col_reorder", C.c_int32), ("cols_referenced", C.c_int64)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k != "row_length_histogram"}
@@ -208,7 +208,7 @@ def mm_read_info(path):
 def mm_read_coo(path):
     """(info, rows, cols, vals): the entries of a coordinate file in file order, 1-based (host only)."""
     info = mm_read_info(path)
-    L = info["entries"]
+    L = min(info["entries"], os.path.getsize(path) // 6 + 1)   # an entry is at least 6 bytes: a corrupt size line sizes nothing
     rows, cols, vals = np.zeros(L, np.int32), np.zeros(L, np.int32), np.zeros(L, np.float64)
     cnt = C.c_int64()
     check(lib().cask_b200_mm_read_coo(os.fsencode(path), L, _p(rows), _p(cols), _p(vals), C.byref(cnt)))
@@ -217,7 +217,7 @@ def mm_read_coo(path):
 
 def mm_read_vector(path):
     """io::readVector (host only)."""
-    n = mm_read_info(path)["n"]
+    n = min(mm_read_info(path)["n"], os.path.getsize(path) + 1)
     out = np.zeros(n, np.float64)
     cnt = C.c_int64()
     check(lib().cask_b200_mm_read_vector(os.fsencode(path), n, _p(out), C.byref(cnt)))
@@ -358,6 +358,13 @@ class Context:
         check(lib().cask_b200_partition_export(self.h, pipe, _p(colptr), _p(pairs)))
         return d, colptr, pairs
 
+    def _vec(self, v, want, what, copy=False):
+        """float64 contiguous view (or copy) of a host vector whose length the C side takes on trust."""
+        v = np.array(v, np.float64) if copy else np.ascontiguousarray(v, np.float64)
+        if v.ndim != 1 or len(v) != want:
+            raise ValueError('%s has %s entries, the matrix needs %d' % (what, v.shape, want))
+        return v
+
     def spmv(self, x):
         x = np.ascontiguousarray(x, np.float64)
         if self.m and len(x) != self.m:
@@ -367,10 +374,12 @@ class Context:
         return y
 
     def spmv_into(self, x, y):
+        if len(x) != self.m or len(y) != self.n or x.dtype != np.float64 or y.dtype != np.float64:
+            raise ValueError('spmv_into: x needs %d and y %d float64 entries' % (self.m, self.n))
         check(lib().cask_b200_spmv(self.h, _p(x), _p(y)))
 
     def spmv_refformat(self, x):
-        x = np.ascontiguousarray(x, np.float64)
+        x = self._vec(x, self.m, 'x')
         y = np.empty(self.n, np.float64)
         check(lib().cask_b200_spmv_refformat(self.h, _p(x), _p(y)))
         return y
@@ -380,8 +389,8 @@ class Context:
 
     def cg(self, rhs, x0=None, maxiters=2000, tol=1e-5, iterations=0):
         """Returns (converged, iterations, x, rs_final) — iterations with the reference's convention."""
-        rhs = np.ascontiguousarray(rhs, np.float64)
-        x = np.zeros(self.n, np.float64) if x0 is None else np.array(x0, np.float64)
+        rhs = self._vec(rhs, self.n, 'rhs')
+        x = np.zeros(self.n, np.float64) if x0 is None else self._vec(x0, self.n, 'x0', copy=True)
         it, conv, rs = C.c_int32(iterations), C.c_int32(0), C.c_double(0)
         check(lib().cask_b200_cg(self.h, _p(rhs), _p(x), maxiters, tol, C.byref(it), C.byref(conv), C.byref(rs)))
         return bool(conv.value), it.value, x, rs.value
@@ -395,8 +404,8 @@ class Context:
     def pcg(self, rhs, precon, x0=None, maxiters=2000, tol=1e-5, iterations=0):
         """pcg<double, Precon>: returns (converged, iterations, x, rs_final); x is returned even when an ILU solve met a
         zero pivot (CaskError is raised after the download in that case)."""
-        rhs = np.ascontiguousarray(rhs, np.float64)
-        x = np.zeros(self.n, np.float64) if x0 is None else np.array(x0, np.float64)
+        rhs = self._vec(rhs, self.n, 'rhs')
+        x = np.zeros(self.n, np.float64) if x0 is None else self._vec(x0, self.n, 'x0', copy=True)
         it, conv, rs = C.c_int32(iterations), C.c_int32(0), C.c_double(0)
         check(lib().cask_b200_pcg(self.h, _p(rhs), _p(x), maxiters, tol, precon, C.byref(it), C.byref(conv), C.byref(rs)))
         return bool(conv.value), it.value, x, rs.value
@@ -419,14 +428,14 @@ class Context:
         return pc[:nnz], ll.value, lu.value
 
     def ilu_apply(self, x, unit_lower=False):
-        x = np.ascontiguousarray(x, np.float64)
+        x = self._vec(x, self.n, 'x')
         z = np.zeros(len(x), np.float64)
         zp = C.c_int32()
         check(lib().cask_b200_ilu_apply(self.h, 1 if unit_lower else 0, _p(x), _p(z), C.byref(zp)))
         return z, bool(zp.value)
 
     def bicgstab(self, b, tol=0.0, maxit=0):
-        b = np.ascontiguousarray(b, np.float64)
+        b = self._vec(b, self.n, 'b')
         x = np.zeros(self.n, np.float64)
         it, te = C.c_int32(maxit), C.c_double(tol)
         check(lib().cask_b200_bicgstab(self.h, _p(b), _p(x), C.byref(it), C.byref(te)))

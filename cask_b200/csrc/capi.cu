@@ -40,7 +40,11 @@ void reset_matrix(cask_b200_ctx* ctx) {
 }
 
 int finish_preprocess(cask_b200_ctx* ctx) {
-  CB_TRY(build_plan(ctx));
+  const int rc = build_plan(ctx);
+  if (rc != CASK_B200_OK) {  // nothing half-built survives (device temporaries of the plan, an owned CSR copy)
+    reset_matrix(ctx);
+    return rc;
+  }
   ctx->have_design = true;
   if (dist_active(ctx)) CB_TRY(dist_plan_halo(ctx));
   return CASK_B200_OK;
@@ -107,6 +111,7 @@ int cask_b200_create(cask_b200_ctx** out, int device) {
   if (const char* e = getenv("CASK_B200_CSR_KERNEL")) ctx->csr_kernel = atoi(e);
   if (const char* e = getenv("CASK_B200_L2_KEEP")) ctx->l2_keep = atoi(e);
   if (const char* e = getenv("CASK_B200_MERGE_ITEMS")) ctx->merge_items = atoi(e);
+  if (const char* e = getenv("CASK_B200_COL_REORDER")) ctx->col_reorder = atoi(e);
   if (const char* e = getenv("CASK_B200_VALUE_DICT")) ctx->value_dict = atoi(e);
   if (const char* e = getenv("CASK_B200_PERSIST_CTAS")) ctx->persist_ctas = atoi(e);
   *out = ctx;
@@ -169,6 +174,7 @@ int cask_b200_set_option(cask_b200_ctx* ctx, const char* name, double value) {
   else if (k == "csr_item_nnz") ctx->csr_item_nnz = (int32_t)value;
   else if (k == "csr_kernel") ctx->csr_kernel = (int32_t)value;
   else if (k == "merge_items") ctx->merge_items = (int32_t)value;
+  else if (k == "col_reorder") ctx->col_reorder = (int32_t)value;
   else if (k == "value_dict") ctx->value_dict = (int32_t)value;
   else if (k == "persist_ctas") ctx->persist_ctas = (int32_t)value;
   else return fail(CASK_B200_ERR_INVALID_ARGUMENT, "set_option: unknown option " + k);
@@ -221,11 +227,17 @@ int cask_b200_preprocess(cask_b200_ctx* ctx, const cask_b200_design* design, int
   if (!row_ptr || (nnz && (!col_ind || !values))) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "preprocess: null CSR arrays");
   if (row_ptr[n] != nnz) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "preprocess: row_ptr[n] != nnz");
   reset_matrix(ctx);
+  // the plan owns the device copy from the first allocation on: an early return below leaks nothing (free_plan)
+  Plan& p = ctx->plan;
+  p.owns_csr = true;
   int32_t *d_rp = nullptr, *d_ci = nullptr;
   double* d_va = nullptr;
   CB_CUDA(cudaMalloc(&d_rp, sizeof(int32_t) * (n + 1)));
+  p.d_row_ptr = d_rp;
   CB_CUDA(cudaMalloc(&d_ci, sizeof(int32_t) * std::max<int64_t>(nnz, 1)));
+  p.d_col = d_ci;
   CB_CUDA(cudaMalloc(&d_va, sizeof(double) * std::max<int64_t>(nnz, 1)));
+  p.d_val = d_va;
   CB_CUDA(cudaMemcpyAsync(d_rp, row_ptr, sizeof(int32_t) * (n + 1), cudaMemcpyHostToDevice, ctx->stream));
   if (nnz) {
     CB_CUDA(cudaMemcpyAsync(d_ci, col_ind, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, ctx->stream));
@@ -233,9 +245,7 @@ int cask_b200_preprocess(cask_b200_ctx* ctx, const cask_b200_design* design, int
   }
   CB_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->design = *design;
-  Plan& p = ctx->plan;
   p.n = n; p.m = m; p.nnz = nnz; p.n_global = n; p.row0_global = 0;
-  p.d_row_ptr = d_rp; p.d_col = d_ci; p.d_val = d_va; p.owns_csr = true;
   return finish_preprocess(ctx);
 }
 

@@ -140,6 +140,11 @@ struct Plan {
   double* d_merge_carry = nullptr;    // per tile: partial sum of the row the tile ends in (0 if it ends on a row boundary)
   int32_t n_merge_tiles = 0;
   int32_t merge_items = kMergeItemsDefault;   // merge items per thread the tiles were cut for
+  // hub clustering (plan.cu: build_col_reorder): columns renumbered by descending reference count for the gather kernel
+  int32_t* d_col_perm = nullptr;      // relabelled copy of d_col (all local nonzeros); nullptr: not reordered
+  int32_t* d_perm = nullptr;          // [m] new column -> old column
+  double* d_xperm = nullptr;          // [cols_used] x in the new numbering, rewritten in front of every SpMV
+  int32_t cols_used = 0;              // columns referenced at least once = the first cols_used new columns
   int32_t max_xcache = 0;
   // persistent staged-ELL kernel configuration (spmv.cu: configure_persistent)
   int32_t persist_ku = 0;       // ELL columns per ring stage (0: persistent kernel not usable)
@@ -291,6 +296,7 @@ struct cask_b200_ctx {
   int32_t csr_stream = 0;    // 1: CSR-stream variant of the gather-CSR kernel (products staged in shared memory)
   int32_t csr_item_nnz = 4096;  // nonzeros per work item of the CSR-stream variant (its shared-memory footprint)
   int32_t merge_items = 0;   // merge-path tiles: merge items per thread (0: default; 5, 7, 11, 17)
+  int32_t col_reorder = 0;   // gather path: 1 = columns renumbered by descending reference count (hub clustering); off by default
   int32_t csr_kernel = -1;   // gather slices: -1 auto (merge-path tiles from kMergeAutoNnz nonzeros), 0 row-group items, 1 merge-path tiles
   int32_t l2_keep = -1;      // -1 auto (vectors of a solver iteration fit L2), 0 never, 1 always: evict-last on vector accesses
   int32_t peer_mode = 1;     // 1: halo pushes and scalar all-reduces by own kernels over mapped peer memory; 0: NCCL

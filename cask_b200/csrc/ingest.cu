@@ -70,6 +70,7 @@ int cask_b200_read_matrix(cask_b200_ctx* ctx, const char* path, int32_t mode, ca
   if (!ctx || !path || !out) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "read_matrix: null");
   *out = nullptr;
   if (mode != 0 && mode != 1) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "read_matrix: mode must be 0 (readMatrix) or 1 (readSymMatrix)");
+  try {  // no C++ exception crosses the C ABI (host allocations of the tokeniser, std::thread)
   mm::File f;
   CB_TRY(mm::read_header(path, &f));
   const std::string p(path);
@@ -80,6 +81,11 @@ int cask_b200_read_matrix(cask_b200_ctx* ctx, const char* path, int32_t mode, ca
   CB_TRY(mm::read_coo(path, &f));
   const int32_t flags = CASK_B200_INGEST_ONE_BASED | (mode == 0 && f.symmetric() ? CASK_B200_INGEST_SYMMETRIC : 0);
   return cask_b200_ingest_coo(ctx, f.n, f.m, f.l, f.rows.data(), f.cols.data(), f.vals.data(), flags, out);
+  } catch (const std::exception& e) {
+    return fail(CASK_B200_ERR_RUNTIME, std::string("read_matrix: ") + e.what());
+  } catch (...) {
+    return fail(CASK_B200_ERR_RUNTIME, "read_matrix: unknown exception");
+  }
 }
 
 int cask_b200_csr_get_info(const cask_b200_csr* csr, int64_t* n, int64_t* m, int64_t* nnz, int64_t* nnzs_field) {

@@ -193,15 +193,17 @@ int read_coo(const std::string& path, File* out) {
   if (out->format != "coordinate")
     return fail(CASK_B200_ERR_INVALID_ARGUMENT, "Expecting a coordinate MatrixMarket file in " + path);  // IO.hpp:133 (assert)
   const int64_t L = out->l;
-  out->rows.assign((size_t)L, 0);
-  out->cols.assign((size_t)L, 0);
-  out->vals.assign((size_t)L, 0.0);
+  // the entry count of the size line is only a claim: the tokens are counted BEFORE anything is sized from it, so a
+  // corrupt header cannot make a tiny file allocate gigabytes
   int T = 1;
   const std::vector<Chunk> ch = make_chunks(f.p, data, f.len, &T);
   const int64_t total = ch.empty() ? 0 : ch.back().first_token + ch.back().tokens;
   if (total < 3 * L)
     return fail(CASK_B200_ERR_INVALID_ARGUMENT, "MatrixMarket file " + path + " ends after " + std::to_string(total / 3) +
                                                     " of " + std::to_string(L) + " entries");
+  out->rows.assign((size_t)L, 0);
+  out->cols.assign((size_t)L, 0);
+  out->vals.assign((size_t)L, 0.0);
   std::atomic<int64_t> bad{INT64_MAX};
   const char* p = f.p;
   int32_t* rows = out->rows.data();
@@ -243,6 +245,9 @@ int read_vector(const std::string& path, std::vector<double>* v) {
   File info;
   size_t data = 0;
   CB_TRY(locate(f, path, &info, &data));
+  if (info.format != "coordinate" && info.n > (int64_t)(f.len - data))  // an array vector needs >= 2 bytes per entry
+    return fail(CASK_B200_ERR_INVALID_ARGUMENT, "MatrixMarket file " + path + " is shorter than the " + std::to_string(info.n) +
+                                                    " entries its size line claims");
   v->assign((size_t)info.n, 0.0);
   int T = 1;
   const char* p = f.p;
@@ -299,18 +304,33 @@ void fill_info(const mm::File& f, cask_b200_mm_info* info) {
 }
 }  // namespace
 
+// No C++ exception may cross the C ABI (std::bad_alloc from a huge size line, std::system_error from std::thread):
+// every entry point maps them to an error code.
+#define CB_ABI_GUARD_BEGIN try {
+#define CB_ABI_GUARD_END(name_)                                                                             \
+  } catch (const std::bad_alloc&) {                                                                         \
+    return fail(CASK_B200_ERR_RUNTIME, std::string(name_) + ": out of host memory");                          \
+  } catch (const std::exception& e) {                                                                       \
+    return fail(CASK_B200_ERR_RUNTIME, std::string(name_) + ": " + e.what());                                 \
+  } catch (...) {                                                                                           \
+    return fail(CASK_B200_ERR_RUNTIME, std::string(name_) + ": unknown exception");                           \
+  }
+
 extern "C" {
 
 int cask_b200_mm_read_info(const char* path, cask_b200_mm_info* info) {
   if (!path || !info) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "mm_read_info: null");
+  CB_ABI_GUARD_BEGIN
   mm::File f;
   CB_TRY(mm::read_header(path, &f));
   fill_info(f, info);
   return CASK_B200_OK;
+  CB_ABI_GUARD_END("mm_read_info")
 }
 
 int cask_b200_mm_read_coo(const char* path, int64_t capacity, int32_t* rows, int32_t* cols, double* vals, int64_t* count) {
   if (!path || !count) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "mm_read_coo: null");
+  CB_ABI_GUARD_BEGIN
   mm::File f;
   CB_TRY(mm::read_coo(path, &f));
   *count = f.l;
@@ -322,10 +342,12 @@ int cask_b200_mm_read_coo(const char* path, int64_t capacity, int32_t* rows, int
     std::memcpy(vals, f.vals.data(), sizeof(double) * (size_t)f.l);
   }
   return CASK_B200_OK;
+  CB_ABI_GUARD_END("mm_read_coo")
 }
 
 int cask_b200_mm_read_vector(const char* path, int64_t capacity, double* out, int64_t* n) {
   if (!path || !n) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "mm_read_vector: null");
+  CB_ABI_GUARD_BEGIN
   std::vector<double> v;
   CB_TRY(mm::read_vector(path, &v));
   *n = (int64_t)v.size();
@@ -333,6 +355,7 @@ int cask_b200_mm_read_vector(const char* path, int64_t capacity, double* out, in
   if (!v.empty() && !out) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "mm_read_vector: null array");
   if (!v.empty()) std::memcpy(out, v.data(), sizeof(double) * v.size());
   return CASK_B200_OK;
+  CB_ABI_GUARD_END("mm_read_vector")
 }
 
 }  // extern "C"

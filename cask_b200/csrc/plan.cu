@@ -273,6 +273,58 @@ __global__ void merge_tiles_kernel(const MergeRun* __restrict__ runs, int nruns,
   tiles[g] = t;
 }
 
+// CSR sanity before anything indexes with it (plan_count_kernel's bitmap, the gathers): row_ptr starts at 0, ends at nnz
+// and never decreases; every column lies in [0, m).  *bad = 1 + the first kind of violation seen (any thread may win).
+__global__ void __launch_bounds__(256) validate_csr_kernel(const int32_t* __restrict__ row_ptr, int64_t n, int64_t nnz,
+                                                           const int32_t* __restrict__ col, int64_t m, int32_t* __restrict__ bad) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int64_t r = t0; r <= n; r += stride) {
+    const int32_t v = row_ptr[r];
+    if ((r == 0 && v != 0) || (r == n && v != nnz) || v < 0 || v > nnz || (r < n && row_ptr[r + 1] < v)) *bad = 1;
+  }
+  for (int64_t k = t0; k < nnz; k += stride) {
+    const int32_t c = col[k];
+    if (c < 0 || c >= m) *bad = 2;
+  }
+}
+
+// ---- column reordering of the gather path (hub clustering) ------------------------------------------------------------
+// A power-law matrix sends most of its x gathers to a small set of hub columns that are scattered over the index space
+// (R-MAT: the columns with few 1-bits), so every gather drags a 32-byte sector through L2 for 8 useful bytes, hot and cold
+// entries share 128-byte lines, and the cache holds far fewer hot entries than its size suggests (ncu on scale 25: 26 % of
+// the x sectors miss L2, 5.2 GB of DRAM reads beside the 6.0 GB matrix stream; profiles/r2c_spmv_merge_rmat_ncu.md).
+// The plan therefore renumbers the columns by descending reference count (stable: equal counts keep their order, never
+// referenced columns go last): y = A x = (A P^T)(P x).  The gather kernel reads a relabelled copy of the column array and a
+// permuted copy of x that a streaming kernel writes in front of every SpMV (only the referenced columns).  Hubs then share
+// lines (L1 hits), every sector the cache holds is full of hot entries, and the cold tail is a compacted stream.
+__global__ void __launch_bounds__(256) col_count_kernel(const int32_t* __restrict__ col, int64_t nnz, int32_t* __restrict__ counts) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += stride) atomicAdd(counts + col[k], 1);
+}
+__global__ void __launch_bounds__(256) col_keys_kernel(const int32_t* __restrict__ counts, int64_t m, uint64_t* __restrict__ keys,
+                                                       uint32_t* __restrict__ ids) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += stride) {
+    keys[j] = (uint64_t)(0x7fffffff - counts[j]);  // ascending key = descending count
+    ids[j] = (uint32_t)j;
+  }
+}
+// inv[old column] = new column; *used = number of columns referenced at least once (they are the first *used new columns)
+__global__ void __launch_bounds__(256) col_inverse_kernel(const uint32_t* __restrict__ perm, const uint64_t* __restrict__ keys,
+                                                          int64_t m, int32_t* __restrict__ inv, int32_t* __restrict__ used) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += stride) {
+    inv[perm[j]] = (int32_t)j;
+    const bool ref = keys[j] != 0x7fffffffull;
+    if (ref && (j == m - 1 || keys[j + 1] == 0x7fffffffull)) *used = (int32_t)(j + 1);
+  }
+}
+__global__ void __launch_bounds__(256) col_relabel_kernel(const int32_t* __restrict__ col, int64_t nnz, const int32_t* __restrict__ inv,
+                                                          int32_t* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += stride) out[k] = inv[col[k]];
+}
+
 }  // namespace
 
 void free_plan(cask_b200_ctx* ctx) {
@@ -287,6 +339,7 @@ void free_plan(cask_b200_ctx* ctx) {
   cudaFree(p.d_list_ell); cudaFree(p.d_list_csr);
   cudaFree(p.d_csr_items); cudaFree(p.d_split_rows); cudaFree(p.d_csr_scratch);
   cudaFree(p.d_merge_tiles); cudaFree(p.d_merge_carry);
+  cudaFree(p.d_col_perm); cudaFree(p.d_perm); cudaFree(p.d_xperm);
   p = Plan();
 }
 
@@ -423,6 +476,56 @@ int build_csr_items(cask_b200_ctx* ctx) {
   return CASK_B200_OK;
 }
 
+// Hub clustering of the gather path (see col_count_kernel above).  Opt-in (option col_reorder = 1): measured on R-MAT
+// scale 25 (profiles/r2k_rmat_reorder.md) the gather phase alone falls from 3.04 to 2.36 ms, DRAM reads from 9.6 to 7.8 GB,
+// but the whole SpMV only from 3.21 to 3.17 ms - with the hubs served by L1 the kernel becomes bound by the LSU wavefront
+// rate its reduction phases share with the gathers, and the permutation of x costs 0.12 ms per call.
+static int build_col_reorder(cask_b200_ctx* ctx) {
+  Plan& p = ctx->plan;
+  cudaFree(p.d_col_perm); cudaFree(p.d_perm); cudaFree(p.d_xperm);
+  p.d_col_perm = nullptr; p.d_perm = nullptr; p.d_xperm = nullptr;
+  p.cols_used = 0;
+  p.stats.col_reorder = 0;
+  p.stats.cols_referenced = 0;
+  if (!p.csr_merge || p.nnz <= 0 || p.m <= 0 || p.m >= (1ll << 30)) return CASK_B200_OK;
+  if (ctx->col_reorder != 1) return CASK_B200_OK;
+  cudaStream_t s = ctx->stream;
+  dev::Exec ex = dev::exec_of(ctx);
+  struct Tmp {
+    void* q[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    ~Tmp() { for (void* x : q) cudaFree(x); }
+  } tmp;
+  const int64_t m = p.m;
+  const int grid = ctx->sm_count * 8;
+  CB_CUDA(cudaMalloc(&tmp.q[0], sizeof(int32_t) * (size_t)m));       // counts, then the inverse permutation
+  CB_CUDA(cudaMalloc(&tmp.q[1], sizeof(uint64_t) * (size_t)m));      // keys
+  CB_CUDA(cudaMalloc(&tmp.q[2], sizeof(uint64_t) * (size_t)m));      // sorted keys
+  CB_CUDA(cudaMalloc(&tmp.q[3], sizeof(uint32_t) * (size_t)m));      // column ids
+  CB_CUDA(cudaMalloc(&tmp.q[4], sizeof(int32_t)));                   // referenced columns
+  CB_CUDA(cudaMalloc(&p.d_perm, sizeof(int32_t) * (size_t)m));
+  CB_CUDA(cudaMemsetAsync(tmp.q[0], 0, sizeof(int32_t) * (size_t)m, s));
+  CB_CUDA(cudaMemsetAsync(tmp.q[4], 0, sizeof(int32_t), s));
+  col_count_kernel<<<grid, 256, 0, s>>>(p.d_col, p.nnz, (int32_t*)tmp.q[0]);
+  col_keys_kernel<<<grid, 256, 0, s>>>((const int32_t*)tmp.q[0], m, (uint64_t*)tmp.q[1], (uint32_t*)tmp.q[3]);
+  ctx->launches += 2;
+  CB_TRY(dev::sort_pairs_u64_u32(ex, (const uint64_t*)tmp.q[1], (uint64_t*)tmp.q[2], (const uint32_t*)tmp.q[3],
+                                 (uint32_t*)p.d_perm, m, 31));
+  col_inverse_kernel<<<grid, 256, 0, s>>>((const uint32_t*)p.d_perm, (const uint64_t*)tmp.q[2], m, (int32_t*)tmp.q[0],
+                                          (int32_t*)tmp.q[4]);
+  CB_CUDA(cudaMalloc(&p.d_col_perm, sizeof(int32_t) * (size_t)p.nnz));
+  col_relabel_kernel<<<grid, 256, 0, s>>>(p.d_col, p.nnz, (const int32_t*)tmp.q[0], p.d_col_perm);
+  ctx->launches += 2;
+  int32_t used = 0;
+  CB_CUDA(cudaMemcpyAsync(&used, tmp.q[4], sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  CB_CUDA(cudaStreamSynchronize(s));
+  CB_CUDA(cudaGetLastError());
+  p.cols_used = used;
+  CB_CUDA(cudaMalloc(&p.d_xperm, sizeof(double) * (size_t)std::max<int64_t>(used, 2)));
+  p.stats.col_reorder = 1;
+  p.stats.cols_referenced = used;
+  return CASK_B200_OK;
+}
+
 // Coded staged ELL (option value_dict): per-slice tables + 8-bit codes (valuedict_logic.inl).
 //   value_dict = 2  (value, x-cache displacement) PAIR codes: 1 byte per stored nonzero, no index stream;
 //   value_dict = 1  value codes beside the 16-bit indices: 3 bytes per stored nonzero.
@@ -498,6 +601,22 @@ int build_plan(cask_b200_ctx* ctx) {
       start += rows;
     }
   }
+  if (n > 0) {
+    int32_t* d_bad = nullptr;
+    int32_t bad = 0;
+    CB_CUDA(cudaMalloc(&d_bad, sizeof(int32_t)));
+    cudaMemsetAsync(d_bad, 0, sizeof(int32_t), s);
+    validate_csr_kernel<<<std::min<int64_t>((std::max(n + 1, p.nnz) + 255) / 256, 148 * 8), 256, 0, s>>>(p.d_row_ptr, n, p.nnz, p.d_col, p.m,
+                                                                                                      d_bad);
+    ctx->launches++;
+    const cudaError_t e = cudaMemcpyAsync(&bad, d_bad, sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+    const cudaError_t e2 = cudaStreamSynchronize(s);
+    cudaFree(d_bad);
+    CB_CUDA(e);
+    CB_CUDA(e2);
+    if (bad == 1) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "preprocess: row_ptr must start at 0, end at nnz and never decrease");
+    if (bad == 2) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "preprocess: a column index lies outside [0, m)");
+  }
   p.nslices = (int32_t)row0s.size();
   p.stats = cask_b200_plan_stats{};
   p.stats.n = n; p.stats.m = p.m; p.stats.nnz = p.nnz;
@@ -509,11 +628,18 @@ int build_plan(cask_b200_ctx* ctx) {
   if (cache > kMaxCacheDoubles) cache = kMaxCacheDoubles;
   const int32_t max_gran = std::max(0, (cache - kZeroSlots) / kGranule);
 
+  struct Scratch {  // device temporaries of this function: released on every exit path
+    std::vector<void*> v;
+    ~Scratch() { for (void* x : v) cudaFree(x); }
+  } scratch;
   int32_t *d_row0 = nullptr, *d_nrows = nullptr;
   SliceCount* d_counts = nullptr;
   CB_CUDA(cudaMalloc(&d_row0, sizeof(int32_t) * p.nslices));
+  scratch.v.push_back(d_row0);
   CB_CUDA(cudaMalloc(&d_nrows, sizeof(int32_t) * p.nslices));
+  scratch.v.push_back(d_nrows);
   CB_CUDA(cudaMalloc(&d_counts, sizeof(SliceCount) * p.nslices));
+  scratch.v.push_back(d_counts);
   CB_CUDA(cudaMemcpyAsync(d_row0, row0s.data(), sizeof(int32_t) * p.nslices, cudaMemcpyHostToDevice, s));
   CB_CUDA(cudaMemcpyAsync(d_nrows, nrows.data(), sizeof(int32_t) * p.nslices, cudaMemcpyHostToDevice, s));
   CB_CUDA(cudaFuncSetAttribute(plan_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SliceSmem)));
@@ -524,7 +650,9 @@ int build_plan(cask_b200_ctx* ctx) {
   unsigned long long* d_hist = nullptr;
   int32_t* d_maxlen = nullptr;
   CB_CUDA(cudaMalloc(&d_hist, sizeof(unsigned long long) * 8));
+  scratch.v.push_back(d_hist);
   CB_CUDA(cudaMalloc(&d_maxlen, sizeof(int32_t)));
+  scratch.v.push_back(d_maxlen);
   CB_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * 8, s));
   CB_CUDA(cudaMemsetAsync(d_maxlen, 0, sizeof(int32_t), s));
   row_length_histogram_kernel<<<std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, s>>>(p.d_row_ptr, n, d_hist, d_maxlen);
@@ -608,7 +736,6 @@ int build_plan(cask_b200_ctx* ctx) {
   }
   CB_CUDA(cudaStreamSynchronize(s));
   CB_CUDA(cudaGetLastError());
-  cudaFree(d_row0); cudaFree(d_nrows); cudaFree(d_counts); cudaFree(d_hist); cudaFree(d_maxlen);
 
   CB_TRY(build_value_dict(ctx, val_off));
   CB_TRY(configure_persistent(ctx));
@@ -619,6 +746,7 @@ int build_plan(cask_b200_ctx* ctx) {
   p.stats.max_row_length = maxlen;
   p.stats.csr_nnz = csr_nnz;
   p.stats.csr_rows = csr_rows;
+  CB_TRY(build_col_reorder(ctx));
   p.stats.persist_ku = ctx->ell_kernel == 1 ? p.persist_ku : 0;
   p.stats.persist_stages = p.persist_stages;
   p.stats.persist_ctas_per_sm = p.persist_ctas_per_sm;
@@ -627,7 +755,8 @@ int build_plan(cask_b200_ctx* ctx) {
   p.stats.device_bytes = val_off * (p.coded ? 11 : 10) + (p.coded == 1 ? (int64_t)p.nslices * valuedict::kStride * 8 : 0) +
                          (p.coded == 2 ? (int64_t)p.nslices * valuedict::kPairStride * 16 : 0) +
                          (int64_t)run_off * sizeof(Run) + (int64_t)p.nslices * sizeof(SliceDesc) +
-                         (p.n_csr ? (csr_nnz * 12 + csr_rows * 4) : 0);
+                         (p.n_csr ? (csr_nnz * 12 + csr_rows * 4) : 0) +
+                         (p.d_col_perm ? p.nnz * 4 + p.m * 4 + (int64_t)p.cols_used * 8 : 0);
   return CASK_B200_OK;
 }
 

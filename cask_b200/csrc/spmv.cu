@@ -639,12 +639,32 @@ spmv_csr_fixup_kernel(const SplitRow* __restrict__ rows, int count, const double
 //      carry[tile], and spmv_csr_merge_fixup_kernel adds the carries of the tiles a long row spans, in tile order.
 // Everything is deterministic (fixed tile -> CTA and item -> thread maps, ordered carries); the summation order inside a
 // row differs from CsrMatrix::dot, as for every gather kernel (parity bar: 1e-12 relative to sum |a_ij x_j|).
+constexpr int kMergeXPastL1 = 1;     // x gathers with ld.global.cg
+constexpr int kMergeStreamOnly = 2;  // diagnostic: stop after phase A (what the matrix stream + gathers cost alone)
+constexpr int kMergeNoGather = 4;    // diagnostic: x = 1 instead of the gather (what everything but the gathers costs)
+
+// x in the plan's hub-clustered column numbering (plan.cu: build_col_reorder): xp[i] = x[perm[i]] for the referenced
+// columns.  perm is ascending inside every run of equal reference counts, so beyond the hubs the reads are a handful of
+// interleaved forward sweeps over x; two entries per thread, 16-byte stores.
+__global__ void __launch_bounds__(256) permute_x_kernel(const int32_t* __restrict__ perm, const double* __restrict__ x,
+                                                        double* __restrict__ xp, int32_t used) {
+  const int32_t stride = (int32_t)(gridDim.x * blockDim.x) * 2;
+  for (int32_t i = (int32_t)(blockIdx.x * blockDim.x + threadIdx.x) * 2; i < used; i += stride) {
+    if (i + 1 < used) {
+      const int2 q = __ldcs(reinterpret_cast<const int2*>(perm + i));
+      *reinterpret_cast<double2*>(xp + i) = make_double2(__ldg(x + q.x), __ldg(x + q.y));
+    } else {
+      xp[i] = __ldg(x + perm[i]);
+    }
+  }
+}
+
 template <bool kDot, int ITEMS>
 __global__ void __launch_bounds__(kMergeThreads, ITEMS > 11 ? 4 : 5)
 spmv_csr_merge_kernel(const MergeTile* __restrict__ tiles, int32_t n_rows, const int32_t* __restrict__ row_ptr,
                       const int32_t* __restrict__ col, const double* __restrict__ val, const double* __restrict__ x,
                       double* __restrict__ y, const double* __restrict__ dot_with, double* __restrict__ partials,
-                      double* __restrict__ carry, int x_past_l1) {
+                      double* __restrict__ carry, int flags) {
   constexpr int TILE = kMergeThreads * ITEMS;       // merge items (row ends + nonzeros) per tile
   constexpr int BATCH = ITEMS < 8 ? ITEMS : 8;      // nonzeros per thread in flight in phase A
   extern __shared__ __align__(16) unsigned char merge_smem[];
@@ -676,7 +696,8 @@ spmv_csr_merge_kernel(const MergeTile* __restrict__ tiles, int32_t n_rows, const
       v[u] = ok ? __ldcs(vp + j) : 0.0;
     }
 #pragma unroll
-    for (int u = 0; u < BATCH; u++) xv[u] = x_past_l1 ? __ldcg(x + c[u]) : __ldg(x + c[u]);  // A/B: gathers cached in L2 only
+    for (int u = 0; u < BATCH; u++)  // A/B: gathers cached in L2 only; diagnostic: no gather at all
+      xv[u] = (flags & kMergeNoGather) ? 1.0 : (flags & kMergeXPastL1) ? __ldcg(x + c[u]) : __ldg(x + c[u]);
 #pragma unroll
     for (int u = 0; u < BATCH; u++) {
       const int j = j0 + u * kMergeThreads + tid;
@@ -684,6 +705,10 @@ spmv_csr_merge_kernel(const MergeTile* __restrict__ tiles, int32_t n_rows, const
     }
   }
   __syncthreads();
+  if (flags & kMergeStreamOnly) {  // diagnostic (CASK_B200_MERGE_DIAG): phase A alone, y is NOT computed
+    if (tid == 0) carry[blockIdx.x] = prod[0];
+    return;
+  }
 
   // ---- B: this thread's stretch of the merge path ----
   const int total = nnzT + nrowsT;
@@ -980,13 +1005,24 @@ int launch_spmv_range(cask_b200_ctx* ctx, const double* d_x, double* d_y, int el
       const int fix = (tiles + 255) / 256;
       // x gathers cached in L2 only: an L1 line per scattered 8-byte gather buys nothing (4 % sector hit rate) and costs
       // the miss tracking the next gathers need; measured 3.25 vs 3.33 ms on R-MAT scale 25 (profiles/r2c_rmat_sweep.md)
-      static const int x_past_l1 = getenv("CASK_B200_MERGE_XCG") ? atoi(getenv("CASK_B200_MERGE_XCG")) : 1;
+      // with hub-clustered columns (plan.cu: build_col_reorder) the hubs share lines and L1 is what serves them
+      static const int xcg_env = getenv("CASK_B200_MERGE_XCG") ? atoi(getenv("CASK_B200_MERGE_XCG")) : -1;
+      static const int diag = getenv("CASK_B200_MERGE_DIAG") ? atoi(getenv("CASK_B200_MERGE_DIAG")) & 6 : 0;
+      const int32_t* cols = p.d_col;
+      const double* xg = d_x;
+      if (p.d_col_perm) {
+        permute_x_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(p.d_perm, d_x, p.d_xperm, p.cols_used);
+        ctx->launches++;
+        cols = p.d_col_perm;
+        xg = p.d_xperm;
+      }
+      const int flags = ((xcg_env >= 0 ? xcg_env : (p.d_col_perm ? 0 : 1)) ? kMergeXPastL1 : 0) | diag;
 #define CB_MERGE(DOT, ITEMS)                                                                                              \
   do {                                                                                                                    \
     CB_CUDA(cudaFuncSetAttribute(spmv_csr_merge_kernel<DOT, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    spmv_csr_merge_kernel<DOT, ITEMS><<<tiles, kMergeThreads, smem, s>>>(p.d_merge_tiles + i_lo, (int32_t)p.n, p.d_row_ptr, p.d_col, \
-                                                                         p.d_val, d_x, d_y, w, partials, p.d_merge_carry + i_lo,     \
-                                                                         x_past_l1);                                                 \
+    spmv_csr_merge_kernel<DOT, ITEMS><<<tiles, kMergeThreads, smem, s>>>(p.d_merge_tiles + i_lo, (int32_t)p.n, p.d_row_ptr, cols,    \
+                                                                         p.d_val, xg, d_y, w, partials, p.d_merge_carry + i_lo,      \
+                                                                         flags);                                                     \
   } while (0)
 #define CB_MERGE_ITEMS(DOT)                                                      \
   switch (p.merge_items) {                                                       \

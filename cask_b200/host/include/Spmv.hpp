@@ -7,7 +7,9 @@
 // reference's messages.  The north_star's older spellings are kept as aliases at the bottom.
 #ifndef CASK_B200_HOST_SPMV_HPP
 #define CASK_B200_HOST_SPMV_HPP
+#include <algorithm>
 #include <chrono>
+#include <iostream>
 #include <memory>
 #include <sstream>
 #include <stdexcept>
@@ -120,20 +122,55 @@ class Spmv {
     preprocessed = true;
   }
 
-  // Spmv::spmv, Spmv.cpp:185-328 (argument checks happen behind the ABI with the same messages)
+  // Spmv::spmv, Spmv.cpp:185-328 (argument checks happen behind the ABI with the same messages).  Prints the complete
+  // set of "Result  <key>=" lines of Spmv.cpp:266-301 in the reference's order, so the frontend's scrapers
+  // (src/frontend/cask.py:360-368) keep working: the three per-partition cycle lists come from the reference-format
+  // partitions the GPU partitioner emits (empty lists where that format cannot exist, rows x blocks > INT32_MAX), the
+  // estimates follow the reference's formulas on its 200 MHz model clock, "Iterations" is 1 (the reference's device call
+  // runs the product twice and halves the time), "Took (ms)" and "Gflops (actual)" are measured around the ABI call.
   Vector spmv(const Vector& x) {
     if (!preprocessed) throw std::runtime_error("numPipes should equal numPartitions");  // Spmv.cpp:222-224: nothing preprocessed
     if (x.size() < mat.m) throw std::invalid_argument("spmv: x has fewer entries than the matrix has columns");
     Vector y(mat.n);
+    std::vector<int> totalCycles, paddingCycles, reductionCycles;
+    if (log_results) {
+      for (int p = 0; p < impl.num_pipes; p++) {
+        cask_b200_partition_info info;
+        if (cask_b200_partition_get_info(ctx.get(), p, &info) != CASK_B200_OK) {
+          totalCycles.clear(); paddingCycles.clear(); reductionCycles.clear();
+          break;
+        }
+        totalCycles.push_back(info.totalCycles);
+        paddingCycles.push_back(info.paddingCycles);
+        reductionCycles.push_back(info.reductionCycles);
+      }
+      std::cout << "Running on B200" << std::endl;  // Spmv.cpp:262 prints "Running on DFE" here (not scraped)
+      utils::logResult("Total cycles", totalCycles);
+      utils::logResult("Padding cycles", paddingCycles);
+      utils::logResult("Reduction cycles", reductionCycles);
+    }
+    const int nIterations = 1;
     const auto t0 = std::chrono::high_resolution_clock::now();
     detail::throw_on(cask_b200_spmv(ctx.get(), x.data.data(), y.data.data()));
-    const double took = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
-    utils::logResult("Input width ", impl.input_width);  // Spmv.cpp:293-300 keeps the frontend's scrapers working
-    utils::logResult("Pipes ", impl.num_pipes);
-    utils::logResult("Took (ms)", took * 1e3);
-    utils::logResult("Gflops (actual)", 2.0 * (double)mat.nnzs / took / 1e9);
+    const double took = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count() / nIterations;
+    if (log_results) {
+      const double maxCycles = totalCycles.empty() ? 0.0 : (double)*std::max_element(totalCycles.begin(), totalCycles.end());
+      const double bwidthEst = impl.num_pipes * impl.input_width * getFrequency() * 12 / 1E9;  // Spmv.cpp:285-289
+      const double scalingFactor = std::max(bwidthEst / 65.0, 1.0);
+      const double est = maxCycles / getFrequency();
+      const double gflopsEst = est > 0 ? (2.0 * (double)mat.nnzs / (est * scalingFactor)) / 1E9 : 0.0;
+      utils::logResult("Input width ", impl.input_width);
+      utils::logResult("Pipes ", impl.num_pipes);
+      utils::logResult("Iterations", nIterations);
+      utils::logResult("Took (ms)", took * 1e3);
+      utils::logResult("Est (ms)", est);
+      utils::logResult("Gflops (est)", gflopsEst);
+      utils::logResult("Gflops (actual)", 2.0 * (double)mat.nnzs / took / 1e9);
+      utils::logResult("BWidth (est)", bwidthEst);
+    }
     return y;
   }
+  bool log_results = true;  // solver loops that call spmv() every iteration switch the Result lines off
 
   // Spmv::do_blocking, Spmv.cpp:42-107: the reference-format partition of a (stripe) matrix
   Partition do_blocking(const CsrMatrix& m, int blockSize, int inputWidth) {

@@ -85,6 +85,8 @@ typedef struct {
   int32_t persist_ku;           /* persistent staged-ELL kernel: ELL columns per ring stage (0: kernel not in use) */
   int32_t persist_stages, persist_ctas_per_sm;
   int32_t value_dict;           /* format in use: 0 uncoded, 1 value codes, 2 pair codes */
+  int32_t col_reorder;          /* 1: the gather kernel runs on columns renumbered by descending reference count */
+  int64_t cols_referenced;      /* columns referenced at least once (valid when col_reorder is 1) */
 } cask_b200_plan_stats;
 
 /* ---- context ---------------------------------------------------------------------------- */
@@ -104,7 +106,9 @@ int cask_b200_synchronize(cask_b200_ctx* ctx);
  * "force_csr_vec" (0 auto, else 2/4/8/16/32 lanes per row), "peer_mode" (row-sharded solvers: 1 = halo pushes
  * and scalar all-reduces by the library's own kernels over IPC-mapped peer memory, 0 = NCCL send/recv and
  * all-reduce; every rank must use the same value), "value_dict" (0 default, 1 / 2 = coded staged ELL, see
- * cask_b200_plan_value_dict), "persist_ctas" (coded format: CTAs per SM of the persistent kernel, 0 auto).
+ * cask_b200_plan_value_dict), "persist_ctas" (coded format: CTAs per SM of the persistent kernel, 0 auto),
+ * "col_reorder" (gather path, default 0; 1 = columns renumbered by descending reference count so that the hub columns
+ * of a power-law matrix share cache lines; x is permuted by a streaming kernel in front of every SpMV).
  * Takes effect at the next preprocess. */
 int cask_b200_set_option(cask_b200_ctx* ctx, const char* name, double value);
 

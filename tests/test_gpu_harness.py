@@ -51,6 +51,13 @@ def test_host_mirror_test_spmv(mtx_dir):
     for impl in ("0", "1", "2"):
         rc, out = _run([exe, str(mtx_dir / "test_cage6.mtx"), impl])
         assert rc == 0, out[-2000:]
+        # the complete "Result  <key>=" set of Spmv.cpp:266-301, in the reference's order, one cycle figure per pipe
+        keys = [l.split("=")[0][len("Result  "):] for l in out.splitlines() if l.startswith("Result  ")]
+        assert keys == ["Total cycles", "Padding cycles", "Reduction cycles", "Input width ", "Pipes ", "Iterations",
+                        "Took (ms)", "Est (ms)", "Gflops (est)", "Gflops (actual)", "BWidth (est)"], keys
+        pipes = int([l for l in out.splitlines() if l.startswith("Result  Pipes ")][0].split("=")[1].rstrip(","))
+        total = [l for l in out.splitlines() if l.startswith("Result  Total cycles")][0].split("=")[1]
+        assert len([v for v in total.split(",") if v]) == pipes and all(int(v) > 0 for v in total.split(",") if v)
     rc, out = _run([exe, str(mtx_dir / "test_cage6.mtx"), "7"])  # vector::at -> std::out_of_range like the reference
     assert rc != 0
 

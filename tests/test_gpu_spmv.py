@@ -202,3 +202,66 @@ def test_merge_path_fused_dot_in_cg(gpu_lib, ctx, oracle):
     oc, oi, ox, _ = oracle.pcg(n, rp, ci, va, b, lower=False)
     assert res[1][0] and abs(res[1][1] - oi) <= 1 and abs(res[1][1] - res[0][1]) <= 1
     assert np.allclose(res[1][2], ox, rtol=0, atol=1e-6)
+
+
+# ---- hub clustering of the gather path (option col_reorder, off by default) -----------------------------------------
+def test_col_reorder_all_fixtures_and_edge_cases(golden, gpu_lib, ctx, oracle):
+    """Columns renumbered by descending reference count + x permuted in front of every SpMV: same y (tolerance of the
+    gather kernels) on every fixture, on rectangular matrices whose referenced-column count is odd, on matrices most of
+    whose columns are never referenced, and with a fused dot inside CG."""
+    ctx.set_option("csr_kernel", 1)
+    ctx.set_option("force_kind", 1)
+    ctx.set_option("col_reorder", 1)
+    _check_all(golden, gpu_lib, ctx, gpu_lib.design(3, 2048, 16), exact=False)
+    st = ctx.plan_stats()
+    assert st["col_reorder"] == 1 and 0 < st["cols_referenced"] <= st["m"], st
+    ctx.set_option("force_kind", -1)   # mixed plans: staged slices read x, gather slices the permuted copy
+    _check_all(golden, gpu_lib, ctx, gpu_lib.design(4, 512, 8, arch=1), exact=False)
+    ctx.set_option("force_kind", 1)
+    rng = np.random.default_rng(5)
+    import scipy.sparse as sp
+    for n, m, used in ((700, 90001, 333), (5000, 4097, 4097), (1, 9, 9), (3000, 3000, 1)):
+        cols_pool = rng.choice(m, used, replace=False)
+        lens = rng.integers(0, 9, n)
+        rows = np.repeat(np.arange(n), lens)
+        a = sp.csr_matrix((np.ones(len(rows)), (rows, cols_pool[rng.integers(0, used, len(rows))])), shape=(n, m))
+        a.sum_duplicates()
+        a.sort_indices()
+        a.data = rng.standard_normal(len(a.data))
+        rp, ci, va = a.indptr.astype(np.int32), a.indices.astype(np.int32), a.data.astype(np.float64)
+        x = rng.standard_normal(m)
+        ctx.preprocess(gpu_lib.design(2, 64, 4), n, m, rp, ci, va)
+        st = ctx.plan_stats()
+        if len(ci):
+            assert st["col_reorder"] == 1 and st["cols_referenced"] == len(np.unique(ci)), st
+        got = ctx.spmv(x)
+        assert_y_close(got, oracle.csr_dot(n, rp, ci, va, x), row_scale(n, rp, ci, va, x))
+        x2 = rng.standard_normal(m)                                        # x is re-permuted on every call
+        assert_y_close(ctx.spmv(x2), oracle.csr_dot(n, rp, ci, va, x2), row_scale(n, rp, ci, va, x2))
+        assert np.array_equal(got, ctx.spmv(x))
+    n, rp, ci, va = oracle.gen_poisson3d27(12)
+    b = oracle.csr_dot(n, rp, ci, va, 1.0 + 0.25 * (np.arange(n) % 4))
+    ctx.preprocess(gpu_lib.design(1, 8192, 16), n, n, rp, ci, va)
+    assert ctx.plan_stats()["col_reorder"] == 1
+    conv, iters, sol, _ = ctx.cg(b)
+    oc, oi, ox, _ = oracle.pcg(n, rp, ci, va, b, lower=False)
+    assert conv and abs(iters - oi) <= 1 and np.allclose(sol, ox, rtol=0, atol=1e-6)
+
+
+def test_col_reorder_rmat(gpu_lib, ctx, oracle):
+    """R-MAT twin: the reordered plan agrees with the plain merge kernel, the oracle, and puts the hubs first."""
+    n, rp, ci, va = oracle.gen_rmat(16, 24, 3)
+    x = np.random.default_rng(2).standard_normal(n)
+    d = gpu_lib.design(1, 8192, 16)
+    ctx.preprocess(d, n, n, rp, ci, va)
+    st = ctx.plan_stats()
+    assert st["csr_kernel"] == 1 and st["col_reorder"] == 0, st     # opt-in
+    y0 = ctx.spmv(x)
+    ctx.set_option("col_reorder", 1)
+    ctx.preprocess(d, n, n, rp, ci, va)
+    st = ctx.plan_stats()
+    assert st["col_reorder"] == 1 and st["cols_referenced"] == len(np.unique(ci)), st
+    y1 = ctx.spmv(x)
+    scale = row_scale(n, rp, ci, va, x)
+    assert_y_close(y1, oracle.csr_dot(n, rp, ci, va, x), scale)
+    assert_y_close(y1, y0, scale)

@@ -92,6 +92,17 @@ def test_malformed_and_truncated_files_fail_loudly(tmp_path):
         f.write("%%MatrixMarket matrix coordinate real general\n% only comments\n")
     with pytest.raises(cb.CaskError):
         cb.mm_read_info(p)
+    # a size line that claims 2^31-1 entries in a 70-byte file is an error code, not a 32 GB allocation / std::terminate
+    with open(p, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate real general\n2 2 2147483647\n1 1 1.0\n")
+    with pytest.raises(cb.CaskError) as e:
+        cb.mm_read_coo(p)
+    assert "ends after 1 of 2147483647 entries" in e.value.message
+    with open(p, "w") as f:
+        f.write("%%MatrixMarket matrix array real general\n2147483647 1\n1.0\n")
+    with pytest.raises(cb.CaskError) as e:
+        cb.mm_read_vector(p)
+    assert "shorter than" in e.value.message
 
 
 def test_large_file_takes_the_multithreaded_path(tmp_path):
