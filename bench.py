@@ -696,8 +696,43 @@ def main():
         barrier()
         pg_s = (time.perf_counter() - t0) / e2e_steps
         assert np.array_equal(py, hy.numpy())
-        e2e["pageable"] = {"value": flops / pg_s / 1e9, "ms_per_step": 1e3 * pg_s}
+        e2e["pageable"] = {"value": flops / pg_s / 1e9, "ms_per_step": 1e3 * pg_s,
+                           "how": "library-staged: pinned 4 MB rings filled / drained by host copy threads (hostcopy.hpp)"}
+        # ... and with the staging left to the driver (what round 1 measured)
+        ctx.set_option("host_staging", 0)
+        ctx.spmv_into(px, py)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            ctx.spmv_into(px, py)
+        barrier()
+        e2e["pageable"]["driver_staged_ms_per_step"] = 1e3 * (time.perf_counter() - t0) / 3
+        ctx.set_option("host_staging", 1)
         del px, py
+        # the floor under any host-buffer call: the same bytes over PCIe in both directions at once, no kernel
+        try:
+            s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+            dx_probe, dy_probe = torch.empty(n_local, dtype=torch.float64, device=dev), torch.empty(n_local, dtype=torch.float64, device=dev)
+            def duplex(up, dn):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(5):
+                    if up:
+                        with torch.cuda.stream(s_up):
+                            dx_probe.copy_(hx, non_blocking=True)
+                    if dn:
+                        with torch.cuda.stream(s_dn):
+                            hy.copy_(dy_probe, non_blocking=True)
+                torch.cuda.synchronize()
+                return (time.perf_counter() - t0) / 5
+            duplex(True, True)
+            t_up, t_dn, t_both = duplex(True, False), duplex(False, True), duplex(True, True)
+            e2e["pcie"] = {"h2d_gbs": 8.0 * n_local / t_up / 1e9, "d2h_gbs": 8.0 * n_local / t_dn / 1e9,
+                           "duplex_ms_for_one_step": 1e3 * t_both,
+                           "note": "pinned copies of one step's x and y alone, both directions at once: the floor of e2e"}
+            del dx_probe, dy_probe
+        except Exception as ex:  # noqa: BLE001 - informational
+            e2e["pcie"] = {"error": repr(ex)[:200]}
 
     # ---- CG iterations / s on the 3D 27-point system (strong scaling: fixed 256^3 grid) -----------
     cg = bicg = rmat = None

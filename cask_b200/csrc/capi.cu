@@ -104,6 +104,7 @@ int cask_b200_create(cask_b200_ctx** out, int device) {
   if (const char* e = getenv("CASK_B200_ELL_KERNEL")) ctx->ell_kernel = atoi(e);
   if (const char* e = getenv("CASK_B200_PERSIST_KU")) ctx->persist_ku = atoi(e);
   if (const char* e = getenv("CASK_B200_HOST_CHUNKS")) ctx->host_pipeline_chunks = atoi(e);
+  if (const char* e = getenv("CASK_B200_HOST_STAGING")) ctx->host_staging = atoi(e);
   if (const char* e = getenv("CASK_B200_PEER")) ctx->peer_mode = atoi(e);
   if (const char* e = getenv("CASK_B200_L2_KEEP")) ctx->l2_keep = atoi(e);
   if (const char* e = getenv("CASK_B200_CSR_STREAM")) ctx->csr_stream = atoi(e);
@@ -112,6 +113,8 @@ int cask_b200_create(cask_b200_ctx** out, int device) {
   if (const char* e = getenv("CASK_B200_L2_KEEP")) ctx->l2_keep = atoi(e);
   if (const char* e = getenv("CASK_B200_MERGE_ITEMS")) ctx->merge_items = atoi(e);
   if (const char* e = getenv("CASK_B200_COL_REORDER")) ctx->col_reorder = atoi(e);
+  if (const char* e = getenv("CASK_B200_DIST_SPARSE")) ctx->dist_sparse = atoi(e);
+  if (const char* e = getenv("CASK_B200_ILU_GRAPH")) ctx->ilu_graph = atoi(e);
   if (const char* e = getenv("CASK_B200_VALUE_DICT")) ctx->value_dict = atoi(e);
   if (const char* e = getenv("CASK_B200_PERSIST_CTAS")) ctx->persist_ctas = atoi(e);
   *out = ctx;
@@ -128,6 +131,9 @@ int cask_b200_destroy(cask_b200_ctx* ctx) {
   cudaFree(ctx->d_x);
   cudaFree(ctx->d_y);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  if (ctx->h_ring) cudaFreeHost(ctx->h_ring);
+  for (auto e : ctx->ring_events) cudaEventDestroy(e);
+  delete ctx->copy_pool;
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
   for (auto e : ctx->pipe_events) cudaEventDestroy(e);
@@ -167,6 +173,7 @@ int cask_b200_set_option(cask_b200_ctx* ctx, const char* name, double value) {
   else if (k == "force_csr_vec") ctx->force_csr_vec = (int32_t)value;
   else if (k == "ell_kernel") ctx->ell_kernel = (int32_t)value;
   else if (k == "host_pipeline_chunks") ctx->host_pipeline_chunks = (int32_t)value;
+  else if (k == "host_staging") ctx->host_staging = (int32_t)value;
   else if (k == "persist_ku") ctx->persist_ku = (int32_t)value;
   else if (k == "peer_mode") ctx->peer_mode = (int32_t)value;
   else if (k == "l2_keep") ctx->l2_keep = (int32_t)value;
@@ -175,6 +182,8 @@ int cask_b200_set_option(cask_b200_ctx* ctx, const char* name, double value) {
   else if (k == "csr_kernel") ctx->csr_kernel = (int32_t)value;
   else if (k == "merge_items") ctx->merge_items = (int32_t)value;
   else if (k == "col_reorder") ctx->col_reorder = (int32_t)value;
+  else if (k == "dist_sparse") ctx->dist_sparse = (int32_t)value;
+  else if (k == "ilu_graph") ctx->ilu_graph = (int32_t)value;
   else if (k == "value_dict") ctx->value_dict = (int32_t)value;
   else if (k == "persist_ctas") ctx->persist_ctas = (int32_t)value;
   else return fail(CASK_B200_ERR_INVALID_ARGUMENT, "set_option: unknown option " + k);
@@ -352,9 +361,45 @@ static int stage_in(cask_b200_ctx* ctx, const double* x, int64_t m, int64_t n) {
 // third — PCIe is full duplex, so for banded matrices the call costs about max(H2D, D2H) instead of their
 // sum.  A chunk waits only for the upload that covers its largest referenced column (SliceDesc::col_hi);
 // matrices whose slices reference far columns degrade gracefully to upload-all-then-overlap-download.
-static int spmv_host_pipelined(cask_b200_ctx* ctx, const double* x, double* y) {
+//
+// PAGEABLE caller buffers (std::vector<double>, i.e. every cask::Vector; hostcopy.hpp): the same pipeline, but both
+// directions go through rings of pinned 4 MB chunks that the library fills / drains itself with several host threads,
+// instead of leaving the staging to the driver's single-threaded bounce buffer.  x: copy into a free ring slot, DMA
+// from it, the slot is free again when that DMA's event has completed.  y: DMA into a ring slot, a drain thread waits
+// for the event and copies the rows out while the issuing thread carries on with the next uploads.
+static bool is_pageable(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+
+constexpr size_t kRingChunk = 4u << 20;  // bytes per pinned ring slot
+constexpr int kRingSlots = 4;            // per direction
+
+static int ensure_ring(cask_b200_ctx* ctx) {
+  if (!ctx->h_ring) {
+    CB_CUDA(cudaHostAlloc((void**)&ctx->h_ring, kRingChunk * kRingSlots * 2, cudaHostAllocDefault));
+    for (int i = 0; i < 2 * kRingSlots; i++) {
+      cudaEvent_t e;
+      CB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ctx->ring_events.push_back(e);
+    }
+  }
+  if (!ctx->copy_pool) {
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int t = getenv("CASK_B200_HOST_COPY_THREADS") ? atoi(getenv("CASK_B200_HOST_COPY_THREADS")) : (int)std::min(8u, std::max(2u, hw / 2));
+    ctx->copy_pool = new HostCopyPool(std::max(1, t));
+  }
+  return CASK_B200_OK;
+}
+
+static int spmv_host_pipelined(cask_b200_ctx* ctx, const double* x, double* y, bool stage_x, bool stage_y) {
   const Plan& p = ctx->plan;
-  const int K = std::max(1, std::min<int>(ctx->host_pipeline_chunks, p.nslices / 64));
+  // merge-path tiles cross slice boundaries: such plans run as one chunk (upload, all kernels, download)
+  const int K = p.csr_merge ? 1 : std::max(1, std::min<int>(ctx->host_pipeline_chunks, p.nslices / 64));
   CB_TRY(grow(&ctx->d_x, &ctx->d_x_len, p.m));
   CB_TRY(grow(&ctx->d_y, &ctx->d_y_len, p.n));
   if (!ctx->h2d_stream) CB_CUDA(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
@@ -364,7 +409,66 @@ static int spmv_host_pipelined(cask_b200_ctx* ctx, const double* x, double* y) {
     CB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     ctx->pipe_events.push_back(e);
   }
+  if (stage_x || stage_y) CB_TRY(ensure_ring(ctx));
   cudaStream_t cs = ctx->stream;
+
+  // y side of the staged path: the drain thread lives exactly as long as this call
+  DrainQueue drain;
+  struct Joiner {
+    DrainQueue* q;
+    std::thread t;
+    ~Joiner() {
+      if (t.joinable()) {
+        q->close();
+        t.join();
+      }
+    }
+  } joiner{&drain, {}};
+  if (stage_y) joiner.t = std::thread([&] { drain.run(ctx->copy_pool); });
+  int64_t up_slot = 0, dn_slot = 0;  // ring positions (monotonic)
+  unsigned char* up_ring = ctx->h_ring;
+  unsigned char* dn_ring = ctx->h_ring ? ctx->h_ring + kRingChunk * kRingSlots : nullptr;
+
+  // x[lo, hi) to the device on the upload stream
+  auto upload = [&](int64_t lo, int64_t hi) -> int {
+    if (!stage_x) {
+      CB_CUDA(cudaMemcpyAsync(ctx->d_x + lo, x + lo, sizeof(double) * (hi - lo), cudaMemcpyHostToDevice, ctx->h2d_stream));
+      return CASK_B200_OK;
+    }
+    const int64_t per = (int64_t)(kRingChunk / sizeof(double));
+    for (int64_t a = lo; a < hi; a += per) {
+      const int64_t b = std::min(hi, a + per);
+      const int slot = (int)(up_slot % kRingSlots);
+      if (up_slot >= kRingSlots) CB_CUDA(cudaEventSynchronize(ctx->ring_events[slot]));  // the DMA that last read this slot
+      unsigned char* buf = up_ring + kRingChunk * slot;
+      ctx->copy_pool->copy(buf, x + a, sizeof(double) * (b - a));
+      CB_CUDA(cudaMemcpyAsync(ctx->d_x + a, buf, sizeof(double) * (b - a), cudaMemcpyHostToDevice, ctx->h2d_stream));
+      CB_CUDA(cudaEventRecord(ctx->ring_events[slot], ctx->h2d_stream));
+      up_slot++;
+    }
+    return CASK_B200_OK;
+  };
+  // rows [lo, hi) of y to the host on the download stream (which already waits for their kernels)
+  auto download = [&](int64_t lo, int64_t hi) -> int {
+    if (!stage_y) {
+      CB_CUDA(cudaMemcpyAsync(y + lo, ctx->d_y + lo, sizeof(double) * (hi - lo), cudaMemcpyDeviceToHost, ctx->d2h_stream));
+      return CASK_B200_OK;
+    }
+    const int64_t per = (int64_t)(kRingChunk / sizeof(double));
+    for (int64_t a = lo; a < hi; a += per) {
+      const int64_t b = std::min(hi, a + per);
+      const int slot = (int)(dn_slot % kRingSlots);
+      drain.wait_in_flight(kRingSlots - 1);  // the drain thread has emptied this slot
+      if (drain.error() != cudaSuccess) return fail(CASK_B200_ERR_CUDA, std::string("spmv download: ") + cudaGetErrorString(drain.error()));
+      unsigned char* buf = dn_ring + kRingChunk * slot;
+      CB_CUDA(cudaMemcpyAsync(buf, ctx->d_y + a, sizeof(double) * (b - a), cudaMemcpyDeviceToHost, ctx->d2h_stream));
+      CB_CUDA(cudaEventRecord(ctx->ring_events[kRingSlots + slot], ctx->d2h_stream));
+      drain.push(DrainItem{y + a, buf, sizeof(double) * (size_t)(b - a), ctx->ring_events[kRingSlots + slot]});
+      dn_slot++;
+    }
+    return CASK_B200_OK;
+  };
+
   // uploads must not start before earlier work queued on the compute stream (e.g. a previous async call) is done
   CB_CUDA(cudaEventRecord(ctx->pipe_events[2 * K], cs));
   CB_CUDA(cudaStreamWaitEvent(ctx->h2d_stream, ctx->pipe_events[2 * K], 0));
@@ -376,10 +480,10 @@ static int spmv_host_pipelined(cask_b200_ctx* ctx, const double* x, double* y) {
     int64_t need = 0;
     for (int s = s_lo; s < s_hi; s++) need = std::max<int64_t>(need, p.h_slices[s].col_hi);
     need = std::min<int64_t>(std::max<int64_t>(need, 0), p.m);
-    if (c == K - 1) need = std::max(need, uploaded);  // nothing beyond `need` is ever read
+    if (c == K - 1 && !p.csr_merge) need = std::max(need, uploaded);  // nothing beyond `need` is ever read
+    if (p.csr_merge) need = p.m;                                      // hub-clustered plans permute all of x
     if (need > uploaded) {
-      CB_CUDA(cudaMemcpyAsync(ctx->d_x + uploaded, x + uploaded, sizeof(double) * (need - uploaded), cudaMemcpyHostToDevice,
-                              ctx->h2d_stream));
+      CB_TRY(upload(uploaded, need));
       uploaded = need;
     }
     CB_CUDA(cudaEventRecord(ctx->pipe_events[2 * c], ctx->h2d_stream));
@@ -391,9 +495,15 @@ static int spmv_host_pipelined(cask_b200_ctx* ctx, const double* x, double* y) {
     CB_CUDA(cudaEventRecord(ctx->pipe_events[2 * c + 1], cs));
     CB_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, ctx->pipe_events[2 * c + 1], 0));
     const int64_t r_lo = p.h_slices[s_lo].row0, r_hi = (int64_t)p.h_slices[s_hi - 1].row0 + p.h_slices[s_hi - 1].nrows;
-    CB_CUDA(cudaMemcpyAsync(y + r_lo, ctx->d_y + r_lo, sizeof(double) * (r_hi - r_lo), cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    CB_TRY(download(r_lo, r_hi));
+  }
+  if (stage_y) {
+    drain.close();
+    joiner.t.join();
+    if (drain.error() != cudaSuccess) return fail(CASK_B200_ERR_CUDA, std::string("spmv download: ") + cudaGetErrorString(drain.error()));
   }
   CB_CUDA(cudaStreamSynchronize(ctx->d2h_stream));
+  CB_CUDA(cudaStreamSynchronize(ctx->h2d_stream));
   CB_CUDA(cudaStreamSynchronize(cs));
   return CASK_B200_OK;
 }
@@ -403,8 +513,12 @@ int cask_b200_spmv(cask_b200_ctx* ctx, const double* x, double* y) {
   if (dist_active(ctx)) return fail(CASK_B200_ERR_UNSUPPORTED, "spmv (host buffers, whole vectors) is single-rank; sharded: cask_b200_spmv_shard");
   const Plan& p = ctx->plan;
   if ((!x && p.m) || (!y && p.n)) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "spmv: null vector");
+  // vectors of at least 4 MB in pageable memory are staged through the library's own pinned rings (hostcopy.hpp)
+  const bool big = (p.m + p.n) * (int64_t)sizeof(double) >= (int64_t)kRingChunk && ctx->host_staging != 0;
+  const bool stage_x = big && p.m && is_pageable(x), stage_y = big && p.n && is_pageable(y);
   // merge-path tiles cross slice boundaries, so the chunked pipeline (which launches slice ranges) is for plans without them
-  if (ctx->host_pipeline_chunks > 1 && p.nslices >= 128 && !p.csr_merge) return spmv_host_pipelined(ctx, x, y);
+  if ((ctx->host_pipeline_chunks > 1 && p.nslices >= 128 && !p.csr_merge) || stage_x || stage_y)
+    return spmv_host_pipelined(ctx, x, y, stage_x, stage_y);
   CB_TRY(stage_in(ctx, x, p.m, p.n));
   CB_TRY(launch_spmv(ctx, ctx->d_x, ctx->d_y, 0, ctx->stream, nullptr));
   if (p.n) CB_CUDA(cudaMemcpyAsync(y, ctx->d_y, sizeof(double) * p.n, cudaMemcpyDeviceToHost, ctx->stream));

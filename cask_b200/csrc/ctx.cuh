@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/cask_b200.h"
+#include "hostcopy.hpp"
 
 namespace caskb200 {
 
@@ -145,6 +146,7 @@ struct Plan {
   int32_t* d_perm = nullptr;          // [m] new column -> old column
   double* d_xperm = nullptr;          // [cols_used] x in the new numbering, rewritten in front of every SpMV
   int32_t cols_used = 0;              // columns referenced at least once = the first cols_used new columns
+  bool xperm_external = false;        // d_xperm is filled by the sparse exchange of a sharded plan (dist.cu), not by permute_x_kernel
   int32_t max_xcache = 0;
   // persistent staged-ELL kernel configuration (spmv.cu: configure_persistent)
   int32_t persist_ku = 0;       // ELL columns per ring stage (0: persistent kernel not usable)
@@ -299,6 +301,9 @@ struct cask_b200_ctx {
   int32_t col_reorder = 0;   // gather path: 1 = columns renumbered by descending reference count (hub clustering); off by default
   int32_t csr_kernel = -1;   // gather slices: -1 auto (merge-path tiles from kMergeAutoNnz nonzeros), 0 row-group items, 1 merge-path tiles
   int32_t l2_keep = -1;      // -1 auto (vectors of a solver iteration fit L2), 0 never, 1 always: evict-last on vector accesses
+  int32_t dist_sparse = 1;   // row-sharded gather plans: 1 = sparse exchange (each rank receives only the x entries its rows
+                             // reference, packed by their owners), 0 = every slice broadcast to all
+  int32_t ilu_graph = 1;     // ILU(0) application: 1 = the per-level launches replayed as one CUDA graph, 0 = launched one by one
   int32_t peer_mode = 1;     // 1: halo pushes and scalar all-reduces by own kernels over mapped peer memory; 0: NCCL
 
   // host-call staging buffers
@@ -309,6 +314,11 @@ struct cask_b200_ctx {
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
   std::vector<cudaEvent_t> pipe_events;
   int32_t host_pipeline_chunks = 16;
+  // pageable caller buffers (hostcopy.hpp): pinned rings + host copy threads, created on first use
+  int32_t host_staging = 1;  // 0: leave pageable buffers to the driver's own staging
+  unsigned char* h_ring = nullptr;
+  std::vector<cudaEvent_t> ring_events;
+  caskb200::HostCopyPool* copy_pool = nullptr;
 
   caskb200::SolverWork work;
   caskb200::DistState* dist = nullptr;
@@ -327,6 +337,7 @@ int refformat_stripe(cudaStream_t s, int64_t* launches, const int32_t* d_colptr,
 // plan.cu
 int build_plan(cask_b200_ctx* ctx);
 int build_csr_items(cask_b200_ctx* ctx);
+int build_col_reorder(cask_b200_ctx* ctx, int mode);  // 0 none, 1 hub clustering, 2 referenced columns in column order
 void free_plan(cask_b200_ctx* ctx);
 
 // spmv.cu

@@ -9,7 +9,14 @@
 //                   (stencils: one plane per neighbour), grouped ncclSend/ncclRecv straight from / into
 //                   the vectors (no packing), on a communication stream that overlaps the interior slices;
 //   ALLGATHER mode  irregular matrices (gather-CSR slices present or too many ranges): every rank's
-//                   slice is broadcast to all.
+//                   slice is broadcast to all;
+//   SPARSE mode     the same matrices when every slice of every rank runs the merge-path gather kernel (default,
+//                   option dist_sparse): a rank receives only the x entries its rows reference.  The plan renumbers the
+//                   referenced columns compactly (plan.cu: build_col_reorder mode 2), every owner packs the entries each
+//                   peer asked for at preprocess time into one send buffer (sparse_pack_kernel), and grouped
+//                   ncclSend/ncclRecv move them straight into the segments of the receiver's compact x.  R-MAT scale
+//                   25 over 8 ranks: a rank references about 5 M of the 33.5 M columns, so it receives tens of MB
+//                   instead of 235 MB and its gathers run on an L2-resident vector.
 // NCCL is bound at run time with dlopen("libnccl.so.2") so that the library shares the NCCL that the
 // hosting process (e.g. torch) already loaded, and so that single-GPU users need no NCCL at all.
 #include <dlfcn.h>
@@ -26,7 +33,7 @@ namespace {
 
 typedef struct { char internal[128]; } NcclUniqueId;
 typedef void* NcclComm;
-enum { kNcclInt8 = 0, kNcclInt64 = 4, kNcclFloat64 = 8, kNcclSum = 0 };
+enum { kNcclInt8 = 0, kNcclInt32 = 2, kNcclInt64 = 4, kNcclFloat64 = 8, kNcclSum = 0 };
 
 struct NcclApi {
   void* lib = nullptr;
@@ -86,6 +93,13 @@ struct DistState {
   NcclComm comm_halo = nullptr, comm_red = nullptr;
   cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
   bool allgather = false;
+  // SPARSE mode (see the header comment): segment q of the compact x = the referenced columns owned by rank q
+  bool sparse = false;
+  bool ell_all_local = true;       // staged slices (if any) read own columns only: they need nothing from the exchange
+  std::vector<int64_t> seg;        // [world + 1] segment boundaries inside the compact x (plan.d_xperm)
+  std::vector<int64_t> send_off;   // [world + 1] offsets into the send list / send buffer, by destination rank
+  int32_t* d_send_list = nullptr;  // global columns (all inside the own slice) the peers asked for, by destination
+  double* d_sendbuf = nullptr;
   std::vector<std::vector<Range>> recv_from;  // [peer] ranges of x this rank receives
   std::vector<std::vector<Range>> send_to;    // [peer] ranges of its own slice this rank sends
   int64_t n_global = 0;
@@ -131,6 +145,8 @@ void dist_free(cask_b200_ctx* ctx) {
   DistState* d = ctx->dist;
   peer_unmap(d);
   for (auto& a : d->d_ack) { cudaFree(a); a = nullptr; }
+  cudaFree(d->d_send_list);
+  cudaFree(d->d_sendbuf);
   if (d->comm_red && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm_red);
   if (d->comm_halo && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm_halo);
   if (d->ev_ready) cudaEventDestroy(d->ev_ready);
@@ -186,6 +202,82 @@ static int64_t halo_ranges_from_runs(int64_t n_global, int world, int me, const 
   return nranges;
 }
 
+
+// ---- SPARSE mode ---------------------------------------------------------------------------------------------------
+// sendbuf[i] = x[send_list[i]] for the entries the peers asked for, and the own segment of the compact x directly.
+// Both index lists are ascending inside a destination, so the reads sweep the own slice forward.
+__global__ void __launch_bounds__(256) sparse_pack_kernel(const double* __restrict__ x_full, const int32_t* __restrict__ send_list,
+                                                          int64_t n_send, double* __restrict__ sendbuf,
+                                                          const int32_t* __restrict__ own_cols, int64_t n_own,
+                                                          double* __restrict__ xp_own) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_send + n_own; i += stride) {
+    if (i < n_send) sendbuf[i] = __ldg(x_full + send_list[i]);
+    else xp_own[i - n_send] = __ldg(x_full + own_cols[i - n_send]);
+  }
+}
+
+// Collective.  Decides (all ranks together) whether the sparse exchange applies, renumbers the columns, and tells every
+// owner which of its entries each peer needs.
+static int dist_plan_sparse(cask_b200_ctx* ctx) {
+  DistState* d = ctx->dist;
+  Plan& p = ctx->plan;
+  cudaStream_t s = ctx->stream;
+  const int W = d->world, me = d->rank;
+  d->sparse = false;
+  cudaFree(d->d_send_list); cudaFree(d->d_sendbuf);
+  d->d_send_list = nullptr; d->d_sendbuf = nullptr;
+  struct Tmp {
+    int64_t* q = nullptr;
+    ~Tmp() { cudaFree(q); }
+  } tmp;
+  const size_t cap = (size_t)W + 1;
+  CB_CUDA(cudaMalloc(&tmp.q, sizeof(int64_t) * cap * (size_t)(W + 1)));
+  std::vector<int64_t> mine(cap, 0), all(cap * W, 0);
+  auto gather_all = [&]() -> int {
+    CB_CUDA(cudaMemcpyAsync(tmp.q + cap * W, mine.data(), sizeof(int64_t) * cap, cudaMemcpyHostToDevice, s));
+    CB_NCCL(g_nccl.AllGather(tmp.q + cap * W, tmp.q, cap, kNcclInt64, d->comm_halo, s));
+    CB_CUDA(cudaMemcpyAsync(all.data(), tmp.q, sizeof(int64_t) * cap * W, cudaMemcpyDeviceToHost, s));
+    CB_CUDA(cudaStreamSynchronize(s));
+    return CASK_B200_OK;
+  };
+  // 1. every slice that reads remote columns runs the merge-path gather kernel, on every rank (a rank without rows
+  //    qualifies trivially; staged slices that stage own columns only read the full-layout x as before)
+  mine[0] = d->allgather && ctx->dist_sparse != 0 && d->ell_all_local && (p.n_csr == 0 || p.csr_merge) && p.m < (1ll << 30) ? 1 : 0;
+  CB_TRY(gather_all());
+  for (int q = 0; q < W; q++)
+    if (!all[cap * q]) return CASK_B200_OK;
+  // 2. compact column numbering; segment q = referenced columns owned by rank q
+  CB_TRY(build_col_reorder(ctx, 2));
+  if (!p.d_perm) return fail(CASK_B200_ERR_RUNTIME, "sparse exchange: the column renumbering was refused");
+  std::vector<int32_t> need((size_t)p.cols_used);
+  if (p.cols_used) CB_CUDA(cudaMemcpyAsync(need.data(), p.d_perm, sizeof(int32_t) * need.size(), cudaMemcpyDeviceToHost, s));
+  CB_CUDA(cudaStreamSynchronize(s));
+  d->seg.assign((size_t)W + 1, 0);
+  for (int q = 0; q <= W; q++)
+    d->seg[q] = std::lower_bound(need.begin(), need.end(), d->bounds[q], [](int32_t a, int64_t b) { return (int64_t)a < b; }) - need.begin();
+  // 3. how many entries every rank needs from every owner
+  for (int q = 0; q < W; q++) mine[1 + q] = q == me ? 0 : d->seg[q + 1] - d->seg[q];
+  CB_TRY(gather_all());
+  d->send_off.assign((size_t)W + 1, 0);
+  for (int q = 0; q < W; q++) d->send_off[q + 1] = d->send_off[q] + (q == me ? 0 : all[cap * q + 1 + me]);
+  const int64_t total_send = d->send_off[W];
+  CB_CUDA(cudaMalloc(&d->d_send_list, sizeof(int32_t) * (size_t)std::max<int64_t>(total_send, 1)));
+  CB_CUDA(cudaMalloc(&d->d_sendbuf, sizeof(double) * (size_t)std::max<int64_t>(total_send, 1)));
+  // 4. the requests themselves: my segment for owner q goes to q, q's request list lands in my send list
+  CB_NCCL(g_nccl.GroupStart());
+  for (int q = 0; q < W; q++) {
+    if (q == me) continue;
+    const int64_t n_out = d->seg[q + 1] - d->seg[q], n_in = d->send_off[q + 1] - d->send_off[q];
+    if (n_out) CB_NCCL(g_nccl.Send(p.d_perm + d->seg[q], (size_t)n_out, kNcclInt32, q, d->comm_halo, s));
+    if (n_in) CB_NCCL(g_nccl.Recv(d->d_send_list + d->send_off[q], (size_t)n_in, kNcclInt32, q, d->comm_halo, s));
+  }
+  CB_NCCL(g_nccl.GroupEnd());
+  CB_CUDA(cudaStreamSynchronize(s));
+  d->sparse = true;
+  return CASK_B200_OK;
+}
+
 // Derives, from the plan's staged runs, which x ranges come from which peer; exchanges the requests so
 // every rank also knows what to send; splits the slice lists into interior / halo-dependent.
 int dist_plan_halo(cask_b200_ctx* ctx) {
@@ -222,6 +314,7 @@ int dist_plan_halo(cask_b200_ctx* ctx) {
   if (total_runs) CB_CUDA(cudaMemcpyAsync(runs.data(), p.d_runs, sizeof(Run) * total_runs, cudaMemcpyDeviceToHost, s));
   CB_CUDA(cudaStreamSynchronize(s));
 
+  d->ell_all_local = true;  // no staged slice stages a column of another rank (e.g. the empty slices of a power-law matrix)
   for (auto& sd : p.h_slices) {
     sd.remote = 0;
     if (sd.kind != kSliceStagedEll) { sd.remote = 1; continue; }
@@ -229,6 +322,7 @@ int dist_plan_halo(cask_b200_ctx* ctx) {
       const Run& r = runs[sd.run_off + i];
       if (r.col0 < own_lo || (int64_t)r.col0 + r.len > own_hi) sd.remote = 1;
     }
+    if (sd.remote) d->ell_all_local = false;
   }
   std::vector<int64_t> run_col0(runs.size()), run_len(runs.size());
   for (size_t i = 0; i < runs.size(); i++) { run_col0[i] = runs[i].col0; run_len[i] = runs[i].len; }
@@ -321,7 +415,7 @@ int dist_plan_halo(cask_b200_ctx* ctx) {
   CB_CUDA(cudaStreamSynchronize(s));
   cudaFree(d_ok);
   d->peer_plan_ok = bad_all == 0;
-  return CASK_B200_OK;
+  return dist_plan_sparse(ctx);
 }
 
 // ---- peer-memory layer: arena, halo push, scalar all-reduce --------------------------------------------------
@@ -602,9 +696,33 @@ int dist_exchange_begin(cask_b200_ctx* ctx, double* d_full, cudaStream_t after) 
   DistState* d = ctx->dist;
   const Plan& p = ctx->plan;
   cudaStream_t cs = ctx->comm_stream;
+  const int W = d->world, me = d->rank;
+  if (d->sparse) {
+    // own entries into the send buffer and into the own segment of the compact x, then one grouped exchange
+    const int64_t n_send = d->send_off[W], n_own = d->seg[me + 1] - d->seg[me];
+    if (n_send + n_own) {
+      const int64_t ctas = (n_send + n_own + 255) / 256;
+      sparse_pack_kernel<<<(int)std::min<int64_t>(ctas, (int64_t)ctx->sm_count * 8), 256, 0, after>>>(
+          d_full, d->d_send_list, n_send, d->d_sendbuf, p.d_perm + d->seg[me], n_own, p.d_xperm + d->seg[me]);
+      ctx->launches++;
+      CB_CUDA(cudaGetLastError());
+    }
+    CB_CUDA(cudaEventRecord(d->ev_ready, after));
+    CB_CUDA(cudaStreamWaitEvent(cs, d->ev_ready, 0));
+    CB_NCCL(g_nccl.GroupStart());
+    for (int q = 0; q < W; q++) {
+      if (q == me) continue;
+      const int64_t n_out = d->send_off[q + 1] - d->send_off[q], n_in = d->seg[q + 1] - d->seg[q];
+      if (n_out) CB_NCCL(g_nccl.Send(d->d_sendbuf + d->send_off[q], (size_t)n_out, kNcclFloat64, q, d->comm_halo, cs));
+      if (n_in) CB_NCCL(g_nccl.Recv(p.d_xperm + d->seg[q], (size_t)n_in, kNcclFloat64, q, d->comm_halo, cs));
+    }
+    CB_NCCL(g_nccl.GroupEnd());
+    CB_CUDA(cudaEventRecord(d->ev_done, cs));
+    ctx->launches++;
+    return CASK_B200_OK;
+  }
   CB_CUDA(cudaEventRecord(d->ev_ready, after));
   CB_CUDA(cudaStreamWaitEvent(cs, d->ev_ready, 0));
-  const int W = d->world, me = d->rank;
   CB_NCCL(g_nccl.GroupStart());
   if (d->allgather) {
     // every rank's slice to everybody, in place.  Stripes may differ widely in rows (equal-nonzero stripes of a power-law
@@ -723,7 +841,9 @@ extern "C" int cask_b200_dist_halo_counts(cask_b200_ctx* ctx, int64_t* recv_coun
   DistState* d = ctx->dist;
   for (int q = 0; q < d->world; q++) {
     int64_t c = 0;
-    if (d->allgather) {
+    if (d->sparse) {
+      c = q == d->rank ? 0 : d->seg[q + 1] - d->seg[q];
+    } else if (d->allgather) {
       int64_t q0, qn;
       owner_range(d->bounds.empty() ? nullptr : d->bounds.data(), d->n_global, d->world, q, &q0, &qn);
       c = q == d->rank ? 0 : qn;

@@ -301,11 +301,13 @@ __global__ void __launch_bounds__(256) col_count_kernel(const int32_t* __restric
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += stride) atomicAdd(counts + col[k], 1);
 }
+// by_count: ascending key = descending count (hub clustering); else referenced columns first, in column order (compaction)
 __global__ void __launch_bounds__(256) col_keys_kernel(const int32_t* __restrict__ counts, int64_t m, uint64_t* __restrict__ keys,
-                                                       uint32_t* __restrict__ ids) {
+                                                       uint32_t* __restrict__ ids, int by_count) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += stride) {
-    keys[j] = (uint64_t)(0x7fffffff - counts[j]);  // ascending key = descending count
+    const int32_t c = counts[j];
+    keys[j] = (uint64_t)(by_count ? 0x7fffffff - c : (c ? 0 : 0x7fffffff));
     ids[j] = (uint32_t)j;
   }
 }
@@ -480,15 +482,21 @@ int build_csr_items(cask_b200_ctx* ctx) {
 // scale 25 (profiles/r2k_rmat_reorder.md) the gather phase alone falls from 3.04 to 2.36 ms, DRAM reads from 9.6 to 7.8 GB,
 // but the whole SpMV only from 3.21 to 3.17 ms - with the hubs served by L1 the kernel becomes bound by the LSU wavefront
 // rate its reduction phases share with the gathers, and the permutation of x costs 0.12 ms per call.
-static int build_col_reorder(cask_b200_ctx* ctx) {
+//
+// mode 1: hub clustering as above (option col_reorder).  mode 2 (dist.cu, sparse exchange of a row-sharded gather plan):
+// the referenced columns only, in ascending column order - the compact local numbering of a distributed SpMV; the
+// permuted x is then filled by the exchange (own columns by a pack kernel, the others received from their owners), not by
+// permute_x_kernel.
+int build_col_reorder(cask_b200_ctx* ctx, int mode) {
   Plan& p = ctx->plan;
   cudaFree(p.d_col_perm); cudaFree(p.d_perm); cudaFree(p.d_xperm);
   p.d_col_perm = nullptr; p.d_perm = nullptr; p.d_xperm = nullptr;
   p.cols_used = 0;
+  p.xperm_external = false;
   p.stats.col_reorder = 0;
   p.stats.cols_referenced = 0;
-  if (!p.csr_merge || p.nnz <= 0 || p.m <= 0 || p.m >= (1ll << 30)) return CASK_B200_OK;
-  if (ctx->col_reorder != 1) return CASK_B200_OK;
+  if (mode == 0 || p.m <= 0 || p.m >= (1ll << 30)) return CASK_B200_OK;
+  if (mode == 1 && (!p.csr_merge || p.nnz <= 0)) return CASK_B200_OK;
   cudaStream_t s = ctx->stream;
   dev::Exec ex = dev::exec_of(ctx);
   struct Tmp {
@@ -505,15 +513,15 @@ static int build_col_reorder(cask_b200_ctx* ctx) {
   CB_CUDA(cudaMalloc(&p.d_perm, sizeof(int32_t) * (size_t)m));
   CB_CUDA(cudaMemsetAsync(tmp.q[0], 0, sizeof(int32_t) * (size_t)m, s));
   CB_CUDA(cudaMemsetAsync(tmp.q[4], 0, sizeof(int32_t), s));
-  col_count_kernel<<<grid, 256, 0, s>>>(p.d_col, p.nnz, (int32_t*)tmp.q[0]);
-  col_keys_kernel<<<grid, 256, 0, s>>>((const int32_t*)tmp.q[0], m, (uint64_t*)tmp.q[1], (uint32_t*)tmp.q[3]);
+  if (p.nnz) col_count_kernel<<<grid, 256, 0, s>>>(p.d_col, p.nnz, (int32_t*)tmp.q[0]);
+  col_keys_kernel<<<grid, 256, 0, s>>>((const int32_t*)tmp.q[0], m, (uint64_t*)tmp.q[1], (uint32_t*)tmp.q[3], mode == 1 ? 1 : 0);
   ctx->launches += 2;
   CB_TRY(dev::sort_pairs_u64_u32(ex, (const uint64_t*)tmp.q[1], (uint64_t*)tmp.q[2], (const uint32_t*)tmp.q[3],
-                                 (uint32_t*)p.d_perm, m, 31));
+                                 (uint32_t*)p.d_perm, m, 31));  // stable: equal keys keep ascending column order
   col_inverse_kernel<<<grid, 256, 0, s>>>((const uint32_t*)p.d_perm, (const uint64_t*)tmp.q[2], m, (int32_t*)tmp.q[0],
                                           (int32_t*)tmp.q[4]);
-  CB_CUDA(cudaMalloc(&p.d_col_perm, sizeof(int32_t) * (size_t)p.nnz));
-  col_relabel_kernel<<<grid, 256, 0, s>>>(p.d_col, p.nnz, (const int32_t*)tmp.q[0], p.d_col_perm);
+  CB_CUDA(cudaMalloc(&p.d_col_perm, sizeof(int32_t) * (size_t)std::max<int64_t>(p.nnz, 1)));
+  if (p.nnz) col_relabel_kernel<<<grid, 256, 0, s>>>(p.d_col, p.nnz, (const int32_t*)tmp.q[0], p.d_col_perm);
   ctx->launches += 2;
   int32_t used = 0;
   CB_CUDA(cudaMemcpyAsync(&used, tmp.q[4], sizeof(int32_t), cudaMemcpyDeviceToHost, s));
@@ -521,7 +529,8 @@ static int build_col_reorder(cask_b200_ctx* ctx) {
   CB_CUDA(cudaGetLastError());
   p.cols_used = used;
   CB_CUDA(cudaMalloc(&p.d_xperm, sizeof(double) * (size_t)std::max<int64_t>(used, 2)));
-  p.stats.col_reorder = 1;
+  p.xperm_external = mode == 2;
+  p.stats.col_reorder = mode;
   p.stats.cols_referenced = used;
   return CASK_B200_OK;
 }
@@ -746,7 +755,7 @@ int build_plan(cask_b200_ctx* ctx) {
   p.stats.max_row_length = maxlen;
   p.stats.csr_nnz = csr_nnz;
   p.stats.csr_rows = csr_rows;
-  CB_TRY(build_col_reorder(ctx));
+  CB_TRY(build_col_reorder(ctx, ctx->col_reorder == 1 ? 1 : 0));
   p.stats.persist_ku = ctx->ell_kernel == 1 ? p.persist_ku : 0;
   p.stats.persist_stages = p.persist_stages;
   p.stats.persist_ctas_per_sm = p.persist_ctas_per_sm;

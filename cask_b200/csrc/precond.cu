@@ -23,6 +23,13 @@ struct PrecondState {
   double* invd = nullptr;          // Jacobi
   bool jacobi_ready = false;
   const cask_b200_csr* pc_matrix = nullptr;  // optional: build the preconditioner from this matrix instead of A
+  // the level sequence of one ILU application (one launch per dependency level: 1 786 for the 256^3 27-point system) as
+  // ONE instantiated CUDA graph: captured on first use for a given (r, z, unit_lower), replayed by every later iteration
+  cudaGraphExec_t ilu_graph = nullptr;
+  const double* graph_r = nullptr;
+  double* graph_z = nullptr;
+  int graph_unit = -1;
+  int64_t graph_nodes = 0;
   // work vectors of the loop
   double* vec[4] = {nullptr, nullptr, nullptr, nullptr};  // r, p, Ap, z
   int64_t vec_len = 0;
@@ -35,6 +42,7 @@ void free_precond(cask_b200_ctx* ctx) {
   PrecondState* st = ctx->precond;
   if (!st) return;
   precond::ilu_free(&st->ilu);
+  if (st->ilu_graph) cudaGraphExecDestroy(st->ilu_graph);
   cudaFree(st->invd);
   for (auto& v : st->vec) cudaFree(v);
   cudaFree(st->partials);
@@ -148,9 +156,18 @@ int precond_matrix(cask_b200_ctx* ctx, MatrixView* mv) {
   return CASK_B200_OK;
 }
 
+void drop_ilu_graph(PrecondState* st) {
+  if (st->ilu_graph) cudaGraphExecDestroy(st->ilu_graph);
+  st->ilu_graph = nullptr;
+  st->graph_r = nullptr;
+  st->graph_z = nullptr;
+  st->graph_unit = -1;
+}
+
 int ensure_ilu(cask_b200_ctx* ctx) {
   PrecondState* st = state(ctx);
   if (st->ilu_ready) return CASK_B200_OK;
+  drop_ilu_graph(st);
   MatrixView mv;
   CB_TRY(precond_matrix(ctx, &mv));
   dev::Exec ex = dev::exec_of(ctx);
@@ -219,7 +236,37 @@ int apply(cask_b200_ctx* ctx, int32_t precon, int64_t n, const double* r, double
     return CASK_B200_OK;
   }
   dev::Exec ex = dev::exec_of(ctx);
-  return precond::ilu_apply(ex, &st->ilu, precon == CASK_B200_PRECON_ILU_UNIT ? 1 : 0, r, z, nullptr);
+  const int unit = precon == CASK_B200_PRECON_ILU_UNIT ? 1 : 0;
+  const size_t levels = st->ilu.ptr_l.size() + st->ilu.ptr_u.size();
+  cudaStream_t s = ctx->stream;
+  // stream capture needs a real stream (not the legacy default one a caller may have handed over with set_stream(NULL))
+  const bool graphable = ctx->ilu_graph != 0 && levels > 16 && s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread;
+  if (!graphable) return precond::ilu_apply(ex, &st->ilu, unit, r, z, nullptr);
+  if (!st->ilu_graph || st->graph_r != r || st->graph_z != z || st->graph_unit != unit) {
+    drop_ilu_graph(st);
+    int64_t counted = 0;
+    dev::Exec cap = ex;
+    cap.launches = &counted;
+    CB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    const int rc = precond::ilu_apply(cap, &st->ilu, unit, r, z, nullptr);
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(s, &g);  // always ends the capture, also after a failed launch
+    if (rc != CASK_B200_OK) {
+      if (g) cudaGraphDestroy(g);
+      return rc;
+    }
+    CB_CUDA(e);
+    const cudaError_t ei = cudaGraphInstantiate(&st->ilu_graph, g, 0);
+    cudaGraphDestroy(g);
+    if (ei != cudaSuccess) {
+      st->ilu_graph = nullptr;
+      return fail(CASK_B200_ERR_CUDA, std::string("cudaGraphInstantiate (ILU levels): ") + cudaGetErrorString(ei));
+    }
+    st->graph_r = r; st->graph_z = z; st->graph_unit = unit; st->graph_nodes = counted;
+  }
+  CB_CUDA(cudaGraphLaunch(st->ilu_graph, s));
+  ctx->launches += st->graph_nodes;
+  return CASK_B200_OK;
 }
 
 }  // namespace
@@ -233,6 +280,7 @@ int cask_b200_precond_set_matrix(cask_b200_ctx* ctx, const cask_b200_csr* csr) {
   if (!ctx) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "precond_set_matrix: null context");
   PrecondState* st = state(ctx);
   st->pc_matrix = csr;
+  drop_ilu_graph(st);
   st->ilu_ready = false;
   st->jacobi_ready = false;
   return CASK_B200_OK;

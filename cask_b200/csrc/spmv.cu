@@ -1011,12 +1011,14 @@ int launch_spmv_range(cask_b200_ctx* ctx, const double* d_x, double* d_y, int el
       const int32_t* cols = p.d_col;
       const double* xg = d_x;
       if (p.d_col_perm) {
-        permute_x_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(p.d_perm, d_x, p.d_xperm, p.cols_used);
-        ctx->launches++;
+        if (!p.xperm_external) {  // sharded sparse exchange: dist_exchange_begin / wait has filled d_xperm
+          permute_x_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(p.d_perm, d_x, p.d_xperm, p.cols_used);
+          ctx->launches++;
+        }
         cols = p.d_col_perm;
         xg = p.d_xperm;
       }
-      const int flags = ((xcg_env >= 0 ? xcg_env : (p.d_col_perm ? 0 : 1)) ? kMergeXPastL1 : 0) | diag;
+      const int flags = ((xcg_env >= 0 ? xcg_env : (p.d_col_perm && !p.xperm_external ? 0 : 1)) ? kMergeXPastL1 : 0) | diag;
 #define CB_MERGE(DOT, ITEMS)                                                                                              \
   do {                                                                                                                    \
     CB_CUDA(cudaFuncSetAttribute(spmv_csr_merge_kernel<DOT, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \

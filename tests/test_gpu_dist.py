@@ -93,6 +93,55 @@ for name, gen, N in (("poisson2d", O.gen_poisson2d, 96), ("poisson3d27", O.gen_p
         out[name]["cg_repeat_same"] = bool(conv2 == conv and it2 == it and rs2 == rs)
         if name == "poisson2d":
             n2, rp2, ci2, va2 = O.gen_convdiff3d7(16)
+# ---- sparse exchange of the gather path (every slice on the merge-path kernel): a rank receives only the x entries its
+# rows reference, packed by their owners, into a compactly renumbered x; unequal stripes (rank 0 owns few, long rows)
+def shard(n, rp, ci, va, bounds):
+    r0, nr = bounds[rank], bounds[rank + 1] - bounds[rank]
+    return (r0, nr, torch.tensor(rp[r0:r0 + nr + 1] - rp[r0], dtype=torch.int32, device=dev),
+            torch.tensor(ci[rp[r0]:rp[r0 + nr]], dtype=torch.int32, device=dev),
+            torch.tensor(va[rp[r0]:rp[r0 + nr]], dtype=torch.float64, device=dev))
+n, rp, ci, va = O.gen_rmat(13, 8, 3)
+cuts = [0] + [int(np.searchsorted(rp, rp[-1] * q // world)) for q in range(1, world)] + [n]   # equal nonzero count
+r0, nr, lrp, lci, lva = shard(n, rp, ci, va, cuts)
+ctx.set_option("csr_kernel", 1)
+sp = {}
+for mode in (1, 0):
+    ctx.set_option("dist_sparse", mode)
+    ctx.preprocess_shard_device(cb.design(1, 8192, 16), n, n, r0, nr, len(lva), lrp.data_ptr(), lci.data_ptr(), lva.data_ptr())
+    st = ctx.plan_stats()
+    errs = []
+    for rep in range(3):
+        x = np.random.default_rng(40 + rep).standard_normal(n)
+        xf = torch.zeros(n, dtype=torch.float64, device=dev)
+        xf[r0:r0 + nr] = torch.tensor(x[r0:r0 + nr], device=dev)
+        y = torch.empty(nr, dtype=torch.float64, device=dev)
+        ctx.spmv_device(xf.data_ptr(), y.data_ptr()); ctx.synchronize()
+        exp = O.csr_dot(n, rp, ci, va, x)[r0:r0 + nr]
+        sc = O.csr_dot(n, rp, ci, np.abs(va), np.abs(x))[r0:r0 + nr]
+        errs.append(float((np.abs(y.cpu().numpy() - exp) / np.maximum(sc, 1e-300)).max()) if nr else 0.0)
+    t = torch.tensor([max(errs), float(sum(ctx.halo_counts(world).tolist())), float(st["col_reorder"]),
+                      float(st["cols_referenced"] == len(np.unique(ci[rp[r0]:rp[r0 + nr]])))], dtype=torch.float64, device=dev)
+    tl = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(tl, t)
+    sp[mode] = {"err": max(float(v[0]) for v in tl), "recv_total": sum(float(v[1]) for v in tl),
+                "col_reorder": [int(v[2]) for v in tl], "cols_ok": all(bool(v[3]) for v in tl)}
+out["rmat_sparse"] = sp
+# the solver loop over the same exchange: CG on an SPD stencil forced through the gather kernel
+n, rp, ci, va = O.gen_poisson3d27(12)
+bnd = [cb.shard_rows(n, world, q)[0] for q in range(world)] + [n]
+r0, nr, lrp, lci, lva = shard(n, rp, ci, va, bnd)
+ctx.set_option("dist_sparse", 1)
+ctx.set_option("force_kind", 1)
+ctx.preprocess_shard_device(cb.design(1, 8192, 16), n, n, r0, nr, len(lva), lrp.data_ptr(), lci.data_ptr(), lva.data_ptr())
+b = O.csr_dot(n, rp, ci, va, 1.0 + 0.25 * (np.arange(n) %% 4))
+oc, oi, ox, ors = O.pcg(n, rp, ci, va, b, lower=False)
+db = torch.tensor(b[r0:r0 + nr], device=dev)
+dx = torch.zeros(nr, dtype=torch.float64, device=dev)
+conv, it, rs, trips = ctx.cg_device(db.data_ptr(), dx.data_ptr())
+out["cg_sparse"] = {"conv": conv, "it": it, "oracle_it": oi, "err": float(np.abs(dx.cpu().numpy() - ox[r0:r0 + nr]).max()),
+                    "col_reorder": ctx.plan_stats()["col_reorder"]}
+ctx.set_option("force_kind", -1)
+ctx.set_option("csr_kernel", -1)
 n, rp, ci, va = O.gen_convdiff3d7(16)
 r0, nr = cb.shard_rows(n, world, rank)
 lrp = torch.tensor(rp[r0:r0 + nr + 1] - rp[r0], dtype=torch.int32, device=dev)
@@ -140,5 +189,11 @@ def test_sharded_spmv_and_solvers(world, peer, tmp_path):
             assert r["arena_ok"] and r["arena_launches_per_spmv"] == 1.0, r   # the push happens inside the SpMV kernel
     assert res["bicgstab"]["peer"] == bool(peer), res["bicgstab"]
     assert res["rmat"]["spmv_max_rel"] < 1e-12, res["rmat"]
+    sp = res["rmat_sparse"]
+    assert sp["1"]["err"] < 1e-12 and sp["0"]["err"] < 1e-12, sp
+    assert all(c == 2 for c in sp["1"]["col_reorder"]) and all(c == 0 for c in sp["0"]["col_reorder"]) and sp["1"]["cols_ok"], sp
+    assert 0 < sp["1"]["recv_total"] < sp["0"]["recv_total"], sp       # fewer entries travel than with the broadcast of every slice
+    cs = res["cg_sparse"]
+    assert cs["conv"] and abs(cs["it"] - cs["oracle_it"]) <= 1 and cs["err"] < 1e-6 and cs["col_reorder"] == 2, cs
     bi = res["bicgstab"]
     assert bi["err"] <= 1e-10 and bi["sol_err"] < 1e-7 and abs(bi["it"] - bi["oracle_it"]) <= max(2, bi["oracle_it"] // 10), bi

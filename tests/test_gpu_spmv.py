@@ -265,3 +265,33 @@ def test_col_reorder_rmat(gpu_lib, ctx, oracle):
     scale = row_scale(n, rp, ci, va, x)
     assert_y_close(y1, oracle.csr_dot(n, rp, ci, va, x), scale)
     assert_y_close(y1, y0, scale)
+
+
+# ---- pageable caller buffers: the library's own pinned rings + host copy threads (hostcopy.hpp) -----------------------
+def test_pageable_host_buffers_are_staged_by_the_library(gpu_lib, ctx, oracle):
+    """numpy arrays are pageable memory, like the std::vector<double> inside every cask::Vector: from 4 MB of vectors on,
+    cask_b200_spmv moves them through pinned 4 MB ring slots with its own copy threads.  Same y, bit for bit, as with the
+    driver's staging (host_staging = 0) and as the reference's dot - on the chunked pipeline (staged ELL), on a one-chunk
+    plan (merge-path gather) and with ring wrap-around in both directions (9.7 MB per vector = 3 slots of 4)."""
+    n, rp, ci, va = oracle.gen_poisson2d(1100)
+    x = np.random.default_rng(8).standard_normal(n)
+    exp = oracle.csr_dot(n, rp, ci, va, x)
+    d = gpu_lib.design(1, 8192, 16)
+    ctx.preprocess(d, n, n, rp, ci, va)
+    assert ctx.plan_stats()["slices_gather_csr"] == 0
+    y_staged = ctx.spmv(x)
+    assert np.array_equal(y_staged, exp)
+    for rep in range(3):                                   # rings and events are reused across calls
+        x2 = np.random.default_rng(20 + rep).standard_normal(n)
+        assert np.array_equal(ctx.spmv(x2), oracle.csr_dot(n, rp, ci, va, x2))
+    ctx.set_option("host_staging", 0)
+    assert np.array_equal(ctx.spmv(x), y_staged)
+    ctx.set_option("host_staging", 1)
+    ctx.set_option("force_kind", 1)
+    ctx.set_option("csr_kernel", 1)
+    ctx.preprocess(d, n, n, rp, ci, va)
+    assert ctx.plan_stats()["csr_kernel"] == 1
+    assert_y_close(ctx.spmv(x), exp, row_scale(n, rp, ci, va, x))
+    ctx.set_option("col_reorder", 1)
+    ctx.preprocess(d, n, n, rp, ci, va)
+    assert_y_close(ctx.spmv(x), exp, row_scale(n, rp, ci, va, x))
