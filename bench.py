@@ -58,6 +58,8 @@ def parse():
     ap.add_argument("--soak", type=int, default=1500,
                     help="untimed launches between the warm-up and the timed region (clock sampling under load)")
     ap.add_argument("--only-rmat", action="store_true", help="profiling: run only the C3 R-MAT SpMV side measurement")
+    ap.add_argument("--only-pcg-ilu", action="store_true", help="profiling: run only the ILU-preconditioned CG side measurement")
+    ap.add_argument("--rmat-stripe", default=None, help="profiling, one GPU: W,r = run stripe r of W of the C3 matrix as rank r of a W-rank job would")
     ap.add_argument("--only-bicgstab", action="store_true", help="profiling: run only the C5 BiCGStab side measurement")
     ap.add_argument("--bicg-cap", type=int, default=4000, help="iteration cap of the C5 BiCGStab solve (profiling runs)")
     ap.add_argument("--cg-maxiters", type=int, default=2000, help="cap on CG iterations (profiling runs)")
@@ -735,7 +737,7 @@ def main():
             e2e["pcie"] = {"error": repr(ex)[:200]}
 
     # ---- CG iterations / s on the 3D 27-point system (strong scaling: fixed 256^3 grid) -----------
-    cg = bicg = rmat = None
+    cg = bicg = rmat = pcg_ilu = None
     del x_full, x_ref_full, y, cols, vals, rp
     torch.cuda.empty_cache()
     # The side measurements never take the headline line down with them: a failure is recorded in place of the numbers.
@@ -752,10 +754,12 @@ def main():
     if not args.no_cg:
         cg = side(bench_cg, ctx, cb, torch, dist, dev, rank, world, barrier, args.cg_maxiters, args.cg_emulate_shard)
     if not args.no_extra:
-        if not args.only_rmat:
+        if not args.only_rmat and not args.only_pcg_ilu:
             bicg = side(bench_bicgstab, ctx, cb, torch, dist, dev, rank, world, barrier, args.bicg_cap)
-        if not args.only_bicgstab:
-            rmat = side(bench_rmat, ctx, cb, torch, dist, dev, rank, world, barrier)
+        if not args.only_bicgstab and not args.only_pcg_ilu:
+            rmat = side(bench_rmat, ctx, cb, torch, dist, dev, rank, world, barrier, 25, 15, args.rmat_stripe)
+        if world == 1 and not args.only_rmat and not args.only_bicgstab:
+            pcg_ilu = side(bench_pcg_ilu, ctx, cb, torch, dev)
 
     if rank == 0:
         stored_per_launch = vd_matrix_bytes + 8 * (n_local + n_local) + 12 * stats.get("csr_nnz", 0)
@@ -795,6 +799,11 @@ def main():
             details["cg"] = cg
             line["cg"] = compact(cg, ("iters_per_s", "us_per_iteration_marginal", "loop_trips", "iterations_reported", "converged",
                                       "max_abs_err_vs_x_true", "gpu_launches", "peer_memory_path", "roofline", "error"))
+        if pcg_ilu:
+            details["pcg_ilu"] = pcg_ilu
+            line["pcg_ilu"] = compact(pcg_ilu, ("iters_per_s", "loop_trips", "converged", "levels_per_triangular_solve", "error"))
+            if "launched_one_by_one" in pcg_ilu:
+                line["pcg_ilu"]["iters_per_s_launched_one_by_one"] = pcg_ilu["launched_one_by_one"]["iters_per_s"]
         if bicg:
             details["bicgstab"] = bicg
             line["bicgstab"] = compact(bicg, ("iters_per_s", "iterations", "converged", "rel_residual", "max_abs_err_vs_ones",
@@ -924,6 +933,46 @@ def bench_cg(ctx, cb, torch, dist, dev, rank, world, barrier, maxiters=2000, emu
             "traffic_bound_iters_per_s_1gpu": 1.0 / ((algorithmic_bytes(nnz_total, n, n) + 72 * n) / (measured_peak()[0] * 1e9))}
 
 
+def bench_pcg_ilu(ctx, cb, torch, dev, N=64):
+    """pcg<double, ILUPreconditioner> with a unit lower solve on the 3D 27-point Poisson twin N^3
+    (single rank: the dependency levels of ILU(0) cross every stripe).  One launch per level, 7 (N - 1) + 1 levels per
+    triangular solve; the level sequence is replayed as ONE CUDA graph (ilu_graph = 1) or launched kernel by kernel (0)."""
+    kind = cb.SYNTH_POISSON3D27
+    n = cb.synth_rows(kind, N)
+    nnz = cb.synth_nnz(kind, N, 0, n)
+    rp = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    ci = torch.empty(nnz, dtype=torch.int32, device=dev)
+    va = torch.empty(nnz, dtype=torch.float64, device=dev)
+    cb.synth_device(kind, N, 0, n, rp.data_ptr(), ci.data_ptr(), va.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    xt = (1.0 + 0.25 * (torch.arange(n, device=dev) % 4).double()).contiguous()
+    b = torch.empty(n, dtype=torch.float64, device=dev)
+    out = {"workload": "pcg<ILU(0), unit lower solve> on 3D 27-pt Poisson %d^3 (%d rows, %d nnz), one GPU" % (N, n, nnz),
+           "levels_per_triangular_solve": 7 * (N - 1) + 1}
+    for graph in (1, 0):
+        ctx.set_option("ilu_graph", graph)
+        ctx.preprocess_device(cb.design(num_pipes=1, cache_size=8192, input_width=16), n, n, nnz, rp.data_ptr(), ci.data_ptr(), va.data_ptr())
+        ctx.spmv_device(xt.data_ptr(), b.data_ptr())
+        ctx.synchronize()
+        x = torch.zeros(n, dtype=torch.float64, device=dev)
+        ctx.pcg_device(b.data_ptr(), x.data_ptr(), cb.PRECON_ILU_UNIT, maxiters=3)   # factorisation + graph capture outside the timing
+        x.zero_()
+        torch.cuda.synchronize()
+        l0 = ctx.launch_count()
+        t0 = time.perf_counter()
+        conv, it, rs = ctx.pcg_device(b.data_ptr(), x.data_ptr(), cb.PRECON_ILU_UNIT, maxiters=500, tol=1e-5)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        trips = it + 2 if conv else it + 1   # `iterations` = index of the last non-converged iteration (SparseLinearSolvers.hpp:231)
+        rec = {"iters_per_s": trips / dt, "loop_trips": trips, "converged": bool(conv), "seconds": dt, "rs_final": rs,
+               "max_abs_err_vs_x_true": float((x - xt).abs().max().item()), "kernel_nodes_or_launches": int(ctx.launch_count() - l0)}
+        if graph:
+            out.update(rec)
+        else:
+            out["launched_one_by_one"] = rec
+    ctx.set_option("ilu_graph", 1)
+    return out
+
+
 def bench_bicgstab(ctx, cb, torch, dist, dev, rank, world, barrier, cap=4000):
     """BASELINE configs[4]: BiCGStab (Eigen's loop, Jacobi preconditioner) on the nonsymmetric 3D 7-point
     convection-diffusion system, 512^3 grid (134M rows, 0.94B nnz), row-sharded; b = A 1; 40 iterations timed."""
@@ -989,7 +1038,7 @@ def bench_bicgstab(ctx, cb, torch, dist, dev, rank, world, barrier, cap=4000):
             "gpu_launches": launches, "roofline": roof, "clocks": clocks}
 
 
-def bench_rmat(ctx, cb, torch, dist, dev, rank, world, barrier, scale=25, edge_factor=15):
+def bench_rmat(ctx, cb, torch, dist, dev, rank, world, barrier, scale=25, edge_factor=15, rmat_stripe=None):
     """BASELINE configs[2]: R-MAT power-law matrix, 2^25 rows, ~5e8 nnz, (a,b,c,d) = (0.57,0.19,0.19,0.05),
     duplicates merged, rows sorted by column; generated on the device with torch (bench-side synthetic data),
     row-sharded; y = A x with x gathered through L2 (irregular rows -> vector-per-row kernels)."""
@@ -1013,18 +1062,28 @@ def bench_rmat(ctx, cb, torch, dist, dev, rank, world, barrier, scale=25, edge_f
         del row, col, u, rb, cbit
     key = torch.cat(keys)
     del keys
-    # Row stripes.  One GPU: everything.  Sharded: stripes of (nearly) equal NONZERO count, cut at multiples of 1024 rows
-    # from the edge histogram - under the reference's equal-row rule (Spmv.cpp:334) rank 0 of 8 would own 0.76^3 = 44 % of
-    # this matrix and bound the whole job; the library takes any contiguous partition (cask_b200_preprocess_shard_device)
-    if world > 1:
+    # Row stripes.  One GPU: everything.  Sharded: stripes of (nearly) equal WORK, cut at multiples of 1024 rows from the
+    # edge histogram - under the reference's equal-row rule (Spmv.cpp:334) rank 0 of 8 would own 0.76^3 = 44 % of this
+    # matrix and bound the whole job; the library takes any contiguous partition (cask_b200_preprocess_shard_device).
+    # Work = merge items of the gather kernel = nonzeros + rows (CASK_B200_RMAT_BALANCE=nnz: nonzeros only).
+    # --rmat-stripe W,r (one GPU): stripe r of W as a rectangular matrix with the compact column numbering of the sparse
+    # exchange (col_reorder 2) - what rank r's kernels do in a W-rank job, measurable (and profilable) on one GPU.
+    emu = None
+    if world == 1 and rmat_stripe:
+        emu = tuple(int(v) for v in rmat_stripe.split(","))
+    parts, part = (world, rank) if world > 1 else (emu if emu else (1, 0))
+    balance = os.environ.get("CASK_B200_RMAT_BALANCE", "items")
+    if parts > 1:
         hist = torch.bincount(key >> (scale + 10), minlength=n >> 10).double()
+        if balance != "nnz":
+            hist = hist + 1024.0
         cum = torch.cumsum(hist, 0)
-        targets = cum[-1] * torch.arange(1, world, device=dev, dtype=torch.float64) / world
+        targets = cum[-1] * torch.arange(1, parts, device=dev, dtype=torch.float64) / parts
         cuts = (torch.searchsorted(cum, targets) + 1).clamp(max=n >> 10) << 10
         bounds = [0] + [int(c) for c in cuts.tolist()] + [n]
         for i in range(1, len(bounds)):
             bounds[i] = max(bounds[i], bounds[i - 1])
-        r0, nr = bounds[rank], bounds[rank + 1] - bounds[rank]
+        r0, nr = bounds[part], bounds[part + 1] - bounds[part]
         del hist, cum
     else:
         r0, nr = 0, n
@@ -1047,11 +1106,19 @@ def bench_rmat(ctx, cb, torch, dist, dev, rank, world, barrier, scale=25, edge_f
     if world > 1:
         ctx.preprocess_shard_device(dsg, n, n, r0, nr, nnz, rp.data_ptr(), ci.data_ptr(), va.data_ptr())
     else:
-        ctx.preprocess_device(dsg, n, n, nnz, rp.data_ptr(), ci.data_ptr(), va.data_ptr())
+        if emu:
+            ctx.set_option("col_reorder", 2)
+        ctx.preprocess_device(dsg, nr, n, nnz, rp.data_ptr(), ci.data_ptr(), va.data_ptr())
+        if emu:
+            ctx.set_option("col_reorder", int(os.environ.get("CASK_B200_COL_REORDER", "0")))
     ctx.synchronize()
     prep = time.perf_counter() - t0
     stats = ctx.plan_stats()
-    x = torch.rand(n, device=dev, dtype=torch.float64, generator=g).contiguous()
+    # x from its own generator: g has drawn a different number of values on every rank by now (va has the rank's nnz
+    # entries), and only the OWN slice of x is an input of the sharded call - the check below needs the same x everywhere
+    gx = torch.Generator(device=dev)
+    gx.manual_seed(2)
+    x = torch.rand(n, device=dev, dtype=torch.float64, generator=gx).contiguous()
     y = torch.empty(nr, dtype=torch.float64, device=dev)
     for _ in range(3):
         ctx.spmv_device(x.data_ptr(), y.data_ptr())
@@ -1107,7 +1174,9 @@ def bench_rmat(ctx, cb, torch, dist, dev, rank, world, barrier, scale=25, edge_f
             "algorithmic_gbs": algorithmic_bytes(nnz_total, n, n) / (ms * 1e-3) / 1e9, "preprocess_s": prep,
             "kernel": kernel, "l2_hit_rate_on_x_pct": l2, "roofline": roof, "col_reorder": int(stats.get("col_reorder", 0)),
             "nnz_share_max_rank": float(share.item()) / nnz_total,
-            "stripes": "one" if world == 1 else "equal nonzero count, cut at multiples of 1024 rows (rows of this rank: %d)" % nr,
+            "stripes": "one" if parts == 1 else "equal %s, cut at multiples of 1024 rows (rows of this %s: %d)" % (
+                "nonzero count" if balance == "nnz" else "nonzeros + rows", "rank" if world > 1 else "emulated stripe %d of %d" % (part, parts), nr),
+            "rows_this_rank": nr, "nnz_this_rank": nnz,
             "max_rel_diff_256_sampled_rows": rel, "max_err_all_rows_rel_to_sum_abs": rel_all,
             "plan": {k: stats[k] for k in ("slices_staged_ell", "slices_gather_csr", "csr_lanes_per_row", "max_row_length",
                                            "row_length_histogram", "csr_items", "csr_kernel", "col_reorder", "cols_referenced")}}

@@ -22,7 +22,7 @@ PAIR_DTYPE = np.dtype([("value", "<f8"), ("indptr", "<i4")], align=False)  # ind
 EXPORTED_SYMBOLS = (
     "cask_b200_device_count", "cask_b200_create", "cask_b200_destroy", "cask_b200_last_error",
     "cask_b200_set_stream", "cask_b200_use_own_stream", "cask_b200_synchronize", "cask_b200_set_option", "cask_b200_preprocess",
-    "cask_b200_preprocess_device", "cask_b200_plan_get_stats", "cask_b200_partition_get_info",
+    "cask_b200_preprocess_device", "cask_b200_plan_get_stats", "cask_b200_plan_estimate", "cask_b200_partition_get_info",
     "cask_b200_partition_export", "cask_b200_spmv", "cask_b200_spmv_device", "cask_b200_spmv_refformat",
     "cask_b200_cg", "cask_b200_cg_device", "cask_b200_bicgstab", "cask_b200_bicgstab_device",
     "cask_b200_nccl_unique_id", "cask_b200_dist_init", "cask_b200_shard_rows",
@@ -67,6 +67,24 @@ class PlanStats(C.Structure):
         return d
 
 
+def plan_estimate(stats, hbm_gbs=0.0, l2_bytes=0.0, sm_clock_hz=0.0, sms=0):
+    """(bytes, seconds) of one SpMV on a plan with these statistics (dict from Context.plan_stats() or a PlanStats):
+    cask_b200_plan_estimate, the selector's model.  No GPU needed."""
+    if not isinstance(stats, PlanStats):
+        st = PlanStats()
+        for k, _ in PlanStats._fields_:
+            if k == "row_length_histogram":
+                for i, v in enumerate(stats.get(k, [0] * 8)):
+                    st.row_length_histogram[i] = int(v)
+            elif k in stats:
+                setattr(st, k, int(stats[k]))
+        stats = st
+    b, s = C.c_double(), C.c_double()
+    check(lib().cask_b200_plan_estimate(C.byref(stats), C.c_double(hbm_gbs), C.c_double(l2_bytes), C.c_double(sm_clock_hz), int(sms),
+                                        C.byref(b), C.byref(s)))
+    return b.value, s.value
+
+
 class MmInfo(C.Structure):
     """cask_b200_mm_info == struct MmInfo (IO.hpp:39-58) + the size line."""
     _fields_ = [("type", C.c_char * 16), ("format", C.c_char * 16), ("data_type", C.c_char * 16),
@@ -108,6 +126,7 @@ def lib():
         L.cask_b200_preprocess_shard_device.argtypes = [vp, C.POINTER(Design), i64, i64, i64, i64, i64, vp, vp, vp]
         L.cask_b200_plan_get_stats.argtypes = [vp, C.POINTER(PlanStats)]
         L.cask_b200_plan_value_dict.argtypes = [vp, vp, vp, vp]
+        L.cask_b200_plan_estimate.argtypes = [C.POINTER(PlanStats), dbl, dbl, dbl, C.c_int32, C.POINTER(dbl), C.POINTER(dbl)]
         L.cask_b200_partition_get_info.argtypes = [vp, i32, C.POINTER(PartitionInfo)]
         L.cask_b200_partition_export.argtypes = [vp, i32, vp, vp]
         L.cask_b200_spmv.argtypes = [vp, vp, vp]

@@ -105,6 +105,7 @@ int cask_b200_create(cask_b200_ctx** out, int device) {
   if (const char* e = getenv("CASK_B200_PERSIST_KU")) ctx->persist_ku = atoi(e);
   if (const char* e = getenv("CASK_B200_HOST_CHUNKS")) ctx->host_pipeline_chunks = atoi(e);
   if (const char* e = getenv("CASK_B200_HOST_STAGING")) ctx->host_staging = atoi(e);
+  if (const char* e = getenv("CASK_B200_HOST_RAMP")) ctx->host_pipeline_ramp = atoi(e);
   if (const char* e = getenv("CASK_B200_PEER")) ctx->peer_mode = atoi(e);
   if (const char* e = getenv("CASK_B200_L2_KEEP")) ctx->l2_keep = atoi(e);
   if (const char* e = getenv("CASK_B200_CSR_STREAM")) ctx->csr_stream = atoi(e);
@@ -261,6 +262,27 @@ int cask_b200_preprocess(cask_b200_ctx* ctx, const cask_b200_design* design, int
 int cask_b200_plan_get_stats(cask_b200_ctx* ctx, cask_b200_plan_stats* out) {
   if (!ctx || !out || !ctx->have_design) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "plan_get_stats: preprocess first");
   *out = ctx->plan.stats;
+  return CASK_B200_OK;
+}
+
+int cask_b200_plan_estimate(const cask_b200_plan_stats* st, double hbm_gbs, double l2_bytes, double sm_clock_hz, int32_t sms,
+                            double* bytes, double* seconds) {
+  if (!st) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "plan_estimate: null stats");
+  if (hbm_gbs <= 0) hbm_gbs = 6456.5;
+  if (l2_bytes <= 0) l2_bytes = 126.0e6;
+  if (sm_clock_hz <= 0) sm_clock_hz = 1.965e9;
+  if (sms <= 0) sms = 148;
+  const double nnz_csr = (double)(st->nnz - st->ell_nnz);
+  const double rows_csr = (double)st->slices_gather_csr * st->slice_rows;
+  const double miss = std::max(0.0, 1.0 - l2_bytes / std::max(8.0 * (double)st->m, 1.0));
+  const double b = 10.0 * (double)st->ell_padded_entries + 12.0 * nnz_csr + 4.0 * rows_csr + 8.0 * (double)st->m + 8.0 * (double)st->n +
+                   32.0 * nnz_csr * miss;
+  // a scattered 8-byte gather is one L1 wavefront per distinct line of the warp (about 28 of 32), the coalesced stream,
+  // the product round trip through shared memory and the merge-path walk add 11 per 32 nonzeros; the gather kernels keep
+  // the LSU pipe 0.64 busy (R-MAT scale 25: 3.2 ms measured, 1.92 ms at one wavefront per clock per SM)
+  const double gather_s = nnz_csr * (39.0 / 32.0) / ((double)sms * sm_clock_hz * 0.64);
+  if (bytes) *bytes = b;
+  if (seconds) *seconds = std::max(b / (hbm_gbs * 1e9), gather_s);
   return CASK_B200_OK;
 }
 
@@ -474,8 +496,26 @@ static int spmv_host_pipelined(cask_b200_ctx* ctx, const double* x, double* y, b
   CB_CUDA(cudaStreamWaitEvent(ctx->h2d_stream, ctx->pipe_events[2 * K], 0));
   int64_t uploaded = 0;
   size_t ie = 0, ic = 0;  // cursors into the (ascending) slice lists
+  // Chunk sizes grow geometrically from both ends (weights 1, 2, 4, 8, 16, 16, ... 16, 8, 4, 2, 1): the first upload and
+  // the last download overlap nothing, so they are kept small, while the middle of the vector moves in few large
+  // copies - every chunk costs about 17 us of copy-engine and launch latency (profiles/r2n_stripes_chunks_ilu.md).
+  std::vector<int> bound((size_t)K + 1, 0);
+  {
+    std::vector<int64_t> w((size_t)K);
+    int64_t total = 0;
+    for (int c = 0; c < K; c++) {
+      const int e = std::min(std::min(c, K - 1 - c), 4);
+      w[c] = ctx->host_pipeline_ramp ? (int64_t)1 << e : 1;
+      total += w[c];
+    }
+    int64_t run = 0;
+    for (int c = 0; c < K; c++) {
+      run += w[c];
+      bound[c + 1] = (int)((int64_t)p.nslices * run / total);
+    }
+  }
   for (int c = 0; c < K; c++) {
-    const int s_lo = (int)((int64_t)p.nslices * c / K), s_hi = (int)((int64_t)p.nslices * (c + 1) / K);
+    const int s_lo = bound[c], s_hi = bound[c + 1];
     if (s_hi == s_lo) continue;
     int64_t need = 0;
     for (int s = s_lo; s < s_hi; s++) need = std::max<int64_t>(need, p.h_slices[s].col_hi);

@@ -147,6 +147,7 @@ struct Plan {
   double* d_xperm = nullptr;          // [cols_used] x in the new numbering, rewritten in front of every SpMV
   int32_t cols_used = 0;              // columns referenced at least once = the first cols_used new columns
   bool xperm_external = false;        // d_xperm is filled by the sparse exchange of a sharded plan (dist.cu), not by permute_x_kernel
+  bool xperm_owned = true;            // false: d_xperm lives in the symmetric arena (peers store into it over NVLink)
   int32_t max_xcache = 0;
   // persistent staged-ELL kernel configuration (spmv.cu: configure_persistent)
   int32_t persist_ku = 0;       // ELL columns per ring stage (0: persistent kernel not usable)
@@ -200,6 +201,16 @@ struct PushDesc {       // by-value kernel argument of every kernel that produce
   double* dst[kMaxPush];               // peer's copy of the vector, rebased: dst[i] is its entry for local row i
   PeerCtrl* peer_ctrl[kMaxPush];       // that peer's control block
   PeerCtrl* ctrl = nullptr;            // this rank's control block
+};
+
+struct SparsePushDesc {  // by-value kernel argument of sparse_push_kernel (dist.cu): the sparse exchange over peer memory
+  PeerCtrl* ctrl = nullptr;              // this rank's control block
+  PeerCtrl* peers[kMaxPeers] = {nullptr};
+  double* dst[kMaxPeers] = {nullptr};    // rank q's compact x, rebased to the segment this rank fills there
+  int64_t send_off[kMaxPeers + 1] = {0}; // send list positions by destination rank
+  uint32_t send_mask = 0, recv_mask = 0; // ranks this rank stores entries for / receives entries from
+  int32_t me = 0, world = 1;
+  unsigned long long done = 0;           // sparse exchanges this rank has completed (host-counted, equal on all ranks)
 };
 
 struct AckDesc {        // device-resident (one per channel): the plain sharded SpMV's in-kernel boundary-row push
@@ -298,7 +309,9 @@ struct cask_b200_ctx {
   int32_t csr_stream = 0;    // 1: CSR-stream variant of the gather-CSR kernel (products staged in shared memory)
   int32_t csr_item_nnz = 4096;  // nonzeros per work item of the CSR-stream variant (its shared-memory footprint)
   int32_t merge_items = 0;   // merge-path tiles: merge items per thread (0: default; 5, 7, 11, 17)
-  int32_t col_reorder = 0;   // gather path: 1 = columns renumbered by descending reference count (hub clustering); off by default
+  int32_t col_reorder = 0;   // gather path: 1 = columns renumbered by descending reference count (hub clustering), 2 = referenced
+                             // columns only, in column order (the numbering of the sharded sparse exchange); off by default
+  bool dist_sparse_active = false;  // set by dist.cu while it builds the compact numbering of a sparse exchange
   int32_t csr_kernel = -1;   // gather slices: -1 auto (merge-path tiles from kMergeAutoNnz nonzeros), 0 row-group items, 1 merge-path tiles
   int32_t l2_keep = -1;      // -1 auto (vectors of a solver iteration fit L2), 0 never, 1 always: evict-last on vector accesses
   int32_t dist_sparse = 1;   // row-sharded gather plans: 1 = sparse exchange (each rank receives only the x entries its rows
@@ -314,6 +327,7 @@ struct cask_b200_ctx {
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
   std::vector<cudaEvent_t> pipe_events;
   int32_t host_pipeline_chunks = 16;
+  int32_t host_pipeline_ramp = 1;  // chunk sizes grow geometrically from both ends (0: equal chunks)
   // pageable caller buffers (hostcopy.hpp): pinned rings + host copy threads, created on first use
   int32_t host_staging = 1;  // 0: leave pageable buffers to the driver's own staging
   unsigned char* h_ring = nullptr;

@@ -100,6 +100,8 @@ struct DistState {
   std::vector<int64_t> send_off;   // [world + 1] offsets into the send list / send buffer, by destination rank
   int32_t* d_send_list = nullptr;  // global columns (all inside the own slice) the peers asked for, by destination
   double* d_sendbuf = nullptr;
+  bool sparse_peer = false;        // the exchange runs as ONE kernel that stores into the peers' compact x over NVLink
+  SparsePushDesc sparse_push;      // (peer-memory layer, channel 1 of the arena); false: grouped ncclSend / ncclRecv
   std::vector<std::vector<Range>> recv_from;  // [peer] ranges of x this rank receives
   std::vector<std::vector<Range>> send_to;    // [peer] ranges of its own slice this rank sends
   int64_t n_global = 0;
@@ -217,6 +219,59 @@ __global__ void __launch_bounds__(256) sparse_pack_kernel(const double* __restri
   }
 }
 
+// The same exchange without NCCL (peer_mode 1, IPC arena mapped): the compact x lives in channel 1 of the symmetric arena
+// and ONE kernel per SpMV does everything.  Protocol (host-counted epochs, as the acknowledged boundary-row push of the
+// plain sharded SpMV, peer.cuh: acked_push):
+//   1. CTA 0 tells every peer how many exchanges this rank has finished (stream order: the SpMV that read the previous
+//      epoch is complete when this kernel runs); every CTA waits until the ranks it stores for have said the same -
+//      only then may their compact x be overwritten.  Acknowledgements leave before any wait: no deadlock.
+//   2. all CTAs: entries the peers asked for go straight into their compact x (coalesced 8-byte stores over NVLink),
+//      the own segment into the local one.
+//   3. every CTA fences its stores system-wide and takes a ticket; the last CTA publishes epoch done + 1 to the ranks it
+//      stored for, then waits for the same epoch from the ranks it receives from - the gather kernel queued behind this
+//      kernel starts with all of x in place.
+// The grid is at most 2 CTAs per SM (always co-resident), every wait carries the peer timeout.
+__global__ void __launch_bounds__(256) sparse_push_kernel(const double* __restrict__ x_full, const int32_t* __restrict__ send_list,
+                                                          const int32_t* __restrict__ own_cols, int64_t n_own,
+                                                          double* __restrict__ xp_own, const SparsePushDesc sd) {
+  __shared__ int s_last;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    if (blockIdx.x == 0)
+      for (int q = 0; q < sd.world; q++)
+        if (q != sd.me) st_volatile_u64(&sd.peers[q]->halo_ack[1][sd.me], sd.done);
+    if (sd.done)
+      for (int q = 0; q < sd.world; q++)
+        if (sd.send_mask & (1u << q)) peer_wait_ge(&sd.ctrl->halo_ack[1][q], sd.done, &sd.ctrl->error);
+  }
+  __syncthreads();
+  const int64_t n_send = sd.send_off[sd.world];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + tid; i < n_send + n_own; i += stride) {
+    if (i < n_send) {
+      int q = 0;
+      while (i >= sd.send_off[q + 1]) q++;
+      sd.dst[q][i - sd.send_off[q]] = __ldg(x_full + send_list[i]);
+    } else {
+      xp_own[i - n_send] = __ldg(x_full + own_cols[i - n_send]);
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence_system();  // this CTA's peer stores (ordered before by the barrier) are visible system-wide
+    s_last = atomicAdd(&sd.ctrl->push_ticket[1], 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  if (tid == 0) {
+    sd.ctrl->push_ticket[1] = 0;
+    __threadfence_system();
+    for (int q = 0; q < sd.world; q++)
+      if (sd.send_mask & (1u << q)) st_volatile_u64(&sd.peers[q]->halo_flag_acked[1][sd.me], sd.done + 1);
+  }
+  if (tid < sd.world && ((sd.recv_mask >> tid) & 1u)) peer_wait_ge(&sd.ctrl->halo_flag_acked[1][tid], sd.done + 1, &sd.ctrl->error);
+}
+
 // Collective.  Decides (all ranks together) whether the sparse exchange applies, renumbers the columns, and tells every
 // owner which of its entries each peer needs.
 static int dist_plan_sparse(cask_b200_ctx* ctx) {
@@ -225,6 +280,7 @@ static int dist_plan_sparse(cask_b200_ctx* ctx) {
   cudaStream_t s = ctx->stream;
   const int W = d->world, me = d->rank;
   d->sparse = false;
+  d->sparse_peer = false;
   cudaFree(d->d_send_list); cudaFree(d->d_sendbuf);
   d->d_send_list = nullptr; d->d_sendbuf = nullptr;
   struct Tmp {
@@ -248,7 +304,10 @@ static int dist_plan_sparse(cask_b200_ctx* ctx) {
   for (int q = 0; q < W; q++)
     if (!all[cap * q]) return CASK_B200_OK;
   // 2. compact column numbering; segment q = referenced columns owned by rank q
-  CB_TRY(build_col_reorder(ctx, 2));
+  ctx->dist_sparse_active = true;
+  const int rc_reorder = build_col_reorder(ctx, 2);
+  ctx->dist_sparse_active = false;
+  CB_TRY(rc_reorder);
   if (!p.d_perm) return fail(CASK_B200_ERR_RUNTIME, "sparse exchange: the column renumbering was refused");
   std::vector<int32_t> need((size_t)p.cols_used);
   if (p.cols_used) CB_CUDA(cudaMemcpyAsync(need.data(), p.d_perm, sizeof(int32_t) * need.size(), cudaMemcpyDeviceToHost, s));
@@ -275,6 +334,32 @@ static int dist_plan_sparse(cask_b200_ctx* ctx) {
   CB_NCCL(g_nccl.GroupEnd());
   CB_CUDA(cudaStreamSynchronize(s));
   d->sparse = true;
+  // 5. peer-memory variant: the compact x moves into channel 1 of the symmetric arena (gather plans use no other
+  //    channel: cask_b200_dist_vector and the solvers' peer path are for staged-ELL plans), every rank learns where its
+  //    segment starts inside every peer's compact x
+  for (int q = 0; q <= W; q++) mine[q] = d->seg[q];
+  CB_TRY(gather_all());  // collective whatever the outcome below
+  if (ctx->peer_mode != 0 && W <= kMaxPeers) {
+    CB_TRY(peer_ensure_arena(ctx, p.m));  // collective; all ranks agree on peer_mapped
+    if (d->peer_mapped) {
+      if (p.xperm_owned) cudaFree(p.d_xperm);
+      p.d_xperm = peer_vector(ctx, 1);
+      p.xperm_owned = false;
+      SparsePushDesc sp;
+      sp.ctrl = reinterpret_cast<PeerCtrl*>(d->arena);
+      sp.me = me;
+      sp.world = W;
+      for (int q = 0; q < W; q++) {
+        sp.peers[q] = reinterpret_cast<PeerCtrl*>(d->peer_base[q]);
+        sp.dst[q] = reinterpret_cast<double*>(d->peer_base[q] + kCtrlBytes + d->vec_stride) + all[cap * q + me];  // seg of rank q at [me]
+        sp.send_off[q + 1] = d->send_off[q + 1];
+        if (d->send_off[q + 1] > d->send_off[q]) sp.send_mask |= 1u << q;
+        if (q != me && d->seg[q + 1] > d->seg[q]) sp.recv_mask |= 1u << q;
+      }
+      d->sparse_push = sp;
+      d->sparse_peer = true;
+    }
+  }
   return CASK_B200_OK;
 }
 
@@ -697,6 +782,17 @@ int dist_exchange_begin(cask_b200_ctx* ctx, double* d_full, cudaStream_t after) 
   const Plan& p = ctx->plan;
   cudaStream_t cs = ctx->comm_stream;
   const int W = d->world, me = d->rank;
+  if (d->sparse && d->sparse_peer) {
+    const int64_t n_send = d->send_off[W], n_own = d->seg[me + 1] - d->seg[me];
+    SparsePushDesc sp = d->sparse_push;
+    sp.done = d->acked_pushes[1]++;
+    const int64_t ctas = std::max<int64_t>(1, (n_send + n_own + 255) / 256);
+    sparse_push_kernel<<<(int)std::min<int64_t>(ctas, (int64_t)ctx->sm_count * 2), 256, 0, after>>>(
+        d_full, d->d_send_list, p.d_perm + d->seg[me], n_own, p.d_xperm + d->seg[me], sp);
+    ctx->launches++;
+    CB_CUDA(cudaGetLastError());
+    return CASK_B200_OK;
+  }
   if (d->sparse) {
     // own entries into the send buffer and into the own segment of the compact x, then one grouped exchange
     const int64_t n_send = d->send_off[W], n_own = d->seg[me + 1] - d->seg[me];
@@ -748,6 +844,7 @@ int dist_exchange_begin(cask_b200_ctx* ctx, double* d_full, cudaStream_t after) 
 }
 
 int dist_exchange_wait(cask_b200_ctx* ctx, cudaStream_t consumer) {
+  if (ctx->dist->sparse && ctx->dist->sparse_peer) return CASK_B200_OK;  // the push kernel on the consumer's stream did the waiting
   CB_CUDA(cudaStreamWaitEvent(consumer, ctx->dist->ev_done, 0));
   return CASK_B200_OK;
 }

@@ -341,7 +341,8 @@ void free_plan(cask_b200_ctx* ctx) {
   cudaFree(p.d_list_ell); cudaFree(p.d_list_csr);
   cudaFree(p.d_csr_items); cudaFree(p.d_split_rows); cudaFree(p.d_csr_scratch);
   cudaFree(p.d_merge_tiles); cudaFree(p.d_merge_carry);
-  cudaFree(p.d_col_perm); cudaFree(p.d_perm); cudaFree(p.d_xperm);
+  cudaFree(p.d_col_perm); cudaFree(p.d_perm);
+  if (p.xperm_owned) cudaFree(p.d_xperm);
   p = Plan();
 }
 
@@ -489,14 +490,17 @@ int build_csr_items(cask_b200_ctx* ctx) {
 // permute_x_kernel.
 int build_col_reorder(cask_b200_ctx* ctx, int mode) {
   Plan& p = ctx->plan;
-  cudaFree(p.d_col_perm); cudaFree(p.d_perm); cudaFree(p.d_xperm);
+  cudaFree(p.d_col_perm); cudaFree(p.d_perm);
+  if (p.xperm_owned) cudaFree(p.d_xperm);
   p.d_col_perm = nullptr; p.d_perm = nullptr; p.d_xperm = nullptr;
+  p.xperm_owned = true;
   p.cols_used = 0;
   p.xperm_external = false;
   p.stats.col_reorder = 0;
   p.stats.cols_referenced = 0;
   if (mode == 0 || p.m <= 0 || p.m >= (1ll << 30)) return CASK_B200_OK;
   if (mode == 1 && (!p.csr_merge || p.nnz <= 0)) return CASK_B200_OK;
+  if (mode == 2 && !ctx->dist_sparse_active && (!p.csr_merge || p.nnz <= 0)) return CASK_B200_OK;  // as an option: gather plans only
   cudaStream_t s = ctx->stream;
   dev::Exec ex = dev::exec_of(ctx);
   struct Tmp {
@@ -529,7 +533,7 @@ int build_col_reorder(cask_b200_ctx* ctx, int mode) {
   CB_CUDA(cudaGetLastError());
   p.cols_used = used;
   CB_CUDA(cudaMalloc(&p.d_xperm, sizeof(double) * (size_t)std::max<int64_t>(used, 2)));
-  p.xperm_external = mode == 2;
+  p.xperm_external = mode == 2 && ctx->dist_sparse_active;
   p.stats.col_reorder = mode;
   p.stats.cols_referenced = used;
   return CASK_B200_OK;
@@ -755,7 +759,7 @@ int build_plan(cask_b200_ctx* ctx) {
   p.stats.max_row_length = maxlen;
   p.stats.csr_nnz = csr_nnz;
   p.stats.csr_rows = csr_rows;
-  CB_TRY(build_col_reorder(ctx, ctx->col_reorder == 1 ? 1 : 0));
+  CB_TRY(build_col_reorder(ctx, ctx->col_reorder == 1 || ctx->col_reorder == 2 ? ctx->col_reorder : 0));
   p.stats.persist_ku = ctx->ell_kernel == 1 ? p.persist_ku : 0;
   p.stats.persist_stages = p.persist_stages;
   p.stats.persist_ctas_per_sm = p.persist_ctas_per_sm;

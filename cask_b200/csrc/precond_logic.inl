@@ -67,6 +67,12 @@ inline bool compute_levels(int64_t n, const int32_t* rp, const int32_t* ci, bool
 }
 
 // ---- device: one thread per row of a level ------------------------------------------------------------------
+#ifdef __CUDACC__
+#define CB_UNROLL _Pragma("unroll")
+#else
+#define CB_UNROLL
+#endif
+constexpr int kRowBatch = 8;  // entries of a row whose operands are in flight together in the triangular solves
 struct FactorRow {  // SparseLinearSolvers.hpp:93-117 for one row i
   const int32_t* row_ptr;
   const int32_t* col;
@@ -108,10 +114,27 @@ struct LowerRow {  // y_i = (x_i - sum_{j<i} L_ij y_j) / d,  d = pc_ii (the refe
   CB_DEV void operator()(int64_t t) const {
     const int32_t i = order[t];
     double acc = x[i];
-    for (int32_t k = row_ptr[i]; k < row_ptr[i + 1]; k++) {
-      const int32_t j = col[k];
-      if (j >= i) break;
-      acc = dev::sub_rn(acc, dev::mul_rn(pc[k], y[j]));
+    // A level kernel is a handful of rows deep and latency bound: the operands of kRowBatch entries are loaded before the
+    // first of them is used (two dependent memory round trips per batch instead of per entry).  The subtractions
+    // still happen one by one in ascending column order - the reference's order, bit for bit.  Rows are sorted
+    // (ilu_analyse refuses others), so the entries left of the diagonal are a prefix.
+    const int32_t rb = row_ptr[i], re = row_ptr[i + 1];
+    bool more = true;
+    for (int32_t k0 = rb; k0 < re && more; k0 += kRowBatch) {
+      int32_t j[kRowBatch];
+      double a[kRowBatch], v[kRowBatch];
+      CB_UNROLL
+      for (int u = 0; u < kRowBatch; u++) {
+        const bool in = k0 + u < re;
+        j[u] = in ? col[k0 + u] : i;
+        a[u] = in ? pc[k0 + u] : 0.0;
+      }
+      CB_UNROLL
+      for (int u = 0; u < kRowBatch; u++) v[u] = j[u] < i ? y[j[u]] : 0.0;
+      CB_UNROLL
+      for (int u = 0; u < kRowBatch; u++)
+        if (j[u] < i) acc = dev::sub_rn(acc, dev::mul_rn(a[u], v[u]));
+      more = j[kRowBatch - 1] < i;
     }
     double d = 1.0;
     if (!unit_lower) {
@@ -136,11 +159,22 @@ struct UpperRow {  // z_i = (y_i - sum_{j>i} U_ij z_j) / U_ii
     const int32_t i = order[t];
     const int32_t dp = diag_pos[i];
     double acc = y[i];
-    // without a stored diagonal the row still has to skip its lower part
-    int32_t k = dp >= 0 ? dp + 1 : row_ptr[i];
-    for (; k < row_ptr[i + 1]; k++) {
-      const int32_t j = col[k];
-      if (j > i) acc = dev::sub_rn(acc, dev::mul_rn(pc[k], z[j]));
+    // without a stored diagonal the row still has to skip its lower part; operands in batches as in LowerRow
+    const int32_t re = row_ptr[i + 1];
+    for (int32_t k0 = dp >= 0 ? dp + 1 : row_ptr[i]; k0 < re; k0 += kRowBatch) {
+      int32_t j[kRowBatch];
+      double a[kRowBatch], v[kRowBatch];
+      CB_UNROLL
+      for (int u = 0; u < kRowBatch; u++) {
+        const bool in = k0 + u < re;
+        j[u] = in ? col[k0 + u] : i;
+        a[u] = in ? pc[k0 + u] : 0.0;
+      }
+      CB_UNROLL
+      for (int u = 0; u < kRowBatch; u++) v[u] = j[u] > i ? z[j[u]] : 0.0;
+      CB_UNROLL
+      for (int u = 0; u < kRowBatch; u++)
+        if (j[u] > i) acc = dev::sub_rn(acc, dev::mul_rn(a[u], v[u]));
     }
     const double d = dp >= 0 ? pc[dp] : 0.0;
     if (d == 0.0) dev::atomic_or_i32(flag, 1);

@@ -36,6 +36,7 @@ struct B200Model {  // stands where DeviceModel / Max4Model stand in the referen
   double hbmGBs = 6553.0;      // measured copy bandwidth of this pool's B200s (MEASURED_PEAKS.json); nominal 8000
   double l2Bytes = 126.0e6;
   double smClockHz = 1.965e9;
+  int sms = 148;
   std::string getId() const { return "B200"; }
 };
 }  // namespace model
@@ -79,18 +80,16 @@ struct Estimate {
   double bytes = 0, seconds = 0, gflops = 0, clockCycles = 0, ellFill = 0, memoryBandwidthGBs = 0;
 };
 
+// The model itself lives behind the ABI (cask_b200_plan_estimate): one definition for this selector, for bench-side
+// validation (profiles/dse_validate.py) and for callers in other languages.
 inline Estimate estimate(const cask_b200_plan_stats& s, const model::B200Model& dm) {
   Estimate e;
-  const double nnz_csr = (double)(s.nnz - s.ell_nnz);
-  const double rows_csr = (double)s.slices_gather_csr * s.slice_rows;
-  const double miss = std::max(0.0, 1.0 - dm.l2Bytes / std::max(8.0 * (double)s.m, 1.0));
-  e.bytes = 10.0 * (double)s.ell_padded_entries + 12.0 * nnz_csr + 4.0 * rows_csr + 8.0 * (double)s.m + 8.0 * (double)s.n +
-            32.0 * nnz_csr * miss;
-  e.seconds = e.bytes / (dm.hbmGBs * 1e9);
+  if (cask_b200_plan_estimate(&s, dm.hbmGBs, dm.l2Bytes, dm.smClockHz, dm.sms, &e.bytes, &e.seconds) != CASK_B200_OK)
+    throw std::runtime_error(cask_b200_last_error());
   e.gflops = e.seconds > 0 ? 2.0 * (double)s.nnz / e.seconds / 1e9 : 0.0;
   e.clockCycles = e.seconds * dm.smClockHz;
   e.ellFill = s.ell_padded_entries ? (double)s.ell_nnz / (double)s.ell_padded_entries : 0.0;
-  e.memoryBandwidthGBs = dm.hbmGBs;  // every candidate is memory bound on this device
+  e.memoryBandwidthGBs = dm.hbmGBs;  // the denominator of the byte term (stencil plans are bound by it)
   return e;
 }
 

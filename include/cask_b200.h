@@ -108,7 +108,12 @@ int cask_b200_synchronize(cask_b200_ctx* ctx);
  * all-reduce; every rank must use the same value), "value_dict" (0 default, 1 / 2 = coded staged ELL, see
  * cask_b200_plan_value_dict), "persist_ctas" (coded format: CTAs per SM of the persistent kernel, 0 auto),
  * "col_reorder" (gather path, default 0; 1 = columns renumbered by descending reference count so that the hub columns
- * of a power-law matrix share cache lines; x is permuted by a streaming kernel in front of every SpMV).
+ * of a power-law matrix share cache lines, 2 = referenced columns only, in column order; x is permuted by a streaming
+ * kernel in front of every SpMV), "dist_sparse" (row-sharded gather plans, default 1: every rank receives only the x
+ * entries its rows reference, packed by their owners; 0: every slice of x is broadcast to all ranks),
+ * "host_staging" (default 1: pageable caller vectors of cask_b200_spmv go through the library's pinned rings and copy
+ * threads; 0: left to the driver), "ilu_graph" (default 1: the per-level launches of an ILU application are replayed
+ * as one CUDA graph).
  * Takes effect at the next preprocess. */
 int cask_b200_set_option(cask_b200_ctx* ctx, const char* name, double value);
 
@@ -122,6 +127,15 @@ int cask_b200_preprocess_device(cask_b200_ctx* ctx, const cask_b200_design* desi
                                 int64_t m, int64_t nnz, const int32_t* d_row_ptr,
                                 const int32_t* d_col_ind, const double* d_values);
 int cask_b200_plan_get_stats(cask_b200_ctx* ctx, cask_b200_plan_stats* out);
+/* Time model of one SpMV on the plan described by *stats - the B200 stand-in for the reference's cycle model
+ * (countComputeCycles, src/runtime/Spmv.cpp:25-40, and getEstimatedClockCycles, Spmv.hpp:103-109), used by the
+ * architecture selector (host/include/Dse.hpp) and validated against measured kernel times by profiles/dse_validate.py.
+ * No GPU needed.  *bytes = what the format streams from HBM: 10 B per stored staged-ELL entry, 12 B per gathered nonzero
+ * + 4 B per gathered row, x and y once, and one 32-byte sector per gathered nonzero for the share of x that cannot stay in
+ * L2.  *seconds = max(bytes / hbm_gbs, gather time), gather time = 39/32 LSU wavefronts per gathered nonzero at 0.64 of
+ * one wavefront per clock per SM (measured: profiles/r2k_rmat_reorder.md).  hbm_gbs <= 0: 6456.5 (measured copy peak). */
+int cask_b200_plan_estimate(const cask_b200_plan_stats* stats, double hbm_gbs, double l2_bytes, double sm_clock_hz,
+                            int32_t sms, double* bytes, double* seconds);
 /* Coded staged ELL (option "value_dict", off by default; set before preprocess).
  *   1  When every staged slice holds at most 256 distinct fp64 bit patterns - constant-coefficient stencils hold 2-6 -
  *      the values are stored as 8-bit codes into a per-slice table that travels with the slice's x windows: 3 bytes

@@ -32,8 +32,10 @@ if [ "$MODE" != bench ]; then
 step "multi-rank GPU tests (world 2 on both paths; 4 and 8 as the box allows)"
 timeout 1200 $PY -m pytest tests/test_gpu_dist.py -q -rs -x > $OUT/${TAG}_pytest_dist.log 2>&1; tail -25 $OUT/${TAG}_pytest_dist.log
 fi
-step "C3 at N=$GPUS: sparse exchange"
+step "C3 at N=$GPUS: sparse exchange, one kernel over peer memory (default)"
 run $OUT/${TAG}_rmat_n${GPUS}_sparse.json CASK_B200_DIST_SPARSE=1 -- --only-rmat --no-cg --no-cpu --no-probe --steps 20 --warmup 3 --soak 0
+step "C3 at N=$GPUS: sparse exchange over NCCL send/recv (peer_mode 0)"
+run $OUT/${TAG}_rmat_n${GPUS}_sparse_nccl.json CASK_B200_DIST_SPARSE=1 CASK_B200_PEER=0 -- --only-rmat --no-cg --no-cpu --no-probe --steps 20 --warmup 3 --soak 0
 step "C3 at N=$GPUS: every slice broadcast to all"
 run $OUT/${TAG}_rmat_n${GPUS}_allgather.json CASK_B200_DIST_SPARSE=0 -- --only-rmat --no-cg --no-cpu --no-probe --steps 20 --warmup 3 --soak 0
 step "done"
