@@ -850,6 +850,15 @@ def main():
             line["details_file"] = os.path.relpath(dpath, ROOT)
         except OSError:
             pass
+        # the headline stays compact (<= 4 KB): explanatory strings live in the details file, which holds the full line
+
+        def slim(o):
+            if isinstance(o, dict):
+                return {k: slim(v) for k, v in o.items() if k not in ("note", "per", "how", "what", "peak_source", "window")}
+            if isinstance(o, float):
+                return float("%.6g" % o)
+            return o
+        line = slim(line)
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

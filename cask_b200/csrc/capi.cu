@@ -505,7 +505,7 @@ static int spmv_host_pipelined(cask_b200_ctx* ctx, const double* x, double* y, b
     int64_t total = 0;
     for (int c = 0; c < K; c++) {
       const int e = std::min(std::min(c, K - 1 - c), 4);
-      w[c] = ctx->host_pipeline_ramp ? (int64_t)1 << e : 1;
+      w[c] = ctx->host_pipeline_ramp && !stage_x && !stage_y ? (int64_t)1 << e : 1;  // staged vectors move in 4 MB ring slots anyway
       total += w[c];
     }
     int64_t run = 0;

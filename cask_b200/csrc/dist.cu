@@ -315,30 +315,43 @@ static int dist_plan_sparse(cask_b200_ctx* ctx) {
   d->seg.assign((size_t)W + 1, 0);
   for (int q = 0; q <= W; q++)
     d->seg[q] = std::lower_bound(need.begin(), need.end(), d->bounds[q], [](int32_t a, int64_t b) { return (int64_t)a < b; }) - need.begin();
-  // 3. how many entries every rank needs from every owner
-  for (int q = 0; q < W; q++) mine[1 + q] = q == me ? 0 : d->seg[q + 1] - d->seg[q];
+  // 3. every rank's segment boundaries: what rank q needs from owner r is its segment r, so one all-gather of the
+  //    boundaries tells every owner how much it sends to whom, and (peer-memory variant) where its entries start
+  //    inside every peer's compact x
+  for (int q = 0; q <= W; q++) mine[q] = d->seg[q];
   CB_TRY(gather_all());
+  auto seg_of = [&](int q, int r) -> int64_t { return all[cap * q + r]; };  // boundary r of rank q's compact x
   d->send_off.assign((size_t)W + 1, 0);
-  for (int q = 0; q < W; q++) d->send_off[q + 1] = d->send_off[q] + (q == me ? 0 : all[cap * q + 1 + me]);
+  int64_t max_used = 0;
+  for (int q = 0; q < W; q++) {
+    d->send_off[q + 1] = d->send_off[q] + (q == me ? 0 : seg_of(q, me + 1) - seg_of(q, me));
+    max_used = std::max(max_used, seg_of(q, W));
+  }
   const int64_t total_send = d->send_off[W];
   CB_CUDA(cudaMalloc(&d->d_send_list, sizeof(int32_t) * (size_t)std::max<int64_t>(total_send, 1)));
   CB_CUDA(cudaMalloc(&d->d_sendbuf, sizeof(double) * (size_t)std::max<int64_t>(total_send, 1)));
-  // 4. the requests themselves: my segment for owner q goes to q, q's request list lands in my send list
-  CB_NCCL(g_nccl.GroupStart());
-  for (int q = 0; q < W; q++) {
-    if (q == me) continue;
-    const int64_t n_out = d->seg[q + 1] - d->seg[q], n_in = d->send_off[q + 1] - d->send_off[q];
-    if (n_out) CB_NCCL(g_nccl.Send(p.d_perm + d->seg[q], (size_t)n_out, kNcclInt32, q, d->comm_halo, s));
-    if (n_in) CB_NCCL(g_nccl.Recv(d->d_send_list + d->send_off[q], (size_t)n_in, kNcclInt32, q, d->comm_halo, s));
+  // 4. the requests themselves: ONE all-gather of the ranks' referenced-column lists (padded to the longest; d_perm holds
+  //    m entries, the tail beyond cols_used is never looked at), from which every owner cuts the pieces addressed to it.
+  //    An all-gather runs over the communicator's warmed ring; point-to-point sends between all pairs would pay NCCL's
+  //    lazy connection set-up here (measured: 5.5 s at 8 ranks).
+  if (max_used > 0) {
+    struct TmpI {
+      int32_t* q = nullptr;
+      ~TmpI() { cudaFree(q); }
+    } lists;
+    CB_CUDA(cudaMalloc(&lists.q, sizeof(int32_t) * (size_t)max_used * (size_t)W));
+    CB_NCCL(g_nccl.AllGather(p.d_perm, lists.q, (size_t)max_used, kNcclInt32, d->comm_halo, s));
+    for (int q = 0; q < W; q++) {
+      const int64_t n_in = d->send_off[q + 1] - d->send_off[q];
+      if (n_in)
+        CB_CUDA(cudaMemcpyAsync(d->d_send_list + d->send_off[q], lists.q + (size_t)q * (size_t)max_used + seg_of(q, me),
+                                sizeof(int32_t) * (size_t)n_in, cudaMemcpyDeviceToDevice, s));
+    }
+    CB_CUDA(cudaStreamSynchronize(s));
   }
-  CB_NCCL(g_nccl.GroupEnd());
-  CB_CUDA(cudaStreamSynchronize(s));
   d->sparse = true;
   // 5. peer-memory variant: the compact x moves into channel 1 of the symmetric arena (gather plans use no other
-  //    channel: cask_b200_dist_vector and the solvers' peer path are for staged-ELL plans), every rank learns where its
-  //    segment starts inside every peer's compact x
-  for (int q = 0; q <= W; q++) mine[q] = d->seg[q];
-  CB_TRY(gather_all());  // collective whatever the outcome below
+  //    channel: cask_b200_dist_vector and the solvers' peer path are for staged-ELL plans)
   if (ctx->peer_mode != 0 && W <= kMaxPeers) {
     CB_TRY(peer_ensure_arena(ctx, p.m));  // collective; all ranks agree on peer_mapped
     if (d->peer_mapped) {
@@ -351,7 +364,7 @@ static int dist_plan_sparse(cask_b200_ctx* ctx) {
       sp.world = W;
       for (int q = 0; q < W; q++) {
         sp.peers[q] = reinterpret_cast<PeerCtrl*>(d->peer_base[q]);
-        sp.dst[q] = reinterpret_cast<double*>(d->peer_base[q] + kCtrlBytes + d->vec_stride) + all[cap * q + me];  // seg of rank q at [me]
+        sp.dst[q] = reinterpret_cast<double*>(d->peer_base[q] + kCtrlBytes + d->vec_stride) + seg_of(q, me);
         sp.send_off[q + 1] = d->send_off[q + 1];
         if (d->send_off[q + 1] > d->send_off[q]) sp.send_mask |= 1u << q;
         if (q != me && d->seg[q + 1] > d->seg[q]) sp.recv_mask |= 1u << q;
