@@ -443,33 +443,43 @@ int dist_plan_halo(cask_b200_ctx* ctx) {
   d->allgather = any_allgather;
   cudaFree(d_buf);
   if (!d->allgather) {
-    // ranges requested from me by q: all[cap*q + 1 + me] of them
-    std::vector<int64_t*> d_send(W, nullptr), d_recv(W, nullptr);
-    std::vector<std::vector<int64_t>> h_recv(W);
-    CB_NCCL(g_nccl.GroupStart());
+    // ranges requested from me by q: all[cap*q + 1 + me] of them.  The request lists travel in ONE all-gather (every rank's
+    // list, ordered by owner, padded to the longest) from which each owner cuts its piece: point-to-point sends here
+    // would make NCCL build its send/recv connections between all pairs at preprocess time (about a second at 8 ranks),
+    // and the peer-memory path never needs them.
+    int64_t max_req = 0;
     for (int q = 0; q < W; q++) {
-      if (q == me) continue;
-      const size_t n_out = d->recv_from[q].size(), n_in = (size_t)all[cap * q + 1 + me];
-      if (n_out) {
-        CB_CUDA(cudaMalloc(&d_send[q], sizeof(int64_t) * 2 * n_out));
-        CB_CUDA(cudaMemcpyAsync(d_send[q], d->recv_from[q].data(), sizeof(int64_t) * 2 * n_out, cudaMemcpyHostToDevice, s));
-        CB_NCCL(g_nccl.Send(d_send[q], 2 * n_out, kNcclInt64, q, d->comm_halo, s));
-      }
-      if (n_in) {
-        CB_CUDA(cudaMalloc(&d_recv[q], sizeof(int64_t) * 2 * n_in));
-        CB_NCCL(g_nccl.Recv(d_recv[q], 2 * n_in, kNcclInt64, q, d->comm_halo, s));
+      int64_t t = 0;
+      for (int r = 0; r < W; r++) t += all[cap * q + 1 + r];
+      max_req = std::max(max_req, t);
+    }
+    if (max_req > 0) {
+      std::vector<int64_t> req((size_t)max_req * 2, 0), got((size_t)max_req * 2 * (size_t)W, 0);
+      size_t k = 0;
+      for (int q = 0; q < W; q++)
+        for (auto& r : d->recv_from[q]) { req[k++] = r.col0; req[k++] = r.len; }
+      int64_t* d_req = nullptr;
+      CB_CUDA(cudaMalloc(&d_req, sizeof(int64_t) * (size_t)max_req * 2 * (size_t)(W + 1)));
+      cudaError_t e = cudaMemcpyAsync(d_req + (size_t)max_req * 2 * (size_t)W, req.data(), sizeof(int64_t) * req.size(), cudaMemcpyHostToDevice, s);
+      int nrc = 0;
+      if (e == cudaSuccess) nrc = g_nccl.AllGather(d_req + (size_t)max_req * 2 * (size_t)W, d_req, (size_t)max_req * 2, kNcclInt64, d->comm_halo, s);
+      if (e == cudaSuccess && nrc == 0) e = cudaMemcpyAsync(got.data(), d_req, sizeof(int64_t) * got.size(), cudaMemcpyDeviceToHost, s);
+      if (e == cudaSuccess && nrc == 0) e = cudaStreamSynchronize(s);
+      cudaFree(d_req);
+      if (nrc != 0) return fail(CASK_B200_ERR_NCCL, std::string("ncclAllGather (halo requests): ") + g_nccl.GetErrorString(nrc));
+      CB_CUDA(e);
+      for (int q = 0; q < W; q++) {
+        if (q == me) continue;
+        int64_t off = 0;
+        for (int r = 0; r < me; r++) off += all[cap * q + 1 + r];
+        const int64_t n_in = all[cap * q + 1 + me];
+        d->send_to[q].resize((size_t)n_in);
+        for (int64_t i = 0; i < n_in; i++) {
+          const size_t at = ((size_t)q * (size_t)max_req + (size_t)(off + i)) * 2;
+          d->send_to[q][(size_t)i] = Range{got[at], got[at + 1]};
+        }
       }
     }
-    CB_NCCL(g_nccl.GroupEnd());
-    for (int q = 0; q < W; q++) {
-      const size_t n_in = q == me ? 0 : (size_t)all[cap * q + 1 + me];
-      if (n_in) {
-        d->send_to[q].resize(n_in);
-        CB_CUDA(cudaMemcpyAsync(d->send_to[q].data(), d_recv[q], sizeof(int64_t) * 2 * n_in, cudaMemcpyDeviceToHost, s));
-      }
-    }
-    CB_CUDA(cudaStreamSynchronize(s));
-    for (int q = 0; q < W; q++) { cudaFree(d_send[q]); cudaFree(d_recv[q]); }
   } else {
     for (auto& sd : p.h_slices) sd.remote = 1;
   }
