@@ -1167,7 +1167,9 @@ def bench_rmat(ctx, cb, torch, dist, dev, rank, world, barrier, scale=25, edge_f
         dist.all_reduce(reordered)
     stored += 20.0 * float(reordered.item())   # hub clustering: perm (4 B) + x read + permuted x written per referenced column
     roof = roofline_of(algorithmic_bytes(nnz_total, n, n), stored, ms * 1e-3, measured_peak()[0] * world)
-    kernel = "spmv_csr_merge_kernel<false>" if stats.get("csr_kernel") == 1 else "spmv_csr_items_kernel<0,0>"
+    # instantiation name as ncu prints it (template arguments: fused dot, items per thread, resident CTAs per SM)
+    kernel = ("spmv_csr_merge_kernel<0,%d,%d>" % (stats.get("merge_items", 7), stats.get("merge_ctas", 5))
+              if stats.get("csr_kernel") == 1 else "spmv_csr_items_kernel<0,0>")
     roof["traffic"], roof["traffic_source"] = ncu_traffic(kernel)
     roof["per"] = "SpMV, whole job; peak = %d x measured HBM copy peak; the kernel is bound by the x gather, not by these bytes" % world
     l2 = None
@@ -1188,7 +1190,8 @@ def bench_rmat(ctx, cb, torch, dist, dev, rank, world, barrier, scale=25, edge_f
             "rows_this_rank": nr, "nnz_this_rank": nnz,
             "max_rel_diff_256_sampled_rows": rel, "max_err_all_rows_rel_to_sum_abs": rel_all,
             "plan": {k: stats[k] for k in ("slices_staged_ell", "slices_gather_csr", "csr_lanes_per_row", "max_row_length",
-                                           "row_length_histogram", "csr_items", "csr_kernel", "col_reorder", "cols_referenced")}}
+                                           "row_length_histogram", "csr_items", "csr_kernel", "col_reorder", "cols_referenced",
+                                           "merge_items", "merge_ctas")}}
 
 
 if __name__ == "__main__":

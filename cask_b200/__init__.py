@@ -59,7 +59,8 @@ class PlanStats(C.Structure):
                 ("device_bytes", C.c_int64), ("row_length_histogram", C.c_int64 * 8),
                 ("csr_nnz", C.c_int64), ("csr_rows", C.c_int64), ("csr_items", C.c_int32), ("csr_kernel", C.c_int32),
                 ("persist_ku", C.c_int32), ("persist_stages", C.c_int32), ("persist_ctas_per_sm", C.c_int32),
-                ("value_dict", C.c_int32), ("col_reorder", C.c_int32), ("cols_referenced", C.c_int64)]
+                ("value_dict", C.c_int32), ("col_reorder", C.c_int32), ("cols_referenced", C.c_int64),
+                ("merge_items", C.c_int32), ("merge_ctas", C.c_int32)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k != "row_length_histogram"}

@@ -163,7 +163,7 @@ int cask_b200_synchronize(cask_b200_ctx* ctx) {
   CB_TRY(ensure_device(ctx));
   CB_CUDA(cudaStreamSynchronize(ctx->stream));
   CB_CUDA(cudaStreamSynchronize(ctx->comm_stream));
-  return CASK_B200_OK;
+  return peer_check_error(ctx);  // a peer that stopped participating surfaces here as an error code (no-op on one rank)
 }
 
 int cask_b200_set_option(cask_b200_ctx* ctx, const char* name, double value) {

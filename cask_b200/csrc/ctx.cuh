@@ -91,6 +91,10 @@ constexpr int kMergeItemsDefault = 7;  // merge items per thread (5, 7, 11 or 17
                                        // (12 bytes per item), and what shared memory takes L1 loses - the x gathers in
                                        // flight are bounded by the L1 that is left (profiles/r2b_spmv_merge_rmat_ncu.md)
 constexpr int64_t kMergeAutoNnz = 1 << 20;  // gather slices holding at least this many nonzeros run the merge kernel
+// automatic hub clustering of a single-rank gather plan (plan.cu: build_col_reorder): from this many gathered nonzeros,
+// when x is larger than this (and the column reference counts are skewed)
+constexpr int64_t kReorderAutoNnz = 1 << 24;
+constexpr int64_t kReorderAutoXBytes = 64 << 20;
 
 struct RefPartition {  // reference-format partition resident on the device
   cask_b200_partition_info info{};
@@ -141,6 +145,7 @@ struct Plan {
   double* d_merge_carry = nullptr;    // per tile: partial sum of the row the tile ends in (0 if it ends on a row boundary)
   int32_t n_merge_tiles = 0;
   int32_t merge_items = kMergeItemsDefault;   // merge items per thread the tiles were cut for
+  int32_t merge_ctas = 0;                     // resident CTAs per SM the merge kernel instantiation is compiled for (0: default of the item count)
   // hub clustering (plan.cu: build_col_reorder): columns renumbered by descending reference count for the gather kernel
   int32_t* d_col_perm = nullptr;      // relabelled copy of d_col (all local nonzeros); nullptr: not reordered
   int32_t* d_perm = nullptr;          // [m] new column -> old column
@@ -309,8 +314,9 @@ struct cask_b200_ctx {
   int32_t csr_stream = 0;    // 1: CSR-stream variant of the gather-CSR kernel (products staged in shared memory)
   int32_t csr_item_nnz = 4096;  // nonzeros per work item of the CSR-stream variant (its shared-memory footprint)
   int32_t merge_items = 0;   // merge-path tiles: merge items per thread (0: default; 5, 7, 11, 17)
-  int32_t col_reorder = 0;   // gather path: 1 = columns renumbered by descending reference count (hub clustering), 2 = referenced
-                             // columns only, in column order (the numbering of the sharded sparse exchange); off by default
+  int32_t col_reorder = -1;  // gather path: -1 auto (hub clustering for large skewed single-rank plans), 0 off, 1 = columns renumbered
+                             // by descending reference count (hub clustering), 2 = referenced columns only, in column order (the
+                             // numbering of the sharded sparse exchange)
   bool dist_sparse_active = false;  // set by dist.cu while it builds the compact numbering of a sparse exchange
   int32_t csr_kernel = -1;   // gather slices: -1 auto (merge-path tiles from kMergeAutoNnz nonzeros), 0 row-group items, 1 merge-path tiles
   int32_t l2_keep = -1;      // -1 auto (vectors of a solver iteration fit L2), 0 never, 1 always: evict-last on vector accesses

@@ -789,9 +789,10 @@ int peer_allreduce_partials(cask_b200_ctx* ctx, const double* d_partials, int co
   return CASK_B200_OK;
 }
 
-// after a solve: did any wait on a peer time out?
+// after a solve / at a synchronisation point: did any wait on a peer time out?  (halo pushes, in-kernel all-reduces and
+// the sparse exchange all raise the same flag of this rank's control block)
 int peer_check_error(cask_b200_ctx* ctx) {
-  if (!peer_ready(ctx)) return CASK_B200_OK;
+  if (!dist_active(ctx) || !ctx->dist->peer_mapped || !ctx->dist->arena) return CASK_B200_OK;
   int err = 0;
   CB_CUDA(cudaMemcpy(&err, ctx->dist->arena + offsetof(PeerCtrl, error), sizeof(int), cudaMemcpyDeviceToHost));
   if (err) return fail(CASK_B200_ERR_RUNTIME, "peer-memory wait timed out: a rank stopped participating");

@@ -321,6 +321,15 @@ __global__ void __launch_bounds__(256) col_inverse_kernel(const uint32_t* __rest
     if (ref && (j == m - 1 || keys[j + 1] == 0x7fffffffull)) *used = (int32_t)(j + 1);
   }
 }
+// *sum += reference counts of the first k columns of the hub ordering (keys = 0x7fffffff - count, sorted ascending)
+__global__ void __launch_bounds__(256) col_head_count_kernel(const uint64_t* __restrict__ keys, int64_t k, unsigned long long* __restrict__ sum) {
+  unsigned long long acc = 0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < k; j += stride) acc += 0x7fffffffull - keys[j];
+#pragma unroll
+  for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(sum, acc);
+}
 __global__ void __launch_bounds__(256) col_relabel_kernel(const int32_t* __restrict__ col, int64_t nnz, const int32_t* __restrict__ inv,
                                                           int32_t* __restrict__ out) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -354,14 +363,16 @@ void free_plan(cask_b200_ctx* ctx) {
 // scale 25, nonzero counts per slice are already known from plan_count_kernel) to find the runs of consecutive gather
 // slices; every tile boundary is then one binary search over row_ptr by one GPU thread.  Runs never cross the
 // interior / halo-dependent split of the list, so either part can be launched on its own.
-static int build_merge_tiles(cask_b200_ctx* ctx) {
+static int build_merge_tiles(cask_b200_ctx* ctx, int items_override = 0) {
   Plan& p = ctx->plan;
+  cudaFree(p.d_merge_tiles); cudaFree(p.d_merge_carry);
+  p.d_merge_tiles = nullptr; p.d_merge_carry = nullptr;
   cudaStream_t s = ctx->stream;
   std::vector<int64_t> k_at(p.nslices + 1, 0);  // row_ptr at every slice boundary = prefix sum of the slices' nonzeros
   for (int32_t i = 0; i < p.nslices; i++) k_at[i + 1] = k_at[i] + p.h_slices[i].nnz;
   std::vector<MergeRun> runs;
   p.merge_items = ctx->merge_items == 5 || ctx->merge_items == 7 || ctx->merge_items == 11 || ctx->merge_items == 17
-                      ? ctx->merge_items : kMergeItemsDefault;
+                      ? ctx->merge_items : items_override ? items_override : kMergeItemsDefault;
   const int64_t tile_items = (int64_t)kMergeThreads * p.merge_items;
   p.h_item_begin.assign((size_t)p.n_csr + 1, -1);
   p.h_split_begin.assign((size_t)p.n_csr + 1, 0);
@@ -479,11 +490,18 @@ int build_csr_items(cask_b200_ctx* ctx) {
   return CASK_B200_OK;
 }
 
-// Hub clustering of the gather path (see col_count_kernel above).  Opt-in (option col_reorder = 1): measured on R-MAT
-// scale 25 (profiles/r2k_rmat_reorder.md) the gather phase alone falls from 3.04 to 2.36 ms, DRAM reads from 9.6 to 7.8 GB,
-// but the whole SpMV only from 3.21 to 3.17 ms - with the hubs served by L1 the kernel becomes bound by the LSU wavefront
-// rate its reduction phases share with the gathers, and the permutation of x costs 0.12 ms per call.
+// Hub clustering of the gather path (see col_count_kernel above).  Measured on R-MAT scale 25
+// (profiles/r2k_rmat_reorder.md): the gather phase alone falls from 3.04 to 2.36 ms, DRAM reads from 9.6 to 7.8 GB, but with
+// the default tile shape the whole SpMV only from 3.21 to 3.17 ms - with the hubs served by L1 the kernel becomes bound by
+// the LSU wavefront rate its reduction phases share with the gathers, and the permutation of x costs 0.12 ms per call.
+// Smaller tiles and more resident CTAs recover part of it (profiles/r2s_rmat_ctas.md).
 //
+// mode -1: hub clustering if it pays (the automatic rule of a single-rank plan): the merge-path kernel runs at least
+// kReorderAutoNnz nonzeros, x is larger than kReorderAutoXBytes (below that every gather hits L2 anyway), and the matrix IS
+// skewed - the most referenced 1/64 of the referenced columns draw at least a quarter of all gathers (R-MAT: about half;
+// uniformly scattered columns: 1/64, for which the permutation of x would be pure cost).  The tiles are then re-cut for
+// 5 merge items per thread and the kernel compiled for 8 resident CTAs per SM: measured on R-MAT scale 25
+// (profiles/r2s_rmat_ctas.md) 2.99 ms per SpMV, permutation included, against 3.23 ms without clustering.
 // mode 1: hub clustering as above (option col_reorder).  mode 2 (dist.cu, sparse exchange of a row-sharded gather plan):
 // the referenced columns only, in ascending column order - the compact local numbering of a distributed SpMV; the
 // permuted x is then filled by the exchange (own columns by a pack kernel, the others received from their owners), not by
@@ -498,7 +516,13 @@ int build_col_reorder(cask_b200_ctx* ctx, int mode) {
   p.xperm_external = false;
   p.stats.col_reorder = 0;
   p.stats.cols_referenced = 0;
+  p.merge_ctas = 0;
   if (mode == 0 || p.m <= 0 || p.m >= (1ll << 30)) return CASK_B200_OK;
+  const bool automatic = mode < 0;
+  if (automatic) {
+    if (dist_active(ctx) || !p.csr_merge || p.stats.csr_nnz < kReorderAutoNnz || p.m * 8 < kReorderAutoXBytes) return CASK_B200_OK;
+    mode = 1;
+  }
   if (mode == 1 && (!p.csr_merge || p.nnz <= 0)) return CASK_B200_OK;
   if (mode == 2 && !ctx->dist_sparse_active && (!p.csr_merge || p.nnz <= 0)) return CASK_B200_OK;  // as an option: gather plans only
   cudaStream_t s = ctx->stream;
@@ -531,6 +555,26 @@ int build_col_reorder(cask_b200_ctx* ctx, int mode) {
   CB_CUDA(cudaMemcpyAsync(&used, tmp.q[4], sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   CB_CUDA(cudaStreamSynchronize(s));
   CB_CUDA(cudaGetLastError());
+  if (automatic) {
+    // skew test: share of all gathers that go to the most referenced 1/64 of the referenced columns
+    unsigned long long head = 0;
+    CB_CUDA(cudaMemsetAsync(tmp.q[1], 0, sizeof(unsigned long long), s));  // the unsorted keys are no longer needed
+    const int64_t k = std::max<int64_t>(1, used / 64);
+    col_head_count_kernel<<<grid, 256, 0, s>>>((const uint64_t*)tmp.q[2], k, (unsigned long long*)tmp.q[1]);
+    ctx->launches++;
+    CB_CUDA(cudaMemcpyAsync(&head, tmp.q[1], sizeof(head), cudaMemcpyDeviceToHost, s));
+    CB_CUDA(cudaStreamSynchronize(s));
+    if ((double)head < 0.25 * (double)p.nnz) {
+      cudaFree(p.d_col_perm); cudaFree(p.d_perm);
+      p.d_col_perm = nullptr; p.d_perm = nullptr;
+      return CASK_B200_OK;
+    }
+    if (!(ctx->merge_items == 5 || ctx->merge_items == 7 || ctx->merge_items == 11 || ctx->merge_items == 17)) {
+      CB_TRY(build_merge_tiles(ctx, 5));
+      p.stats.csr_items = p.n_merge_tiles;
+      p.merge_ctas = 8;
+    }
+  }
   p.cols_used = used;
   CB_CUDA(cudaMalloc(&p.d_xperm, sizeof(double) * (size_t)std::max<int64_t>(used, 2)));
   p.xperm_external = mode == 2 && ctx->dist_sparse_active;
@@ -759,11 +803,13 @@ int build_plan(cask_b200_ctx* ctx) {
   p.stats.max_row_length = maxlen;
   p.stats.csr_nnz = csr_nnz;
   p.stats.csr_rows = csr_rows;
-  CB_TRY(build_col_reorder(ctx, ctx->col_reorder == 1 || ctx->col_reorder == 2 ? ctx->col_reorder : 0));
+  CB_TRY(build_col_reorder(ctx, ctx->col_reorder == 1 || ctx->col_reorder == 2 || ctx->col_reorder < 0 ? ctx->col_reorder : 0));
   p.stats.persist_ku = ctx->ell_kernel == 1 ? p.persist_ku : 0;
   p.stats.persist_stages = p.persist_stages;
   p.stats.persist_ctas_per_sm = p.persist_ctas_per_sm;
   p.stats.value_dict = p.coded;
+  p.stats.merge_items = p.csr_merge ? p.merge_items : 0;
+  p.stats.merge_ctas = p.csr_merge ? (p.merge_ctas ? p.merge_ctas : (p.merge_items > 11 ? 4 : 5)) : 0;
   for (int i = 0; i < 8; i++) p.stats.row_length_histogram[i] = (int64_t)hist[i];
   p.stats.device_bytes = val_off * (p.coded ? 11 : 10) + (p.coded == 1 ? (int64_t)p.nslices * valuedict::kStride * 8 : 0) +
                          (p.coded == 2 ? (int64_t)p.nslices * valuedict::kPairStride * 16 : 0) +

@@ -659,8 +659,8 @@ __global__ void __launch_bounds__(256) permute_x_kernel(const int32_t* __restric
   }
 }
 
-template <bool kDot, int ITEMS>
-__global__ void __launch_bounds__(kMergeThreads, ITEMS > 11 ? 4 : 5)
+template <bool kDot, int ITEMS, int CTAS = (ITEMS > 11 ? 4 : 5)>
+__global__ void __launch_bounds__(kMergeThreads, CTAS)
 spmv_csr_merge_kernel(const MergeTile* __restrict__ tiles, int32_t n_rows, const int32_t* __restrict__ row_ptr,
                       const int32_t* __restrict__ col, const double* __restrict__ val, const double* __restrict__ x,
                       double* __restrict__ y, const double* __restrict__ dot_with, double* __restrict__ partials,
@@ -1019,19 +1019,32 @@ int launch_spmv_range(cask_b200_ctx* ctx, const double* d_x, double* d_y, int el
         xg = p.d_xperm;
       }
       const int flags = ((xcg_env >= 0 ? xcg_env : (p.stats.col_reorder == 1 ? 0 : 1)) ? kMergeXPastL1 : 0) | diag;
-#define CB_MERGE(DOT, ITEMS)                                                                                              \
+#define CB_MERGE(DOT, ITEMS, CTAS)                                                                                        \
   do {                                                                                                                    \
-    CB_CUDA(cudaFuncSetAttribute(spmv_csr_merge_kernel<DOT, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    spmv_csr_merge_kernel<DOT, ITEMS><<<tiles, kMergeThreads, smem, s>>>(p.d_merge_tiles + i_lo, (int32_t)p.n, p.d_row_ptr, cols,    \
-                                                                         p.d_val, xg, d_y, w, partials, p.d_merge_carry + i_lo,      \
-                                                                         flags);                                                     \
+    CB_CUDA(cudaFuncSetAttribute(spmv_csr_merge_kernel<DOT, ITEMS, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    spmv_csr_merge_kernel<DOT, ITEMS, CTAS><<<tiles, kMergeThreads, smem, s>>>(p.d_merge_tiles + i_lo, (int32_t)p.n, p.d_row_ptr,   \
+                                                                               cols, p.d_val, xg, d_y, w, partials,                \
+                                                                               p.d_merge_carry + i_lo, flags);                     \
   } while (0)
+      // resident CTAs per SM the kernel is compiled for (register budget): 5 x 46 registers by default; profiling sessions
+      // try more warps in flight (CASK_B200_MERGE_CTAS = 6: 40 registers, 7: 36, 8 with 5 items: 32)
+      static const int env_ctas = getenv("CASK_B200_MERGE_CTAS") ? atoi(getenv("CASK_B200_MERGE_CTAS")) : -1;
+      const int want_ctas = env_ctas >= 0 ? env_ctas : p.merge_ctas;
 #define CB_MERGE_ITEMS(DOT)                                                      \
   switch (p.merge_items) {                                                       \
-    case 5: CB_MERGE(DOT, 5); break;                                             \
-    case 7: CB_MERGE(DOT, 7); break;                                             \
-    case 11: CB_MERGE(DOT, 11); break;                                           \
-    case 17: CB_MERGE(DOT, 17); break;                                           \
+    case 5:                                                                      \
+      if (want_ctas == 8) CB_MERGE(DOT, 5, 8);                                   \
+      else if (want_ctas == 7) CB_MERGE(DOT, 5, 7);                              \
+      else if (want_ctas == 6) CB_MERGE(DOT, 5, 6);                              \
+      else CB_MERGE(DOT, 5, 5);                                                  \
+      break;                                                                     \
+    case 7:                                                                      \
+      if (want_ctas == 7) CB_MERGE(DOT, 7, 7);                                   \
+      else if (want_ctas == 6) CB_MERGE(DOT, 7, 6);                              \
+      else CB_MERGE(DOT, 7, 5);                                                  \
+      break;                                                                     \
+    case 11: CB_MERGE(DOT, 11, 5); break;                                        \
+    case 17: CB_MERGE(DOT, 17, 4); break;                                        \
     default: return fail(CASK_B200_ERR_RUNTIME, "merge_items must be 5, 7, 11 or 17"); \
   }
       if (dot) {

@@ -85,8 +85,10 @@ typedef struct {
   int32_t persist_ku;           /* persistent staged-ELL kernel: ELL columns per ring stage (0: kernel not in use) */
   int32_t persist_stages, persist_ctas_per_sm;
   int32_t value_dict;           /* format in use: 0 uncoded, 1 value codes, 2 pair codes */
-  int32_t col_reorder;          /* 1: the gather kernel runs on columns renumbered by descending reference count */
-  int64_t cols_referenced;      /* columns referenced at least once (valid when col_reorder is 1) */
+  int32_t col_reorder;          /* gather kernel's column numbering: 0 original, 1 by descending reference count, 2 compact */
+  int64_t cols_referenced;      /* columns referenced at least once (valid when col_reorder is not 0) */
+  int32_t merge_items;          /* merge-path tiles: merge items per thread (tile = 256 x merge_items) */
+  int32_t merge_ctas;           /* resident CTAs per SM the merge kernel instantiation is compiled for */
 } cask_b200_plan_stats;
 
 /* ---- context ---------------------------------------------------------------------------- */
@@ -107,9 +109,10 @@ int cask_b200_synchronize(cask_b200_ctx* ctx);
  * and scalar all-reduces by the library's own kernels over IPC-mapped peer memory, 0 = NCCL send/recv and
  * all-reduce; every rank must use the same value), "value_dict" (0 default, 1 / 2 = coded staged ELL, see
  * cask_b200_plan_value_dict), "persist_ctas" (coded format: CTAs per SM of the persistent kernel, 0 auto),
- * "col_reorder" (gather path, default 0; 1 = columns renumbered by descending reference count so that the hub columns
- * of a power-law matrix share cache lines, 2 = referenced columns only, in column order; x is permuted by a streaming
- * kernel in front of every SpMV), "dist_sparse" (row-sharded gather plans, default 1: every rank receives only the x
+ * "col_reorder" (gather path; -1 default = automatic: hub clustering for single-rank gather plans of at least 2^24
+ * nonzeros whose column reference counts are skewed, 0 = off, 1 = columns renumbered by descending reference count so
+ * that the hub columns of a power-law matrix share cache lines, 2 = referenced columns only, in column order; x is
+ * permuted by a streaming kernel in front of every SpMV), "dist_sparse" (row-sharded gather plans, default 1: every rank receives only the x
  * entries its rows reference, packed by their owners; 0: every slice of x is broadcast to all ranks),
  * "host_staging" (default 1: pageable caller vectors of cask_b200_spmv go through the library's pinned rings and copy
  * threads; 0: left to the driver), "ilu_graph" (default 1: the per-level launches of an ILU application are replayed

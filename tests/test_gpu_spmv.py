@@ -295,3 +295,30 @@ def test_pageable_host_buffers_are_staged_by_the_library(gpu_lib, ctx, oracle):
     ctx.set_option("col_reorder", 1)
     ctx.preprocess(d, n, n, rp, ci, va)
     assert_y_close(ctx.spmv(x), exp, row_scale(n, rp, ci, va, x))
+
+
+def test_col_reorder_automatic_rule(gpu_lib, ctx, oracle):
+    """Default options: a single-rank gather plan of >= 2^24 nonzeros over an x of >= 64 MB is hub-clustered when its column
+    reference counts are skewed (here: column = n u^6, the most referenced 1/64 of the columns draw over 40 % of the
+    gathers; tiles re-cut for 5 items per thread) and left alone when they are not (uniformly scattered columns: the
+    permutation of x would be pure cost).  Same y either way - one nonzero per row, so y is exact."""
+    n = 1 << 24
+    rng = np.random.default_rng(6)
+    rp = np.arange(n + 1, dtype=np.int32)
+    va = rng.standard_normal(n)
+    x = rng.standard_normal(n)
+    d = gpu_lib.design(1, 8192, 16)
+    for skewed in (True, False):
+        u = rng.random(n)
+        ci = np.minimum((n * (u ** 6 if skewed else u)).astype(np.int64), n - 1).astype(np.int32)
+        ctx.set_option("col_reorder", -1)
+        ctx.preprocess(d, n, n, rp, ci, va)
+        st = ctx.plan_stats()
+        assert st["csr_kernel"] == 1 and st["slices_staged_ell"] == 0, st
+        assert st["col_reorder"] == (1 if skewed else 0), st
+        if skewed:
+            assert st["cols_referenced"] == len(np.unique(ci))
+        assert np.array_equal(ctx.spmv(x), va * x[ci])
+        ctx.set_option("col_reorder", 0)
+        ctx.preprocess(d, n, n, rp, ci, va)
+        assert ctx.plan_stats()["col_reorder"] == 0 and np.array_equal(ctx.spmv(x), va * x[ci])
