@@ -804,6 +804,8 @@ def main():
             line["pcg_ilu"] = compact(pcg_ilu, ("iters_per_s", "loop_trips", "converged", "levels_per_triangular_solve", "error"))
             if "launched_one_by_one" in pcg_ilu:
                 line["pcg_ilu"]["iters_per_s_launched_one_by_one"] = pcg_ilu["launched_one_by_one"]["iters_per_s"]
+            if "level_graph" in pcg_ilu:
+                line["pcg_ilu"]["iters_per_s_level_graph"] = pcg_ilu["level_graph"]["iters_per_s"]
         if bicg:
             details["bicgstab"] = bicg
             line["bicgstab"] = compact(bicg, ("iters_per_s", "iterations", "converged", "rel_residual", "max_abs_err_vs_ones",
@@ -945,7 +947,8 @@ def bench_cg(ctx, cb, torch, dist, dev, rank, world, barrier, maxiters=2000, emu
 def bench_pcg_ilu(ctx, cb, torch, dev, N=64):
     """pcg<double, ILUPreconditioner> with a unit lower solve on the 3D 27-point Poisson twin N^3
     (single rank: the dependency levels of ILU(0) cross every stripe).  One launch per level, 7 (N - 1) + 1 levels per
-    triangular solve; the level sequence is replayed as ONE CUDA graph (ilu_graph = 1) or launched kernel by kernel (0)."""
+    triangular solve; all levels run in ONE cooperative kernel behind grid barriers (default), as a CUDA graph of the
+    per-level kernels (ilu_persistent = 0), or kernel by kernel (ilu_graph = 0 as well)."""
     kind = cb.SYNTH_POISSON3D27
     n = cb.synth_rows(kind, N)
     nnz = cb.synth_nnz(kind, N, 0, n)
@@ -957,7 +960,8 @@ def bench_pcg_ilu(ctx, cb, torch, dev, N=64):
     b = torch.empty(n, dtype=torch.float64, device=dev)
     out = {"workload": "pcg<ILU(0), unit lower solve> on 3D 27-pt Poisson %d^3 (%d rows, %d nnz), one GPU" % (N, n, nnz),
            "levels_per_triangular_solve": 7 * (N - 1) + 1}
-    for graph in (1, 0):
+    for mode, (persistent, graph) in (("persistent", (1, 1)), ("graph", (0, 1)), ("launches", (0, 0))):
+        ctx.set_option("ilu_persistent", persistent)
         ctx.set_option("ilu_graph", graph)
         ctx.preprocess_device(cb.design(num_pipes=1, cache_size=8192, input_width=16), n, n, nnz, rp.data_ptr(), ci.data_ptr(), va.data_ptr())
         ctx.spmv_device(xt.data_ptr(), b.data_ptr())
@@ -974,10 +978,13 @@ def bench_pcg_ilu(ctx, cb, torch, dev, N=64):
         trips = it + 2 if conv else it + 1   # `iterations` = index of the last non-converged iteration (SparseLinearSolvers.hpp:231)
         rec = {"iters_per_s": trips / dt, "loop_trips": trips, "converged": bool(conv), "seconds": dt, "rs_final": rs,
                "max_abs_err_vs_x_true": float((x - xt).abs().max().item()), "kernel_nodes_or_launches": int(ctx.launch_count() - l0)}
-        if graph:
+        if mode == "persistent":
             out.update(rec)
+        elif mode == "graph":
+            out["level_graph"] = rec
         else:
             out["launched_one_by_one"] = rec
+    ctx.set_option("ilu_persistent", 1)
     ctx.set_option("ilu_graph", 1)
     return out
 

@@ -322,7 +322,8 @@ struct cask_b200_ctx {
   int32_t l2_keep = -1;      // -1 auto (vectors of a solver iteration fit L2), 0 never, 1 always: evict-last on vector accesses
   int32_t dist_sparse = 1;   // row-sharded gather plans: 1 = sparse exchange (each rank receives only the x entries its rows
                              // reference, packed by their owners), 0 = every slice broadcast to all
-  int32_t ilu_graph = 1;     // ILU(0) application: 1 = the per-level launches replayed as one CUDA graph, 0 = launched one by one
+  int32_t ilu_persistent = 1;  // ILU(0) application: 1 = all levels of both solves in ONE cooperative kernel with grid barriers
+  int32_t ilu_graph = 1;     // ILU(0) application (when not persistent): 1 = the per-level launches replayed as one CUDA graph, 0 = launched one by one
   int32_t peer_mode = 1;     // 1: halo pushes and scalar all-reduces by own kernels over mapped peer memory; 0: NCCL
 
   // host-call staging buffers

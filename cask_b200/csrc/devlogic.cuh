@@ -115,6 +115,9 @@ inline int inclusive_sum_i32(Exec& ex, const int32_t* in, int32_t* out, int64_t 
 // IEEE multiply / subtract that the compiler may not contract into an FMA (the oracle is built with -ffp-contract=off)
 CB_DEV double mul_rn(double a, double b) { return __dmul_rn(a, b); }
 CB_DEV double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+// load of an entry another SM may have written earlier in the SAME kernel (persistent level loop of the triangular solves):
+// served by L2, never by a stale L1 line
+CB_DEV double ld_l2(const double* p) { return __ldcg(p); }
 
 CB_DEV void atomic_or_i32(int32_t* p, int32_t v) { atomicOr(reinterpret_cast<int*>(p), (int)v); }
 CB_DEV void atomic_add_i64(int64_t* p, int64_t v) {

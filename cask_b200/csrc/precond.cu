@@ -8,10 +8,13 @@
 // by the level-by-level solves, not by the vector passes; the identity-preconditioned loop in solvers.cu stays the
 // tuned path for BASELINE's CG configuration.
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "ctx.cuh"
 #include "devlogic.cuh"
+#include "peer.cuh"
 
 #include "precond_logic.inl"
 
@@ -25,6 +28,12 @@ struct PrecondState {
   const cask_b200_csr* pc_matrix = nullptr;  // optional: build the preconditioner from this matrix instead of A
   // the level sequence of one ILU application (one launch per dependency level: 1 786 for the 256^3 27-point system) as
   // ONE instantiated CUDA graph: captured on first use for a given (r, z, unit_lower), replayed by every later iteration
+  // ... or, by default, ONE cooperative kernel that walks all levels of both solves with a grid barrier between them
+  // (ilu_levels_kernel): level boundaries on the device, a monotonic barrier counter whose base the host tracks
+  int64_t* d_level_ptr = nullptr;        // [ptr_l | ptr_u]
+  unsigned long long* d_level_bar = nullptr;
+  unsigned long long level_bar_base = 0;
+  int64_t max_level_rows = 0;
   cudaGraphExec_t ilu_graph = nullptr;
   const double* graph_r = nullptr;
   double* graph_z = nullptr;
@@ -43,6 +52,8 @@ void free_precond(cask_b200_ctx* ctx) {
   if (!st) return;
   precond::ilu_free(&st->ilu);
   if (st->ilu_graph) cudaGraphExecDestroy(st->ilu_graph);
+  cudaFree(st->d_level_ptr);
+  cudaFree(st->d_level_bar);
   cudaFree(st->invd);
   for (auto& v : st->vec) cudaFree(v);
   cudaFree(st->partials);
@@ -117,6 +128,123 @@ __global__ void __launch_bounds__(kT) pcg_p_kernel(int64_t n, double beta, const
   for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < n; i += stride) p[i] = z[i] + beta * p[i];
 }
 
+// Both triangular solves of one ILU application in ONE launch: every level is a grid-stride loop over its rows (the same
+// row functors as the per-level kernels: same arithmetic, same order, same bits), levels are separated by a grid barrier.
+// A level of the 64^3 27-point twin holds ~600 rows and costs a per-level KERNEL about 7 us, most of it launch and drain;
+// the barrier of a small co-resident grid costs 1-2 us.  Rows read the entries earlier levels wrote with L2 loads
+// (dev::ld_l2): a stale L1 line must never serve them.  Launched cooperatively, so co-residency is guaranteed by the
+// runtime; the spin traps after the peer timeout instead of hanging.
+// (A thread-block cluster behind the hardware cluster barrier - barrier.cluster.arrive.release / wait.acquire - was tried for
+// the narrow levels of the 64^3 twin, 2 CTAs x 512 threads: 7.7 us per level against 5.4 us for this barrier through L2,
+// session r2w; not kept.)
+__device__ __forceinline__ void level_barrier(unsigned long long* bar, unsigned long long target) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(bar, 1ull);
+    const unsigned long long t0 = globaltimer_ns();
+    unsigned int spins = 0;
+    while (ld_volatile_u64(bar) < target)
+      if ((++spins & 0x3ffu) == 0 && globaltimer_ns() - t0 > kPeerTimeoutNs) asm volatile("trap;");
+  }
+  __syncthreads();
+}
+
+// What a thread can fetch of its next row BEFORE the barrier that releases the level: everything but the entries of the
+// solution vector - row number, extent, the first kPre column indices and factors, the right-hand side / pivot.  The
+// loads then fly during the barrier wait and the dependent chain behind the barrier shrinks from
+// order -> row_ptr -> (col, pc) -> y to the y loads alone.
+constexpr int kPre = 16;
+struct RowPre {
+  int32_t i, k0, re, dp;   // row (-1: none), first entry of interest, end of the row, diagonal position
+  int32_t j[kPre];
+  double a[kPre];
+  double rhs, d;           // lower solve: x_i and (non-unit) the pivot; upper solve: the pivot
+};
+
+template <bool kLower>
+__device__ __forceinline__ void row_prefetch(RowPre& q, const int32_t* __restrict__ order, int64_t t, int64_t count,
+                                             const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
+                                             const int32_t* __restrict__ diag_pos, const double* __restrict__ pc,
+                                             const double* __restrict__ x, int unit_lower) {
+  q.i = -1;
+  if (t >= count) return;
+  const int32_t i = order[t];
+  q.i = i;
+  const int32_t rb = row_ptr[i];
+  q.re = row_ptr[i + 1];
+  q.dp = diag_pos[i];
+  q.k0 = kLower ? rb : (q.dp >= 0 ? q.dp + 1 : rb);
+#pragma unroll
+  for (int u = 0; u < kPre; u++) {
+    const bool in = q.k0 + u < q.re;
+    q.j[u] = in ? col[q.k0 + u] : i;
+    q.a[u] = in ? pc[q.k0 + u] : 0.0;
+  }
+  q.rhs = kLower ? x[i] : 0.0;
+  q.d = (kLower && unit_lower) ? 1.0 : (q.dp >= 0 ? pc[q.dp] : 0.0);
+}
+
+// The row itself, after the barrier: the same subtractions in the same (ascending column) order as LowerRow / UpperRow.
+template <bool kLower>
+__device__ __forceinline__ void row_finish(const RowPre& q, const int32_t* __restrict__ col, const double* __restrict__ pc,
+                                           const double* in_vec /* lower: y (own output); upper: z */, const double* y,
+                                           double* out, int unit_lower, int32_t* flag) {
+  if (q.i < 0) return;
+  const int32_t i = q.i;
+  double v[kPre];
+#pragma unroll
+  for (int u = 0; u < kPre; u++) v[u] = (kLower ? q.j[u] < i : q.j[u] > i) ? dev::ld_l2(in_vec + q.j[u]) : 0.0;
+  double acc = kLower ? q.rhs : dev::ld_l2(y + i);
+#pragma unroll
+  for (int u = 0; u < kPre; u++)
+    if (kLower ? q.j[u] < i : q.j[u] > i) acc = dev::sub_rn(acc, dev::mul_rn(q.a[u], v[u]));
+  // rows with more than kPre entries of interest: the rest with plain dependent loads
+  if (kLower ? q.j[kPre - 1] < i : q.k0 + kPre < q.re) {
+    for (int32_t k = q.k0 + kPre; k < q.re; k++) {
+      const int32_t j = col[k];
+      if (kLower && j >= i) break;
+      if (kLower || j > i) acc = dev::sub_rn(acc, dev::mul_rn(pc[k], dev::ld_l2(in_vec + j)));
+    }
+  }
+  if (!(kLower && unit_lower) && q.d == 0.0) dev::atomic_or_i32(flag, 1);
+  out[i] = acc / q.d;
+}
+
+__global__ void __launch_bounds__(kT)
+ilu_levels_kernel(precond::LowerRow lo, precond::UpperRow up, const int64_t* __restrict__ ptr_l, int nlev_l,
+                  const int64_t* __restrict__ ptr_u, int nlev_u, unsigned long long* bar, unsigned long long base) {
+  const int64_t gsize = (int64_t)gridDim.x * blockDim.x, gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long target = base;
+  const int32_t* order_l = lo.order;
+  const int32_t* order_u = up.order;
+  RowPre q;
+  if (nlev_l > 0) row_prefetch<true>(q, order_l + ptr_l[0], gtid, ptr_l[1] - ptr_l[0], lo.row_ptr, lo.col, lo.diag_pos, lo.pc, lo.x, lo.unit_lower);
+  for (int l = 0; l < nlev_l; l++) {
+    const int64_t b = ptr_l[l], e = ptr_l[l + 1];
+    row_finish<true>(q, lo.col, lo.pc, lo.y, lo.y, lo.y, lo.unit_lower, lo.flag);
+    lo.order = order_l + b;
+    for (int64_t t = gtid + gsize; t < e - b; t += gsize) lo(t);  // levels wider than the grid: the generic row functor
+    if (l + 1 < nlev_l) row_prefetch<true>(q, order_l + e, gtid, ptr_l[l + 2] - e, lo.row_ptr, lo.col, lo.diag_pos, lo.pc, lo.x, lo.unit_lower);
+    else if (nlev_u > 0) row_prefetch<false>(q, order_u + ptr_u[0], gtid, ptr_u[1] - ptr_u[0], up.row_ptr, up.col, up.diag_pos, up.pc, nullptr, 0);
+    target += gridDim.x;
+    level_barrier(bar, target);
+  }
+  if (nlev_l == 0 && nlev_u > 0)
+    row_prefetch<false>(q, order_u + ptr_u[0], gtid, ptr_u[1] - ptr_u[0], up.row_ptr, up.col, up.diag_pos, up.pc, nullptr, 0);
+  for (int l = 0; l < nlev_u; l++) {
+    const int64_t b = ptr_u[l], e = ptr_u[l + 1];
+    row_finish<false>(q, up.col, up.pc, up.z, up.y, up.z, 0, up.flag);
+    up.order = order_u + b;
+    for (int64_t t = gtid + gsize; t < e - b; t += gsize) up(t);
+    if (l + 1 < nlev_u) {
+      row_prefetch<false>(q, order_u + e, gtid, ptr_u[l + 2] - e, up.row_ptr, up.col, up.diag_pos, up.pc, nullptr, 0);
+      target += gridDim.x;
+      level_barrier(bar, target);
+    }
+  }
+}
+
 int vgrid(const cask_b200_ctx* ctx, int64_t n) {
   const int64_t ctas = (n + kT - 1) / kT;
   return (int)std::max<int64_t>(1, std::min<int64_t>(ctas, (int64_t)ctx->sm_count * 4));
@@ -173,6 +301,22 @@ int ensure_ilu(cask_b200_ctx* ctx) {
   dev::Exec ex = dev::exec_of(ctx);
   CB_TRY(precond::ilu_analyse(ex, mv.n, mv.nnz, mv.rp, mv.ci, &st->ilu));
   CB_TRY(precond::ilu_factor(ex, mv.va, &st->ilu));
+  // level boundaries for the persistent solve kernel
+  cudaFree(st->d_level_ptr);
+  st->d_level_ptr = nullptr;
+  std::vector<int64_t> lp(st->ilu.ptr_l);
+  lp.insert(lp.end(), st->ilu.ptr_u.begin(), st->ilu.ptr_u.end());
+  st->max_level_rows = 0;
+  for (size_t l = 0; l + 1 < st->ilu.ptr_l.size(); l++) st->max_level_rows = std::max(st->max_level_rows, st->ilu.ptr_l[l + 1] - st->ilu.ptr_l[l]);
+  for (size_t l = 0; l + 1 < st->ilu.ptr_u.size(); l++) st->max_level_rows = std::max(st->max_level_rows, st->ilu.ptr_u[l + 1] - st->ilu.ptr_u[l]);
+  CB_CUDA(cudaMalloc(&st->d_level_ptr, sizeof(int64_t) * std::max<size_t>(lp.size(), 1)));
+  if (!lp.empty()) CB_CUDA(cudaMemcpyAsync(st->d_level_ptr, lp.data(), sizeof(int64_t) * lp.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CB_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (!st->d_level_bar) {
+    CB_CUDA(cudaMalloc(&st->d_level_bar, sizeof(unsigned long long)));
+    CB_CUDA(cudaMemset(st->d_level_bar, 0, sizeof(unsigned long long)));
+    st->level_bar_base = 0;
+  }
   st->ilu_ready = true;
   return CASK_B200_OK;
 }
@@ -239,6 +383,34 @@ int apply(cask_b200_ctx* ctx, int32_t precon, int64_t n, const double* r, double
   const int unit = precon == CASK_B200_PRECON_ILU_UNIT ? 1 : 0;
   const size_t levels = st->ilu.ptr_l.size() + st->ilu.ptr_u.size();
   cudaStream_t s = ctx->stream;
+  if (ctx->ilu_persistent != 0 && levels > 16 && st->ilu.factored && st->d_level_ptr) {
+    const int nl = (int)st->ilu.ptr_l.size() - 1, nu = (int)st->ilu.ptr_u.size() - 1;
+    precond::LowerRow lo{st->ilu.row_ptr, st->ilu.col, st->ilu.diag_pos, st->ilu.order_l, st->ilu.pc, r, st->ilu.y, unit, st->ilu.flag};
+    precond::UpperRow up{st->ilu.row_ptr, st->ilu.col, st->ilu.diag_pos, st->ilu.order_u, st->ilu.pc, st->ilu.y, z, st->ilu.flag};
+    const int64_t* pl = st->d_level_ptr;
+    const int64_t* pu = st->d_level_ptr + st->ilu.ptr_l.size();
+    cudaLaunchConfig_t cfg = {};
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // one cooperative launch; the grid covers the widest level once (more CTAs only make the barrier dearer)
+    int occ = 0;
+    CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ilu_levels_kernel, kT, 0));
+    const int64_t want = std::max<int64_t>(1, (st->max_level_rows + kT - 1) / kT);
+    const int grid = (int)std::min<int64_t>(want, (int64_t)std::max(occ, 1) * ctx->sm_count);
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kT);
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, ilu_levels_kernel, lo, up, pl, nl, pu, nu, st->d_level_bar, st->level_bar_base);
+    if (e == cudaSuccess) st->level_bar_base += (unsigned long long)grid * (unsigned long long)(nl + std::max(nu - 1, 0));
+    if (e == cudaSuccess) {
+      ctx->launches++;
+      return CASK_B200_OK;
+    }
+    cudaGetLastError();  // cooperative launch not available here: the graph / per-level paths below
+  }
   // stream capture needs a real stream (not the legacy default one a caller may have handed over with set_stream(NULL))
   const bool graphable = ctx->ilu_graph != 0 && levels > 16 && s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread;
   if (!graphable) return precond::ilu_apply(ex, &st->ilu, unit, r, z, nullptr);

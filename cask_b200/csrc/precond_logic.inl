@@ -130,7 +130,7 @@ struct LowerRow {  // y_i = (x_i - sum_{j<i} L_ij y_j) / d,  d = pc_ii (the refe
         a[u] = in ? pc[k0 + u] : 0.0;
       }
       CB_UNROLL
-      for (int u = 0; u < kRowBatch; u++) v[u] = j[u] < i ? y[j[u]] : 0.0;
+      for (int u = 0; u < kRowBatch; u++) v[u] = j[u] < i ? dev::ld_l2(y + j[u]) : 0.0;
       CB_UNROLL
       for (int u = 0; u < kRowBatch; u++)
         if (j[u] < i) acc = dev::sub_rn(acc, dev::mul_rn(a[u], v[u]));
@@ -158,7 +158,7 @@ struct UpperRow {  // z_i = (y_i - sum_{j>i} U_ij z_j) / U_ii
   CB_DEV void operator()(int64_t t) const {
     const int32_t i = order[t];
     const int32_t dp = diag_pos[i];
-    double acc = y[i];
+    double acc = dev::ld_l2(y + i);
     // without a stored diagonal the row still has to skip its lower part; operands in batches as in LowerRow
     const int32_t re = row_ptr[i + 1];
     for (int32_t k0 = dp >= 0 ? dp + 1 : row_ptr[i]; k0 < re; k0 += kRowBatch) {
@@ -171,7 +171,7 @@ struct UpperRow {  // z_i = (y_i - sum_{j>i} U_ij z_j) / U_ii
         a[u] = in ? pc[k0 + u] : 0.0;
       }
       CB_UNROLL
-      for (int u = 0; u < kRowBatch; u++) v[u] = j[u] > i ? z[j[u]] : 0.0;
+      for (int u = 0; u < kRowBatch; u++) v[u] = j[u] > i ? dev::ld_l2(z + j[u]) : 0.0;
       CB_UNROLL
       for (int u = 0; u < kRowBatch; u++)
         if (j[u] > i) acc = dev::sub_rn(acc, dev::mul_rn(a[u], v[u]));

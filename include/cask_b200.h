@@ -115,8 +115,9 @@ int cask_b200_synchronize(cask_b200_ctx* ctx);
  * permuted by a streaming kernel in front of every SpMV), "dist_sparse" (row-sharded gather plans, default 1: every rank receives only the x
  * entries its rows reference, packed by their owners; 0: every slice of x is broadcast to all ranks),
  * "host_staging" (default 1: pageable caller vectors of cask_b200_spmv go through the library's pinned rings and copy
- * threads; 0: left to the driver), "ilu_graph" (default 1: the per-level launches of an ILU application are replayed
- * as one CUDA graph).
+ * threads; 0: left to the driver), "ilu_persistent" (default 1: all dependency levels of an ILU application run in one
+ * cooperative kernel with grid barriers), "ilu_graph" (when not persistent; default 1: the per-level launches are
+ * replayed as one CUDA graph).
  * Takes effect at the next preprocess. */
 int cask_b200_set_option(cask_b200_ctx* ctx, const char* name, double value);
 

@@ -104,6 +104,7 @@ inline int inclusive_sum_i32(Exec& ex, const int32_t* in, int32_t* out, int64_t 
 }
 
 inline double mul_rn(double a, double b) { return a * b; }  // built with -ffp-contract=off
+inline double ld_l2(const double* p) { return *p; }
 inline double sub_rn(double a, double b) { return a - b; }
 inline void atomic_or_i32(int32_t* p, int32_t v) { *p |= v; }
 inline void atomic_add_i64(int64_t* p, int64_t v) { *p += v; }

@@ -92,21 +92,26 @@ def test_unsorted_rows_are_refused(gpu_lib, ctx):
     assert e.value.code == gpu_lib.ERR_UNSUPPORTED
 
 
-def test_ilu_level_graph_replays_the_same_solves(gpu_lib, ctx, oracle):
-    """The per-level launches of an ILU application are captured once into a CUDA graph and replayed: same iterates bit
-    for bit as launching them one by one (ilu_graph = 0), across solves, preconditioner kinds and a change of matrix."""
+def test_ilu_level_kernel_and_graph_replay_the_same_solves(gpu_lib, ctx, oracle):
+    """An ILU application runs as ONE cooperative kernel that walks all levels of both solves behind grid barriers (default),
+    as a CUDA graph of the per-level kernels (ilu_persistent = 0), or kernel by kernel (ilu_graph = 0 as well): the same
+    iterates bit for bit, across solves, preconditioner kinds and a change of matrix."""
     res = {}
-    for graph in (1, 0):
+    for mode, (persistent, graph) in enumerate(((1, 1), (0, 1), (0, 0))):
+        ctx.set_option("ilu_persistent", persistent)
         ctx.set_option("ilu_graph", graph)
         out = []
-        for gen, arg in (("gen_poisson2d", 40), ("gen_poisson3d27", 10)):
+        for gen, arg in (("gen_poisson2d", 40), ("gen_poisson3d27", 10), ("gen_convdiff3d7", 12)):
             n, rp, ci, va = getattr(oracle, gen)(arg)
             prep(gpu_lib, ctx, n, rp, ci, va)
             b = oracle.csr_dot(n, rp, ci, va, 1.0 + 0.25 * (np.arange(n) % 4))
             for code in (gpu_lib.PRECON_ILU_UNIT, gpu_lib.PRECON_ILU_UNIT, gpu_lib.PRECON_ILU):
                 conv, it, x, rs = ctx.pcg(b, code, maxiters=60)
                 out.append((conv, it, rs, x))
-        res[graph] = out
-    for a, b in zip(res[1], res[0]):
-        assert a[:3] == b[:3] and np.array_equal(a[3], b[3])
-    assert res[1][0][0] and res[1][3][0]      # the unit-lower solves converge
+        res[mode] = out
+    for other in (1, 2):
+        for a, b in zip(res[0], res[other]):
+            assert a[:3] == b[:3] and np.array_equal(a[3], b[3])
+    assert res[0][0][0] and res[0][3][0]      # the unit-lower solves converge on the SPD systems
+    ctx.set_option("ilu_persistent", 1)
+    ctx.set_option("ilu_graph", 1)
