@@ -559,8 +559,14 @@ int cask_b200_spmv(cask_b200_ctx* ctx, const double* x, double* y) {
   const bool big = (p.m + p.n) * (int64_t)sizeof(double) >= (int64_t)kRingChunk && ctx->host_staging != 0;
   const bool stage_x = big && p.m && is_pageable(x), stage_y = big && p.n && is_pageable(y);
   // merge-path tiles cross slice boundaries, so the chunked pipeline (which launches slice ranges) is for plans without them
-  if ((ctx->host_pipeline_chunks > 1 && p.nslices >= 128 && !p.csr_merge) || stage_x || stage_y)
-    return spmv_host_pipelined(ctx, x, y, stage_x, stage_y);
+  if ((ctx->host_pipeline_chunks > 1 && p.nslices >= 128 && !p.csr_merge) || stage_x || stage_y) {
+    try {  // the staged path starts host threads: std::system_error / bad_alloc must not cross the C ABI
+      return spmv_host_pipelined(ctx, x, y, stage_x, stage_y);
+    } catch (const std::exception& e) {
+      cudaStreamSynchronize(ctx->stream);
+      return fail(CASK_B200_ERR_RUNTIME, std::string("spmv (host buffers): ") + e.what());
+    }
+  }
   CB_TRY(stage_in(ctx, x, p.m, p.n));
   CB_TRY(launch_spmv(ctx, ctx->d_x, ctx->d_y, 0, ctx->stream, nullptr));
   if (p.n) CB_CUDA(cudaMemcpyAsync(y, ctx->d_y, sizeof(double) * p.n, cudaMemcpyDeviceToHost, ctx->stream));
