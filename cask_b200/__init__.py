@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = (
     "cask_b200_partition_export", "cask_b200_spmv", "cask_b200_spmv_device", "cask_b200_spmv_refformat",
     "cask_b200_cg", "cask_b200_cg_device", "cask_b200_bicgstab", "cask_b200_bicgstab_device",
     "cask_b200_nccl_unique_id", "cask_b200_dist_init", "cask_b200_shard_rows",
-    "cask_b200_preprocess_shard_device", "cask_b200_dist_halo_counts", "cask_b200_dist_peer_active", "cask_b200_dist_vector", "cask_b200_spmv_shard", "cask_b200_halo_plan_host", "cask_b200_synth_rows",
+    "cask_b200_preprocess_shard_device", "cask_b200_dist_halo_counts", "cask_b200_dist_peer_active", "cask_b200_dist_vector", "cask_b200_spmv_shard", "cask_b200_halo_plan_host", "cask_b200_sparse_segments_host", "cask_b200_sparse_send_plan_host", "cask_b200_synth_rows",
     "cask_b200_synth_nnz", "cask_b200_synth_device", "cask_b200_launch_count", "cask_b200_legacy_write",
     "cask_b200_legacy_read", "cask_b200_legacy_run", "cask_b200_legacy_reset", "cask_b200_legacy_launch_count",
     "cask_b200_mm_read_info", "cask_b200_mm_read_coo", "cask_b200_mm_read_vector", "cask_b200_ingest_coo",
@@ -145,6 +145,8 @@ def lib():
         L.cask_b200_dist_vector.argtypes = [vp, i32, C.POINTER(vp)]
         L.cask_b200_spmv_shard.argtypes = [vp, vp, vp]
         L.cask_b200_halo_plan_host.argtypes = [i64, i32, i32, i64, vp, vp, i64, vp, vp, vp, vp]
+        L.cask_b200_sparse_segments_host.argtypes = [vp, i32, vp, i64, vp]
+        L.cask_b200_sparse_send_plan_host.argtypes = [vp, i32, i32, vp, vp]
         L.cask_b200_synth_rows.argtypes = [i32, i32, vp]
         L.cask_b200_synth_nnz.argtypes = [i32, i32, i64, i64, vp]
         L.cask_b200_synth_device.argtypes = [i32, i32, i64, i64, vp, vp, vp, vp]
@@ -204,6 +206,24 @@ def halo_plan_host(n_global, world, rank, run_col0, run_len):
     check(lib().cask_b200_halo_plan_host(n_global, world, rank, len(c0), _p(c0), _p(ln), cap, _p(peer), _p(col0), _p(length),
                                          C.byref(cnt)))
     return [(int(peer[i]), int(col0[i]), int(length[i])) for i in range(cnt.value)]
+
+
+def sparse_segments_host(bounds, need):
+    """seg[world + 1]: where each owner's columns start inside the ascending list `need` of referenced columns."""
+    b = np.ascontiguousarray(bounds, np.int64)
+    nd = np.ascontiguousarray(need, np.int32)
+    seg = np.zeros(len(b), np.int64)
+    check(lib().cask_b200_sparse_segments_host(_p(b), len(b) - 1, _p(nd), len(nd), _p(seg)))
+    return seg
+
+
+def sparse_send_plan_host(all_seg, rank):
+    """(send_off[world + 1], dst_off[world]) of `rank` from every rank's segment boundaries (world x (world + 1))."""
+    a = np.ascontiguousarray(all_seg, np.int64)
+    world = a.shape[0]
+    send_off, dst_off = np.zeros(world + 1, np.int64), np.zeros(world, np.int64)
+    check(lib().cask_b200_sparse_send_plan_host(_p(a), world, rank, _p(send_off), _p(dst_off)))
+    return send_off, dst_off
 
 
 def synth_rows(kind, N):

@@ -272,6 +272,21 @@ __global__ void __launch_bounds__(256) sparse_push_kernel(const double* __restri
   if (tid < sd.world && ((sd.recv_mask >> tid) & 1u)) peer_wait_ge(&sd.ctrl->halo_flag_acked[1][tid], sd.done + 1, &sd.ctrl->error);
 }
 
+// Pure host arithmetic of the sparse exchange (exported as cask_b200_sparse_segments_host / cask_b200_sparse_send_plan_host
+// and exercised by the gloo tests on CPU).
+static void sparse_segments(const int64_t* bounds, int world, const int32_t* need, int64_t count, int64_t* seg) {
+  for (int q = 0; q <= world; q++)
+    seg[q] = std::lower_bound(need, need + count, bounds[q], [](int32_t a, int64_t b) { return (int64_t)a < b; }) - need;
+}
+static void sparse_send_plan(const int64_t* all_seg, int world, int me, int64_t* send_off, int64_t* dst_off) {
+  const size_t cap = (size_t)world + 1;
+  send_off[0] = 0;
+  for (int q = 0; q < world; q++) {
+    send_off[q + 1] = send_off[q] + (q == me ? 0 : all_seg[cap * q + me + 1] - all_seg[cap * q + me]);
+    if (dst_off) dst_off[q] = all_seg[cap * q + me];
+  }
+}
+
 // Collective.  Decides (all ranks together) whether the sparse exchange applies, renumbers the columns, and tells every
 // owner which of its entries each peer needs.
 static int dist_plan_sparse(cask_b200_ctx* ctx) {
@@ -313,8 +328,7 @@ static int dist_plan_sparse(cask_b200_ctx* ctx) {
   if (p.cols_used) CB_CUDA(cudaMemcpyAsync(need.data(), p.d_perm, sizeof(int32_t) * need.size(), cudaMemcpyDeviceToHost, s));
   CB_CUDA(cudaStreamSynchronize(s));
   d->seg.assign((size_t)W + 1, 0);
-  for (int q = 0; q <= W; q++)
-    d->seg[q] = std::lower_bound(need.begin(), need.end(), d->bounds[q], [](int32_t a, int64_t b) { return (int64_t)a < b; }) - need.begin();
+  sparse_segments(d->bounds.data(), W, need.data(), (int64_t)need.size(), d->seg.data());
   // 3. every rank's segment boundaries: what rank q needs from owner r is its segment r, so one all-gather of the
   //    boundaries tells every owner how much it sends to whom, and (peer-memory variant) where its entries start
   //    inside every peer's compact x
@@ -322,11 +336,9 @@ static int dist_plan_sparse(cask_b200_ctx* ctx) {
   CB_TRY(gather_all());
   auto seg_of = [&](int q, int r) -> int64_t { return all[cap * q + r]; };  // boundary r of rank q's compact x
   d->send_off.assign((size_t)W + 1, 0);
+  sparse_send_plan(all.data(), W, me, d->send_off.data(), nullptr);
   int64_t max_used = 0;
-  for (int q = 0; q < W; q++) {
-    d->send_off[q + 1] = d->send_off[q] + (q == me ? 0 : seg_of(q, me + 1) - seg_of(q, me));
-    max_used = std::max(max_used, seg_of(q, W));
-  }
+  for (int q = 0; q < W; q++) max_used = std::max(max_used, seg_of(q, W));
   const int64_t total_send = d->send_off[W];
   CB_CUDA(cudaMalloc(&d->d_send_list, sizeof(int32_t) * (size_t)std::max<int64_t>(total_send, 1)));
   CB_CUDA(cudaMalloc(&d->d_sendbuf, sizeof(double) * (size_t)std::max<int64_t>(total_send, 1)));
@@ -948,6 +960,23 @@ extern "C" int cask_b200_halo_plan_host(int64_t n_global, int32_t world, int32_t
       if (out_len) out_len[k] = r.len;
       k++;
     }
+  return CASK_B200_OK;
+}
+
+extern "C" int cask_b200_sparse_segments_host(const int64_t* bounds, int32_t world, const int32_t* need, int64_t count, int64_t* seg) {
+  if (!bounds || world < 1 || count < 0 || (count && !need) || !seg) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "sparse_segments_host: bad arguments");
+  for (int q = 0; q < world; q++)
+    if (bounds[q] > bounds[q + 1]) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "sparse_segments_host: bounds must not decrease");
+  for (int64_t i = 1; i < count; i++)
+    if (need[i - 1] >= need[i]) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "sparse_segments_host: need[] must be strictly ascending");
+  sparse_segments(bounds, world, need, count, seg);
+  return CASK_B200_OK;
+}
+
+extern "C" int cask_b200_sparse_send_plan_host(const int64_t* all_seg, int32_t world, int32_t rank, int64_t* send_off, int64_t* dst_off) {
+  if (!all_seg || world < 1 || rank < 0 || rank >= world || !send_off || !dst_off)
+    return fail(CASK_B200_ERR_INVALID_ARGUMENT, "sparse_send_plan_host: bad arguments");
+  sparse_send_plan(all_seg, world, rank, send_off, dst_off);
   return CASK_B200_OK;
 }
 

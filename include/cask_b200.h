@@ -204,6 +204,17 @@ int cask_b200_shard_rows(int64_t n, int32_t world, int32_t rank, int64_t* row0, 
 int cask_b200_halo_plan_host(int64_t n_global, int32_t world, int32_t rank, int64_t nruns, const int64_t* run_col0,
                              const int64_t* run_len, int64_t capacity, int32_t* out_peer, int64_t* out_col0,
                              int64_t* out_len, int64_t* out_count);
+
+/* Host-side arithmetic of the SPARSE exchange of a row-sharded gather plan (no GPU needed; the same routines the GPU path
+ * runs, exercised by world-size 2/3 gloo tests on CPU).  A rank renumbers the columns its rows reference compactly, in
+ * column order: need[0 .. count) ascending.  bounds[q] = first row (= first column) rank q owns, bounds[world] = n.
+ *   segments:  seg[q] = first position of need[] that belongs to owner q (seg[world] = count): segment q of the rank's
+ *              compact x holds the entries it receives from rank q (its own segment is filled locally).
+ *   send plan: all_seg = every rank's seg array, rank-major (world x (world + 1)).  For rank `rank`:
+ *              send_off[q] .. send_off[q + 1] = positions of its send list that go to rank q (nothing to itself), and
+ *              dst_off[q] = where those entries start inside rank q's compact x. */
+int cask_b200_sparse_segments_host(const int64_t* bounds, int32_t world, const int32_t* need, int64_t count, int64_t* seg);
+int cask_b200_sparse_send_plan_host(const int64_t* all_seg, int32_t world, int32_t rank, int64_t* send_off, int64_t* dst_off);
 /* Local stripe of the global n x m matrix: d_row_ptr has nrows+1 entries rebased to 0 (exactly
  * CsrMatrix::sliceRows, SparseMatrix.hpp:426-443), column indices stay global.  Collective.  The ranks' row ranges must be
  * contiguous, in rank order and cover all rows; cask_b200_shard_rows gives the reference's partition (equal row counts),

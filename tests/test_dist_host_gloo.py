@@ -117,3 +117,83 @@ def test_reference_arm_under_torchrun_prints_once(tmp_path):
     assert p.returncode == 0
     lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1 and json.loads(lines[0])["impl"] == "reference" and json.loads(lines[0])["n_gpus"] == 2
+
+
+SPARSE_WORKER = r'''
+import os, sys, json
+sys.path.insert(0, %r)
+import numpy as np, torch, torch.distributed as dist
+import cask_b200 as cb
+from oracle import oraclebind as O
+O.build()
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+n, rp, ci, va = O.gen_rmat(12, 8, 3)
+# stripes of equal nonzero count (rank 0 owns the few, long hub rows), as the R-MAT leg of bench.py cuts them
+bounds = [0] + [int(np.searchsorted(rp, rp[-1] * q // world)) for q in range(1, world)] + [n]
+r0, nr = bounds[rank], bounds[rank + 1] - bounds[rank]
+lci = ci[rp[r0]:rp[r0 + nr]]
+need = np.unique(lci).astype(np.int32)                     # the compact numbering: referenced columns, ascending
+seg = cb.sparse_segments_host(bounds, need)
+assert seg[0] == 0 and seg[-1] == len(need) and all(seg[q] <= seg[q + 1] for q in range(world))
+for q in range(world):                                     # segment q holds exactly the columns rank q owns
+    s = need[seg[q]:seg[q + 1]]
+    assert len(s) == 0 or (bounds[q] <= s[0] and s[-1] < bounds[q + 1])
+segs = [torch.zeros(world + 1, dtype=torch.int64) for _ in range(world)]
+dist.all_gather(segs, torch.from_numpy(seg.copy()))
+all_seg = np.stack([t.numpy() for t in segs])
+send_off, dst_off = cb.sparse_send_plan_host(all_seg, rank)
+# request lists: what every rank needs (the GPU path all-gathers the padded lists and cuts its pieces)
+lists = [None] * world
+dist.all_gather_object(lists, need)
+x = np.random.default_rng(3).standard_normal(n)
+xp = torch.full((max(len(need), 1),), float("nan"), dtype=torch.float64)     # the compact x, poisoned
+xp[seg[rank]:seg[rank + 1]] = torch.from_numpy(x[need[seg[rank]:seg[rank + 1]]])   # own segment, filled locally
+ops, keep = [], []
+for q in range(world):
+    if q == rank:
+        continue
+    want = lists[q][all_seg[q][rank]:all_seg[q][rank + 1]]      # columns of MINE that rank q references
+    assert len(want) == send_off[q + 1] - send_off[q] and dst_off[q] == all_seg[q][rank]
+    assert len(want) == 0 or (bounds[rank] <= want[0] and want[-1] < bounds[rank + 1])
+    if len(want):
+        buf = torch.from_numpy(x[want].copy()); keep.append(buf)  # a rank only ever reads its OWN slice of x
+        ops.append(dist.P2POp(dist.isend, buf, q))
+    if seg[q + 1] > seg[q]:
+        ops.append(dist.P2POp(dist.irecv, xp[seg[q]:seg[q + 1]], q))
+if ops:
+    for r in dist.batch_isend_irecv(ops):
+        r.wait()
+got = xp.numpy()[:len(need)]
+assert not np.isnan(got).any() and np.array_equal(got, x[need])                # every referenced entry arrived, in place
+# the relabelled stripe times the compact x == the global product
+relabel = np.searchsorted(need, lci).astype(np.int32)
+lrp = (rp[r0:r0 + nr + 1] - rp[r0]).astype(np.int32)
+y = O.csr_dot(nr, lrp, relabel, va[rp[r0]:rp[r0 + nr]], got) if nr else np.zeros(0)
+exp = O.csr_dot(n, rp, ci, va, x)[r0:r0 + nr]
+ok = bool(np.array_equal(y, exp))
+t = torch.tensor([1.0 if ok else 0.0, float(len(need)), float(send_off[-1])], dtype=torch.float64)
+tl = [torch.zeros_like(t) for _ in range(world)]
+dist.all_gather(tl, t)
+if rank == 0:
+    print("RESULT " + json.dumps({"ok": [bool(v[0]) for v in tl], "need": [int(v[1]) for v in tl], "sent": [int(v[2]) for v in tl], "n": n}))
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sparse_exchange_plan_over_gloo(world, tmp_path):
+    """The sparse exchange of a row-sharded gather plan, host arithmetic only (cask_b200_sparse_segments_host /
+    cask_b200_sparse_send_plan_host - the routines dist.cu runs), with gloo standing in for NVLink: every rank receives
+    exactly the x entries its rows reference into its compactly renumbered x, nothing else travels, and the relabelled
+    stripe times the compact x equals the global product bit for bit."""
+    script = tmp_path / "worker.py"
+    script.write_text(SPARSE_WORKER % ROOT)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(29640 + world), str(script)]
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-4000:]
+    res = json.loads([l for l in p.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
+    assert all(res["ok"]) and len(res["ok"]) == world
+    assert all(0 < k < res["n"] for k in res["need"])          # every rank references a strict subset of the columns
+    assert 0 < sum(res["sent"]) < sum(res["need"])          # what travels = what is referenced minus the own segments
