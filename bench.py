@@ -1126,7 +1126,7 @@ def bench_rmat(ctx, cb, torch, dist, dev, rank, world, barrier, scale=25, edge_f
             ctx.set_option("col_reorder", 2)
         ctx.preprocess_device(dsg, nr, n, nnz, rp.data_ptr(), ci.data_ptr(), va.data_ptr())
         if emu:
-            ctx.set_option("col_reorder", int(os.environ.get("CASK_B200_COL_REORDER", "0")))
+            ctx.set_option("col_reorder", int(os.environ.get("CASK_B200_COL_REORDER", "-1")))
     ctx.synchronize()
     prep = time.perf_counter() - t0
     stats = ctx.plan_stats()
