@@ -1123,7 +1123,7 @@ def bench_rmat(ctx, cb, torch, dist, dev, rank, world, barrier, scale=25, edge_f
         ctx.preprocess_shard_device(dsg, n, n, r0, nr, nnz, rp.data_ptr(), ci.data_ptr(), va.data_ptr())
     else:
         if emu:
-            ctx.set_option("col_reorder", 2)
+            ctx.set_option("col_reorder", int(os.environ.get("CASK_B200_STRIPE_REORDER", "2")))
         ctx.preprocess_device(dsg, nr, n, nnz, rp.data_ptr(), ci.data_ptr(), va.data_ptr())
         if emu:
             ctx.set_option("col_reorder", int(os.environ.get("CASK_B200_COL_REORDER", "-1")))

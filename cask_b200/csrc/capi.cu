@@ -115,6 +115,7 @@ int cask_b200_create(cask_b200_ctx** out, int device) {
   if (const char* e = getenv("CASK_B200_MERGE_ITEMS")) ctx->merge_items = atoi(e);
   if (const char* e = getenv("CASK_B200_COL_REORDER")) ctx->col_reorder = atoi(e);
   if (const char* e = getenv("CASK_B200_DIST_SPARSE")) ctx->dist_sparse = atoi(e);
+  if (const char* e = getenv("CASK_B200_DIST_SPARSE_HUB")) ctx->dist_sparse_hub = atoi(e);
   if (const char* e = getenv("CASK_B200_ILU_GRAPH")) ctx->ilu_graph = atoi(e);
   if (const char* e = getenv("CASK_B200_ILU_PERSISTENT")) ctx->ilu_persistent = atoi(e);
   if (const char* e = getenv("CASK_B200_VALUE_DICT")) ctx->value_dict = atoi(e);
@@ -185,6 +186,7 @@ int cask_b200_set_option(cask_b200_ctx* ctx, const char* name, double value) {
   else if (k == "merge_items") ctx->merge_items = (int32_t)value;
   else if (k == "col_reorder") ctx->col_reorder = (int32_t)value;
   else if (k == "dist_sparse") ctx->dist_sparse = (int32_t)value;
+  else if (k == "dist_sparse_hub") ctx->dist_sparse_hub = (int32_t)value;
   else if (k == "ilu_graph") ctx->ilu_graph = (int32_t)value;
   else if (k == "ilu_persistent") ctx->ilu_persistent = (int32_t)value;
   else if (k == "value_dict") ctx->value_dict = (int32_t)value;

@@ -152,6 +152,7 @@ struct Plan {
   double* d_xperm = nullptr;          // [cols_used] x in the new numbering, rewritten in front of every SpMV
   int32_t cols_used = 0;              // columns referenced at least once = the first cols_used new columns
   bool xperm_external = false;        // d_xperm is filled by the sparse exchange of a sharded plan (dist.cu), not by permute_x_kernel
+  bool hub_ordered = false;           // the renumbering puts the most referenced columns first: gathers go through L1
   bool xperm_owned = true;            // false: d_xperm lives in the symmetric arena (peers store into it over NVLink)
   int32_t max_xcache = 0;
   // persistent staged-ELL kernel configuration (spmv.cu: configure_persistent)
@@ -320,6 +321,7 @@ struct cask_b200_ctx {
   bool dist_sparse_active = false;  // set by dist.cu while it builds the compact numbering of a sparse exchange
   int32_t csr_kernel = -1;   // gather slices: -1 auto (merge-path tiles from kMergeAutoNnz nonzeros), 0 row-group items, 1 merge-path tiles
   int32_t l2_keep = -1;      // -1 auto (vectors of a solver iteration fit L2), 0 never, 1 always: evict-last on vector accesses
+  int32_t dist_sparse_hub = 1;  // sparse exchange: inside every owner's segment of the compact x the most referenced columns come first
   int32_t dist_sparse = 1;   // row-sharded gather plans: 1 = sparse exchange (each rank receives only the x entries its rows
                              // reference, packed by their owners), 0 = every slice broadcast to all
   int32_t ilu_persistent = 1;  // ILU(0) application: 1 = all levels of both solves in ONE cooperative kernel with grid barriers
@@ -358,7 +360,9 @@ int refformat_stripe(cudaStream_t s, int64_t* launches, const int32_t* d_colptr,
 // plan.cu
 int build_plan(cask_b200_ctx* ctx);
 int build_csr_items(cask_b200_ctx* ctx);
-int build_col_reorder(cask_b200_ctx* ctx, int mode);  // 0 none, 1 hub clustering, 2 referenced columns in column order
+// mode 0 none, -1 automatic, 1 hub clustering, 2 compact numbering of the referenced columns (grouped by owning rank,
+// hubs first inside a group, when the owners' first columns are given; else in column order)
+int build_col_reorder(cask_b200_ctx* ctx, int mode, const int64_t* owner_first, int world);
 void free_plan(cask_b200_ctx* ctx);
 
 // spmv.cu

@@ -207,7 +207,8 @@ static int64_t halo_ranges_from_runs(int64_t n_global, int world, int me, const 
 
 // ---- SPARSE mode ---------------------------------------------------------------------------------------------------
 // sendbuf[i] = x[send_list[i]] for the entries the peers asked for, and the own segment of the compact x directly.
-// Both index lists are ascending inside a destination, so the reads sweep the own slice forward.
+// Inside a destination the list is in the RECEIVER's order (its hubs first, then ascending runs of equally often
+// referenced columns), so beyond the hubs the reads are a handful of forward sweeps over the own slice.
 __global__ void __launch_bounds__(256) sparse_pack_kernel(const double* __restrict__ x_full, const int32_t* __restrict__ send_list,
                                                           int64_t n_send, double* __restrict__ sendbuf,
                                                           const int32_t* __restrict__ own_cols, int64_t n_own,
@@ -320,7 +321,7 @@ static int dist_plan_sparse(cask_b200_ctx* ctx) {
     if (!all[cap * q]) return CASK_B200_OK;
   // 2. compact column numbering; segment q = referenced columns owned by rank q
   ctx->dist_sparse_active = true;
-  const int rc_reorder = build_col_reorder(ctx, 2);
+  const int rc_reorder = build_col_reorder(ctx, 2, ctx->dist_sparse_hub != 0 ? d->bounds.data() : nullptr, W);
   ctx->dist_sparse_active = false;
   CB_TRY(rc_reorder);
   if (!p.d_perm) return fail(CASK_B200_ERR_RUNTIME, "sparse exchange: the column renumbering was refused");
@@ -967,8 +968,13 @@ extern "C" int cask_b200_sparse_segments_host(const int64_t* bounds, int32_t wor
   if (!bounds || world < 1 || count < 0 || (count && !need) || !seg) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "sparse_segments_host: bad arguments");
   for (int q = 0; q < world; q++)
     if (bounds[q] > bounds[q + 1]) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "sparse_segments_host: bounds must not decrease");
-  for (int64_t i = 1; i < count; i++)
-    if (need[i - 1] >= need[i]) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "sparse_segments_host: need[] must be strictly ascending");
+  // need[] is grouped by owner, owners ascending (column order is the special case); the order inside a group is free
+  int q = 0;
+  for (int64_t i = 0; i < count; i++) {
+    if (need[i] < bounds[0] || need[i] >= bounds[world]) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "sparse_segments_host: column outside the owners' ranges");
+    if (need[i] < bounds[q]) return fail(CASK_B200_ERR_INVALID_ARGUMENT, "sparse_segments_host: need[] must be grouped by owner, owners ascending");
+    while (need[i] >= bounds[q + 1]) q++;
+  }
   sparse_segments(bounds, world, need, count, seg);
   return CASK_B200_OK;
 }

@@ -301,13 +301,32 @@ __global__ void __launch_bounds__(256) col_count_kernel(const int32_t* __restric
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += stride) atomicAdd(counts + col[k], 1);
 }
-// by_count: ascending key = descending count (hub clustering); else referenced columns first, in column order (compaction)
+// Sort keys of the three numberings; never referenced columns get kColKeyEmpty and go last.
+//   by_count, no owners   ascending key = descending count (hub clustering)
+//   owners                (owner of the column) << 32 | (descending count): the compact numbering of a sharded plan - one
+//                         segment per owning rank, the segment's hubs first
+//   neither               referenced columns in column order
+constexpr uint64_t kColKeyEmpty = 64ull << 32;
+constexpr int kMaxOwners = 64;
+struct ColOwners {
+  int32_t world = 0;              // 0: no owner grouping
+  int64_t first[kMaxOwners + 1];  // first column of every owner (+ m)
+};
 __global__ void __launch_bounds__(256) col_keys_kernel(const int32_t* __restrict__ counts, int64_t m, uint64_t* __restrict__ keys,
-                                                       uint32_t* __restrict__ ids, int by_count) {
+                                                       uint32_t* __restrict__ ids, int by_count, const ColOwners own) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += stride) {
     const int32_t c = counts[j];
-    keys[j] = (uint64_t)(by_count ? 0x7fffffff - c : (c ? 0 : 0x7fffffff));
+    uint64_t key = kColKeyEmpty;
+    if (c) {
+      key = by_count ? (uint64_t)(0x7fffffff - c) : 0;
+      if (own.world) {
+        int q = 0;
+        while (q + 1 < own.world && j >= own.first[q + 1]) q++;
+        key |= (uint64_t)q << 32;
+      }
+    }
+    keys[j] = key;
     ids[j] = (uint32_t)j;
   }
 }
@@ -317,15 +336,15 @@ __global__ void __launch_bounds__(256) col_inverse_kernel(const uint32_t* __rest
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += stride) {
     inv[perm[j]] = (int32_t)j;
-    const bool ref = keys[j] != 0x7fffffffull;
-    if (ref && (j == m - 1 || keys[j + 1] == 0x7fffffffull)) *used = (int32_t)(j + 1);
+    const bool ref = keys[j] != kColKeyEmpty;
+    if (ref && (j == m - 1 || keys[j + 1] == kColKeyEmpty)) *used = (int32_t)(j + 1);
   }
 }
 // *sum += reference counts of the first k columns of the hub ordering (keys = 0x7fffffff - count, sorted ascending)
 __global__ void __launch_bounds__(256) col_head_count_kernel(const uint64_t* __restrict__ keys, int64_t k, unsigned long long* __restrict__ sum) {
   unsigned long long acc = 0;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < k; j += stride) acc += 0x7fffffffull - keys[j];
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < k; j += stride) acc += 0x7fffffffull - (keys[j] & 0xffffffffull);
 #pragma unroll
   for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
   if ((threadIdx.x & 31) == 0 && acc) atomicAdd(sum, acc);
@@ -506,7 +525,7 @@ int build_csr_items(cask_b200_ctx* ctx) {
 // the referenced columns only, in ascending column order - the compact local numbering of a distributed SpMV; the
 // permuted x is then filled by the exchange (own columns by a pack kernel, the others received from their owners), not by
 // permute_x_kernel.
-int build_col_reorder(cask_b200_ctx* ctx, int mode) {
+int build_col_reorder(cask_b200_ctx* ctx, int mode, const int64_t* owner_first, int world) {
   Plan& p = ctx->plan;
   cudaFree(p.d_col_perm); cudaFree(p.d_perm);
   if (p.xperm_owned) cudaFree(p.d_xperm);
@@ -514,6 +533,7 @@ int build_col_reorder(cask_b200_ctx* ctx, int mode) {
   p.xperm_owned = true;
   p.cols_used = 0;
   p.xperm_external = false;
+  p.hub_ordered = false;
   p.stats.col_reorder = 0;
   p.stats.cols_referenced = 0;
   p.merge_ctas = 0;
@@ -542,10 +562,18 @@ int build_col_reorder(cask_b200_ctx* ctx, int mode) {
   CB_CUDA(cudaMemsetAsync(tmp.q[0], 0, sizeof(int32_t) * (size_t)m, s));
   CB_CUDA(cudaMemsetAsync(tmp.q[4], 0, sizeof(int32_t), s));
   if (p.nnz) col_count_kernel<<<grid, 256, 0, s>>>(p.d_col, p.nnz, (int32_t*)tmp.q[0]);
-  col_keys_kernel<<<grid, 256, 0, s>>>((const int32_t*)tmp.q[0], m, (uint64_t*)tmp.q[1], (uint32_t*)tmp.q[3], mode == 1 ? 1 : 0);
+  // sharded compact numbering: one segment per owning rank, hubs first inside a segment (measured on the stripes of the
+  // 8- and 2-rank C3 jobs run alone, profiles/r2u2_stripe_hub.md: 7-12 % faster than column order)
+  ColOwners own;
+  const bool grouped = mode == 2 && owner_first && world >= 1 && world <= kMaxOwners;
+  if (grouped) {
+    own.world = world;
+    for (int q = 0; q <= world; q++) own.first[q] = owner_first[q];
+  }
+  col_keys_kernel<<<grid, 256, 0, s>>>((const int32_t*)tmp.q[0], m, (uint64_t*)tmp.q[1], (uint32_t*)tmp.q[3], mode == 1 || grouped ? 1 : 0, own);
   ctx->launches += 2;
   CB_TRY(dev::sort_pairs_u64_u32(ex, (const uint64_t*)tmp.q[1], (uint64_t*)tmp.q[2], (const uint32_t*)tmp.q[3],
-                                 (uint32_t*)p.d_perm, m, 31));  // stable: equal keys keep ascending column order
+                                 (uint32_t*)p.d_perm, m, 39));  // stable: equal keys keep ascending column order
   col_inverse_kernel<<<grid, 256, 0, s>>>((const uint32_t*)p.d_perm, (const uint64_t*)tmp.q[2], m, (int32_t*)tmp.q[0],
                                           (int32_t*)tmp.q[4]);
   CB_CUDA(cudaMalloc(&p.d_col_perm, sizeof(int32_t) * (size_t)std::max<int64_t>(p.nnz, 1)));
@@ -575,6 +603,15 @@ int build_col_reorder(cask_b200_ctx* ctx, int mode) {
       p.merge_ctas = 8;
     }
   }
+  if (grouped && p.csr_merge && p.stats.csr_nnz >= kReorderAutoNnz &&
+      !(ctx->merge_items == 5 || ctx->merge_items == 7 || ctx->merge_items == 11 || ctx->merge_items == 17)) {
+    CB_TRY(build_merge_tiles(ctx, 5));  // the configuration of the hub-clustered single-rank plans
+    p.stats.csr_items = p.n_merge_tiles;
+    p.merge_ctas = 8;
+    p.stats.merge_items = p.merge_items;
+    p.stats.merge_ctas = p.merge_ctas;
+  }
+  p.hub_ordered = mode == 1 || grouped;
   p.cols_used = used;
   CB_CUDA(cudaMalloc(&p.d_xperm, sizeof(double) * (size_t)std::max<int64_t>(used, 2)));
   p.xperm_external = mode == 2 && ctx->dist_sparse_active;
@@ -803,7 +840,7 @@ int build_plan(cask_b200_ctx* ctx) {
   p.stats.max_row_length = maxlen;
   p.stats.csr_nnz = csr_nnz;
   p.stats.csr_rows = csr_rows;
-  CB_TRY(build_col_reorder(ctx, ctx->col_reorder == 1 || ctx->col_reorder == 2 || ctx->col_reorder < 0 ? ctx->col_reorder : 0));
+  CB_TRY(build_col_reorder(ctx, ctx->col_reorder == 1 || ctx->col_reorder == 2 || ctx->col_reorder < 0 ? ctx->col_reorder : 0, nullptr, 0));
   p.stats.persist_ku = ctx->ell_kernel == 1 ? p.persist_ku : 0;
   p.stats.persist_stages = p.persist_stages;
   p.stats.persist_ctas_per_sm = p.persist_ctas_per_sm;

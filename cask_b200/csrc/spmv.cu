@@ -1018,7 +1018,7 @@ int launch_spmv_range(cask_b200_ctx* ctx, const double* d_x, double* d_y, int el
         cols = p.d_col_perm;
         xg = p.d_xperm;
       }
-      const int flags = ((xcg_env >= 0 ? xcg_env : (p.stats.col_reorder == 1 ? 0 : 1)) ? kMergeXPastL1 : 0) | diag;
+      const int flags = ((xcg_env >= 0 ? xcg_env : (p.hub_ordered ? 0 : 1)) ? kMergeXPastL1 : 0) | diag;
 #define CB_MERGE(DOT, ITEMS, CTAS)                                                                                        \
   do {                                                                                                                    \
     CB_CUDA(cudaFuncSetAttribute(spmv_csr_merge_kernel<DOT, ITEMS, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
