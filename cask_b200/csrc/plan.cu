@@ -522,9 +522,9 @@ int build_csr_items(cask_b200_ctx* ctx) {
 // 5 merge items per thread and the kernel compiled for 8 resident CTAs per SM: measured on R-MAT scale 25
 // (profiles/r2s_rmat_ctas.md) 2.99 ms per SpMV, permutation included, against 3.23 ms without clustering.
 // mode 1: hub clustering as above (option col_reorder).  mode 2 (dist.cu, sparse exchange of a row-sharded gather plan):
-// the referenced columns only, in ascending column order - the compact local numbering of a distributed SpMV; the
-// permuted x is then filled by the exchange (own columns by a pack kernel, the others received from their owners), not by
-// permute_x_kernel.
+// the referenced columns only - the compact local numbering of a distributed SpMV - grouped by owning rank, hubs first
+// inside a group (owner_first given), or in ascending column order (single-rank option); in a sharded plan the permuted x
+// is filled by the exchange (own columns by a pack kernel, the others received from their owners), not by permute_x_kernel.
 int build_col_reorder(cask_b200_ctx* ctx, int mode, const int64_t* owner_first, int world) {
   Plan& p = ctx->plan;
   cudaFree(p.d_col_perm); cudaFree(p.d_perm);
